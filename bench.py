@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — k-mers hashed per second on N B200s (BASELINE.json metric), one process per GPU.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                 # this repo's CUDA engine
+    torchrun ... bench.py --gpus N ...                             # N ranks, weak scaling (one shard per GPU)
+    python bench.py --impl reference ...                           # the reference's own CPU roll() loop
+
+A "step" is one pass of the hot path (NtHash roll over every read) over one batch of synthetic
+reads: BASELINE.json configs[1], 10 M x 150 bp, k=31, h=1 per GPU.  `value` is device-resident
+throughput (inputs in HBM, CUDA events on the launching stream, max over ranks); `e2e` is the same
+metric through the host-buffer C ABI call (pinned host buffers, H2D + kernel + D2H inside the timed
+region); `roofline` compares the kernel's algorithmic bytes/s with the measured HBM copy peak;
+`cpu_baseline` is the compiled reference (oracle/_ref) timed on this box's host cores.
+The oracle/ directory is executed here only for cpu_baseline / --impl reference and a checksum check.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CONFIGS = {
+    # name: (reads per GPU, read length, k, hashes)
+    "c2": dict(n_reads=10_000_000, read_len=150, k=31, h=1, desc="10M x 150bp reads, k=31, h=1 canonical (BASELINE.json configs[1])"),
+    "c3": dict(n_reads=10_000_000, read_len=150, k=31, h=4, desc="10M x 150bp reads, k=31, h=4 (configs[2])"),
+    "c5": dict(n_reads=12_500, read_len=50_000, k=63, h=1, desc="12.5k x 50kb reads per GPU, k=63, h=1 (configs[4] shard)"),
+}
+METRIC = "kmers_hashed_per_sec"
+UNIT = "kmers/s"
+
+
+def algorithmic_bytes(n_reads, read_len, k, H):
+    """every base read once + every hash written once."""
+    return n_reads * read_len + n_reads * max(read_len - k + 1, 0) * H * 8
+
+
+def load_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def synth_reads_device(torch, n_bases, seed):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device="cuda")
+    buf = torch.zeros(n_bases + 64, dtype=torch.uint8, device="cuda")  # readable slack past the last base
+    step = 1 << 28
+    for o in range(0, n_bases, step):
+        m = min(step, n_bases - o)
+        buf[o:o + m] = lut[torch.randint(0, 4, (m,), dtype=torch.uint8, device="cuda", generator=g).long()]
+    return buf
+
+
+def cpu_reference_pass(lib, bases_np, n_reads, read_len, k, h, threads):
+    """One pass of the reference's own loop over `n_reads` reads -> (k-mers/s, emitted, sum)."""
+    import numpy as np
+    off = np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(read_len)
+    t0 = time.perf_counter()
+    r = lib.kmer_batch(bases_np, off, k, h, want=(), threads=threads)
+    dt = time.perf_counter() - t0
+    return r["n_emit"] / dt, r["n_emit"], r["sum"], dt
+
+
+def run_reference(args, cfg):
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle_lib import ORACLE, REF
+    lib = REF if REF is not None else ORACLE
+    threads = os.cpu_count() or 1
+    sample_reads = min(cfg["n_reads"], args.ref_sample_reads)
+    bases = ORACLE.gen_bases(sample_reads * cfg["read_len"], 42)
+    for _ in range(args.warmup):
+        cpu_reference_pass(lib, bases, sample_reads, cfg["read_len"], cfg["k"], cfg["h"], threads)
+    t0 = time.perf_counter()
+    emitted = 0
+    for _ in range(args.steps):
+        _, ne, _, _ = cpu_reference_pass(lib, bases, sample_reads, cfg["read_len"], cfg["k"], cfg["h"], threads)
+        emitted += ne
+    dt = time.perf_counter() - t0
+    value = emitted / dt
+    sample = f"{sample_reads} reads x {cfg['read_len']} bp per step (a bounded sample of the {cfg['n_reads']}-read batch)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": cfg["desc"], "reads_per_step": sample_reads, "read_len": cfg["read_len"], "k": cfg["k"], "h": cfg["h"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": lib.kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--reads", type=int, default=0, help="override reads per GPU (debugging only; invalidates the number)")
+    ap.add_argument("--ref-sample-reads", type=int, default=2_000_000)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.reads:
+        cfg["n_reads"] = args.reads
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import nthash_b200
+    from nthash_b200._lib import LIB, check
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_reads, L, k, h = cfg["n_reads"], cfg["read_len"], cfg["k"], cfg["h"]
+    nk = L - k + 1
+    rows = n_reads * nk
+    n_bases = n_reads * L
+    bases_buf = synth_reads_device(torch, n_bases, 1234 + rank)
+    bases = bases_buf[:n_bases]
+    out = torch.empty((rows, h), dtype=torch.int64, device="cuda")
+    valid = torch.empty(int(LIB.nthash_valid_words(rows)), dtype=torch.int32, device="cuda")
+
+    def step(with_valid=True):
+        nthash_b200.kmer_hashes_uniform(bases, n_reads, L, k, h, want_valid=with_valid, out=out,
+                                        valid_bits=valid if with_valid else None)
+
+    # ---- device-resident throughput (value) -------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        ev0.record()
+        for _ in range(args.steps):
+            step()
+        ev1.record()
+        torch.cuda.synchronize()
+    barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    # ---- dominant kernel alone (roofline): same launch without the bitmap memset ------------
+    step(False)
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(args.steps):
+        step(False)
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / args.steps
+    t = torch.tensor([ms, kernel_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, kernel_ms = float(t[0]), float(t[1])
+
+    # ---- end to end through the host-buffer C ABI call ----------------------------------------
+    e2e = None
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 0
+    e2e_reads = n_reads
+    need = (n_bases + rows * h * 8) * world
+    while e2e_reads > 100_000 and avail and need * e2e_reads / n_reads > 0.5 * avail:
+        e2e_reads //= 2
+    e_rows = e2e_reads * nk
+    h_bases = torch.empty(e2e_reads * L, dtype=torch.uint8).pin_memory()
+    h_bases.copy_(bases[: e2e_reads * L])
+    h_off = (torch.arange(e2e_reads + 1, dtype=torch.int64) * L)
+    h_out = torch.empty((e_rows, h), dtype=torch.int64).pin_memory()
+    h_valid = torch.empty(int(LIB.nthash_valid_words(e_rows)), dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        check(LIB.nthash_kmer_batch(h_bases.data_ptr(), h_off.data_ptr(), e2e_reads, k, h, h_out.data_ptr(),
+                                    h_valid.data_ptr(), None, None, local))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e_dt = (time.perf_counter() - t0) / args.e2e_steps
+    te = torch.tensor([e_dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e_dt = float(te[0])
+    # parity of the e2e result with the device-resident one (same reads): checksum of checksums
+    same = bool((h_out[: 1000 * nk].cuda() == out[: 1000 * nk]).all())
+    e2e = {"value": world * e_rows / e_dt, "unit": UNIT, "h2d_bytes_per_step": int(h_bases.numel() + h_off.numel() * 8),
+           "d2h_bytes_per_step": int(h_out.numel() * 8 + h_valid.numel() * 4), "reads_per_step": e2e_reads,
+           "ms_per_step": e_dt * 1e3, "matches_device_path": same}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline: the compiled reference on this box's host cores -------------------------
+    cpu = None
+    checksum_ok = None
+    if not args.no_cpu_baseline:
+        from oracle_lib import ORACLE, REF
+        lib = REF if REF is not None else ORACLE
+        threads = os.cpu_count() or 1
+        sample_reads = min(n_reads, args.ref_sample_reads)
+        h_sample = bases[: sample_reads * L].cpu().numpy()
+        v, ne, s, dt = cpu_reference_pass(lib, h_sample, sample_reads, L, k, h, threads)
+        # grow the sample until it is a meaningful amount of CPU work (about 10-30 core-seconds)
+        if dt * threads < 10 and sample_reads < n_reads:
+            sample_reads = min(n_reads, int(sample_reads * 20 / max(dt * threads, 0.5)))
+            h_sample = bases[: sample_reads * L].cpu().numpy()
+            v, ne, s, dt = cpu_reference_pass(lib, h_sample, sample_reads, L, k, h, threads)
+        got = int(out[: sample_reads * nk].cpu().numpy().view(np.uint64).sum(dtype=np.uint64))
+        checksum_ok = (got == s) and ne == sample_reads * nk
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": lib.kind,
+               "sample": f"first {sample_reads} of {n_reads} reads, {dt:.2f} s wall on {threads} threads", "checksum_matches_gpu": checksum_ok}
+
+    peak, peak_src = load_peak()
+    abytes = algorithmic_bytes(n_reads, L, k, h)
+    achieved = abytes / (kernel_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": world * rows / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": cfg["desc"], "reads_per_gpu": n_reads, "read_len": L, "k": k, "h": h,
+                   "l2_policy": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2; no explicit flush" % (abytes / 1e9),
+                   "sharding": "independent read shards per GPU, no collective"},
+        "clocks": clk.summary(), "e2e": e2e, "gpu_launches": args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "kmer_kernel<1,false>", "kernel_ms": kernel_ms,
+                     "algorithmic_bytes_per_launch": abytes},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

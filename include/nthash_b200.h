@@ -1,0 +1,99 @@
+/*
+ * nthash_b200.h — C ABI of the B200-native ntHash v2 batch engine (libnthash_b200.so).
+ *
+ * The reference (bcgsc/ntHash 2.4.0) has no FFI: its only interface is the C++ iterator
+ * classes of include/nthash/nthash.hpp, whose hot loop `while (obj.roll())` lives in user
+ * code and costs one library call per k-mer.  Each entry point below replaces that loop
+ * for a whole batch of reads; the reference interface it stands in for is cited per
+ * function as file:line in the reference tree.  include/nthash/nthash.hpp of THIS repo
+ * re-exposes the reference's class API on top of these calls.
+ *
+ * Conventions
+ *  - Plain C: pointers and sizes only.  Return 0 (NTHASH_OK) or a negative error code;
+ *    the reference's raise_error() -> exit(1) (src/internal.hpp:16-22) never happens here.
+ *    nthash_last_error() returns the thread-local message of the last failure.
+ *  - Hash values are bit-identical to the reference ("ntHash_v2", nthash.hpp:18).
+ *  - Input: reads laid back to back in `bases` (ASCII, one byte per base, as the reference
+ *    takes them: nthash.hpp:74-78); read r is bases[read_off[r] .. read_off[r+1]).
+ *  - Output: DENSE WINDOW ROWS.  koff[r] = sum_{r'<r} max(0, len_r' - k + 1) (reads shorter
+ *    than k own no windows; the reference refuses to construct on them, kmer.cpp:215-220).
+ *    The window of read r starting at base p (what the reference reports as get_pos()==p,
+ *    nthash.hpp:170) is row w = koff[r] + p:
+ *        out[w*H + j]      j-th hash of the window, H = num_hashes (k-mers) or
+ *                          n_seeds*num_hashes_per_seed, seed-major (seed.cpp:167-171)
+ *        valid_bits        bit (w & 31) of word (w >> 5) is 1 iff the reference's
+ *                          while(roll()) loop visits that window (it skips windows by the
+ *                          rules of kmer.cpp:228-264 / seed.cpp:493-544); rows whose bit is 0
+ *                          read back as 0.  Bits past the last row are unspecified.
+ *        out_fwd/out_rev   get_forward_hash()/get_reverse_hash() per window (k-mers) or per
+ *                          window per seed (spaced seeds); optional.
+ *    `valid_bits`, `out_fwd`, `out_rev` may be NULL (both of fwd/rev or neither).
+ *  - `*_dev` entry points take DEVICE pointers on the current CUDA device and only enqueue
+ *    work on `stream` (a cudaStream_t, NULL = default stream); nothing is copied and the
+ *    host is not synchronised unless stated.  `bases` must be 16-byte aligned (cudaMalloc
+ *    memory is).  The un-suffixed entry points take HOST pointers and do H2D, the kernel
+ *    and D2H themselves on `device`.
+ *  - Supported domain: 3 <= k <= 65535 (the reference segfaults for k < 3, kmer.cpp:47),
+ *    1 <= num_hashes <= 255 (uint8_t in the reference), any read lengths.
+ *  - Thread-safe: no mutable global state besides per-thread error text.
+ */
+#ifndef NTHASH_B200_H
+#define NTHASH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NTHASH_OK 0
+#define NTHASH_ERR_INVALID_ARG (-1) /* what the reference answers with raise_error()/exit(1) */
+#define NTHASH_ERR_CUDA (-2)        /* a CUDA runtime call failed; see nthash_last_error() */
+#define NTHASH_ERR_NO_DEVICE (-3)   /* no usable sm_100 device: the engine has no CPU fallback */
+#define NTHASH_ERR_UNSUPPORTED (-4)
+
+/* NTHASH_FN_NAME, include/nthash/nthash.hpp:18 */
+const char* nthash_fn_name(void);
+const char* nthash_last_error(void);
+int nthash_b200_abi_version(void);
+/* Number of CUDA devices the engine can run on (compute capability 10.x). */
+int nthash_device_count(void);
+
+/* ---- layout helpers (host arithmetic only) --------------------------------------- */
+/* Fills koff[0..n_reads] (nullable) and returns the total number of window rows. */
+uint64_t nthash_window_rows(const uint64_t* read_off, uint64_t n_reads, uint32_t k, uint64_t* koff);
+/* Number of 32-bit words of a valid_bits array for `rows` rows. */
+uint64_t nthash_valid_words(uint64_t rows);
+
+/* ---- NtHash: contiguous k-mers ------------------------------------------------------
+ * Replaces `nthash::NtHash it(seq, len, h, k); while (it.roll()) use(it.hashes())`
+ * (nthash.hpp:62-211; NtHash::init/roll src/kmer.cpp:228-264; extend_hashes
+ * src/internal.hpp:104-118) run over every read of the batch.                           */
+
+/* Fixed-length reads: read r is bases[r*read_len .. (r+1)*read_len); koff[r] = r*(read_len-k+1).
+ * `n_bases_readable` = readable extent of d_bases (>= n_reads*read_len). */
+int nthash_kmer_batch_uniform_dev(const uint8_t* d_bases, uint64_t n_bases_readable, uint64_t n_reads,
+                                  uint32_t read_len, uint32_t k, uint32_t num_hashes, uint64_t* d_out,
+                                  uint32_t* d_valid_bits, uint64_t* d_out_fwd, uint64_t* d_out_rev,
+                                  void* stream);
+
+/* Ragged reads, step 1: d_koff[0..n_reads] from d_read_off on the device.  Synchronises
+ * `stream` to return the totals the caller needs to size its buffers.                    */
+int nthash_kmer_plan_dev(const uint64_t* d_read_off, uint64_t n_reads, uint32_t k, uint64_t* d_koff,
+                         uint64_t* total_rows, uint64_t* max_read_len, void* stream);
+/* Ragged reads, step 2.  d_koff/max_read_len as produced by nthash_kmer_plan_dev. */
+int nthash_kmer_batch_dev(const uint8_t* d_bases, uint64_t n_bases_readable, const uint64_t* d_read_off,
+                          const uint64_t* d_koff, uint64_t n_reads, uint64_t max_read_len, uint32_t k,
+                          uint32_t num_hashes, uint64_t* d_out, uint32_t* d_valid_bits, uint64_t* d_out_fwd,
+                          uint64_t* d_out_rev, void* stream);
+
+/* Host buffers in, host buffers out (H2D + kernel + D2H on `device`). */
+int nthash_kmer_batch(const char* bases, const uint64_t* read_off, uint64_t n_reads, uint32_t k,
+                      uint32_t num_hashes, uint64_t* out, uint32_t* valid_bits, uint64_t* out_fwd,
+                      uint64_t* out_rev, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

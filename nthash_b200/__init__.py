@@ -1,0 +1,10 @@
+"""nthash_b200 — B200-native (sm_100a) batch engine for the ntHash v2 rolling k-mer hash.
+
+Layout: csrc/ holds the hand-written CUDA kernels and the C ABI (include/nthash_b200.h);
+_lib.py binds that ABI with ctypes; api.py is a thin device-resident front end that uses
+PyTorch only for HBM buffers and streams; host.py drives host-buffer calls and multi-GPU shards.
+"""
+from ._lib import LIB, LIB_PATH, NtHashError  # noqa: F401
+from .api import HashBatch, kmer_hashes, kmer_hashes_uniform  # noqa: F401
+
+FN_NAME = LIB.nthash_fn_name().decode()

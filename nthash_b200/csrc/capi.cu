@@ -1,0 +1,309 @@
+// capi.cu — the extern "C" boundary declared in include/nthash_b200.h.
+// Argument validation mirrors the reference constructors (src/kmer.cpp:212-225,
+// src/seed.cpp:85-104, :467-469) but reports through return codes instead of exit(1).
+#include "../../include/nthash_b200.h"
+#include "engine.hpp"
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace nthb {
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define NTH_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e__ = (expr);                                                                       \
+    if (e__ != cudaSuccess) return fail(NTHASH_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+uint32_t span_bound(uint32_t seg, uint32_t segs, uint32_t k)
+{
+  // KMER_NT consecutive items advance by seg bytes each, plus a (k-1)-base tail per read end crossed
+  const uint64_t b = (uint64_t)KMER_NT * seg + ((uint64_t)KMER_NT / segs + 2) * (k - 1) + 64;
+  return b > 0xffffffffull ? 0xffffffffu : (uint32_t)b;
+}
+
+static const uint32_t SMEM_MAX = 227 * 1024;
+
+bool plan_uniform(uint64_t n_reads, uint32_t read_len, uint32_t k, KmerGeom& g, uint32_t& tile_cap)
+{
+  g = KmerGeom();
+  g.read_len = read_len;
+  g.nk = read_len >= k ? read_len - k + 1 : 0;
+  if (g.nk == 0 || n_reads == 0) {
+    g.n_items = 0;
+    tile_cap = 0;
+    return true;
+  }
+  if ((uint64_t)KMER_NT * read_len + 64 <= TILE_BUDGET) { // one item per read
+    g.seg = g.nk;
+    g.segs = 1;
+    tile_cap = KMER_NT * read_len + 64;
+  } else {
+    g.seg = SEG_LONG;
+    g.segs = (g.nk + g.seg - 1) / g.seg;
+    tile_cap = span_bound(g.seg, g.segs, k);
+  }
+  g.n_items = n_reads * g.segs;
+  return kmer_smem_bytes(tile_cap) <= SMEM_MAX;
+}
+
+static int check_kh(uint32_t k, uint32_t h)
+{
+  if (k < 3 || k > 65535) return fail(NTHASH_ERR_INVALID_ARG, "k=%u outside the supported range [3, 65535]", k);
+  if (h < 1 || h > 255) return fail(NTHASH_ERR_INVALID_ARG, "num_hashes=%u outside [1, 255]", h);
+  return NTHASH_OK;
+}
+
+static int check_outputs(const void* out, const void* fwd, const void* rev)
+{
+  if (!out) return fail(NTHASH_ERR_INVALID_ARG, "out must not be NULL");
+  if ((fwd == nullptr) != (rev == nullptr))
+    return fail(NTHASH_ERR_INVALID_ARG, "out_fwd and out_rev must be given together");
+  return NTHASH_OK;
+}
+
+static int check_device_ready()
+{
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(NTHASH_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10)
+    return fail(NTHASH_ERR_NO_DEVICE, "device %d is sm_%d?: the engine is built for sm_100a only", dev, major);
+  return NTHASH_OK;
+}
+
+static int run_kmer(KmerParams& P, uint64_t rows, cudaStream_t st)
+{
+  if (P.valid_bits && rows) NTH_CUDA(cudaMemsetAsync(P.valid_bits, 0xFF, ((rows + 31) / 32) * 4, st));
+  if (P.g.n_items == 0) return NTHASH_OK;
+  NTH_CUDA(launch_kmer(P, st));
+  return NTHASH_OK;
+}
+
+} // namespace nthb
+
+using namespace nthb;
+
+extern "C" {
+
+const char* nthash_fn_name(void) { return "ntHash_v2"; }
+const char* nthash_last_error(void) { return g_err.c_str(); }
+int nthash_b200_abi_version(void) { return 1; }
+
+int nthash_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  int ok = 0;
+  for (int d = 0; d < n; ++d) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+  }
+  return ok;
+}
+
+uint64_t nthash_window_rows(const uint64_t* read_off, uint64_t n_reads, uint32_t k, uint64_t* koff)
+{
+  uint64_t acc = 0;
+  for (uint64_t r = 0; r < n_reads; ++r) {
+    if (koff) koff[r] = acc;
+    const uint64_t len = read_off[r + 1] - read_off[r];
+    if (len >= k) acc += len - k + 1;
+  }
+  if (koff) koff[n_reads] = acc;
+  return acc;
+}
+
+uint64_t nthash_valid_words(uint64_t rows) { return (rows + 31) / 32; }
+
+int nthash_kmer_batch_uniform_dev(const uint8_t* d_bases, uint64_t n_bases_readable, uint64_t n_reads,
+                                  uint32_t read_len, uint32_t k, uint32_t num_hashes, uint64_t* d_out,
+                                  uint32_t* d_valid_bits, uint64_t* d_out_fwd, uint64_t* d_out_rev, void* stream)
+{
+  if (int rc = check_kh(k, num_hashes)) return rc;
+  if (n_reads == 0 || read_len < k) return NTHASH_OK; // no windows anywhere
+  if (int rc = check_outputs(d_out, d_out_fwd, d_out_rev)) return rc;
+  if (!d_bases || ((uintptr_t)d_bases & 15)) return fail(NTHASH_ERR_INVALID_ARG, "d_bases must be 16-byte aligned");
+  if (n_bases_readable < n_reads * (uint64_t)read_len)
+    return fail(NTHASH_ERR_INVALID_ARG, "n_bases_readable smaller than n_reads*read_len");
+  if (int rc = check_device_ready()) return rc;
+  KmerParams P;
+  if (!plan_uniform(n_reads, read_len, k, P.g, P.tile_cap))
+    return fail(NTHASH_ERR_UNSUPPORTED, "k=%u with read_len=%u needs a %u-byte tile", k, read_len, P.tile_cap);
+  P.bases = d_bases;
+  P.n_bases = n_bases_readable;
+  P.k = k;
+  P.h = num_hashes;
+  P.out = d_out;
+  P.valid_bits = d_valid_bits;
+  P.out_fwd = d_out_fwd;
+  P.out_rev = d_out_rev;
+  return run_kmer(P, n_reads * (uint64_t)P.g.nk, (cudaStream_t)stream);
+}
+
+int nthash_kmer_plan_dev(const uint64_t* d_read_off, uint64_t n_reads, uint32_t k, uint64_t* d_koff,
+                         uint64_t* total_rows, uint64_t* max_read_len, void* stream)
+{
+  if (int rc = check_kh(k, 1)) return rc;
+  if (!d_read_off || !d_koff) return fail(NTHASH_ERR_INVALID_ARG, "d_read_off and d_koff must not be NULL");
+  if (int rc = check_device_ready()) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint64_t* d_stats = nullptr;
+  NTH_CUDA(cudaMallocAsync(&d_stats, 2 * sizeof(uint64_t), st));
+  cudaError_t e = launch_koff_scan(d_read_off, n_reads, k, 0, d_koff, d_stats, st);
+  uint64_t h_stats[2] = { 0, 0 };
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_stats, d_stats, sizeof h_stats, cudaMemcpyDeviceToHost, st);
+  cudaFreeAsync(d_stats, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  NTH_CUDA(e);
+  if (total_rows) *total_rows = h_stats[0];
+  if (max_read_len) *max_read_len = h_stats[1];
+  return NTHASH_OK;
+}
+
+int nthash_kmer_batch_dev(const uint8_t* d_bases, uint64_t n_bases_readable, const uint64_t* d_read_off,
+                          const uint64_t* d_koff, uint64_t n_reads, uint64_t max_read_len, uint32_t k,
+                          uint32_t num_hashes, uint64_t* d_out, uint32_t* d_valid_bits, uint64_t* d_out_fwd,
+                          uint64_t* d_out_rev, void* stream)
+{
+  if (int rc = check_kh(k, num_hashes)) return rc;
+  if (n_reads == 0 || max_read_len < k) return NTHASH_OK;
+  if (int rc = check_outputs(d_out, d_out_fwd, d_out_rev)) return rc;
+  if (!d_bases || ((uintptr_t)d_bases & 15)) return fail(NTHASH_ERR_INVALID_ARG, "d_bases must be 16-byte aligned");
+  if (!d_read_off || !d_koff) return fail(NTHASH_ERR_INVALID_ARG, "d_read_off and d_koff must not be NULL");
+  if (int rc = check_device_ready()) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  // total rows is needed to pre-set the validity bitmap
+  uint64_t rows = 0;
+  if (d_valid_bits) {
+    NTH_CUDA(cudaMemcpyAsync(&rows, d_koff + n_reads, sizeof rows, cudaMemcpyDeviceToHost, st));
+    NTH_CUDA(cudaStreamSynchronize(st));
+  }
+  KmerParams P;
+  P.bases = d_bases;
+  P.n_bases = n_bases_readable;
+  P.k = k;
+  P.h = num_hashes;
+  P.out = d_out;
+  P.valid_bits = d_valid_bits;
+  P.out_fwd = d_out_fwd;
+  P.out_rev = d_out_rev;
+  uint64_t* d_items = nullptr;
+  if ((uint64_t)KMER_NT * max_read_len + 64 <= TILE_BUDGET) { // every read is one item
+    P.g.item_byte = d_read_off;
+    P.g.item_out = d_koff;
+    P.g.n_items = n_reads;
+    P.tile_cap = (uint32_t)(KMER_NT * max_read_len + 64);
+  } else { // cut reads into SEG_LONG-window items
+    P.tile_cap = span_bound(SEG_LONG, 1, k);
+    if (kmer_smem_bytes(P.tile_cap) > SMEM_MAX)
+      return fail(NTHASH_ERR_UNSUPPORTED, "k=%u needs a %u-byte tile for ragged long reads", k, P.tile_cap);
+    uint64_t* d_tmp = nullptr;
+    NTH_CUDA(cudaMallocAsync(&d_tmp, (n_reads + 3) * sizeof(uint64_t), st));
+    cudaError_t e = launch_koff_scan(d_read_off, n_reads, k, SEG_LONG, d_tmp, d_tmp + n_reads + 1, st);
+    uint64_t n_items = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&n_items, d_tmp + n_reads + 1, sizeof n_items, cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(d_tmp, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    NTH_CUDA(e);
+    if (n_items == 0) return NTHASH_OK;
+    NTH_CUDA(cudaMallocAsync(&d_items, 2 * (n_items + 1) * sizeof(uint64_t), st));
+    e = launch_item_fill(d_read_off, d_koff, n_reads, k, SEG_LONG, d_items, d_items + n_items + 1, n_items, st);
+    if (e != cudaSuccess) {
+      cudaFreeAsync(d_items, st);
+      NTH_CUDA(e);
+    }
+    P.g.item_byte = d_items;
+    P.g.item_out = d_items + n_items + 1;
+    P.g.n_items = n_items;
+  }
+  int rc = run_kmer(P, rows, st);
+  if (d_items) cudaFreeAsync(d_items, st);
+  return rc;
+}
+
+int nthash_kmer_batch(const char* bases, const uint64_t* read_off, uint64_t n_reads, uint32_t k,
+                      uint32_t num_hashes, uint64_t* out, uint32_t* valid_bits, uint64_t* out_fwd,
+                      uint64_t* out_rev, int device)
+{
+  if (int rc = check_kh(k, num_hashes)) return rc;
+  if (n_reads == 0) return NTHASH_OK;
+  if (!bases || !read_off) return fail(NTHASH_ERR_INVALID_ARG, "bases and read_off must not be NULL");
+  if (int rc = check_outputs(out, out_fwd, out_rev)) return rc;
+  if (cudaSetDevice(device) != cudaSuccess) return fail(NTHASH_ERR_NO_DEVICE, "cannot select CUDA device %d", device);
+  if (int rc = check_device_ready()) return rc;
+  std::vector<uint64_t> koff(n_reads + 1);
+  const uint64_t rows = nthash_window_rows(read_off, n_reads, k, koff.data());
+  if (rows == 0) return NTHASH_OK;
+  uint64_t max_len = 0;
+  for (uint64_t r = 0; r < n_reads; ++r) max_len = std::max(max_len, read_off[r + 1] - read_off[r]);
+  const uint64_t n_bases = read_off[n_reads], base0 = read_off[0];
+  const uint64_t nb_pad = (n_bases + 31) & ~15ull;
+  const uint64_t H = num_hashes, vwords = (rows + 31) / 32;
+
+  cudaStream_t st = nullptr;
+  uint8_t* d_bases = nullptr;
+  uint64_t *d_off = nullptr, *d_out = nullptr, *d_fwd = nullptr, *d_rev = nullptr;
+  uint32_t* d_valid = nullptr;
+  int rc = NTHASH_OK;
+  auto cleanup = [&]() {
+    cudaFree(d_bases); cudaFree(d_off); cudaFree(d_out); cudaFree(d_fwd); cudaFree(d_rev); cudaFree(d_valid);
+    if (st) cudaStreamDestroy(st);
+  };
+#define NTH_TRY(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      rc = fail(NTHASH_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__));                \
+      cleanup();                                                                           \
+      return rc;                                                                           \
+    }                                                                                      \
+  } while (0)
+  (void)base0;
+  NTH_TRY(cudaStreamCreate(&st));
+  NTH_TRY(cudaMalloc(&d_bases, nb_pad));
+  NTH_TRY(cudaMalloc(&d_off, 2 * (n_reads + 1) * sizeof(uint64_t)));
+  NTH_TRY(cudaMalloc(&d_out, rows * H * sizeof(uint64_t)));
+  if (valid_bits) NTH_TRY(cudaMalloc(&d_valid, vwords * 4));
+  if (out_fwd) {
+    NTH_TRY(cudaMalloc(&d_fwd, rows * sizeof(uint64_t)));
+    NTH_TRY(cudaMalloc(&d_rev, rows * sizeof(uint64_t)));
+  }
+  NTH_TRY(cudaMemcpyAsync(d_bases, bases, n_bases, cudaMemcpyHostToDevice, st));
+  NTH_TRY(cudaMemcpyAsync(d_off, read_off, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  NTH_TRY(cudaMemcpyAsync(d_off + n_reads + 1, koff.data(), (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  rc = nthash_kmer_batch_dev(d_bases, nb_pad, d_off, d_off + n_reads + 1, n_reads, max_len, k, num_hashes, d_out,
+                             d_valid, d_fwd, d_rev, st);
+  if (rc != NTHASH_OK) {
+    cleanup();
+    return rc;
+  }
+  NTH_TRY(cudaMemcpyAsync(out, d_out, rows * H * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  if (valid_bits) NTH_TRY(cudaMemcpyAsync(valid_bits, d_valid, vwords * 4, cudaMemcpyDeviceToHost, st));
+  if (out_fwd) {
+    NTH_TRY(cudaMemcpyAsync(out_fwd, d_fwd, rows * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    NTH_TRY(cudaMemcpyAsync(out_rev, d_rev, rows * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  }
+  NTH_TRY(cudaStreamSynchronize(st));
+  cleanup();
+  return NTHASH_OK;
+}
+
+} // extern "C"

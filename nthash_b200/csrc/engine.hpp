@@ -1,0 +1,57 @@
+// engine.hpp — internal interfaces between the C ABI (capi.cu) and the kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace nthb {
+
+constexpr int KMER_NT = 256;      // items (threads) per CTA of the k-mer / seed kernels
+constexpr uint32_t SEG_LONG = 252; // windows per item when a read is cut up (63 words: odd => conflict-free LDS)
+constexpr uint32_t TILE_BUDGET = 72 * 1024; // staged bytes per CTA we are willing to spend on whole-read items
+
+// How work items map onto the base stream and the dense output.
+//   ragged : item i starts at byte item_byte[i]; its windows are dense indices
+//            [item_out[i], item_out[i+1]).  When every read is one item these arrays are
+//            read_off / koff themselves.
+//   uniform: item i = (read r = i / segs, segment s = i % segs) of fixed-length reads.
+struct KmerGeom
+{
+  const uint64_t* item_byte = nullptr;
+  const uint64_t* item_out = nullptr;
+  uint64_t n_items = 0;
+  uint32_t read_len = 0, nk = 0, seg = 0, segs = 1;
+};
+
+struct KmerParams
+{
+  const uint8_t* bases = nullptr;
+  uint64_t n_bases = 0; // readable extent of `bases`
+  KmerGeom g;
+  uint32_t k = 0, h = 0;
+  uint64_t* out = nullptr;
+  uint32_t* valid_bits = nullptr;
+  uint64_t* out_fwd = nullptr;
+  uint64_t* out_rev = nullptr;
+  uint32_t tile_cap = 0; // bytes of base tile a CTA may stage
+  uint64_t s[4], sk[4], mult[4]; // filled by launch_kmer
+};
+
+uint32_t kmer_smem_bytes(uint32_t tile_cap);
+cudaError_t launch_kmer(KmerParams P, cudaStream_t st);
+
+// Uniform geometry for n_reads reads of read_len bases; returns false if unsupported.
+bool plan_uniform(uint64_t n_reads, uint32_t read_len, uint32_t k, KmerGeom& g, uint32_t& tile_cap);
+// Worst-case staged span of one CTA for a geometry cut into `seg`-window items.
+uint32_t span_bound(uint32_t seg, uint32_t segs, uint32_t k);
+
+// ---- ragged-batch preparation (prep_kernels.cu) ---------------------------------------
+// koff[r] = sum_{r'<r} max(0, len_r' - k + 1), koff[n] = total; stats[0]=total, stats[1]=max len,
+// stats[2] = number of items when reads are cut into seg-window items.  All device pointers.
+cudaError_t launch_koff_scan(const uint64_t* read_off, uint64_t n_reads, uint32_t k, uint32_t seg,
+                             uint64_t* koff, uint64_t* stats, cudaStream_t st);
+// Expands reads into items (only needed when some read exceeds the whole-read tile budget).
+cudaError_t launch_item_fill(const uint64_t* read_off, const uint64_t* koff, uint64_t n_reads, uint32_t k,
+                             uint32_t seg, uint64_t* item_byte, uint64_t* item_out, uint64_t n_items,
+                             cudaStream_t st);
+
+} // namespace nthb

@@ -1,0 +1,190 @@
+// prep_kernels.cu — ragged-batch bookkeeping on the device: the dense output offsets
+// koff[r] = sum_{r'<r} max(0, len_r' - k + 1) (the position arithmetic the reference does
+// implicitly with get_pos(), include/nthash/nthash.hpp:170), and the expansion of long reads
+// into seg-window items.  Plain three-pass block scan; this is plumbing, not the hot loop.
+#include "engine.hpp"
+
+namespace nthb {
+
+namespace {
+
+constexpr int SCAN_T = 256, SCAN_E = 8, SCAN_B = SCAN_T * SCAN_E;
+
+__device__ __forceinline__ uint64_t read_value(const uint64_t* read_off, uint64_t r, uint32_t k, uint32_t seg,
+                                               uint64_t& len)
+{
+  len = read_off[r + 1] - read_off[r];
+  const uint64_t nk = len >= k ? len - k + 1 : 0;
+  return seg ? (nk + seg - 1) / seg : nk;
+}
+
+__device__ __forceinline__ uint64_t block_reduce_sum_max(uint64_t v, uint64_t& mx)
+{
+  __shared__ uint64_t ws[SCAN_T / 32], wm[SCAN_T / 32];
+  for (int o = 16; o; o >>= 1) {
+    v += __shfl_down_sync(0xffffffffu, v, o);
+    mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    ws[threadIdx.x >> 5] = v;
+    wm[threadIdx.x >> 5] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < SCAN_T / 32; ++w) {
+      v += ws[w];
+      mx = max(mx, wm[w]);
+    }
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(SCAN_T)
+scan_block_sums(const uint64_t* read_off, uint64_t n, uint32_t k, uint32_t seg, uint64_t* bsum, uint64_t* bmax)
+{
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_B + (uint64_t)threadIdx.x * SCAN_E;
+  uint64_t s = 0, mx = 0;
+  for (int e = 0; e < SCAN_E; ++e) {
+    if (base + e < n) {
+      uint64_t len;
+      s += read_value(read_off, base + e, k, seg, len);
+      mx = max(mx, len);
+    }
+  }
+  s = block_reduce_sum_max(s, mx);
+  if (threadIdx.x == 0) {
+    bsum[blockIdx.x] = s;
+    bmax[blockIdx.x] = mx;
+  }
+}
+
+// one block: bsum -> exclusive offsets in place; stats[0] = total, stats[1] = max len
+__global__ void __launch_bounds__(1024) scan_of_sums(uint64_t* bsum, const uint64_t* bmax, uint64_t nb, uint64_t* stats)
+{
+  __shared__ uint64_t ws[32];
+  __shared__ uint64_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  uint64_t mx = 0;
+  for (uint64_t c0 = 0; c0 < nb; c0 += 1024) {
+    const uint64_t i = c0 + threadIdx.x;
+    const uint64_t v = i < nb ? bsum[i] : 0;
+    if (i < nb) mx = max(mx, bmax[i]);
+    uint64_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint64_t t = ws[threadIdx.x];
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t y = __shfl_up_sync(0xffffffffu, t, o);
+        if (threadIdx.x >= o) t += y;
+      }
+      ws[threadIdx.x] = t;
+    }
+    __syncthreads();
+    const uint64_t warp_off = (threadIdx.x >> 5) ? ws[(threadIdx.x >> 5) - 1] : 0;
+    const uint64_t carry = carry_s;
+    if (i < nb) bsum[i] = carry + warp_off + x - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_off + x;
+    __syncthreads();
+  }
+  for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 32; ++w) mx = max(mx, ws[w]);
+    stats[0] = carry_s;
+    stats[1] = mx;
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_T)
+scan_write(const uint64_t* read_off, uint64_t n, uint32_t k, uint32_t seg, const uint64_t* boff, uint64_t* excl)
+{
+  __shared__ uint64_t ws[SCAN_T / 32];
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_B + (uint64_t)threadIdx.x * SCAN_E;
+  uint64_t v[SCAN_E], tsum = 0;
+  for (int e = 0; e < SCAN_E; ++e) {
+    uint64_t len;
+    v[e] = base + e < n ? read_value(read_off, base + e, k, seg, len) : 0;
+    tsum += v[e];
+  }
+  uint64_t x = tsum;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) >= o) x += y;
+  }
+  if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+  __syncthreads();
+  uint64_t off = boff[blockIdx.x] + x - tsum;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) off += ws[w];
+  for (int e = 0; e < SCAN_E; ++e) {
+    if (base + e < n) excl[base + e] = off;
+    off += v[e];
+    if (base + e == n - 1) excl[n] = off;
+  }
+}
+
+__global__ void item_fill(const uint64_t* read_off, const uint64_t* koff, const uint64_t* ioff, uint64_t n,
+                          uint32_t k, uint32_t seg, uint64_t* item_byte, uint64_t* item_out, uint64_t n_items)
+{
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r == 0) {
+    item_byte[n_items] = read_off[n];
+    item_out[n_items] = koff[n];
+  }
+  if (r >= n) return;
+  const uint64_t i0 = ioff[r], i1 = ioff[r + 1];
+  for (uint64_t i = i0; i < i1; ++i) {
+    item_byte[i] = read_off[r] + (i - i0) * seg;
+    item_out[i] = koff[r] + (i - i0) * seg;
+  }
+}
+
+} // namespace
+
+cudaError_t launch_koff_scan(const uint64_t* read_off, uint64_t n_reads, uint32_t k, uint32_t seg, uint64_t* excl,
+                             uint64_t* stats, cudaStream_t st)
+{
+  if (n_reads == 0) {
+    cudaError_t e = cudaMemsetAsync(excl, 0, sizeof(uint64_t), st);
+    if (e != cudaSuccess) return e;
+    return cudaMemsetAsync(stats, 0, 2 * sizeof(uint64_t), st);
+  }
+  const uint64_t nb = (n_reads + SCAN_B - 1) / SCAN_B;
+  uint64_t* tmp = nullptr;
+  cudaError_t e = cudaMallocAsync(&tmp, 2 * nb * sizeof(uint64_t), st);
+  if (e != cudaSuccess) return e;
+  scan_block_sums<<<(unsigned)nb, SCAN_T, 0, st>>>(read_off, n_reads, k, seg, tmp, tmp + nb);
+  scan_of_sums<<<1, 1024, 0, st>>>(tmp, tmp + nb, nb, stats);
+  scan_write<<<(unsigned)nb, SCAN_T, 0, st>>>(read_off, n_reads, k, seg, tmp, excl);
+  e = cudaGetLastError();
+  cudaFreeAsync(tmp, st);
+  return e;
+}
+
+cudaError_t launch_item_fill(const uint64_t* read_off, const uint64_t* koff, uint64_t n_reads, uint32_t k,
+                             uint32_t seg, uint64_t* item_byte, uint64_t* item_out, uint64_t n_items,
+                             cudaStream_t st)
+{
+  // item offsets per read = exclusive scan of ceil(nk / seg)
+  uint64_t* ioff = nullptr;
+  cudaError_t e = cudaMallocAsync(&ioff, (n_reads + 3) * sizeof(uint64_t), st);
+  if (e != cudaSuccess) return e;
+  e = launch_koff_scan(read_off, n_reads, k, seg, ioff, ioff + n_reads + 1, st);
+  if (e == cudaSuccess) {
+    const unsigned bs = 256;
+    item_fill<<<(unsigned)((n_reads + bs - 1) / bs), bs, 0, st>>>(read_off, koff, ioff, n_reads, k, seg,
+                                                                 item_byte, item_out, n_items);
+    e = cudaGetLastError();
+  }
+  cudaFreeAsync(ioff, st);
+  return e;
+}
+
+} // namespace nthb

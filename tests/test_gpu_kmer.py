@@ -1,0 +1,132 @@
+"""GPU parity of the NtHash batch kernel (csrc/kmer_kernel.cu) against the CPU oracle.
+
+Everything goes through the C ABI (include/nthash_b200.h) via the ctypes binding.  Bar: bit-exact
+uint64 hashes, identical set of emitted positions (reference: NtHash::roll, src/kmer.cpp:246-264).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import assert_batch_equal, ragged_offsets, synth, to_dev, u64
+from oracle_lib import ORACLE
+
+pytestmark = pytest.mark.gpu
+
+import nthash_b200  # noqa: E402  (fails loudly if the CUDA library is missing)
+
+
+def run_ragged(bases, off, k, h, strands=False):
+    d_b, _keep = to_dev(bases)
+    d_off = torch.from_numpy(off).cuda()
+    res = nthash_b200.kmer_hashes(d_b, d_off, k, h, want_valid=True, want_strands=strands)
+    torch.cuda.synchronize()
+    return res
+
+
+def test_golden_vectors_through_gpu():
+    # reference tests/tests.cpp:47-69 (k-mer hash values) and :181-208 (skipping Ns)
+    seq = np.frombuffer(b"ACATGCATGCA", np.uint8)
+    res = run_ragged(seq, ragged_offsets([len(seq)]), 5, 3)
+    out = u64(res.out).reshape(-1, 3)
+    assert [int(x) for x in out[1]] == [0x38CC00F940AEBDAE, 0xAB7E1B110E086FC6, 0x11A1818BCFDD553]
+    assert [int(x) for x in out[2]] == [0x603A48C5A11C794A, 0xE66016E61816B9C4, 0xC5B13CB146996FFE]
+    s = bytearray(b"ACGTACACTGGACTGAGTCT"); s[10] = s[11] = ord("N")
+    res = run_ragged(np.frombuffer(bytes(s), np.uint8), ragged_offsets([20]), 8, 3)
+    assert list(np.flatnonzero(res.valid_mask().cpu().numpy())) == [0, 1, 2, 12]
+
+
+def test_config1_single_1kb_sequence():
+    # BASELINE.json configs[0]; SURVEY.md Appendix C known answers
+    seq = ORACLE.gen_bases(1000, 42)
+    res = run_ragged(seq, ragged_offsets([1000]), 31, 1, strands=True)
+    out = u64(res.out)
+    assert out.shape == (970, 1)
+    assert int(out[0, 0]) == 0xB6A7A648205E25D6 and int(u64(res.fwd)[0]) == 0x54C31B64E55CF218
+    assert int(out.sum(dtype=np.uint64)) == 0x429E8D1795548BB7
+    assert_batch_equal(res, ORACLE.kmer_batch(seq, ragged_offsets([1000]).astype(np.uint64), 31, 1), 1, True)
+    # the uniform entry point gives the same rows
+    d_b, _k = to_dev(seq)
+    resu = nthash_b200.kmer_hashes_uniform(d_b, 1, 1000, 31, 1)
+    assert (u64(resu.out) == out).all()
+
+
+@pytest.mark.parametrize("k", [3, 4, 5, 31, 32, 33, 63, 64, 65, 127, 255])
+def test_ragged_dirty_reads_all_k(k):
+    rng = np.random.default_rng(k)
+    lens = rng.integers(0, 3 * k + 120, 700)
+    lens[:6] = [0, 1, k - 1, k, k + 1, 2 * k]
+    off = ragged_offsets(lens)
+    bases = synth(rng, int(off[-1]), p_bad=0.004, lower=0.1)
+    for h in (1, 2, 3, 4):
+        res = run_ragged(bases, off, k, h, strands=(h == 3))
+        ora = ORACLE.kmer_batch(bases, off.astype(np.uint64), k, h)
+        assert_batch_equal(res, ora, h, check_strands=(h == 3))
+
+
+def test_many_hashes_and_clean_reads():
+    rng = np.random.default_rng(99)
+    off = ragged_offsets(rng.integers(40, 200, 300))
+    bases = synth(rng, int(off[-1]))
+    for h in (7, 255):
+        assert_batch_equal(run_ragged(bases, off, 31, h), ORACLE.kmer_batch(bases, off.astype(np.uint64), 31, h), h)
+
+
+@pytest.mark.parametrize("read_len,k,h", [(150, 31, 1), (150, 31, 4), (151, 31, 1), (100, 21, 2), (36, 31, 1),
+                                          (128, 31, 1), (250, 63, 3), (2000, 63, 1), (5003, 31, 1), (31, 31, 1)])
+def test_uniform_batches(read_len, k, h):
+    rng = np.random.default_rng(read_len * 7 + k)
+    n = 3000 if read_len <= 300 else 150
+    bases = synth(rng, n * read_len, p_bad=0.0005)
+    d_b, _keep = to_dev(bases)
+    res = nthash_b200.kmer_hashes_uniform(d_b, n, read_len, k, h, want_strands=(h == 1))
+    torch.cuda.synchronize()
+    off = (np.arange(n + 1, dtype=np.uint64) * read_len)
+    assert_batch_equal(res, ORACLE.kmer_batch(bases, off, k, h, threads=8), h, check_strands=(h == 1))
+
+
+def test_ragged_long_reads_use_item_table():
+    rng = np.random.default_rng(5)
+    lens = [70000, 10, 30000, 62, 63, 64, 12345, 0, 999]
+    off = ragged_offsets(lens)
+    bases = synth(rng, int(off[-1]), p_bad=0.0002)
+    for k, h in ((63, 1), (31, 2)):
+        assert_batch_equal(run_ragged(bases, off, k, h), ORACLE.kmer_batch(bases, off.astype(np.uint64), k, h, threads=4), h)
+
+
+def test_host_pointer_entry():
+    rng = np.random.default_rng(8)
+    off = ragged_offsets(rng.integers(0, 400, 500)).astype(np.uint64)
+    bases = synth(rng, int(off[-1]), p_bad=0.002)
+    k, h = 31, 2
+    ora = ORACLE.kmer_batch(bases, off, k, h)
+    rows = ora["out"].shape[0]
+    out = np.full((rows, h), 0xAB, np.uint64); fw = np.zeros(rows, np.uint64); rv = np.zeros(rows, np.uint64)
+    vb = np.zeros((rows + 31) // 32, np.uint32)
+    rc = nthash_b200.LIB.nthash_kmer_batch(bases.ctypes.data, off.ctypes.data, len(off) - 1, k, h, out.ctypes.data,
+                                           vb.ctypes.data, fw.ctypes.data, rv.ctypes.data, 0)
+    assert rc == 0, nthash_b200.LIB.nthash_last_error()
+    bits = ((vb[:, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(-1)[:rows]
+    assert (bits == ora["valid"]).all() and (out == ora["out"]).all() and (fw == ora["fwd"]).all() and (rv == ora["rev"]).all()
+
+
+def test_strand_symmetry_and_rna_at_scale():
+    # size-independent properties (reference tests.cpp:119-133, :210-226) on a batch the oracle would take long on
+    rng = np.random.default_rng(3)
+    n, L, k = 200_000, 150, 31
+    fwd = synth(rng, n * L).reshape(n, L)
+    comp = np.zeros(256, np.uint8); comp[list(b"ACGT")] = list(b"TGCA")
+    rc = comp[fwd[:, ::-1]]
+    rna = fwd.copy(); rna[rna == ord("T")] = ord("U")
+    outs = []
+    for arr in (fwd, rc, rna):
+        d_b, _keep = to_dev(np.ascontiguousarray(arr).reshape(-1))
+        outs.append(nthash_b200.kmer_hashes_uniform(d_b, n, L, k, 1).out.view(n, L - k + 1))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1].flip(1))   # canonical: window p of a read == window nk-1-p of its revcomp
+    assert torch.equal(outs[0], outs[2])           # U == T
+    # checksum of checksums against the threaded oracle on the same 30 M bases
+    ora = ORACLE.kmer_batch(fwd.reshape(-1), np.arange(n + 1, dtype=np.uint64) * L, k, 1, want=(), threads=8)
+    got = int(u64(outs[0]).sum(dtype=np.uint64))
+    assert got == ora["sum"] and ora["n_emit"] == n * (L - k + 1)
