@@ -93,6 +93,26 @@ int nthash_kmer_batch(const char* bases, const uint64_t* read_off, uint64_t n_re
                       uint32_t num_hashes, uint64_t* out, uint32_t* valid_bits, uint64_t* out_fwd,
                       uint64_t* out_rev, int device);
 
+/* ---- BlindNtHash: caller-fed rolling over many independent states -----------------------
+ * Replaces `blind.roll(char_in)` / `blind.peek(char_in)` (nthash.hpp:213-311; BlindNtHash::roll
+ * src/kmer.cpp:355-364, ::peek :382-393) applied to n states at once, e.g. all frontier nodes of
+ * a de Bruijn graph traversal.  The reference object keeps a deque of its k-mer only to know the
+ * outgoing (first) base; here a state is (fwd[i], rev[i]) and the caller supplies out_base[i].
+ * Initial states: hash the n k-mers with nthash_kmer_batch_uniform_dev(read_len = k) asking for
+ * out_fwd/out_rev (the BlindNtHash constructor, kmer.cpp:338-353).  As in the reference there is
+ * no validity check on the incoming byte.                                                     */
+
+/* roll(in_base[i]): fwd/rev are updated in place, d_out[i*num_hashes + j] receives hashes(). */
+int nthash_blind_roll_batch_dev(uint64_t* d_fwd, uint64_t* d_rev, const uint8_t* d_out_base,
+                                const uint8_t* d_in_base, uint64_t n, uint32_t k, uint32_t num_hashes,
+                                uint64_t* d_out, void* stream);
+/* peek('A'),('C'),('G'),('T') of every state: d_out[(i*4 + e)*num_hashes + j]; states untouched. */
+int nthash_blind_peek4_batch_dev(const uint64_t* d_fwd, const uint64_t* d_rev, const uint8_t* d_out_base,
+                                 uint64_t n, uint32_t k, uint32_t num_hashes, uint64_t* d_out, void* stream);
+/* Host buffers in/out. */
+int nthash_blind_roll_batch(uint64_t* fwd, uint64_t* rev, const char* out_base, const char* in_base,
+                            uint64_t n, uint32_t k, uint32_t num_hashes, uint64_t* out, int device);
+
 #ifdef __cplusplus
 }
 #endif

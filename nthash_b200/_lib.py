@@ -21,6 +21,9 @@ _SIGS = {
     "nthash_kmer_plan_dev": (C.c_int, [u64p, C.c_uint64, C.c_uint32, u64p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]),
     "nthash_kmer_batch_dev": (C.c_int, [u8p, C.c_uint64, u64p, u64p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, u64p, u32p, u64p, u64p, C.c_void_p]),
     "nthash_kmer_batch": (C.c_int, [u8p, u64p, C.c_uint64, C.c_uint32, C.c_uint32, u64p, u32p, u64p, u64p, C.c_int]),
+    "nthash_blind_roll_batch_dev": (C.c_int, [u64p, u64p, u8p, u8p, C.c_uint64, C.c_uint32, C.c_uint32, u64p, C.c_void_p]),
+    "nthash_blind_peek4_batch_dev": (C.c_int, [u64p, u64p, u8p, C.c_uint64, C.c_uint32, C.c_uint32, u64p, C.c_void_p]),
+    "nthash_blind_roll_batch": (C.c_int, [u64p, u64p, u8p, u8p, C.c_uint64, C.c_uint32, C.c_uint32, u64p, C.c_int]),
 }
 
 
@@ -32,7 +35,7 @@ class NtHashError(RuntimeError):
 
 def _load():
     path = _build.LIB
-    if not os.path.exists(path):
+    if not os.path.exists(path) or (_build.stale() and os.path.exists(_build.NVCC)):
         path = _build.build()  # raises if nvcc is missing or compilation fails
     lib = C.CDLL(path)
     for name, (res, args) in _SIGS.items():

@@ -306,4 +306,63 @@ int nthash_kmer_batch(const char* bases, const uint64_t* read_off, uint64_t n_re
   return NTHASH_OK;
 }
 
+int nthash_blind_roll_batch_dev(uint64_t* d_fwd, uint64_t* d_rev, const uint8_t* d_out_base,
+                                const uint8_t* d_in_base, uint64_t n, uint32_t k, uint32_t num_hashes,
+                                uint64_t* d_out, void* stream)
+{
+  if (int rc = check_kh(k, num_hashes)) return rc;
+  if (n == 0) return NTHASH_OK;
+  if (!d_fwd || !d_rev || !d_out_base || !d_in_base || !d_out)
+    return fail(NTHASH_ERR_INVALID_ARG, "blind roll: all pointers are required");
+  if (int rc = check_device_ready()) return rc;
+  NTH_CUDA(launch_blind(d_fwd, d_rev, d_out_base, d_in_base, n, k, num_hashes, d_out, false, (cudaStream_t)stream));
+  return NTHASH_OK;
+}
+
+int nthash_blind_peek4_batch_dev(const uint64_t* d_fwd, const uint64_t* d_rev, const uint8_t* d_out_base,
+                                 uint64_t n, uint32_t k, uint32_t num_hashes, uint64_t* d_out, void* stream)
+{
+  if (int rc = check_kh(k, num_hashes)) return rc;
+  if (n == 0) return NTHASH_OK;
+  if (!d_fwd || !d_rev || !d_out_base || !d_out)
+    return fail(NTHASH_ERR_INVALID_ARG, "blind peek4: all pointers are required");
+  if (int rc = check_device_ready()) return rc;
+  NTH_CUDA(launch_blind(const_cast<uint64_t*>(d_fwd), const_cast<uint64_t*>(d_rev), d_out_base, nullptr, n, k,
+                        num_hashes, d_out, true, (cudaStream_t)stream));
+  return NTHASH_OK;
+}
+
+int nthash_blind_roll_batch(uint64_t* fwd, uint64_t* rev, const char* out_base, const char* in_base,
+                            uint64_t n, uint32_t k, uint32_t num_hashes, uint64_t* out, int device)
+{
+  if (int rc = check_kh(k, num_hashes)) return rc;
+  if (n == 0) return NTHASH_OK;
+  if (!fwd || !rev || !out_base || !in_base || !out)
+    return fail(NTHASH_ERR_INVALID_ARG, "blind roll: all pointers are required");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(NTHASH_ERR_NO_DEVICE, "cannot select CUDA device %d", device);
+  if (int rc = check_device_ready()) return rc;
+  uint64_t* d_state = nullptr; // fwd | rev | out
+  uint8_t* d_chars = nullptr;  // out_base | in_base
+  const size_t sb = n * sizeof(uint64_t);
+  int rc = NTHASH_OK;
+  cudaError_t e = cudaMalloc(&d_state, sb * (2 + (size_t)num_hashes));
+  if (e == cudaSuccess) e = cudaMalloc(&d_chars, 2 * n);
+  if (e == cudaSuccess) e = cudaMemcpy(d_state, fwd, sb, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_state + n, rev, sb, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_chars, out_base, n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_chars + n, in_base, n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    rc = nthash_blind_roll_batch_dev(d_state, d_state + n, d_chars, d_chars + n, n, k, num_hashes, d_state + 2 * n, nullptr);
+    if (rc == NTHASH_OK) {
+      e = cudaMemcpy(fwd, d_state, sb, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemcpy(rev, d_state + n, sb, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemcpy(out, d_state + 2 * n, sb * num_hashes, cudaMemcpyDeviceToHost);
+    }
+  }
+  cudaFree(d_state);
+  cudaFree(d_chars);
+  if (e != cudaSuccess) return fail(NTHASH_ERR_CUDA, "blind roll (host): %s", cudaGetErrorString(e));
+  return rc;
+}
+
 } // extern "C"
