@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -54,7 +55,18 @@ bool plan_uniform(uint64_t n_reads, uint32_t read_len, uint32_t k, KmerGeom& g, 
     g.segs = 1;
     tile_cap = KMER_NT * read_len + 64;
   } else {
-    g.seg = SEG_LONG;
+    // Cut reads into items.  Prefer a segment length that divides nk (all items full => the TMA tile
+    // store applies) and whose byte stride spreads lanes over shared-memory banks.
+    uint32_t best = 0, best_score = 0;
+    for (uint32_t seg = 160; seg <= 384; seg += 2) {
+      if (g.nk % seg) continue;
+      const uint32_t score = (seg % 8 == 4 ? 4 : seg % 4 == 2 ? 3 : seg % 16 == 8 ? 2 : 1) * 1000 - (seg > SEG_LONG ? seg - SEG_LONG : SEG_LONG - seg);
+      if (score > best_score) {
+        best_score = score;
+        best = seg;
+      }
+    }
+    g.seg = best ? best : SEG_LONG;
     g.segs = (g.nk + g.seg - 1) / g.seg;
     tile_cap = span_bound(g.seg, g.segs, k);
   }
@@ -91,6 +103,7 @@ static int check_device_ready()
 
 static int run_kmer(KmerParams& P, uint64_t rows, cudaStream_t st)
 {
+  if (getenv("NTHASH_B200_DISABLE_TMA_STORE")) P.use_tma = false; // A/B switch for tests and profiling
   if (P.valid_bits && rows) NTH_CUDA(cudaMemsetAsync(P.valid_bits, 0xFF, ((rows + 31) / 32) * 4, st));
   if (P.g.n_items == 0) return NTHASH_OK;
   NTH_CUDA(launch_kmer(P, st));

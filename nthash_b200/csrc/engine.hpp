@@ -33,10 +33,14 @@ struct KmerParams
   uint64_t* out_fwd = nullptr;
   uint64_t* out_rev = nullptr;
   uint32_t tile_cap = 0; // bytes of base tile a CTA may stage
+  bool use_tma = true;   // allow the TMA tile-store output path when the geometry permits
   uint64_t s[4], sk[4], mult[4]; // filled by launch_kmer
 };
 
 uint32_t kmer_smem_bytes(uint32_t tile_cap);
+// Fast path (kmer_fast_kernel.cu): uniform batch, all items full, rows 16-byte multiples, h in {1,2,4}.
+bool kmer_fast_ok(const KmerParams& P);
+cudaError_t launch_kmer_fast(const KmerParams& P, cudaStream_t st);
 cudaError_t launch_kmer(KmerParams P, cudaStream_t st);
 
 // BlindNtHash::roll / peek over n independent (fwd, rev) states (blind_kernel.cu).

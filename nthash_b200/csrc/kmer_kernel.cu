@@ -15,8 +15,11 @@
 // Per-base seeds come from two 256-entry shared-memory tables indexed by the raw byte (no
 // per-base decode, exact for any byte value); hashes leave as full 32-byte sectors
 // (st.global.v4.u64 -> STG.E.ENL2.256), four consecutive windows of one item per store.
+//
+// This is the GENERAL kernel (ragged batches, any row pitch, optional strand outputs).  Uniform
+// batches whose rows are 16-byte multiples take kmer_fast_kernel.cu instead (TMA tile stores).
 #include "engine.hpp"
-#include "nthash_dev.cuh"
+#include "kmer_common.cuh"
 
 namespace nthb {
 
@@ -25,34 +28,6 @@ namespace {
 constexpr int TAB_BYTES = 2 * 256 * 16;  // tab_in + tab_out
 constexpr int TILE_OFF = TAB_BYTES + 16; // mbarrier lives in the 16 bytes after the tables
 constexpr int TILE_PAD = 16;             // front pad: byte "-1" of the very first item lands here
-
-struct State
-{
-  uint32_t flo, fhi, rlo, rhi;
-};
-
-// F <- srol(F) ^ a ^ b on a (hi,lo) register pair.
-NTH_D void fwd_step(State& s, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi)
-{
-  const uint32_t lo = s.flo, hi = s.fhi;
-  const uint32_t nlo = (lo << 1) | (hi & 1u);
-  const uint32_t nhi = (__funnelshift_l(lo, hi, 1) & ~2u) | ((hi >> 30) & 2u);
-  s.flo = nlo ^ alo ^ blo;
-  s.fhi = nhi ^ ahi ^ bhi;
-}
-
-// R <- sror(R ^ a ^ b)
-NTH_D void rev_step(State& s, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi)
-{
-  const uint32_t lo = s.rlo ^ alo ^ blo, hi = s.rhi ^ ahi ^ bhi;
-  s.rlo = __funnelshift_r(lo, hi, 1);
-  s.rhi = ((hi >> 1) & 0x7FFFFFFEu) | (lo & 1u) | ((hi & 2u) << 30);
-}
-
-NTH_D uint64_t canonical(const State& s)
-{
-  return (((uint64_t)s.fhi << 32) | s.flo) + (((uint64_t)s.rhi << 32) | s.rlo);
-}
 
 NTH_D void item_geom(const KmerGeom& g, uint64_t i, uint64_t& byte, uint64_t& out, uint32_t& n)
 {
@@ -236,6 +211,7 @@ cudaError_t launch_kmer(KmerParams P, cudaStream_t st)
     P.sk[x] = srol_n(base[x], P.k);
   }
   for (unsigned q = 0; q < 4; ++q) P.mult[q] = ext_mult(q, P.k);
+  if (P.use_tma && kmer_fast_ok(P)) return launch_kmer_fast(P, st);
   const uint32_t smem = kmer_smem_bytes(P.tile_cap);
   const bool strands = P.out_fwd != nullptr;
   if (strands) {

@@ -122,6 +122,21 @@ NTH_D void st_global_v4_u64(uint64_t* p, uint64_t a, uint64_t b, uint64_t c, uin
 {
   asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
+NTH_D void st_shared_v2_u64(uint32_t saddr, uint64_t a, uint64_t b)
+{
+  asm volatile("st.shared.v2.u64 [%0], {%1,%2};" ::"r"(saddr), "l"(a), "l"(b) : "memory");
+}
+// ---- TMA tile store (shared -> global through a tensor map; SASS: UTMASTG) ----
+NTH_D void tma_store_2d(const void* tmap, uint32_t saddr, int c0, int c1)
+{
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0),
+               "r"(c1), "r"(saddr)
+               : "memory");
+}
+NTH_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+NTH_D void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+NTH_D void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+NTH_D void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 NTH_D void st_global_v2_u64(uint64_t* p, uint64_t a, uint64_t b)
 {
   asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(a), "l"(b) : "memory");
