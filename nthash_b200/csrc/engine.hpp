@@ -35,6 +35,8 @@ struct KmerParams
   uint32_t tile_cap = 0; // bytes of base tile a CTA may stage
   bool use_tma = true;   // allow the TMA tile-store output path when the geometry permits
   uint64_t s[4], sk[4], mult[4]; // filled by launch_kmer
+  uint32_t prefetch_ctas = 0;    // fast kernel: L2-prefetch the base tile this many CTAs ahead (0 = off)
+  const uint4* t4 = nullptr;     // tetramer warm-up table (fast kernel only), filled by launch_kmer_fast
 };
 
 uint32_t kmer_smem_bytes(uint32_t tile_cap);

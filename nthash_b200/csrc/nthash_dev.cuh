@@ -117,6 +117,10 @@ NTH_D void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+NTH_D void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 // 32-byte (one full sector) global store; SASS: STG.E.ENL2.256 (sm_100+).
 NTH_D void st_global_v4_u64(uint64_t* p, uint64_t a, uint64_t b, uint64_t c, uint64_t d)
 {
