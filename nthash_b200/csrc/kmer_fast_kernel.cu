@@ -178,16 +178,16 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   }
   {
     // code (byte >> 1) & 3 : 0 = A, 1 = C, 2 = T/U, 3 = G ; complement = code ^ 2
-    const int code2base[4] = { 0, 1, 3, 2 }; // index into P.s / P.sk (A, C, G, T order)
+    auto code2base = [](int c) { return c ^ (c >> 1); }; // code -> index into P.s / P.sk (A, C, G, T order)
     if (tid < 16) {
       const int ci = tid >> 2, co = tid & 3;
-      const uint64_t f = P.s[code2base[ci]] ^ P.sk[code2base[co]];
-      const uint64_t r = P.sk[code2base[ci ^ 2]] ^ P.s[code2base[co ^ 2]];
+      const uint64_t f = P.s[code2base(ci)] ^ P.sk[code2base(co)];
+      const uint64_t r = P.sk[code2base(ci ^ 2)] ^ P.s[code2base(co ^ 2)];
       reinterpret_cast<uint64_t*>(smem + F_PAIR_OFF)[tid] = f;
       reinterpret_cast<uint64_t*>(smem + F_PAIR_R_OFF)[tid] = r;
     } else if (tid < 20) {
       const int ci = tid - 16;
-      const uint64_t f = P.s[code2base[ci]], r = P.sk[code2base[ci ^ 2]];
+      const uint64_t f = P.s[code2base(ci)], r = P.sk[code2base(ci ^ 2)];
       reinterpret_cast<uint4*>(smem + F_IN_OFF)[ci] = make_uint4((uint32_t)f, (uint32_t)(f >> 32), (uint32_t)r, (uint32_t)(r >> 32));
     }
     smem[F_LUT_OFF + tid] = is_acgtu(tid) ? 0 : 1; // KMER_NT == 256 threads, one LUT byte each
