@@ -93,6 +93,41 @@ int nthash_kmer_batch(const char* bases, const uint64_t* read_off, uint64_t n_re
                       uint32_t num_hashes, uint64_t* out, uint32_t* valid_bits, uint64_t* out_fwd,
                       uint64_t* out_rev, int device);
 
+/* ---- SeedNtHash: spaced seeds ----------------------------------------------------------------
+ * Replaces `nthash::SeedNtHash it(seq, len, seeds, h, k); while (it.roll()) use(it.hashes())`
+ * (nthash.hpp:313-521; SeedNtHash::init/roll src/seed.cpp:493-544; ntmsm64 :130-270).
+ * Rows hold n_seeds * num_hashes_per_seed values, seed-major (seed.cpp:167-171); out_fwd/out_rev
+ * hold n_seeds values per row (get_forward_hash()/get_reverse_hash(), nthash.hpp:489-500).
+ * SeedNtHash's own rules are reproduced exactly: non-ACGTU bytes inside a window are hashed, not
+ * skipped (forward seed 0, reverse seed SEED_TAB[c & 7]); a non-ACGTU byte arriving as the incoming
+ * base makes the iterator jump k positions (seed.cpp:527-530); init only rejects NUL bytes at
+ * block positions (seed.cpp:151).                                                              */
+
+/* Compiled seed set, resident on the current device.  Replaces the seed handling of the
+ * SeedNtHash constructors (seed.cpp:449-491: check_seeds :85-104, get_blocks :19-66).  Seeds are
+ * k-character strings of '1' (care) and '0' (don't care).  A length mismatch is an error
+ * (seed.cpp:90-95); an asymmetric seed is accepted, as in the reference, which only warns
+ * (seed.cpp:96-102) — query it with nthash_seed_plan_symmetric().                              */
+typedef struct nthash_seed_plan nthash_seed_plan;
+int nthash_seed_plan_create(const char* const* seeds, uint32_t n_seeds, uint32_t k,
+                            uint32_t num_hashes_per_seed, nthash_seed_plan** plan_out);
+void nthash_seed_plan_destroy(nthash_seed_plan* plan);
+int nthash_seed_plan_symmetric(const nthash_seed_plan* plan);
+
+int nthash_seed_batch_uniform_dev(const nthash_seed_plan* plan, const uint8_t* d_bases,
+                                  uint64_t n_bases_readable, uint64_t n_reads, uint32_t read_len,
+                                  uint64_t* d_out, uint32_t* d_valid_bits, uint64_t* d_out_fwd,
+                                  uint64_t* d_out_rev, void* stream);
+/* Ragged reads: d_koff / max_read_len from nthash_kmer_plan_dev(..., k = seed length, ...). */
+int nthash_seed_batch_dev(const nthash_seed_plan* plan, const uint8_t* d_bases, uint64_t n_bases_readable,
+                          const uint64_t* d_read_off, const uint64_t* d_koff, uint64_t n_reads,
+                          uint64_t max_read_len, uint64_t* d_out, uint32_t* d_valid_bits,
+                          uint64_t* d_out_fwd, uint64_t* d_out_rev, void* stream);
+/* Host buffers in/out; compiles the seeds, runs, and frees the plan. */
+int nthash_seed_batch(const char* bases, const uint64_t* read_off, uint64_t n_reads,
+                      const char* const* seeds, uint32_t n_seeds, uint32_t k, uint32_t num_hashes_per_seed,
+                      uint64_t* out, uint32_t* valid_bits, uint64_t* out_fwd, uint64_t* out_rev, int device);
+
 /* ---- BlindNtHash: caller-fed rolling over many independent states -----------------------
  * Replaces `blind.roll(char_in)` / `blind.peek(char_in)` (nthash.hpp:213-311; BlindNtHash::roll
  * src/kmer.cpp:355-364, ::peek :382-393) applied to n states at once, e.g. all frontier nodes of

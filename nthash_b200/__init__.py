@@ -5,6 +5,7 @@ _lib.py binds that ABI with ctypes; api.py is a thin device-resident front end t
 PyTorch only for HBM buffers and streams; host.py drives host-buffer calls and multi-GPU shards.
 """
 from ._lib import LIB, LIB_PATH, NtHashError  # noqa: F401
-from .api import HashBatch, kmer_hashes, kmer_hashes_uniform  # noqa: F401
+from .api import (HashBatch, SeedPlan, blind_peek4, blind_roll, kmer_hashes, kmer_hashes_uniform,  # noqa: F401
+                  seed_hashes, seed_hashes_uniform)
 
 FN_NAME = LIB.nthash_fn_name().decode()

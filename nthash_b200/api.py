@@ -86,3 +86,93 @@ def kmer_hashes(bases, read_off, k, num_hashes=1, want_valid=True, want_strands=
         check(LIB.nthash_kmer_batch_dev(_ptr(bases), bases.numel(), _ptr(read_off), _ptr(koff), n_reads, max_len.value, k,
                                         num_hashes, _ptr(out), _ptr(valid_bits), _ptr(fwd), _ptr(rev), _stream_ptr(stream)))
     return HashBatch(out, valid_bits, koff, rows, fwd, rev)
+
+
+class SeedPlan:
+    """Compiled spaced-seed set on the current device (C ABI: nthash_seed_plan_create / _destroy).
+
+    Mirrors what the SeedNtHash constructors do with their `seeds` argument
+    (reference src/seed.cpp:449-491): strings of '1' (care) and '0' (don't care), all of length k."""
+
+    def __init__(self, seeds, num_hashes_per_seed=1):
+        self.seeds = list(seeds)
+        self.k = len(self.seeds[0])
+        self.h = num_hashes_per_seed
+        arr = (C.c_char_p * len(self.seeds))(*[s.encode() for s in self.seeds])
+        self._h = C.c_void_p()
+        check(LIB.nthash_seed_plan_create(arr, len(self.seeds), self.k, num_hashes_per_seed, C.byref(self._h)))
+
+    @property
+    def symmetric(self):
+        return bool(LIB.nthash_seed_plan_symmetric(self._h))
+
+    def close(self):
+        if self._h:
+            LIB.nthash_seed_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def seed_hashes_uniform(plan, bases, n_reads, read_len, want_valid=True, want_strands=False, out=None,
+                        valid_bits=None, stream=None) -> HashBatch:
+    """SeedNtHash over fixed-length reads (nthash_seed_batch_uniform_dev); rows hold n_seeds*h values, seed-major."""
+    _check_bases(bases)
+    m, H = len(plan.seeds), len(plan.seeds) * plan.h
+    rows = n_reads * max(read_len - plan.k + 1, 0)
+    dev = bases.device
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((rows, H), dtype=torch.int64, device=dev)
+        if want_valid and valid_bits is None:
+            valid_bits = torch.empty(int(LIB.nthash_valid_words(rows)), dtype=torch.int32, device=dev)
+        fwd = torch.empty((rows, m), dtype=torch.int64, device=dev) if want_strands else None
+        rev = torch.empty((rows, m), dtype=torch.int64, device=dev) if want_strands else None
+        check(LIB.nthash_seed_batch_uniform_dev(plan._h, _ptr(bases), bases.numel(), n_reads, read_len, _ptr(out),
+                                                _ptr(valid_bits), _ptr(fwd), _ptr(rev), _stream_ptr(stream)))
+    return HashBatch(out, valid_bits, None, rows, fwd, rev)
+
+
+def seed_hashes(plan, bases, read_off, want_valid=True, want_strands=False, stream=None) -> HashBatch:
+    """SeedNtHash over ragged reads (nthash_kmer_plan_dev for the layout + nthash_seed_batch_dev)."""
+    _check_bases(bases)
+    n_reads = read_off.numel() - 1
+    m, H = len(plan.seeds), len(plan.seeds) * plan.h
+    dev = bases.device
+    with torch.cuda.device(dev):
+        koff = torch.empty(n_reads + 1, dtype=torch.int64, device=dev)
+        rows = C.c_uint64(0)
+        max_len = C.c_uint64(0)
+        check(LIB.nthash_kmer_plan_dev(_ptr(read_off), n_reads, plan.k, _ptr(koff), C.byref(rows), C.byref(max_len), _stream_ptr(stream)))
+        rows = rows.value
+        out = torch.empty((rows, H), dtype=torch.int64, device=dev)
+        valid_bits = torch.empty(int(LIB.nthash_valid_words(rows)), dtype=torch.int32, device=dev) if want_valid else None
+        fwd = torch.empty((rows, m), dtype=torch.int64, device=dev) if want_strands else None
+        rev = torch.empty((rows, m), dtype=torch.int64, device=dev) if want_strands else None
+        check(LIB.nthash_seed_batch_dev(plan._h, _ptr(bases), bases.numel(), _ptr(read_off), _ptr(koff), n_reads, max_len.value,
+                                        _ptr(out), _ptr(valid_bits), _ptr(fwd), _ptr(rev), _stream_ptr(stream)))
+    return HashBatch(out, valid_bits, koff, rows, fwd, rev)
+
+
+def blind_roll(fwd, rev, out_base, in_base, k, num_hashes=1, stream=None) -> torch.Tensor:
+    """BlindNtHash::roll(char_in) on n states at once; fwd/rev are updated in place, returns hashes [n, h]."""
+    n = fwd.numel()
+    out = torch.empty((n, num_hashes), dtype=torch.int64, device=fwd.device)
+    with torch.cuda.device(fwd.device):
+        check(LIB.nthash_blind_roll_batch_dev(_ptr(fwd), _ptr(rev), _ptr(out_base), _ptr(in_base), n, k, num_hashes,
+                                              _ptr(out), _stream_ptr(stream)))
+    return out
+
+
+def blind_peek4(fwd, rev, out_base, k, num_hashes=1, stream=None) -> torch.Tensor:
+    """BlindNtHash::peek('A'|'C'|'G'|'T') on n states: hashes [n, 4, h]; states untouched."""
+    n = fwd.numel()
+    out = torch.empty((n, 4, num_hashes), dtype=torch.int64, device=fwd.device)
+    with torch.cuda.device(fwd.device):
+        check(LIB.nthash_blind_peek4_batch_dev(_ptr(fwd), _ptr(rev), _ptr(out_base), n, k, num_hashes, _ptr(out),
+                                               _stream_ptr(stream)))
+    return out

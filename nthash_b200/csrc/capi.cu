@@ -3,6 +3,7 @@
 // src/seed.cpp:85-104, :467-469) but reports through return codes instead of exit(1).
 #include "../../include/nthash_b200.h"
 #include "engine.hpp"
+#include "seed_plan.hpp"
 
 #include <cstdarg>
 #include <cstdio>
@@ -107,6 +108,141 @@ static int run_kmer(KmerParams& P, uint64_t rows, cudaStream_t st)
   if (P.valid_bits && rows) NTH_CUDA(cudaMemsetAsync(P.valid_bits, 0xFF, ((rows + 31) / 32) * 4, st));
   if (P.g.n_items == 0) return NTHASH_OK;
   NTH_CUDA(launch_kmer(P, st));
+  return NTHASH_OK;
+}
+
+
+// Host-buffer entry points: device copies of one batch (inputs up, results down) on a private stream.
+struct HostStaging
+{
+  cudaStream_t st = nullptr;
+  uint8_t* d_bases = nullptr;
+  uint64_t *d_off = nullptr, *d_out = nullptr, *d_fwd = nullptr, *d_rev = nullptr;
+  uint32_t* d_valid = nullptr;
+
+  ~HostStaging()
+  {
+    cudaFree(d_bases); cudaFree(d_off); cudaFree(d_out); cudaFree(d_fwd); cudaFree(d_rev); cudaFree(d_valid);
+    if (st) cudaStreamDestroy(st);
+  }
+  int open(const char* bases, uint64_t n_bases, uint64_t nb_pad, const uint64_t* read_off, const uint64_t* koff,
+           uint64_t n_reads, uint64_t rows, uint64_t H, bool want_valid, uint64_t strand_cols)
+  {
+    NTH_CUDA(cudaStreamCreate(&st));
+    NTH_CUDA(cudaMalloc(&d_bases, nb_pad));
+    NTH_CUDA(cudaMalloc(&d_off, 2 * (n_reads + 1) * sizeof(uint64_t)));
+    NTH_CUDA(cudaMalloc(&d_out, rows * H * sizeof(uint64_t)));
+    if (want_valid) NTH_CUDA(cudaMalloc(&d_valid, ((rows + 31) / 32) * 4));
+    if (strand_cols) {
+      NTH_CUDA(cudaMalloc(&d_fwd, rows * strand_cols * sizeof(uint64_t)));
+      NTH_CUDA(cudaMalloc(&d_rev, rows * strand_cols * sizeof(uint64_t)));
+    }
+    NTH_CUDA(cudaMemcpyAsync(d_bases, bases, n_bases, cudaMemcpyHostToDevice, st));
+    NTH_CUDA(cudaMemcpyAsync(d_off, read_off, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    NTH_CUDA(cudaMemcpyAsync(d_off + n_reads + 1, koff, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    return NTHASH_OK;
+  }
+  int fetch(uint64_t* out, uint32_t* valid_bits, uint64_t* out_fwd, uint64_t* out_rev, uint64_t rows, uint64_t H,
+            uint64_t vwords, uint64_t strand_cols)
+  {
+    NTH_CUDA(cudaMemcpyAsync(out, d_out, rows * H * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    if (valid_bits) NTH_CUDA(cudaMemcpyAsync(valid_bits, d_valid, vwords * 4, cudaMemcpyDeviceToHost, st));
+    if (strand_cols) {
+      NTH_CUDA(cudaMemcpyAsync(out_fwd, d_fwd, rows * strand_cols * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+      NTH_CUDA(cudaMemcpyAsync(out_rev, d_rev, rows * strand_cols * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    }
+    NTH_CUDA(cudaStreamSynchronize(st));
+    return NTHASH_OK;
+  }
+};
+
+// Ragged batches: either every read is one item (read_off/koff are the item arrays) or reads are cut
+// into SEG_LONG-window items listed in a scratch table (freed by the caller with cudaFreeAsync).
+struct RaggedItems
+{
+  KmerGeom g;
+  uint32_t tile_cap = 0;
+  uint64_t* d_items = nullptr;         // [item_byte | item_out | item_read]
+  const uint64_t* item_read = nullptr; // NULL when items are reads
+};
+
+static int plan_ragged(const uint64_t* d_read_off, const uint64_t* d_koff, uint64_t n_reads, uint64_t max_read_len,
+                       uint32_t k, uint32_t tile_budget, cudaStream_t st, RaggedItems& R)
+{
+  if ((uint64_t)KMER_NT * max_read_len + 64 <= tile_budget) { // every read is one item
+    R.g.item_byte = d_read_off;
+    R.g.item_out = d_koff;
+    R.g.n_items = n_reads;
+    R.tile_cap = (uint32_t)(KMER_NT * max_read_len + 64);
+    return NTHASH_OK;
+  }
+  R.tile_cap = span_bound(SEG_LONG, 1, k);
+  uint64_t* d_tmp = nullptr;
+  NTH_CUDA(cudaMallocAsync(&d_tmp, (n_reads + 3) * sizeof(uint64_t), st));
+  cudaError_t e = launch_koff_scan(d_read_off, n_reads, k, SEG_LONG, d_tmp, d_tmp + n_reads + 1, st);
+  uint64_t n_items = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&n_items, d_tmp + n_reads + 1, sizeof n_items, cudaMemcpyDeviceToHost, st);
+  cudaFreeAsync(d_tmp, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  NTH_CUDA(e);
+  R.g.n_items = n_items;
+  if (n_items == 0) return NTHASH_OK;
+  NTH_CUDA(cudaMallocAsync(&R.d_items, 3 * (n_items + 1) * sizeof(uint64_t), st));
+  e = launch_item_fill(d_read_off, d_koff, n_reads, k, SEG_LONG, R.d_items, R.d_items + n_items + 1,
+                       R.d_items + 2 * (n_items + 1), n_items, st);
+  if (e != cudaSuccess) {
+    cudaFreeAsync(R.d_items, st);
+    R.d_items = nullptr;
+    NTH_CUDA(e);
+  }
+  R.g.item_byte = R.d_items;
+  R.g.item_out = R.d_items + n_items + 1;
+  R.item_read = R.d_items + 2 * (n_items + 1);
+  return NTHASH_OK;
+}
+
+} // namespace nthb
+
+// Opaque handle of include/nthash_b200.h: a compiled seed set resident on one device.
+struct nthash_seed_plan
+{
+  nthb::SeedPlanHost host;
+  uint8_t* d_blob = nullptr;
+  int device = 0;
+};
+
+namespace nthb {
+
+static void fill_seed_params(const nthash_seed_plan* plan, SeedParams& P)
+{
+  const SeedPlanHost& h = plan->host;
+  P.k = h.k;
+  P.h = h.h;
+  P.n_seeds = h.n_seeds;
+  P.plan_blob = plan->d_blob;
+  P.plan_smem_bytes = h.smem_bytes;
+  P.groups_off = h.groups_off;
+  P.tables_off = h.tables_off;
+  P.care_off = h.care_off;
+  P.refblk_off = h.refblk_off;
+  P.care_words = h.care_words;
+  P.any_ignore = h.any_ignore ? 1u : 0u;
+}
+
+static int run_seed(SeedParams& P, uint64_t n_reads, uint64_t rows, cudaStream_t st)
+{
+  if (P.valid_bits && rows) NTH_CUDA(cudaMemsetAsync(P.valid_bits, 0xFF, ((rows + 31) / 32) * 4, st));
+  if (P.g.n_items == 0) return NTHASH_OK;
+  if (seed_smem_bytes(P.plan_smem_bytes, P.tile_cap) > SMEM_MAX)
+    return fail(NTHASH_ERR_UNSUPPORTED, "seed tables (%u B) plus a %u-byte base tile exceed shared memory",
+                P.plan_smem_bytes, P.tile_cap);
+  uint8_t* d_dirty = nullptr;
+  NTH_CUDA(cudaMallocAsync(&d_dirty, n_reads, st));
+  cudaError_t e = cudaMemsetAsync(d_dirty, 0, n_reads, st);
+  P.read_dirty = d_dirty;
+  if (e == cudaSuccess) e = launch_seed(P, n_reads, st);
+  cudaFreeAsync(d_dirty, st);
+  NTH_CUDA(e);
   return NTHASH_OK;
 }
 
@@ -218,37 +354,16 @@ int nthash_kmer_batch_dev(const uint8_t* d_bases, uint64_t n_bases_readable, con
   P.valid_bits = d_valid_bits;
   P.out_fwd = d_out_fwd;
   P.out_rev = d_out_rev;
-  uint64_t* d_items = nullptr;
-  if ((uint64_t)KMER_NT * max_read_len + 64 <= TILE_BUDGET) { // every read is one item
-    P.g.item_byte = d_read_off;
-    P.g.item_out = d_koff;
-    P.g.n_items = n_reads;
-    P.tile_cap = (uint32_t)(KMER_NT * max_read_len + 64);
-  } else { // cut reads into SEG_LONG-window items
-    P.tile_cap = span_bound(SEG_LONG, 1, k);
-    if (kmer_smem_bytes(P.tile_cap) > SMEM_MAX)
-      return fail(NTHASH_ERR_UNSUPPORTED, "k=%u needs a %u-byte tile for ragged long reads", k, P.tile_cap);
-    uint64_t* d_tmp = nullptr;
-    NTH_CUDA(cudaMallocAsync(&d_tmp, (n_reads + 3) * sizeof(uint64_t), st));
-    cudaError_t e = launch_koff_scan(d_read_off, n_reads, k, SEG_LONG, d_tmp, d_tmp + n_reads + 1, st);
-    uint64_t n_items = 0;
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&n_items, d_tmp + n_reads + 1, sizeof n_items, cudaMemcpyDeviceToHost, st);
-    cudaFreeAsync(d_tmp, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    NTH_CUDA(e);
-    if (n_items == 0) return NTHASH_OK;
-    NTH_CUDA(cudaMallocAsync(&d_items, 2 * (n_items + 1) * sizeof(uint64_t), st));
-    e = launch_item_fill(d_read_off, d_koff, n_reads, k, SEG_LONG, d_items, d_items + n_items + 1, n_items, st);
-    if (e != cudaSuccess) {
-      cudaFreeAsync(d_items, st);
-      NTH_CUDA(e);
-    }
-    P.g.item_byte = d_items;
-    P.g.item_out = d_items + n_items + 1;
-    P.g.n_items = n_items;
+  RaggedItems R;
+  if (int rc = plan_ragged(d_read_off, d_koff, n_reads, max_read_len, k, TILE_BUDGET, st, R)) return rc;
+  P.g = R.g;
+  P.tile_cap = R.tile_cap;
+  if (kmer_smem_bytes(P.tile_cap) > SMEM_MAX) {
+    if (R.d_items) cudaFreeAsync(R.d_items, st);
+    return fail(NTHASH_ERR_UNSUPPORTED, "k=%u needs a %u-byte tile for ragged long reads", k, P.tile_cap);
   }
   int rc = run_kmer(P, rows, st);
-  if (d_items) cudaFreeAsync(d_items, st);
+  if (R.d_items) cudaFreeAsync(R.d_items, st);
   return rc;
 }
 
@@ -267,56 +382,146 @@ int nthash_kmer_batch(const char* bases, const uint64_t* read_off, uint64_t n_re
   if (rows == 0) return NTHASH_OK;
   uint64_t max_len = 0;
   for (uint64_t r = 0; r < n_reads; ++r) max_len = std::max(max_len, read_off[r + 1] - read_off[r]);
-  const uint64_t n_bases = read_off[n_reads], base0 = read_off[0];
-  const uint64_t nb_pad = (n_bases + 31) & ~15ull;
+  const uint64_t n_bases = read_off[n_reads], nb_pad = (n_bases + 31) & ~15ull;
   const uint64_t H = num_hashes, vwords = (rows + 31) / 32;
+  HostStaging hs;
+  int rc = hs.open(bases, n_bases, nb_pad, read_off, koff.data(), n_reads, rows, H, valid_bits != nullptr, out_fwd ? 1 : 0);
+  if (rc == NTHASH_OK)
+    rc = nthash_kmer_batch_dev(hs.d_bases, nb_pad, hs.d_off, hs.d_off + n_reads + 1, n_reads, max_len, k, num_hashes,
+                               hs.d_out, hs.d_valid, hs.d_fwd, hs.d_rev, hs.st);
+  if (rc == NTHASH_OK) rc = hs.fetch(out, valid_bits, out_fwd, out_rev, rows, H, vwords, out_fwd ? 1 : 0);
+  return rc;
+}
 
-  cudaStream_t st = nullptr;
-  uint8_t* d_bases = nullptr;
-  uint64_t *d_off = nullptr, *d_out = nullptr, *d_fwd = nullptr, *d_rev = nullptr;
-  uint32_t* d_valid = nullptr;
-  int rc = NTHASH_OK;
-  auto cleanup = [&]() {
-    cudaFree(d_bases); cudaFree(d_off); cudaFree(d_out); cudaFree(d_fwd); cudaFree(d_rev); cudaFree(d_valid);
-    if (st) cudaStreamDestroy(st);
-  };
-#define NTH_TRY(expr)                                                                      \
-  do {                                                                                     \
-    cudaError_t e__ = (expr);                                                              \
-    if (e__ != cudaSuccess) {                                                              \
-      rc = fail(NTHASH_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__));                \
-      cleanup();                                                                           \
-      return rc;                                                                           \
-    }                                                                                      \
-  } while (0)
-  (void)base0;
-  NTH_TRY(cudaStreamCreate(&st));
-  NTH_TRY(cudaMalloc(&d_bases, nb_pad));
-  NTH_TRY(cudaMalloc(&d_off, 2 * (n_reads + 1) * sizeof(uint64_t)));
-  NTH_TRY(cudaMalloc(&d_out, rows * H * sizeof(uint64_t)));
-  if (valid_bits) NTH_TRY(cudaMalloc(&d_valid, vwords * 4));
-  if (out_fwd) {
-    NTH_TRY(cudaMalloc(&d_fwd, rows * sizeof(uint64_t)));
-    NTH_TRY(cudaMalloc(&d_rev, rows * sizeof(uint64_t)));
+// ---- SeedNtHash -------------------------------------------------------------------------------
+
+int nthash_seed_plan_create(const char* const* seeds, uint32_t n_seeds, uint32_t k, uint32_t num_hashes_per_seed,
+                            nthash_seed_plan** plan_out)
+{
+  if (!plan_out) return fail(NTHASH_ERR_INVALID_ARG, "plan_out must not be NULL");
+  *plan_out = nullptr;
+  if (int rc = check_kh(k, num_hashes_per_seed)) return rc;
+  if (int rc = check_device_ready()) return rc;
+  nthash_seed_plan* plan = new nthash_seed_plan();
+  const std::string err = build_seed_plan(seeds, n_seeds, k, num_hashes_per_seed, plan->host);
+  if (!err.empty()) {
+    delete plan;
+    return fail(NTHASH_ERR_INVALID_ARG, "%s", err.c_str());
   }
-  NTH_TRY(cudaMemcpyAsync(d_bases, bases, n_bases, cudaMemcpyHostToDevice, st));
-  NTH_TRY(cudaMemcpyAsync(d_off, read_off, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-  NTH_TRY(cudaMemcpyAsync(d_off + n_reads + 1, koff.data(), (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-  rc = nthash_kmer_batch_dev(d_bases, nb_pad, d_off, d_off + n_reads + 1, n_reads, max_len, k, num_hashes, d_out,
-                             d_valid, d_fwd, d_rev, st);
-  if (rc != NTHASH_OK) {
-    cleanup();
-    return rc;
+  cudaGetDevice(&plan->device);
+  cudaError_t e = cudaMalloc(&plan->d_blob, plan->host.blob.size());
+  if (e == cudaSuccess) e = cudaMemcpy(plan->d_blob, plan->host.blob.data(), plan->host.blob.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(plan->d_blob);
+    delete plan;
+    return fail(NTHASH_ERR_CUDA, "seed plan upload: %s", cudaGetErrorString(e));
   }
-  NTH_TRY(cudaMemcpyAsync(out, d_out, rows * H * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-  if (valid_bits) NTH_TRY(cudaMemcpyAsync(valid_bits, d_valid, vwords * 4, cudaMemcpyDeviceToHost, st));
-  if (out_fwd) {
-    NTH_TRY(cudaMemcpyAsync(out_fwd, d_fwd, rows * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    NTH_TRY(cudaMemcpyAsync(out_rev, d_rev, rows * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-  }
-  NTH_TRY(cudaStreamSynchronize(st));
-  cleanup();
+  *plan_out = plan;
   return NTHASH_OK;
+}
+
+void nthash_seed_plan_destroy(nthash_seed_plan* plan)
+{
+  if (!plan) return;
+  cudaFree(plan->d_blob);
+  delete plan;
+}
+
+int nthash_seed_plan_symmetric(const nthash_seed_plan* plan) { return plan && plan->host.all_symmetric ? 1 : 0; }
+
+int nthash_seed_batch_uniform_dev(const nthash_seed_plan* plan, const uint8_t* d_bases, uint64_t n_bases_readable,
+                                  uint64_t n_reads, uint32_t read_len, uint64_t* d_out, uint32_t* d_valid_bits,
+                                  uint64_t* d_out_fwd, uint64_t* d_out_rev, void* stream)
+{
+  if (!plan) return fail(NTHASH_ERR_INVALID_ARG, "plan must not be NULL");
+  const uint32_t k = plan->host.k;
+  if (n_reads == 0 || read_len < k) return NTHASH_OK;
+  if (int rc = check_outputs(d_out, d_out_fwd, d_out_rev)) return rc;
+  if (!d_bases || ((uintptr_t)d_bases & 15)) return fail(NTHASH_ERR_INVALID_ARG, "d_bases must be 16-byte aligned");
+  if (n_bases_readable < n_reads * (uint64_t)read_len)
+    return fail(NTHASH_ERR_INVALID_ARG, "n_bases_readable smaller than n_reads*read_len");
+  if (int rc = check_device_ready()) return rc;
+  SeedParams P;
+  fill_seed_params(plan, P);
+  if (!plan_uniform(n_reads, read_len, k, P.g, P.tile_cap))
+    return fail(NTHASH_ERR_UNSUPPORTED, "k=%u with read_len=%u needs a %u-byte tile", k, read_len, P.tile_cap);
+  P.bases = d_bases;
+  P.n_bases = n_bases_readable;
+  P.out = d_out;
+  P.valid_bits = d_valid_bits;
+  P.out_fwd = d_out_fwd;
+  P.out_rev = d_out_rev;
+  return run_seed(P, n_reads, n_reads * (uint64_t)P.g.nk, (cudaStream_t)stream);
+}
+
+int nthash_seed_batch_dev(const nthash_seed_plan* plan, const uint8_t* d_bases, uint64_t n_bases_readable,
+                          const uint64_t* d_read_off, const uint64_t* d_koff, uint64_t n_reads, uint64_t max_read_len,
+                          uint64_t* d_out, uint32_t* d_valid_bits, uint64_t* d_out_fwd, uint64_t* d_out_rev,
+                          void* stream)
+{
+  if (!plan) return fail(NTHASH_ERR_INVALID_ARG, "plan must not be NULL");
+  const uint32_t k = plan->host.k;
+  if (n_reads == 0 || max_read_len < k) return NTHASH_OK;
+  if (int rc = check_outputs(d_out, d_out_fwd, d_out_rev)) return rc;
+  if (!d_bases || ((uintptr_t)d_bases & 15)) return fail(NTHASH_ERR_INVALID_ARG, "d_bases must be 16-byte aligned");
+  if (!d_read_off || !d_koff) return fail(NTHASH_ERR_INVALID_ARG, "d_read_off and d_koff must not be NULL");
+  if (int rc = check_device_ready()) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint64_t rows = 0;
+  if (d_valid_bits) {
+    NTH_CUDA(cudaMemcpyAsync(&rows, d_koff + n_reads, sizeof rows, cudaMemcpyDeviceToHost, st));
+    NTH_CUDA(cudaStreamSynchronize(st));
+  }
+  SeedParams P;
+  fill_seed_params(plan, P);
+  P.bases = d_bases;
+  P.n_bases = n_bases_readable;
+  P.read_off = d_read_off;
+  P.koff = d_koff;
+  P.out = d_out;
+  P.valid_bits = d_valid_bits;
+  P.out_fwd = d_out_fwd;
+  P.out_rev = d_out_rev;
+  RaggedItems R;
+  const uint32_t budget = TILE_BUDGET > P.plan_smem_bytes / 2 ? TILE_BUDGET - P.plan_smem_bytes / 2 : 0;
+  if (int rc = plan_ragged(d_read_off, d_koff, n_reads, max_read_len, k, budget, st, R)) return rc;
+  P.g = R.g;
+  P.tile_cap = R.tile_cap;
+  P.item_read = R.item_read;
+  int rc = run_seed(P, n_reads, rows, st);
+  if (R.d_items) cudaFreeAsync(R.d_items, st);
+  return rc;
+}
+
+int nthash_seed_batch(const char* bases, const uint64_t* read_off, uint64_t n_reads, const char* const* seeds,
+                      uint32_t n_seeds, uint32_t k, uint32_t num_hashes_per_seed, uint64_t* out,
+                      uint32_t* valid_bits, uint64_t* out_fwd, uint64_t* out_rev, int device)
+{
+  if (int rc = check_kh(k, num_hashes_per_seed)) return rc;
+  if (n_reads == 0) return NTHASH_OK;
+  if (!bases || !read_off) return fail(NTHASH_ERR_INVALID_ARG, "bases and read_off must not be NULL");
+  if (int rc = check_outputs(out, out_fwd, out_rev)) return rc;
+  if (cudaSetDevice(device) != cudaSuccess) return fail(NTHASH_ERR_NO_DEVICE, "cannot select CUDA device %d", device);
+  nthash_seed_plan* plan = nullptr;
+  if (int rc = nthash_seed_plan_create(seeds, n_seeds, k, num_hashes_per_seed, &plan)) return rc;
+  std::vector<uint64_t> koff(n_reads + 1);
+  const uint64_t rows = nthash_window_rows(read_off, n_reads, k, koff.data());
+  uint64_t max_len = 0;
+  for (uint64_t r = 0; r < n_reads; ++r) max_len = std::max(max_len, read_off[r + 1] - read_off[r]);
+  const uint64_t n_bases = read_off[n_reads], nb_pad = (n_bases + 31) & ~15ull;
+  const uint64_t H = (uint64_t)n_seeds * num_hashes_per_seed, vwords = (rows + 31) / 32;
+  int rc = NTHASH_OK;
+  if (rows) {
+    HostStaging hs;
+    rc = hs.open(bases, n_bases, nb_pad, read_off, koff.data(), n_reads, rows, H, valid_bits != nullptr,
+                 out_fwd ? n_seeds : 0);
+    if (rc == NTHASH_OK)
+      rc = nthash_seed_batch_dev(plan, hs.d_bases, nb_pad, hs.d_off, hs.d_off + n_reads + 1, n_reads, max_len, hs.d_out,
+                                 hs.d_valid, hs.d_fwd, hs.d_rev, hs.st);
+    if (rc == NTHASH_OK) rc = hs.fetch(out, valid_bits, out_fwd, out_rev, rows, H, vwords, out_fwd ? n_seeds : 0);
+  }
+  nthash_seed_plan_destroy(plan);
+  return rc;
 }
 
 int nthash_blind_roll_batch_dev(uint64_t* d_fwd, uint64_t* d_rev, const uint8_t* d_out_base,

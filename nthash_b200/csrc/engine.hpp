@@ -45,6 +45,30 @@ bool kmer_fast_ok(const KmerParams& P);
 cudaError_t launch_kmer_fast(const KmerParams& P, cudaStream_t st);
 cudaError_t launch_kmer(KmerParams P, cudaStream_t st);
 
+// ---- SeedNtHash (seed_kernel.cu) -------------------------------------------------------------
+struct SeedParams
+{
+  const uint8_t* bases = nullptr;
+  uint64_t n_bases = 0;
+  KmerGeom g;
+  const uint64_t* read_off = nullptr; // ragged batches (NULL: uniform); per READ, for the emission replay
+  const uint64_t* koff = nullptr;
+  const uint64_t* item_read = nullptr; // item -> read when reads are cut into several items
+  uint32_t k = 0, h = 0, n_seeds = 0;
+  uint64_t* out = nullptr;
+  uint32_t* valid_bits = nullptr;
+  uint64_t* out_fwd = nullptr;
+  uint64_t* out_rev = nullptr;
+  uint8_t* read_dirty = nullptr; // one byte per read, zeroed by the caller
+  uint32_t tile_cap = 0;
+  const uint8_t* plan_blob = nullptr; // device copy of SeedPlanHost::blob
+  uint32_t plan_smem_bytes = 0, groups_off = 0, tables_off = 0, care_off = 0, refblk_off = 0, care_words = 0;
+  uint32_t any_ignore = 0;
+  uint64_t s[4], sk[4];
+};
+uint32_t seed_smem_bytes(uint32_t plan_smem, uint32_t tile_cap);
+cudaError_t launch_seed(SeedParams P, uint64_t n_reads, cudaStream_t st);
+
 // BlindNtHash::roll / peek over n independent (fwd, rev) states (blind_kernel.cu).
 cudaError_t launch_blind(uint64_t* fwd, uint64_t* rev, const uint8_t* out_base, const uint8_t* in_base, uint64_t n,
                          uint32_t k, uint32_t h, uint64_t* out, bool peek4, cudaStream_t st);
@@ -61,7 +85,7 @@ cudaError_t launch_koff_scan(const uint64_t* read_off, uint64_t n_reads, uint32_
                              uint64_t* koff, uint64_t* stats, cudaStream_t st);
 // Expands reads into items (only needed when some read exceeds the whole-read tile budget).
 cudaError_t launch_item_fill(const uint64_t* read_off, const uint64_t* koff, uint64_t n_reads, uint32_t k,
-                             uint32_t seg, uint64_t* item_byte, uint64_t* item_out, uint64_t n_items,
-                             cudaStream_t st);
+                             uint32_t seg, uint64_t* item_byte, uint64_t* item_out, uint64_t* item_read,
+                             uint64_t n_items, cudaStream_t st);
 
 } // namespace nthb

@@ -131,18 +131,21 @@ scan_write(const uint64_t* read_off, uint64_t n, uint32_t k, uint32_t seg, const
 }
 
 __global__ void item_fill(const uint64_t* read_off, const uint64_t* koff, const uint64_t* ioff, uint64_t n,
-                          uint32_t k, uint32_t seg, uint64_t* item_byte, uint64_t* item_out, uint64_t n_items)
+                          uint32_t k, uint32_t seg, uint64_t* item_byte, uint64_t* item_out, uint64_t* item_read,
+                          uint64_t n_items)
 {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r == 0) {
     item_byte[n_items] = read_off[n];
     item_out[n_items] = koff[n];
+    item_read[n_items] = n;
   }
   if (r >= n) return;
   const uint64_t i0 = ioff[r], i1 = ioff[r + 1];
   for (uint64_t i = i0; i < i1; ++i) {
     item_byte[i] = read_off[r] + (i - i0) * seg;
     item_out[i] = koff[r] + (i - i0) * seg;
+    item_read[i] = r;
   }
 }
 
@@ -169,8 +172,8 @@ cudaError_t launch_koff_scan(const uint64_t* read_off, uint64_t n_reads, uint32_
 }
 
 cudaError_t launch_item_fill(const uint64_t* read_off, const uint64_t* koff, uint64_t n_reads, uint32_t k,
-                             uint32_t seg, uint64_t* item_byte, uint64_t* item_out, uint64_t n_items,
-                             cudaStream_t st)
+                             uint32_t seg, uint64_t* item_byte, uint64_t* item_out, uint64_t* item_read,
+                             uint64_t n_items, cudaStream_t st)
 {
   // item offsets per read = exclusive scan of ceil(nk / seg)
   uint64_t* ioff = nullptr;
@@ -180,7 +183,7 @@ cudaError_t launch_item_fill(const uint64_t* read_off, const uint64_t* koff, uin
   if (e == cudaSuccess) {
     const unsigned bs = 256;
     item_fill<<<(unsigned)((n_reads + bs - 1) / bs), bs, 0, st>>>(read_off, koff, ioff, n_reads, k, seg,
-                                                                 item_byte, item_out, n_items);
+                                                                 item_byte, item_out, item_read, n_items);
     e = cudaGetLastError();
   }
   cudaFreeAsync(ioff, st);

@@ -1,0 +1,178 @@
+"""GPU parity of the SeedNtHash batch kernels (csrc/seed_kernel.cu) and the BlindNtHash batch kernel
+(csrc/blind_kernel.cu) against the CPU oracle, through the C ABI.
+
+Bar: bit-exact hashes and the reference's exact set of visited windows, including its quirks
+(non-ACGTU bytes hashed inside a window, k-jump on an invalid incoming base, NUL rule:
+reference src/seed.cpp:151, :493-544)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import assert_batch_equal, ragged_offsets, synth, to_dev, u64
+from oracle_lib import ORACLE
+
+pytestmark = pytest.mark.gpu
+
+import nthash_b200  # noqa: E402
+
+SEED_A31 = "1010101010101010101010101010101"
+SEED_B31 = "1101101101101101011011011011011"
+
+SEED_SETS = [
+    ([SEED_A31, SEED_B31], 3),
+    (["11100111"], 3),
+    (["110011", "101101"], 2),
+    (["11111"], 1),
+    (["111110000000011111", "111111100001111111"], 2),
+    (["111111111101111111111", "110111010010010111011"], 4),
+    (["1101100", "0011011", "1000001"], 1),      # asymmetric
+    (["0110", "1001", "0101"], 2),               # leading / trailing don't-cares
+    (["1" * 40 + "0" * 23 + "1" * 40], 1),        # long runs, k = 103
+    (["11011000001100101101011000011010110100110000011011", "01010000101001110100111011011100101110010100001010",
+      "11100000100111010111000100100011101011100100000111", "01111000011000111101000011000010111100011000011110",
+      "00111000011000111101000011000010111100011000011100", "00000000000000000000000011000000000000000000000000",
+      "11111111111111111111111100111111111111111111111111", "11111111111111111111111111111111111111111111111111"], 4),
+]
+
+
+def run_ragged(plan, bases, off, strands=True):
+    d_b, _keep = to_dev(bases)
+    res = nthash_b200.seed_hashes(plan, d_b, torch.from_numpy(off).cuda(), want_strands=strands)
+    torch.cuda.synchronize()
+    return res
+
+
+def test_golden_spaced_seed_values_through_gpu():
+    # reference tests/tests.cpp:228-248
+    plan = nthash_b200.SeedPlan(["11100111"], 3)
+    seq = np.frombuffer(b"ACATGCATGCA", np.uint8)
+    out = u64(run_ragged(plan, seq, ragged_offsets([11])).out).reshape(-1, 3)
+    want = [[0x10BE4904AD8DE5D, 0x3E29E4F4C991628C, 0x3F35C984B13FEB20], [0x8200A7AA3EAF17C8, 0x344198402F4C2A9C, 0xB6423FE62E69C40C],
+            [0x3CE8ADCBEAA56532, 0x162E91A4DBEDBF11, 0x53173F786A031F45]]
+    assert [[int(x) for x in r] for r in out[:3]] == want
+    assert plan.symmetric and not nthash_b200.SeedPlan(["1101100"], 1).symmetric
+
+
+def test_config_seeds_known_answers():
+    # seeds A,B on the 1 kb sequence, and the 200-base dirty read (109 visited windows)
+    plan = nthash_b200.SeedPlan([SEED_A31, SEED_B31], 3)
+    seq = ORACLE.gen_bases(1000, 42)
+    out = u64(run_ragged(plan, seq, ragged_offsets([1000])).out)
+    assert [int(x) for x in out[0]] == [0xE09BC50CEA32E5AA, 0xF206E6A6EBAE2333, 0x5033979BEAA8B115,
+                                       0x194F0B34C1432F4C, 0x74181E1C17687846, 0x282AFC7155FDA2BA]
+    assert int(out.sum(dtype=np.uint64)) == 0x6C20E8349FC9CF61
+    dirty = seq[:200].copy(); dirty[50] = dirty[51] = ord("N"); dirty[120] = ord("n"); dirty[199] = ord("N")
+    plan1 = nthash_b200.SeedPlan([SEED_A31, SEED_B31], 1)
+    res = run_ragged(plan1, dirty, ragged_offsets([200]))
+    assert int(res.valid_mask().sum()) == 109 and int(u64(res.out).sum(dtype=np.uint64)) == 0x69A56848390E3347
+
+
+@pytest.mark.parametrize("seeds,h", SEED_SETS, ids=lambda v: v[0][:10] if isinstance(v, list) else str(v))
+def test_ragged_dirty_reads_all_seed_sets(seeds, h, capfd):
+    k = len(seeds[0])
+    rng = np.random.default_rng(len(seeds) * 1000 + k)
+    lens = rng.integers(0, 3 * k + 100, 400)
+    lens[:6] = [0, 1, k - 1, k, k + 1, 2 * k]
+    off = ragged_offsets(lens)
+    bases = synth(rng, int(off[-1]), p_bad=0.006, lower=0.1)
+    # a cluster of invalid bytes closer than k, and NUL bytes: the jump rule and init's NUL rule
+    for r in (10, 20, 30):
+        s, e = int(off[r]), int(off[r + 1])
+        if e - s > 2 * k:
+            bases[s + k:s + k + 3] = [ord("N"), ord("A"), ord("R")]
+    bases[rng.integers(0, len(bases), 6)] = 0
+    plan = nthash_b200.SeedPlan(seeds, h)
+    res = run_ragged(plan, bases, off)
+    ora = ORACLE.seed_batch(bases, off.astype(np.uint64), seeds, h)
+    assert_batch_equal(res, ora, len(seeds) * h, check_strands=True)
+    capfd.readouterr()
+
+
+@pytest.mark.parametrize("read_len,n,p_bad", [(150, 3000, 0.0), (150, 3000, 0.002), (151, 500, 0.001), (40, 1000, 0.0), (3000, 60, 0.0005)])
+def test_uniform_config4_shape(read_len, n, p_bad):
+    rng = np.random.default_rng(read_len + n)
+    bases = synth(rng, n * read_len, p_bad=p_bad)
+    d_b, _keep = to_dev(bases)
+    plan = nthash_b200.SeedPlan([SEED_A31, SEED_B31], 3)
+    res = nthash_b200.seed_hashes_uniform(plan, d_b, n, read_len, want_strands=True)
+    torch.cuda.synchronize()
+    ora = ORACLE.seed_batch(bases, np.arange(n + 1, dtype=np.uint64) * read_len, [SEED_A31, SEED_B31], 3, threads=8)
+    assert_batch_equal(res, ora, 6, check_strands=True)
+
+
+def test_ragged_long_reads_and_host_entry():
+    rng = np.random.default_rng(77)
+    lens = [40000, 5, 9000, 31, 30, 777]
+    off = ragged_offsets(lens)
+    bases = synth(rng, int(off[-1]), p_bad=0.0003)
+    seeds, h = [SEED_A31, SEED_B31], 2
+    plan = nthash_b200.SeedPlan(seeds, h)
+    ora = ORACLE.seed_batch(bases, off.astype(np.uint64), seeds, h, threads=4)
+    assert_batch_equal(run_ragged(plan, bases, off), ora, 4, check_strands=True)
+    # host-pointer entry (nthash_seed_batch)
+    rows = ora["out"].shape[0]
+    out = np.zeros((rows, 4), np.uint64); fw = np.zeros((rows, 2), np.uint64); rv = np.zeros((rows, 2), np.uint64)
+    vb = np.zeros((rows + 31) // 32, np.uint32)
+    arr = (C.c_char_p * 2)(*[s.encode() for s in seeds])
+    offu = off.astype(np.uint64)
+    rc = nthash_b200.LIB.nthash_seed_batch(bases.ctypes.data, offu.ctypes.data, len(lens), arr, 2, 31, h, out.ctypes.data,
+                                           vb.ctypes.data, fw.ctypes.data, rv.ctypes.data, 0)
+    assert rc == 0, nthash_b200.LIB.nthash_last_error()
+    bits = ((vb[:, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(-1)[:rows]
+    assert (bits == ora["valid"]).all() and (out == ora["out"]).all() and (fw == ora["fwd"]).all() and (rv == ora["rev"]).all()
+
+
+def test_seed_properties_at_scale():
+    # reference tests.cpp:349-377 (strand symmetry of palindromic seeds) and :447-463 (all-ones seed == NtHash)
+    rng = np.random.default_rng(4)
+    n, L, k = 100_000, 150, 31
+    fwd = synth(rng, n * L).reshape(n, L)
+    comp = np.zeros(256, np.uint8); comp[list(b"ACGT")] = list(b"TGCA")
+    rc = np.ascontiguousarray(comp[fwd[:, ::-1]])
+    plan = nthash_b200.SeedPlan([SEED_A31, SEED_B31, "1" * 31], 2)
+    outs = []
+    for arr in (fwd, rc):
+        d_b, _keep = to_dev(arr.reshape(-1))
+        outs.append(nthash_b200.seed_hashes_uniform(plan, d_b, n, L).out.view(n, L - k + 1, 6))
+    d_b, _keep = to_dev(fwd.reshape(-1))
+    kmer = nthash_b200.kmer_hashes_uniform(d_b, n, L, k, 2).out.view(n, L - k + 1, 2)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1].flip(1))
+    assert torch.equal(outs[0][:, :, 4:6], kmer)
+
+
+def test_seed_plan_errors():
+    with pytest.raises(nthash_b200.NtHashError, match="not equal to k"):
+        nthash_b200.SeedPlan(["1101", "101"], 1)   # seed.cpp:90-95
+    with pytest.raises(nthash_b200.NtHashError):
+        nthash_b200.SeedPlan(["11x11"], 1)
+
+
+def test_blind_roll_and_peek_batches():
+    # reference BlindNtHash::roll / peek (src/kmer.cpp:355-393); initial states = k-mer batch with read_len == k
+    rng = np.random.default_rng(6)
+    for k, h in ((5, 3), (31, 1), (64, 2)):
+        n, steps = 2000, 12
+        kmers = synth(rng, n * k).reshape(n, k)
+        ins = rng.choice(np.frombuffer(b"ACGTNacgu", np.uint8), (n, steps))
+        d_k, _keep = to_dev(kmers.reshape(-1))
+        init = nthash_b200.kmer_hashes_uniform(d_k, n, k, k, h, want_strands=True)
+        fwd, rev = init.fwd.clone(), init.rev.clone()
+        window = np.concatenate([kmers, ins], axis=1)
+        want = [ORACLE.blind_read(kmers[i].tobytes(), h, ins[i].tobytes()) for i in range(n)]
+        assert (u64(init.out) == np.stack([w[0] for w in want])).all()
+        for t in range(steps):
+            out_base = torch.from_numpy(np.ascontiguousarray(window[:, t])).cuda()
+            if t == 3:  # peek4 == what roll would give for each of ACGT, states untouched
+                pk = u64(nthash_b200.blind_peek4(fwd, rev, out_base, k, h)).reshape(n, 4, h)
+                for e, ch in enumerate(b"ACGT"):
+                    f2, r2 = fwd.clone(), rev.clone()
+                    got = nthash_b200.blind_roll(f2, r2, out_base, torch.full((n,), ch, dtype=torch.uint8, device="cuda"), k, h)
+                    assert (u64(got) == pk[:, e]).all()
+            in_base = torch.from_numpy(np.ascontiguousarray(ins[:, t])).cuda()
+            got = u64(nthash_b200.blind_roll(fwd, rev, out_base, in_base, k, h))
+            assert (got == np.stack([w[1][t] for w in want])).all()
+            assert (u64(fwd) == np.array([w[2][t] for w in want], np.uint64)).all()
+            assert (u64(rev) == np.array([w[3][t] for w in want], np.uint64)).all()
