@@ -30,6 +30,8 @@ CONFIGS = {
     # name: (reads per GPU, read length, k, hashes)
     "c2": dict(n_reads=10_000_000, read_len=150, k=31, h=1, desc="10M x 150bp reads, k=31, h=1 canonical (BASELINE.json configs[1])"),
     "c3": dict(n_reads=10_000_000, read_len=150, k=31, h=4, desc="10M x 150bp reads, k=31, h=4 (configs[2])"),
+    "c4": dict(n_reads=10_000_000, read_len=150, k=31, h=3, seeds=["1010101010101010101010101010101", "1101101101101101011011011011011"],
+               desc="SeedNtHash: 10M x 150bp reads, two spaced seeds, k=31, h=3 per seed (configs[3])"),
     "c5": dict(n_reads=12_500, read_len=50_000, k=63, h=1, desc="12.5k x 50kb reads per GPU, k=63, h=1 (configs[4] shard)"),
 }
 METRIC = "kmers_hashed_per_sec"
@@ -97,12 +99,15 @@ def synth_reads_device(torch, n_bases, seed):
     return buf
 
 
-def cpu_reference_pass(lib, bases_np, n_reads, read_len, k, h, threads):
-    """One pass of the reference's own loop over `n_reads` reads -> (k-mers/s, emitted, sum)."""
+def cpu_reference_pass(lib, bases_np, n_reads, read_len, k, h, threads, seeds=None):
+    """One pass of the reference's own loop over `n_reads` reads -> (windows/s, emitted, sum)."""
     import numpy as np
     off = np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(read_len)
     t0 = time.perf_counter()
-    r = lib.kmer_batch(bases_np, off, k, h, want=(), threads=threads)
+    if seeds:
+        r = lib.seed_batch(bases_np, off, seeds, h, want=(), threads=threads)
+    else:
+        r = lib.kmer_batch(bases_np, off, k, h, want=(), threads=threads)
     dt = time.perf_counter() - t0
     return r["n_emit"] / dt, r["n_emit"], r["sum"], dt
 
@@ -119,11 +124,11 @@ def run_reference(args, cfg):
     sample_reads = min(cfg["n_reads"], args.ref_sample_reads)
     bases = ORACLE.gen_bases(sample_reads * cfg["read_len"], 42)
     for _ in range(args.warmup):
-        cpu_reference_pass(lib, bases, sample_reads, cfg["read_len"], cfg["k"], cfg["h"], threads)
+        cpu_reference_pass(lib, bases, sample_reads, cfg["read_len"], cfg["k"], cfg["h"], threads, cfg.get("seeds"))
     t0 = time.perf_counter()
     emitted = 0
     for _ in range(args.steps):
-        _, ne, _, _ = cpu_reference_pass(lib, bases, sample_reads, cfg["read_len"], cfg["k"], cfg["h"], threads)
+        _, ne, _, _ = cpu_reference_pass(lib, bases, sample_reads, cfg["read_len"], cfg["k"], cfg["h"], threads, cfg.get("seeds"))
         emitted += ne
     dt = time.perf_counter() - t0
     value = emitted / dt
@@ -158,35 +163,35 @@ def main():
 
     import numpy as np
     import torch
-    import torch.distributed as dist
 
     import nthash_b200
+    from nthash_b200 import dist as nd
     from nthash_b200._lib import LIB, check
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = nd.env_rank()
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    nd.init("nccl", torch.device("cuda", local))
+    barrier = nd.barrier
 
     n_reads, L, k, h = cfg["n_reads"], cfg["read_len"], cfg["k"], cfg["h"]
+    seeds = cfg.get("seeds")
+    H = h * (len(seeds) if seeds else 1)  # u64 values per window
+    plan = nthash_b200.SeedPlan(seeds, h) if seeds else None
     nk = L - k + 1
     rows = n_reads * nk
     n_bases = n_reads * L
     bases_buf = synth_reads_device(torch, n_bases, 1234 + rank)
     bases = bases_buf[:n_bases]
-    out = torch.empty((rows, h), dtype=torch.int64, device="cuda")
+    out = torch.empty((rows, H), dtype=torch.int64, device="cuda")
     valid = torch.empty(int(LIB.nthash_valid_words(rows)), dtype=torch.int32, device="cuda")
 
     def step(with_valid=True):
-        nthash_b200.kmer_hashes_uniform(bases, n_reads, L, k, h, want_valid=with_valid, out=out,
-                                        valid_bits=valid if with_valid else None)
+        if plan is not None:
+            nthash_b200.seed_hashes_uniform(plan, bases, n_reads, L, want_valid=with_valid, out=out,
+                                            valid_bits=valid if with_valid else None)
+        else:
+            nthash_b200.kmer_hashes_uniform(bases, n_reads, L, k, h, want_valid=with_valid, out=out,
+                                            valid_bits=valid if with_valid else None)
 
     # ---- device-resident throughput (value) -------------------------------------------------
     for _ in range(max(args.warmup, 3)):
@@ -211,10 +216,7 @@ def main():
     k1.record()
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / args.steps
-    t = torch.tensor([ms, kernel_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, kernel_ms = float(t[0]), float(t[1])
+    ms, kernel_ms = nd.max_over_ranks([ms, kernel_ms])
 
     # ---- end to end through the host-buffer C ABI call ----------------------------------------
     e2e = None
@@ -224,19 +226,26 @@ def main():
     except Exception:
         avail = 0
     e2e_reads = n_reads
-    need = (n_bases + rows * h * 8) * world
+    need = (n_bases + rows * H * 8) * world
     while e2e_reads > 100_000 and avail and need * e2e_reads / n_reads > 0.5 * avail:
         e2e_reads //= 2
     e_rows = e2e_reads * nk
     h_bases = torch.empty(e2e_reads * L, dtype=torch.uint8).pin_memory()
     h_bases.copy_(bases[: e2e_reads * L])
     h_off = (torch.arange(e2e_reads + 1, dtype=torch.int64) * L)
-    h_out = torch.empty((e_rows, h), dtype=torch.int64).pin_memory()
+    h_out = torch.empty((e_rows, H), dtype=torch.int64).pin_memory()
     h_valid = torch.empty(int(LIB.nthash_valid_words(e_rows)), dtype=torch.int32).pin_memory()
 
+    import ctypes
+    seed_arr = (ctypes.c_char_p * len(seeds))(*[s.encode() for s in seeds]) if seeds else None
+
     def e2e_step():
-        check(LIB.nthash_kmer_batch(h_bases.data_ptr(), h_off.data_ptr(), e2e_reads, k, h, h_out.data_ptr(),
-                                    h_valid.data_ptr(), None, None, local))
+        if seeds:
+            check(LIB.nthash_seed_batch(h_bases.data_ptr(), h_off.data_ptr(), e2e_reads, seed_arr, len(seeds), k, h,
+                                        h_out.data_ptr(), h_valid.data_ptr(), None, None, local))
+        else:
+            check(LIB.nthash_kmer_batch(h_bases.data_ptr(), h_off.data_ptr(), e2e_reads, k, h, h_out.data_ptr(),
+                                        h_valid.data_ptr(), None, None, local))
 
     e2e_step()
     barrier()
@@ -245,10 +254,7 @@ def main():
         e2e_step()
     torch.cuda.synchronize()
     e_dt = (time.perf_counter() - t0) / args.e2e_steps
-    te = torch.tensor([e_dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e_dt = float(te[0])
+    e_dt = nd.max_over_ranks([e_dt])[0]
     # parity of the e2e result with the device-resident one (same reads): checksum of checksums
     same = bool((h_out[: 1000 * nk].cuda() == out[: 1000 * nk]).all())
     e2e = {"value": world * e_rows / e_dt, "unit": UNIT, "h2d_bytes_per_step": int(h_bases.numel() + h_off.numel() * 8),
@@ -256,8 +262,7 @@ def main():
            "ms_per_step": e_dt * 1e3, "matches_device_path": same}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        nd.finalize()
         return
 
     # ---- CPU baseline: the compiled reference on this box's host cores -------------------------
@@ -269,36 +274,35 @@ def main():
         threads = os.cpu_count() or 1
         sample_reads = min(n_reads, args.ref_sample_reads)
         h_sample = bases[: sample_reads * L].cpu().numpy()
-        v, ne, s, dt = cpu_reference_pass(lib, h_sample, sample_reads, L, k, h, threads)
+        v, ne, s, dt = cpu_reference_pass(lib, h_sample, sample_reads, L, k, h, threads, seeds)
         # grow the sample until it is a meaningful amount of CPU work (about 10-30 core-seconds)
         if dt * threads < 10 and sample_reads < n_reads:
             sample_reads = min(n_reads, int(sample_reads * 20 / max(dt * threads, 0.5)))
             h_sample = bases[: sample_reads * L].cpu().numpy()
-            v, ne, s, dt = cpu_reference_pass(lib, h_sample, sample_reads, L, k, h, threads)
+            v, ne, s, dt = cpu_reference_pass(lib, h_sample, sample_reads, L, k, h, threads, seeds)
         got = int(out[: sample_reads * nk].cpu().numpy().view(np.uint64).sum(dtype=np.uint64))
         checksum_ok = (got == s) and ne == sample_reads * nk
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": lib.kind,
                "sample": f"first {sample_reads} of {n_reads} reads, {dt:.2f} s wall on {threads} threads", "checksum_matches_gpu": checksum_ok}
 
     peak, peak_src = load_peak()
-    abytes = algorithmic_bytes(n_reads, L, k, h)
+    abytes = algorithmic_bytes(n_reads, L, k, H)
     achieved = abytes / (kernel_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": world * rows / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": cfg["desc"], "reads_per_gpu": n_reads, "read_len": L, "k": k, "h": h,
+        "config": {"workload": cfg["desc"], "reads_per_gpu": n_reads, "read_len": L, "k": k, "h": h, "seeds": seeds,
                    "l2_policy": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2; no explicit flush" % (abytes / 1e9),
                    "sharding": "independent read shards per GPU, no collective"},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "kmer_kernel<1,false>", "kernel_ms": kernel_ms,
+                     "traffic": None, "peak_source": peak_src, "kernel": ("seed_kernel" if seeds else "kmer_fast_kernel<%d>" % h), "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_launch": abytes},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    nd.finalize()
 
 
 if __name__ == "__main__":
