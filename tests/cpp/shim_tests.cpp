@@ -253,7 +253,8 @@ static void gpu_blocks()
       sum += h.hashes()[0];
     }
     CHECK(n == seq.size() - 31 + 1 - 100 - 31 && last == seq.size() - 31);
-    nthash::NtHash spot(seq.substr(4194300, 40), 1, 31); // straddles the chunk boundary at window 2^22
+    const std::string piece = seq.substr(4194300, 40);   // the classes borrow the sequence, as the reference does
+    nthash::NtHash spot(piece, 1, 31);                   // straddles the chunk boundary at window 2^22
     nthash::NtHash big(seq, 1, 31, 4194300);
     for (int i = 0; i < 10; ++i) CHECK(spot.roll() && big.roll() && spot.hashes()[0] == big.hashes()[0]);
     std::printf("long sequence: %zu windows, checksum %016llx\n", n, (unsigned long long)sum);
