@@ -43,6 +43,15 @@ def algorithmic_bytes(n_reads, read_len, k, H):
     return n_reads * read_len + n_reads * max(read_len - k + 1, 0) * H * 8
 
 
+def load_traffic(config):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(config)
+    except Exception:
+        return None
+
+
 def load_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -297,7 +306,8 @@ def main():
                    "sharding": "independent read shards per GPU, no collective"},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": ("seed_kernel" if seeds else "kmer_fast_kernel<%d>" % h), "kernel_ms": kernel_ms,
+                     "traffic": (load_traffic(args.config) or {}).get("dram_bytes_per_launch") if not args.reads else None,
+                     "traffic_source": (load_traffic(args.config) or {}).get("source"), "peak_source": peak_src, "kernel": ("seed_kernel" if seeds else "kmer_fast_kernel<%d>" % h), "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_launch": abytes},
         "cpu_baseline": cpu,
     }
