@@ -113,6 +113,11 @@ int nthash_seed_plan_create(const char* const* seeds, uint32_t n_seeds, uint32_t
                             uint32_t num_hashes_per_seed, nthash_seed_plan** plan_out);
 void nthash_seed_plan_destroy(nthash_seed_plan* plan);
 int nthash_seed_plan_symmetric(const nthash_seed_plan* plan);
+/* Which kernel serves uniform batches for this plan: the one specialised for the seed set at plan
+ * creation (NVRTC), or — with the reason — the generic one.  Both are CUDA; results are identical. */
+const char* nthash_seed_plan_kernel_note(const nthash_seed_plan* plan);
+/* Build check usable without a GPU: generates and compiles (sm_100a) the specialised kernel. */
+int nthash_seed_jit_selftest(const char* const* seeds, uint32_t n_seeds, uint32_t k, uint32_t num_hashes_per_seed);
 
 int nthash_seed_batch_uniform_dev(const nthash_seed_plan* plan, const uint8_t* d_bases,
                                   uint64_t n_bases_readable, uint64_t n_reads, uint32_t read_len,

@@ -24,6 +24,8 @@ _SIGS = {
     "nthash_seed_plan_create": (C.c_int, [C.POINTER(C.c_char_p), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
     "nthash_seed_plan_destroy": (None, [C.c_void_p]),
     "nthash_seed_plan_symmetric": (C.c_int, [C.c_void_p]),
+    "nthash_seed_plan_kernel_note": (C.c_char_p, [C.c_void_p]),
+    "nthash_seed_jit_selftest": (C.c_int, [C.POINTER(C.c_char_p), C.c_uint32, C.c_uint32, C.c_uint32]),
     "nthash_seed_batch_uniform_dev": (C.c_int, [C.c_void_p, u8p, C.c_uint64, C.c_uint64, C.c_uint32, u64p, u32p, u64p, u64p, C.c_void_p]),
     "nthash_seed_batch_dev": (C.c_int, [C.c_void_p, u8p, C.c_uint64, u64p, u64p, C.c_uint64, C.c_uint64, u64p, u32p, u64p, u64p, C.c_void_p]),
     "nthash_seed_batch": (C.c_int, [u8p, u64p, C.c_uint64, C.POINTER(C.c_char_p), C.c_uint32, C.c_uint32, C.c_uint32, u64p, u32p, u64p, u64p, C.c_int]),

@@ -209,6 +209,8 @@ struct nthash_seed_plan
   nthb::SeedPlanHost host;
   uint8_t* d_blob = nullptr;
   int device = 0;
+  nthb::SeedJit* jit = nullptr; // specialised kernel, or NULL (then jit_note says why)
+  std::string jit_note;
 };
 
 namespace nthb {
@@ -229,7 +231,7 @@ static void fill_seed_params(const nthash_seed_plan* plan, SeedParams& P)
   P.any_ignore = h.any_ignore ? 1u : 0u;
 }
 
-static int run_seed(SeedParams& P, uint64_t n_reads, uint64_t rows, cudaStream_t st)
+static int run_seed(const nthash_seed_plan* plan, SeedParams& P, uint64_t n_reads, uint64_t rows, cudaStream_t st)
 {
   if (P.valid_bits && rows) NTH_CUDA(cudaMemsetAsync(P.valid_bits, 0xFF, ((rows + 31) / 32) * 4, st));
   if (P.g.n_items == 0) return NTHASH_OK;
@@ -240,7 +242,14 @@ static int run_seed(SeedParams& P, uint64_t n_reads, uint64_t rows, cudaStream_t
   NTH_CUDA(cudaMallocAsync(&d_dirty, n_reads, st));
   cudaError_t e = cudaMemsetAsync(d_dirty, 0, n_reads, st);
   P.read_dirty = d_dirty;
-  if (e == cudaSuccess) e = launch_seed(P, n_reads, st);
+  if (e == cudaSuccess) {
+    if (seed_jit_applies(plan->jit, P) && !getenv("NTHASH_B200_DISABLE_SEED_JIT")) {
+      e = launch_seed_jit(plan->jit, P, st);
+      if (e == cudaSuccess) e = launch_seed_emit(P, n_reads, st);
+    } else {
+      e = launch_seed(P, n_reads, st);
+    }
+  }
   cudaFreeAsync(d_dirty, st);
   NTH_CUDA(e);
   return NTHASH_OK;
@@ -416,6 +425,8 @@ int nthash_seed_plan_create(const char* const* seeds, uint32_t n_seeds, uint32_t
     delete plan;
     return fail(NTHASH_ERR_CUDA, "seed plan upload: %s", cudaGetErrorString(e));
   }
+  plan->jit = seed_jit_build(plan->host, plan->jit_note, true);
+  if (plan->jit) plan->jit_note = "specialised kernel compiled with NVRTC";
   *plan_out = plan;
   return NTHASH_OK;
 }
@@ -423,8 +434,23 @@ int nthash_seed_plan_create(const char* const* seeds, uint32_t n_seeds, uint32_t
 void nthash_seed_plan_destroy(nthash_seed_plan* plan)
 {
   if (!plan) return;
+  seed_jit_destroy(plan->jit);
   cudaFree(plan->d_blob);
   delete plan;
+}
+
+const char* nthash_seed_plan_kernel_note(const nthash_seed_plan* plan) { return plan ? plan->jit_note.c_str() : ""; }
+
+int nthash_seed_jit_selftest(const char* const* seeds, uint32_t n_seeds, uint32_t k, uint32_t num_hashes_per_seed)
+{
+  SeedPlanHost host;
+  const std::string err = build_seed_plan(seeds, n_seeds, k, num_hashes_per_seed, host);
+  if (!err.empty()) return fail(NTHASH_ERR_INVALID_ARG, "%s", err.c_str());
+  std::string why;
+  SeedJit* j = seed_jit_build(host, why, false);
+  if (!j) return fail(NTHASH_ERR_UNSUPPORTED, "%s", why.c_str());
+  seed_jit_destroy(j);
+  return NTHASH_OK;
 }
 
 int nthash_seed_plan_symmetric(const nthash_seed_plan* plan) { return plan && plan->host.all_symmetric ? 1 : 0; }
@@ -451,7 +477,7 @@ int nthash_seed_batch_uniform_dev(const nthash_seed_plan* plan, const uint8_t* d
   P.valid_bits = d_valid_bits;
   P.out_fwd = d_out_fwd;
   P.out_rev = d_out_rev;
-  return run_seed(P, n_reads, n_reads * (uint64_t)P.g.nk, (cudaStream_t)stream);
+  return run_seed(plan, P, n_reads, n_reads * (uint64_t)P.g.nk, (cudaStream_t)stream);
 }
 
 int nthash_seed_batch_dev(const nthash_seed_plan* plan, const uint8_t* d_bases, uint64_t n_bases_readable,
@@ -488,7 +514,7 @@ int nthash_seed_batch_dev(const nthash_seed_plan* plan, const uint8_t* d_bases, 
   P.g = R.g;
   P.tile_cap = R.tile_cap;
   P.item_read = R.item_read;
-  int rc = run_seed(P, n_reads, rows, st);
+  int rc = run_seed(plan, P, n_reads, rows, st);
   if (R.d_items) cudaFreeAsync(R.d_items, st);
   return rc;
 }

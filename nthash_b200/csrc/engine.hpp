@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <string>
 
 namespace nthb {
 
@@ -67,7 +68,17 @@ struct SeedParams
   uint64_t s[4], sk[4];
 };
 uint32_t seed_smem_bytes(uint32_t plan_smem, uint32_t tile_cap);
-cudaError_t launch_seed(SeedParams P, uint64_t n_reads, cudaStream_t st);
+cudaError_t launch_seed(SeedParams P, uint64_t n_reads, cudaStream_t st);      // generic hash kernel + emission replay
+cudaError_t launch_seed_emit(const SeedParams& P, uint64_t n_reads, cudaStream_t st); // emission replay only
+
+// Seed kernel specialised per seed set at run time (seed_jit.cu).
+struct SeedJit;
+struct SeedPlanHost;
+SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load);
+void seed_jit_destroy(SeedJit* j);
+const char* seed_jit_source(const SeedJit* j);
+bool seed_jit_applies(const SeedJit* j, const SeedParams& P);
+cudaError_t launch_seed_jit(const SeedJit* j, const SeedParams& P, cudaStream_t st);
 
 // BlindNtHash::roll / peek over n independent (fwd, rev) states (blind_kernel.cu).
 cudaError_t launch_blind(uint64_t* fwd, uint64_t* rev, const uint8_t* out_base, const uint8_t* in_base, uint64_t n,

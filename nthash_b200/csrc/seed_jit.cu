@@ -1,0 +1,521 @@
+// seed_jit.cu — SeedNtHash kernel specialised per seed set at run time (NVRTC -> sm_100a cubin).
+//
+// Same reference lines as seed_kernel.cu (SeedNtHash::init/roll src/seed.cpp:493-544, ntmsm64
+// :130-270); this is the fast path for uniform batches.  The generic seed_kernel interprets the seed
+// plan (loops over seeds/groups/positions, byte loads, descriptor loads) and spends ~700 instructions
+// per window (profiles/r01_ncu_seed_c4_v1.txt).  Here the seed set is baked into the code:
+//  * the window's 2-bit base codes live in registers (a shift register of ceil(k/16) words; one funnel
+//    shift per word per window), so a group index is two rotates and two masks — no byte loads;
+//  * positions are looked up two at a time in 16-entry tables replicated 8x across bank groups
+//    ([entry][lane & 7]): any mix of indices within a quarter-warp is conflict-free (4 wavefronts);
+//  * ignore-mode seeds start from the full-window hash, rolled with the k-mer kernel's pair table;
+//  * hashes leave through TMA tile stores: each warp fills a [32 items] x [TW windows * H] u64 tile.
+// Exactness for non-ACGTU bytes is handled as in seed_kernel.cu: windows holding one are recomputed
+// byte-exactly, and the read is handed to seed_emit_kernel for the visiting-order replay.
+// If NVRTC is unavailable or the seed set does not fit, the caller falls back to seed_kernel.
+#include "engine.hpp"
+#include "nthash_dev.cuh"
+#include "seed_plan.hpp"
+
+#include <cstdio>
+#include <cstring>
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+#include <sstream>
+
+namespace nthb {
+
+namespace {
+
+// Mirrored verbatim in the device source below.
+struct JitParams
+{
+  const uint8_t* bases;
+  uint64_t n_bases;
+  uint64_t n_items;
+  uint32_t read_len, nk, seg, segs;
+  uint64_t* out;
+  uint32_t* valid_bits;
+  uint8_t* read_dirty;
+  const uint8_t* tables;
+  const uint32_t* care;
+  uint32_t tile_cap, care_words;
+};
+
+const char* const JIT_PRELUDE = R"JIT(
+typedef unsigned char uint8_t;
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+struct alignas(64) TensorMap { uint64_t opaque[16]; };
+struct JitParams
+{
+  const uint8_t* bases;
+  uint64_t n_bases;
+  uint64_t n_items;
+  uint32_t read_len, nk, seg, segs;
+  uint64_t* out;
+  uint32_t* valid_bits;
+  uint8_t* read_dirty;
+  const uint8_t* tables;
+  const uint32_t* care;
+  uint32_t tile_cap, care_words;
+};
+#define DI __device__ __forceinline__
+DI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+DI void mbar_init(uint32_t bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+DI void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+DI void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+DI void mbar_wait(uint32_t bar, uint32_t parity)
+{
+  uint32_t done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+DI void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+DI void tma_store_2d(const void* tmap, uint32_t saddr, int c0, int c1)
+{
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(saddr) : "memory");
+}
+DI void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+DI void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+DI void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+DI void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+DI uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+DI uint2 lds_v2(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+DI uint4 lds_v4(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+DI void sts_v2(uint32_t a, uint64_t x, uint64_t y) { asm volatile("st.shared.v2.u64 [%0], {%1,%2};" ::"r"(a), "l"(x), "l"(y) : "memory"); }
+DI void sts_u64(uint32_t a, uint64_t x) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(x) : "memory"); }
+DI void sts_u8(uint32_t a, uint32_t x) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(x) : "memory"); }
+DI uint32_t rotr(uint32_t x, uint32_t r) { return __funnelshift_r(x, x, r); }
+struct State { uint32_t flo, fhi, rlo, rhi; };
+// F <- srol(F) ^ e.xy ; R <- sror(R ^ e.zw)   (src/internal.hpp:41-47, :83-88)
+DI void roll_step(State& s, const uint4 e)
+{
+  const uint32_t lo = s.flo, hi = s.fhi;
+  s.flo = ((lo << 1) | (hi & 1u)) ^ e.x;
+  s.fhi = ((__funnelshift_l(lo, hi, 1) & ~2u) | ((hi >> 30) & 2u)) ^ e.y;
+  const uint32_t rl = s.rlo ^ e.z, rh = s.rhi ^ e.w;
+  s.rlo = __funnelshift_r(rl, rh, 1);
+  s.rhi = (__funnelshift_r(rh, rh >> 1, 1) & ~1u) | (rl & 1u);
+}
+DI uint64_t ext_hash(uint64_t h0, uint64_t mult) { const uint64_t t = h0 * mult; return t ^ (t >> 27); }
+DI uint64_t srol_n(uint64_t x, unsigned d)
+{
+  const uint64_t m33 = (1ULL << 33) - 1, m31 = (1ULL << 31) - 1;
+  uint64_t lo = x & m33, hi = x >> 33;
+  const unsigned a = d % 33, b = d % 31;
+  if (a) lo = ((lo << a) | (lo >> (33 - a))) & m33;
+  if (b) hi = ((hi << b) | (hi >> (31 - b))) & m31;
+  return (hi << 33) | lo;
+}
+DI uint64_t seed_of_byte(unsigned c)
+{
+  switch (c) {
+    case 'A': case 'a': case 4: case 5: return 0x3c8bfbb395c60474ULL;
+    case 'C': case 'c': case 7: return 0x3193c18562a02b4cULL;
+    case 'G': case 'g': case 3: return 0x20323ed082572324ULL;
+    case 'T': case 't': case 'U': case 'u': case 1: return 0x295549f54be24456ULL;
+    default: return 0;
+  }
+}
+)JIT";
+
+const char* const JIT_KERNEL = R"JIT(
+extern "C" __global__ void __launch_bounds__(256, 2)
+seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ TensorMap omap)
+{
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // [tables][validity LUT 256][mbarrier 16][16-byte pad + staged bases][1024-aligned output tiles]
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t lut = sbase + TABLE_BYTES, bar = lut + 256, tile = bar + 16;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t i0 = (uint64_t)blockIdx.x * 256;
+  const uint64_t i1 = i0 + 256 < P.n_items ? i0 + 256 : P.n_items;
+  const uint32_t n = P.seg;
+
+  auto item_byte = [&](uint64_t i) {
+    const uint64_t r = P.segs > 1 ? i / P.segs : i;
+    return r * P.read_len + (i - r * P.segs) * (uint64_t)n;
+  };
+  const bool active = i0 + tid < i1;
+  const uint64_t lo_byte = item_byte(i0), g1 = item_byte(i1 - 1) + n + K - 1;
+  const uint64_t g0 = (lo_byte ? lo_byte - 1 : 0) & ~15ull;
+  if (g1 - g0 > P.tile_cap) __trap();
+  const uint64_t my_byte = active ? item_byte(i0 + tid) : g0 + 1;
+  const uint64_t my_out = (i0 + tid) * (uint64_t)n;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (tid < 16) sts_u8(tile + tid, 'A');
+  __syncthreads();
+  const uint64_t nb16 = P.n_bases & ~15ull;
+  const uint64_t bulk_end = ((g1 + 15) & ~15ull) < nb16 ? ((g1 + 15) & ~15ull) : nb16;
+  const uint32_t bulk_bytes = bulk_end > g0 ? (uint32_t)(bulk_end - g0) : 0u;
+  if (tid == 0) {
+    mbar_expect_tx(bar, bulk_bytes + TABLE_BYTES);
+    if (bulk_bytes) bulk_g2s(tile + 16, P.bases + g0, bulk_bytes, bar);
+    bulk_g2s(sbase, P.tables, TABLE_BYTES, bar);
+  }
+  sts_u8(lut + tid, seed_of_byte(tid) != 0 ? 0u : 1u);
+  for (uint64_t g = (bulk_end > g0 ? bulk_end : g0) + tid; g < g1; g += 256) sts_u8(tile + 16 + (uint32_t)(g - g0), P.bases[g]);
+  mbar_wait(bar, 0);
+  __syncthreads();
+
+  const uint32_t ps = tile + 16 + (uint32_t)(my_byte - g0); // shared address of the item's base 0
+  const uint32_t tb = sbase + (lane & 7) * 16;               // this lane's replica of every group table
+  const uint32_t ot = ((tile + 16 + P.tile_cap + 16 + 1023u) & ~1023u) + warp * OT_BYTES;
+  const uint32_t rowaddr = ot + lane * ROW_BYTES;
+  const int row0 = (int)(i0 + warp * 32);
+
+  // warm-up: shift bases -1 .. k-2 into the code window; roll the full-window hash over them (in-only)
+  DECL_W
+  State full = { 0u, 0u, 0u, 0u };
+  uint32_t bad = 0;
+  for (int j = -1; j < (int)K - 1; ++j) {
+    const uint32_t c = lds_u8(ps + j);
+    if (j >= 0) bad |= lds_u8(lut + c);
+    SHIFT_IN(c >> 1)
+#if ANY_IGNORE
+    roll_step(full, lds_v4(sbase + INTAB_OFF + ((c & 6u) << 3)));
+#endif
+  }
+
+  for (uint32_t p0 = 0; p0 < n; p0 += TW) {
+    if (p0) {
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+    }
+#pragma unroll
+    for (uint32_t i = 0; i < TW; ++i) {
+      if (p0 + i < n) {
+        const uint32_t c = lds_u8(ps + (K - 1) + p0 + i);
+        bad |= lds_u8(lut + c);
+#if ANY_IGNORE
+        {
+          const uint32_t po = ((c << 4) & 0x60u) | (rotr(OUT_WORD, OUT_ROT) & 0x18u); // 8 * (4*code_in + code_out)
+          const uint2 ef = lds_v2(sbase + PAIRF_OFF + po), er = lds_v2(sbase + PAIRR_OFF + po);
+          roll_step(full, make_uint4(ef.x, ef.y, er.x, er.y));
+        }
+#endif
+        SHIFT_IN(c >> 1)
+        uint64_t hv[HT];
+        WINDOW_BODY
+        STORE_WINDOW(rowaddr + i * (HT * 8))
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(&omap, ot, (int)(p0 * HT), row0);
+      bulk_commit();
+    }
+  }
+
+  const bool dirty = active && bad != 0;
+  const bool any_dirty = __any_sync(0xffffffffu, dirty);
+  if (lane == 0) {
+    if (any_dirty) bulk_wait_all0();
+    else bulk_wait_read0();
+  }
+  __syncwarp();
+  if (dirty) {
+    // windows holding a zero-seed byte: byte-exact values (seed.cpp:149-166); then flag the read for the replay
+    uint32_t run = 0;
+    for (uint32_t j = 0; j < n + K - 1; ++j) {
+      run = lds_u8(lut + lds_u8(ps + j)) ? 0 : run + 1;
+      if (j >= K - 1 && run < K) {
+        const uint32_t p = j - (K - 1);
+        const uint64_t row = my_out + p;
+        for (uint32_t s = 0; s < M; ++s) {
+          uint64_t f = 0, r = 0;
+          const uint32_t* care = P.care + (size_t)s * P.care_words;
+          for (uint32_t q = 0; q < K; ++q) {
+            if (care[q >> 5] >> (q & 31) & 1u) {
+              const unsigned c = lds_u8(ps + p + q);
+              f ^= srol_n(seed_of_byte(c), K - 1 - q);
+              r ^= srol_n(seed_of_byte(c & 7u), q);
+            }
+          }
+          const uint64_t h0 = f + r;
+          P.out[row * HT + s * HPS] = h0;
+          for (uint32_t q = 1; q < HPS; ++q) P.out[row * HT + s * HPS + q] = ext_hash(h0, MULT[q]);
+        }
+      }
+    }
+    const uint64_t i = i0 + tid;
+    P.read_dirty[P.segs > 1 ? i / P.segs : i] = 1;
+  }
+}
+)JIT";
+
+struct Nvrtc
+{
+  bool ok = false;
+  nvrtcResult (*create)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  nvrtcResult (*compile)(nvrtcProgram, int, const char* const*) = nullptr;
+  nvrtcResult (*cubin_size)(nvrtcProgram, size_t*) = nullptr;
+  nvrtcResult (*cubin)(nvrtcProgram, char*) = nullptr;
+  nvrtcResult (*log_size)(nvrtcProgram, size_t*) = nullptr;
+  nvrtcResult (*log)(nvrtcProgram, char*) = nullptr;
+  nvrtcResult (*destroy)(nvrtcProgram*) = nullptr;
+};
+
+const Nvrtc& nvrtc()
+{
+  static Nvrtc n = [] {
+    Nvrtc x;
+    void* h = nullptr;
+    for (const char* name : { "libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12" }) {
+      h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+      if (h) break;
+    }
+    if (!h) return x;
+    x.create = (decltype(x.create))dlsym(h, "nvrtcCreateProgram");
+    x.compile = (decltype(x.compile))dlsym(h, "nvrtcCompileProgram");
+    x.cubin_size = (decltype(x.cubin_size))dlsym(h, "nvrtcGetCUBINSize");
+    x.cubin = (decltype(x.cubin))dlsym(h, "nvrtcGetCUBIN");
+    x.log_size = (decltype(x.log_size))dlsym(h, "nvrtcGetProgramLogSize");
+    x.log = (decltype(x.log))dlsym(h, "nvrtcGetProgramLog");
+    x.destroy = (decltype(x.destroy))dlsym(h, "nvrtcDestroyProgram");
+    x.ok = x.create && x.compile && x.cubin_size && x.cubin && x.log_size && x.log && x.destroy;
+    return x;
+  }();
+  return n;
+}
+
+std::string hex64(uint64_t v)
+{
+  char b[32];
+  snprintf(b, sizeof b, "0x%016llxULL", (unsigned long long)v);
+  return b;
+}
+
+} // namespace
+
+struct SeedJit
+{
+  cudaLibrary_t lib = nullptr;
+  cudaKernel_t kernel = nullptr;
+  uint8_t* d_tables = nullptr;
+  uint32_t table_bytes = 0, tw = 0, row_bytes = 0, ot_bytes = 0, ht = 0;
+  std::string source; // kept for inspection (nthash_seed_plan_jit_source)
+};
+
+void seed_jit_destroy(SeedJit* j)
+{
+  if (!j) return;
+  if (j->lib) cudaLibraryUnload(j->lib);
+  cudaFree(j->d_tables);
+  delete j;
+}
+
+const char* seed_jit_source(const SeedJit* j) { return j ? j->source.c_str() : ""; }
+
+// Generates, compiles and loads the kernel for one seed set.  Returns nullptr (with a reason) when the
+// specialised path does not apply; the caller then uses the generic kernel.
+SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
+{
+  const uint32_t k = plan.k, m = plan.n_seeds, hps = plan.h, ht = m * hps;
+  if (k > 128) { why = "k > 128"; return nullptr; }
+  if (ht > 64) { why = "more than 64 hashes per window"; return nullptr; }
+  const uint32_t kw = (k + 15) / 16, off = 16 * kw - k; // window base j sits at code position off + j
+
+  // ---- tables: [pair F 128][pair R 128][in-only 64][group tables: entries x 8 replicas x 16 B] ----
+  const uint64_t seed_of_code[4] = { SEED_A, SEED_C, SEED_T, SEED_G };
+  std::vector<uint8_t> tab(320, 0);
+  for (unsigned ci = 0; ci < 4; ++ci) {
+    for (unsigned co = 0; co < 4; ++co) {
+      const uint64_t f = seed_of_code[ci] ^ srol_n(seed_of_code[co], k);
+      const uint64_t r = srol_n(seed_of_code[ci ^ 2], k) ^ seed_of_code[co ^ 2];
+      memcpy(&tab[(ci * 4 + co) * 8], &f, 8);
+      memcpy(&tab[128 + (ci * 4 + co) * 8], &r, 8);
+    }
+    const uint64_t fi = seed_of_code[ci], ri = srol_n(seed_of_code[ci ^ 2], k);
+    memcpy(&tab[256 + ci * 16], &fi, 8);
+    memcpy(&tab[256 + ci * 16 + 8], &ri, 8);
+  }
+  std::ostringstream body;
+  for (uint32_t s = 0; s < m; ++s) {
+    body << "  { /* seed " << s << (plan.ignore_mode[s] ? " (ignore-mode)" : " (care-mode)") << " */ \\\n";
+    if (plan.ignore_mode[s]) body << "    uint32_t flo = full.flo, fhi = full.fhi, rlo = full.rlo, rhi = full.rhi; \\\n";
+    else body << "    uint32_t flo = 0u, fhi = 0u, rlo = 0u, rhi = 0u; \\\n";
+    const std::vector<uint32_t>& lp = plan.lookups[s];
+    for (size_t a = 0; a < lp.size(); a += 2) {
+      const bool two = a + 1 < lp.size();
+      const uint32_t qa = lp[a], qb = two ? lp[a + 1] : 0;
+      const uint32_t tab_off = (uint32_t)tab.size();
+      const uint32_t n_entries = two ? 16 : 4;
+      tab.resize(tab.size() + n_entries * 128, 0);
+      for (uint32_t e = 0; e < n_entries; ++e) {
+        const uint32_t ca = e & 3, cb = e >> 2;
+        uint64_t f = srol_n(seed_of_code[ca], k - 1 - qa), r = srol_n(seed_of_code[ca ^ 2], qa);
+        if (two) {
+          f ^= srol_n(seed_of_code[cb], k - 1 - qb);
+          r ^= srol_n(seed_of_code[cb ^ 2], qb);
+        }
+        for (uint32_t rep = 0; rep < 8; ++rep) {
+          memcpy(&tab[tab_off + e * 128 + rep * 16], &f, 8);
+          memcpy(&tab[tab_off + e * 128 + rep * 16 + 8], &r, 8);
+        }
+      }
+      // code of position q sits at bit 2*((off+q) % 16) of word (off+q)/16; rotate it to bit 7 (first) / 9 (second)
+      const uint32_t pa = off + qa, pb = off + qb;
+      body << "    { const uint4 e = lds_v4(tb + " << tab_off << "u + ((rotr(W" << pa / 16 << ", " << ((2 * (pa % 16) + 32 - 7) % 32)
+           << "u) & 0x180u)";
+      if (two) body << " | (rotr(W" << pb / 16 << ", " << ((2 * (pb % 16) + 32 - 9) % 32) << "u) & 0x600u)";
+      body << ")); flo ^= e.x; fhi ^= e.y; rlo ^= e.z; rhi ^= e.w; } \\\n";
+    }
+    body << "    const uint64_t h0 = (((uint64_t)fhi << 32) | flo) + (((uint64_t)rhi << 32) | rlo); \\\n";
+    body << "    hv[" << s * hps << "] = h0; \\\n";
+    for (uint32_t q = 1; q < hps; ++q) body << "    hv[" << s * hps + q << "] = ext_hash(h0, " << hex64(ext_mult(q, k)) << "); \\\n";
+    body << "  } \\\n";
+  }
+  const uint32_t table_bytes = (uint32_t)((tab.size() + 15) & ~size_t(15));
+  tab.resize(table_bytes, 0);
+
+  // ---- output tile geometry: TW windows per tile row; prefer an odd number of 16-byte chunks per row ----
+  uint32_t tw = 0, best = 0;
+  for (uint32_t t = 1; t <= 16; ++t) {
+    const uint32_t rb = t * ht * 8;
+    if (rb % 16 || rb > 512 || t * ht > 256) continue;
+    const uint32_t score = ((rb / 16) % 2 ? 1000 : 0) + (rb >= 128 ? 500 : rb) - (rb > 288 ? rb - 288 : 0);
+    if (score > best) { best = score; tw = t; }
+  }
+  if (!tw) { why = "no tile row shape for this number of hashes"; return nullptr; }
+  const uint32_t row_bytes = tw * ht * 8, ot_bytes = (32 * row_bytes + 127) & ~127u;
+
+  std::ostringstream src;
+  src << JIT_PRELUDE;
+  src << "#define K " << k << "u\n#define M " << m << "u\n#define HPS " << hps << "u\n#define HT " << ht << "u\n#define TW " << tw
+      << "u\n#define ROW_BYTES " << row_bytes << "u\n#define OT_BYTES " << ot_bytes << "u\n#define TABLE_BYTES " << table_bytes
+      << "u\n#define ANY_IGNORE " << (plan.any_ignore ? 1 : 0) << "\n#define PAIRF_OFF 0u\n#define PAIRR_OFF 128u\n#define INTAB_OFF 256u\n";
+  src << "#define OUT_WORD W" << off / 16 << "\n#define OUT_ROT " << ((2 * (off % 16) + 32 - 3) % 32) << "u\n";
+  src << "__device__ const uint64_t MULT[" << (hps > 1 ? hps : 1) << "] = { 0";
+  for (uint32_t q = 1; q < hps; ++q) src << ", " << hex64(ext_mult(q, k));
+  src << " };\n#define DECL_W";
+  for (uint32_t w = 0; w < kw; ++w) src << " uint32_t W" << w << " = 0u;";
+  src << "\n#define SHIFT_IN(t) {";
+  for (uint32_t w = 0; w + 1 < kw; ++w) src << " W" << w << " = __funnelshift_r(W" << w << ", W" << w + 1 << ", 2);";
+  src << " W" << kw - 1 << " = __funnelshift_r(W" << kw - 1 << ", (t), 2); }\n";
+  src << "#define WINDOW_BODY \\\n" << body.str() << "\n";
+  src << "#define STORE_WINDOW(addr) {";
+  if (ht % 2 == 0)
+    for (uint32_t q = 0; q < ht; q += 2) src << " sts_v2((addr) + " << q * 8 << "u, hv[" << q << "], hv[" << q + 1 << "]);";
+  else
+    for (uint32_t q = 0; q < ht; ++q) src << " sts_u64((addr) + " << q * 8 << "u, hv[" << q << "]);";
+  src << " }\n";
+  src << JIT_KERNEL;
+
+  const Nvrtc& rt = nvrtc();
+  if (!rt.ok) { why = "libnvrtc could not be loaded"; return nullptr; }
+  SeedJit* j = new SeedJit();
+  j->source = src.str();
+  j->table_bytes = table_bytes;
+  j->tw = tw;
+  j->row_bytes = row_bytes;
+  j->ot_bytes = ot_bytes;
+  j->ht = ht;
+  nvrtcProgram prog = nullptr;
+  if (rt.create(&prog, j->source.c_str(), "seed_jit_kernel.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
+    why = "nvrtcCreateProgram failed";
+    delete j;
+    return nullptr;
+  }
+  const char* opts[] = { "--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo" };
+  const nvrtcResult cr = rt.compile(prog, 3, opts);
+  if (cr != NVRTC_SUCCESS) {
+    size_t ls = 0;
+    rt.log_size(prog, &ls);
+    std::string log(ls, '\0');
+    if (ls) rt.log(prog, &log[0]);
+    why = "NVRTC compilation failed: " + log.substr(0, 1500);
+    rt.destroy(&prog);
+    delete j;
+    return nullptr;
+  }
+  size_t cs = 0;
+  rt.cubin_size(prog, &cs);
+  std::vector<char> cubin(cs);
+  rt.cubin(prog, cubin.data());
+  rt.destroy(&prog);
+  if (!load) return j; // build check on a machine without a GPU
+  cudaError_t e = cudaLibraryLoadData(&j->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+  if (e == cudaSuccess) e = cudaLibraryGetKernel(&j->kernel, j->lib, "seed_jit_kernel");
+  if (e == cudaSuccess) e = cudaMalloc(&j->d_tables, table_bytes);
+  if (e == cudaSuccess) e = cudaMemcpy(j->d_tables, tab.data(), table_bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    why = std::string("loading the specialised kernel failed: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    seed_jit_destroy(j);
+    return nullptr;
+  }
+  return j;
+}
+
+uint32_t seed_jit_smem_bytes(const SeedJit* j, uint32_t tile_cap)
+{
+  return j->table_bytes + 256 + 16 + 16 + tile_cap + 16 + 1024 + (KMER_NT / 32) * j->ot_bytes;
+}
+
+// Uniform batches whose items are all full and whose rows are 16-byte multiples.
+bool seed_jit_applies(const SeedJit* j, const SeedParams& P)
+{
+  const KmerGeom& g = P.g;
+  return j && !g.item_byte && !P.out_fwd && g.seg && g.nk % g.seg == 0 && ((uint64_t)g.seg * j->ht) % 2 == 0 &&
+         g.n_items > 0 && g.n_items < 0x7fffffffull && ((uintptr_t)P.out & 15) == 0 &&
+         seed_jit_smem_bytes(j, P.tile_cap) <= 227u * 1024u;
+}
+
+cudaError_t launch_seed_jit(const SeedJit* j, const SeedParams& P, cudaStream_t st)
+{
+  using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qr);
+    if (e != cudaSuccess) return e;
+    if (!fp || qr != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+    encode = (EncodeFn)fp;
+  }
+  CUtensorMap map;
+  const cuuint64_t dims[2] = { (cuuint64_t)P.g.seg * j->ht, P.g.n_items };
+  const cuuint64_t strides[1] = { (cuuint64_t)P.g.seg * j->ht * 8 };
+  const cuuint32_t box[2] = { j->tw * j->ht, 32 };
+  const cuuint32_t estr[2] = { 1, 1 };
+  if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, P.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return cudaErrorInvalidValue;
+  JitParams jp;
+  jp.bases = P.bases;
+  jp.n_bases = P.n_bases;
+  jp.n_items = P.g.n_items;
+  jp.read_len = P.g.read_len;
+  jp.nk = P.g.nk;
+  jp.seg = P.g.seg;
+  jp.segs = P.g.segs;
+  jp.out = P.out;
+  jp.valid_bits = P.valid_bits;
+  jp.read_dirty = P.read_dirty;
+  jp.tables = j->d_tables;
+  jp.care = reinterpret_cast<const uint32_t*>(P.plan_blob + P.care_off);
+  jp.tile_cap = P.tile_cap;
+  jp.care_words = P.care_words;
+  const uint32_t smem = seed_jit_smem_bytes(j, P.tile_cap);
+  cudaError_t e = cudaFuncSetAttribute((const void*)j->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  void* args[] = { &jp, &map };
+  const uint64_t ctas = (P.g.n_items + KMER_NT - 1) / KMER_NT;
+  return cudaLaunchKernel((const void*)j->kernel, dim3((unsigned)ctas), dim3(KMER_NT), args, smem, st);
+}
+
+} // namespace nthb

@@ -294,8 +294,13 @@ cudaError_t launch_seed(SeedParams P, uint64_t n_reads, cudaStream_t st)
   fn<<<(unsigned)ctas, KMER_NT, smem, st>>>(P);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  return launch_seed_emit(P, n_reads, st);
+}
+
+cudaError_t launch_seed_emit(const SeedParams& P, uint64_t n_reads, cudaStream_t st)
+{
   const unsigned eb = (unsigned)((n_reads + 127) / 128);
-  if (strands) seed_emit_kernel<true><<<eb, 128, 0, st>>>(P, n_reads);
+  if (P.out_fwd) seed_emit_kernel<true><<<eb, 128, 0, st>>>(P, n_reads);
   else seed_emit_kernel<false><<<eb, 128, 0, st>>>(P, n_reads);
   return cudaGetLastError();
 }

@@ -130,6 +130,9 @@ std::string build_seed_plan(const char* const* seeds, uint32_t n_seeds, uint32_t
     refblk.insert(refblk.end(), rb.begin(), rb.end());
     d.rb1 = (uint32_t)refblk.size() / 2;
   }
+  plan.seed_strings = sv;
+  plan.lookups = lookups;
+  plan.ignore_mode = ignore_mode;
   plan.n_groups = (uint32_t)groups.size();
   plan.care_words = (k + 31) / 32;
   std::vector<uint32_t> care_bits((size_t)plan.care_words * n_seeds, 0);

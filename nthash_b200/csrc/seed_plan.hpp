@@ -40,6 +40,10 @@ struct SeedPlanHost
   bool any_ignore = false;
   bool all_symmetric = true; // false where the reference prints its "not symmetric" warning (seed.cpp:96-102)
   std::vector<uint8_t> blob;
+  // kept for the specialised (run-time compiled) kernel, seed_jit.cu
+  std::vector<std::string> seed_strings;
+  std::vector<std::vector<uint32_t>> lookups; // per seed: the window positions it looks up (care or ignored ones)
+  std::vector<uint32_t> ignore_mode;
 };
 
 // Returns an empty string on success, else the reason (what the reference answers with raise_error()).

@@ -54,3 +54,14 @@ def test_invalid_arguments_are_reported_not_fatal():
     assert rc == -1 and b"num_hashes" in L.nthash_last_error()
     rc = L.nthash_kmer_batch(None, None, 1, 31, 1, None, None, None, None, 0)
     assert rc == -1
+
+
+def test_specialised_seed_kernel_compiles_without_a_gpu():
+    # NVRTC generates sm_100a code for a seed set; no device needed (what __graft_entry__.build() also checks)
+    import nthash_b200
+    seeds = ["1010101010101010101010101010101", "1101101101101101011011011011011"]
+    arr = (C.c_char_p * 2)(*[s.encode() for s in seeds])
+    rc = nthash_b200.LIB.nthash_seed_jit_selftest(arr, 2, 31, 3)
+    assert rc == 0, nthash_b200.LIB.nthash_last_error()
+    arr = (C.c_char_p * 1)(b"1101")
+    assert nthash_b200.LIB.nthash_seed_jit_selftest(arr, 1, 5, 1) == -1  # seed length != k (reference seed.cpp:90-95)

@@ -102,6 +102,26 @@ def test_uniform_config4_shape(read_len, n, p_bad):
     assert_batch_equal(res, ora, 6, check_strands=True)
 
 
+def test_generic_and_specialised_kernels_agree(monkeypatch):
+    # uniform batches take the NVRTC-specialised kernel; the generic interpreter must give the same rows
+    rng = np.random.default_rng(12)
+    n, L = 2000, 150
+    bases = synth(rng, n * L, p_bad=0.001)
+    d_b, _keep = to_dev(bases)
+    for seeds, h in ((["1010101010101010101010101010101", "1101101101101101011011011011011"], 3), (["110011", "101101"], 2),
+                     (["1" * 40 + "0" * 23 + "1" * 40], 1), (["1101100", "0011011", "1000001"], 1)):
+        plan = nthash_b200.SeedPlan(seeds, h)
+        assert b"NVRTC" in nthash_b200.LIB.nthash_seed_plan_kernel_note(plan._h), nthash_b200.LIB.nthash_seed_plan_kernel_note(plan._h)
+        fast = nthash_b200.seed_hashes_uniform(plan, d_b, n, L)
+        monkeypatch.setenv("NTHASH_B200_DISABLE_SEED_JIT", "1")
+        slow = nthash_b200.seed_hashes_uniform(plan, d_b, n, L)
+        monkeypatch.delenv("NTHASH_B200_DISABLE_SEED_JIT")
+        torch.cuda.synchronize()
+        assert torch.equal(fast.out, slow.out) and torch.equal(fast.valid_bits, slow.valid_bits)
+        ora = ORACLE.seed_batch(bases, np.arange(n + 1, dtype=np.uint64) * L, seeds, h, threads=8)
+        assert_batch_equal(fast, ora, len(seeds) * h)
+
+
 def test_ragged_long_reads_and_host_entry():
     rng = np.random.default_rng(77)
     lens = [40000, 5, 9000, 31, 30, 777]
