@@ -112,50 +112,6 @@ static int run_kmer(KmerParams& P, uint64_t rows, cudaStream_t st)
 }
 
 
-// Host-buffer entry points: device copies of one batch (inputs up, results down) on a private stream.
-struct HostStaging
-{
-  cudaStream_t st = nullptr;
-  uint8_t* d_bases = nullptr;
-  uint64_t *d_off = nullptr, *d_out = nullptr, *d_fwd = nullptr, *d_rev = nullptr;
-  uint32_t* d_valid = nullptr;
-
-  ~HostStaging()
-  {
-    cudaFree(d_bases); cudaFree(d_off); cudaFree(d_out); cudaFree(d_fwd); cudaFree(d_rev); cudaFree(d_valid);
-    if (st) cudaStreamDestroy(st);
-  }
-  int open(const char* bases, uint64_t n_bases, uint64_t nb_pad, const uint64_t* read_off, const uint64_t* koff,
-           uint64_t n_reads, uint64_t rows, uint64_t H, bool want_valid, uint64_t strand_cols)
-  {
-    NTH_CUDA(cudaStreamCreate(&st));
-    NTH_CUDA(cudaMalloc(&d_bases, nb_pad));
-    NTH_CUDA(cudaMalloc(&d_off, 2 * (n_reads + 1) * sizeof(uint64_t)));
-    NTH_CUDA(cudaMalloc(&d_out, rows * H * sizeof(uint64_t)));
-    if (want_valid) NTH_CUDA(cudaMalloc(&d_valid, ((rows + 31) / 32) * 4));
-    if (strand_cols) {
-      NTH_CUDA(cudaMalloc(&d_fwd, rows * strand_cols * sizeof(uint64_t)));
-      NTH_CUDA(cudaMalloc(&d_rev, rows * strand_cols * sizeof(uint64_t)));
-    }
-    NTH_CUDA(cudaMemcpyAsync(d_bases, bases, n_bases, cudaMemcpyHostToDevice, st));
-    NTH_CUDA(cudaMemcpyAsync(d_off, read_off, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    NTH_CUDA(cudaMemcpyAsync(d_off + n_reads + 1, koff, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    return NTHASH_OK;
-  }
-  int fetch(uint64_t* out, uint32_t* valid_bits, uint64_t* out_fwd, uint64_t* out_rev, uint64_t rows, uint64_t H,
-            uint64_t vwords, uint64_t strand_cols)
-  {
-    NTH_CUDA(cudaMemcpyAsync(out, d_out, rows * H * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    if (valid_bits) NTH_CUDA(cudaMemcpyAsync(valid_bits, d_valid, vwords * 4, cudaMemcpyDeviceToHost, st));
-    if (strand_cols) {
-      NTH_CUDA(cudaMemcpyAsync(out_fwd, d_fwd, rows * strand_cols * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-      NTH_CUDA(cudaMemcpyAsync(out_rev, d_rev, rows * strand_cols * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    }
-    NTH_CUDA(cudaStreamSynchronize(st));
-    return NTHASH_OK;
-  }
-};
-
 // Ragged batches: either every read is one item (read_off/koff are the item arrays) or reads are cut
 // into SEG_LONG-window items listed in a scratch table (freed by the caller with cudaFreeAsync).
 struct RaggedItems
@@ -255,6 +211,221 @@ static int run_seed(const nthash_seed_plan* plan, SeedParams& P, uint64_t n_read
   return NTHASH_OK;
 }
 
+// One device-resident batch, as the internal runners see it.
+struct DevBatch
+{
+  const uint8_t* d_bases = nullptr;
+  uint64_t n_bases = 0;
+  const uint64_t* d_read_off = nullptr; // ragged (uniform_len == 0)
+  const uint64_t* d_koff = nullptr;
+  uint64_t n_reads = 0, max_len = 0;
+  uint32_t uniform_len = 0; // > 0: reads of this length back to back from d_bases
+  uint64_t* d_out = nullptr;
+  uint32_t* d_valid = nullptr;
+  uint64_t valid_row0 = 0; // row 0 of this batch is bit valid_row0 of d_valid
+  uint64_t memset_rows = 0; // > 0: pre-set that many validity bits first
+  uint64_t *d_fwd = nullptr, *d_rev = nullptr;
+};
+
+static int kmer_dev_run(const DevBatch& B, uint32_t k, uint32_t h, cudaStream_t st)
+{
+  KmerParams P;
+  P.bases = B.d_bases;
+  P.n_bases = B.n_bases;
+  P.k = k;
+  P.h = h;
+  P.out = B.d_out;
+  P.valid_bits = B.d_valid;
+  P.valid_row0 = B.valid_row0;
+  P.out_fwd = B.d_fwd;
+  P.out_rev = B.d_rev;
+  RaggedItems R;
+  if (B.uniform_len) {
+    if (!plan_uniform(B.n_reads, B.uniform_len, k, P.g, P.tile_cap))
+      return fail(NTHASH_ERR_UNSUPPORTED, "k=%u with read_len=%u needs a %u-byte tile", k, B.uniform_len, P.tile_cap);
+  } else {
+    if (int rc = plan_ragged(B.d_read_off, B.d_koff, B.n_reads, B.max_len, k, TILE_BUDGET, st, R)) return rc;
+    P.g = R.g;
+    P.tile_cap = R.tile_cap;
+    if (kmer_smem_bytes(P.tile_cap) > SMEM_MAX) {
+      if (R.d_items) cudaFreeAsync(R.d_items, st);
+      return fail(NTHASH_ERR_UNSUPPORTED, "k=%u needs a %u-byte tile for ragged long reads", k, P.tile_cap);
+    }
+  }
+  int rc = run_kmer(P, B.memset_rows, st);
+  if (R.d_items) cudaFreeAsync(R.d_items, st);
+  return rc;
+}
+
+static int seed_dev_run(const nthash_seed_plan* plan, const DevBatch& B, cudaStream_t st)
+{
+  SeedParams P;
+  fill_seed_params(plan, P);
+  P.bases = B.d_bases;
+  P.n_bases = B.n_bases;
+  P.out = B.d_out;
+  P.valid_bits = B.d_valid;
+  P.valid_row0 = B.valid_row0;
+  P.out_fwd = B.d_fwd;
+  P.out_rev = B.d_rev;
+  RaggedItems R;
+  if (B.uniform_len) {
+    if (!plan_uniform(B.n_reads, B.uniform_len, P.k, P.g, P.tile_cap))
+      return fail(NTHASH_ERR_UNSUPPORTED, "k=%u with read_len=%u needs a %u-byte tile", P.k, B.uniform_len, P.tile_cap);
+  } else {
+    P.read_off = B.d_read_off;
+    P.koff = B.d_koff;
+    const uint32_t budget = TILE_BUDGET > P.plan_smem_bytes / 2 ? TILE_BUDGET - P.plan_smem_bytes / 2 : 0;
+    if (int rc = plan_ragged(B.d_read_off, B.d_koff, B.n_reads, B.max_len, P.k, budget, st, R)) return rc;
+    P.g = R.g;
+    P.tile_cap = R.tile_cap;
+    P.item_read = R.item_read;
+  }
+  int rc = run_seed(plan, P, B.n_reads, B.memset_rows, st);
+  if (R.d_items) cudaFreeAsync(R.d_items, st);
+  return rc;
+}
+
+// ---- host-buffer entry points: chunked H2D / kernel / D2H pipeline over a few streams ----------
+struct HostBatch
+{
+  const char* bases;
+  const uint64_t* read_off;
+  uint64_t n_reads;
+  uint32_t k;
+  uint64_t H, strand_cols; // u64 per row in out / in out_fwd,out_rev (0: no strands)
+  uint64_t* out;
+  uint32_t* valid_bits;
+  uint64_t *out_fwd, *out_rev;
+};
+
+template<class Launch>
+static int host_pipeline(const HostBatch& hb, Launch&& launch)
+{
+  constexpr int NS = 3;                         // chunks in flight
+  uint64_t CH_VALUES = 48ull << 20;             // ~384 MB of hashes per chunk
+  const uint64_t CH_BASES = 256ull << 20;
+  if (const char* e = getenv("NTHASH_B200_HOST_CHUNK_VALUES")) CH_VALUES = std::max<uint64_t>(1, strtoull(e, nullptr, 10)); // tests
+  const uint64_t n = hb.n_reads;
+  std::vector<uint64_t> koff(n + 1);
+  const uint64_t rows = nthash_window_rows(hb.read_off, n, hb.k, koff.data());
+  if (rows == 0) return NTHASH_OK;
+  bool uniform = true;
+  const uint64_t len0 = hb.read_off[1] - hb.read_off[0];
+  for (uint64_t r = 1; r < n && uniform; ++r) uniform = hb.read_off[r + 1] - hb.read_off[r] == len0;
+  if (len0 > 0xffffffffull) uniform = false;
+
+  // chunk boundaries at read granularity
+  std::vector<uint64_t> cut(1, 0);
+  uint64_t max_reads = 0, max_bases = 0, max_rows = 0;
+  for (uint64_t r = 0; r < n;) {
+    uint64_t e = r;
+    while (e < n && (e == r || ((koff[e + 1] - koff[r]) * hb.H <= CH_VALUES && hb.read_off[e + 1] - hb.read_off[r] <= CH_BASES))) ++e;
+    cut.push_back(e);
+    max_reads = std::max(max_reads, e - r);
+    max_bases = std::max(max_bases, hb.read_off[e] - hb.read_off[r]);
+    max_rows = std::max(max_rows, koff[e] - koff[r]);
+    r = e;
+  }
+  const size_t n_chunks = cut.size() - 1;
+  const int ns = (int)std::min<size_t>(NS, n_chunks);
+
+  struct Slot
+  {
+    cudaStream_t st = nullptr;
+    uint8_t* d_bases = nullptr;
+    uint64_t *d_off = nullptr, *d_out = nullptr, *d_fwd = nullptr, *d_rev = nullptr;
+    std::vector<uint64_t> h_off;
+  } slot[NS];
+  uint32_t* d_valid = nullptr;
+  cudaEvent_t ev_valid = nullptr;
+  auto cleanup = [&]() {
+    for (int i = 0; i < NS; ++i) {
+      if (slot[i].st) cudaStreamSynchronize(slot[i].st);
+      cudaFree(slot[i].d_bases); cudaFree(slot[i].d_off); cudaFree(slot[i].d_out); cudaFree(slot[i].d_fwd); cudaFree(slot[i].d_rev);
+      if (slot[i].st) cudaStreamDestroy(slot[i].st);
+    }
+    cudaFree(d_valid);
+    if (ev_valid) cudaEventDestroy(ev_valid);
+  };
+#define NTH_TRY(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      const int rc__ = fail(NTHASH_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__));       \
+      cleanup();                                                                               \
+      return rc__;                                                                             \
+    }                                                                                          \
+  } while (0)
+  const uint64_t vwords = (rows + 31) / 32;
+  for (int i = 0; i < ns; ++i) {
+    NTH_TRY(cudaStreamCreateWithFlags(&slot[i].st, cudaStreamNonBlocking));
+    NTH_TRY(cudaMalloc(&slot[i].d_bases, max_bases + 96));
+    if (!uniform) NTH_TRY(cudaMalloc(&slot[i].d_off, 2 * (max_reads + 1) * sizeof(uint64_t)));
+    NTH_TRY(cudaMalloc(&slot[i].d_out, max_rows * hb.H * sizeof(uint64_t)));
+    if (hb.strand_cols) {
+      NTH_TRY(cudaMalloc(&slot[i].d_fwd, max_rows * hb.strand_cols * sizeof(uint64_t)));
+      NTH_TRY(cudaMalloc(&slot[i].d_rev, max_rows * hb.strand_cols * sizeof(uint64_t)));
+    }
+  }
+  if (hb.valid_bits) {
+    NTH_TRY(cudaMalloc(&d_valid, vwords * 4));
+    NTH_TRY(cudaEventCreateWithFlags(&ev_valid, cudaEventDisableTiming));
+    NTH_TRY(cudaMemsetAsync(d_valid, 0xFF, vwords * 4, slot[0].st));
+    NTH_TRY(cudaEventRecord(ev_valid, slot[0].st));
+    for (int i = 1; i < ns; ++i) NTH_TRY(cudaStreamWaitEvent(slot[i].st, ev_valid, 0));
+  }
+  for (size_t c = 0; c < n_chunks; ++c) {
+    Slot& s = slot[c % ns];
+    if (c >= (size_t)ns) NTH_TRY(cudaStreamSynchronize(s.st)); // the slot's previous chunk has been copied out
+    const uint64_t r0 = cut[c], r1 = cut[c + 1], nr = r1 - r0;
+    const uint64_t b0 = hb.read_off[r0], nbytes = hb.read_off[r1] - b0, row0 = koff[r0], nrows = koff[r1] - row0;
+    if (nrows == 0) continue;
+    // chunk bytes sit 16 bytes into the slot so that "the base before the first one" is addressable
+    NTH_TRY(cudaMemcpyAsync(s.d_bases + 16, hb.bases + b0, nbytes, cudaMemcpyHostToDevice, s.st));
+    DevBatch B;
+    B.n_reads = nr;
+    B.d_out = s.d_out;
+    B.d_valid = d_valid;
+    B.valid_row0 = row0;
+    B.d_fwd = s.d_fwd;
+    B.d_rev = s.d_rev;
+    if (uniform) {
+      B.d_bases = s.d_bases + 16;
+      B.n_bases = nbytes + 64;
+      B.uniform_len = (uint32_t)len0;
+    } else {
+      s.h_off.resize(2 * (nr + 1));
+      uint64_t mx = 0;
+      for (uint64_t i = 0; i <= nr; ++i) {
+        s.h_off[i] = hb.read_off[r0 + i] - b0 + 16;
+        s.h_off[nr + 1 + i] = koff[r0 + i] - row0;
+        if (i < nr) mx = std::max(mx, hb.read_off[r0 + i + 1] - hb.read_off[r0 + i]);
+      }
+      NTH_TRY(cudaMemcpyAsync(s.d_off, s.h_off.data(), 2 * (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.st));
+      B.d_bases = s.d_bases;
+      B.n_bases = 16 + nbytes + 64;
+      B.d_read_off = s.d_off;
+      B.d_koff = s.d_off + nr + 1;
+      B.max_len = mx;
+    }
+    if (const int rc = launch(B, s.st)) {
+      cleanup();
+      return rc;
+    }
+    NTH_TRY(cudaMemcpyAsync(hb.out + row0 * hb.H, s.d_out, nrows * hb.H * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.st));
+    if (hb.strand_cols) {
+      NTH_TRY(cudaMemcpyAsync(hb.out_fwd + row0 * hb.strand_cols, s.d_fwd, nrows * hb.strand_cols * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.st));
+      NTH_TRY(cudaMemcpyAsync(hb.out_rev + row0 * hb.strand_cols, s.d_rev, nrows * hb.strand_cols * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.st));
+    }
+  }
+  for (int i = 0; i < ns; ++i) NTH_TRY(cudaStreamSynchronize(slot[i].st));
+  if (hb.valid_bits) NTH_TRY(cudaMemcpy(hb.valid_bits, d_valid, vwords * 4, cudaMemcpyDeviceToHost));
+  cleanup();
+#undef NTH_TRY
+  return NTHASH_OK;
+}
+
 } // namespace nthb
 
 using namespace nthb;
@@ -302,18 +473,17 @@ int nthash_kmer_batch_uniform_dev(const uint8_t* d_bases, uint64_t n_bases_reada
   if (n_bases_readable < n_reads * (uint64_t)read_len)
     return fail(NTHASH_ERR_INVALID_ARG, "n_bases_readable smaller than n_reads*read_len");
   if (int rc = check_device_ready()) return rc;
-  KmerParams P;
-  if (!plan_uniform(n_reads, read_len, k, P.g, P.tile_cap))
-    return fail(NTHASH_ERR_UNSUPPORTED, "k=%u with read_len=%u needs a %u-byte tile", k, read_len, P.tile_cap);
-  P.bases = d_bases;
-  P.n_bases = n_bases_readable;
-  P.k = k;
-  P.h = num_hashes;
-  P.out = d_out;
-  P.valid_bits = d_valid_bits;
-  P.out_fwd = d_out_fwd;
-  P.out_rev = d_out_rev;
-  return run_kmer(P, n_reads * (uint64_t)P.g.nk, (cudaStream_t)stream);
+  DevBatch B;
+  B.d_bases = d_bases;
+  B.n_bases = n_bases_readable;
+  B.n_reads = n_reads;
+  B.uniform_len = read_len;
+  B.d_out = d_out;
+  B.d_valid = d_valid_bits;
+  B.memset_rows = n_reads * (uint64_t)(read_len - k + 1);
+  B.d_fwd = d_out_fwd;
+  B.d_rev = d_out_rev;
+  return kmer_dev_run(B, k, num_hashes, (cudaStream_t)stream);
 }
 
 int nthash_kmer_plan_dev(const uint64_t* d_read_off, uint64_t n_reads, uint32_t k, uint64_t* d_koff,
@@ -348,32 +518,22 @@ int nthash_kmer_batch_dev(const uint8_t* d_bases, uint64_t n_bases_readable, con
   if (!d_read_off || !d_koff) return fail(NTHASH_ERR_INVALID_ARG, "d_read_off and d_koff must not be NULL");
   if (int rc = check_device_ready()) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  // total rows is needed to pre-set the validity bitmap
-  uint64_t rows = 0;
-  if (d_valid_bits) {
-    NTH_CUDA(cudaMemcpyAsync(&rows, d_koff + n_reads, sizeof rows, cudaMemcpyDeviceToHost, st));
+  DevBatch B;
+  if (d_valid_bits) { // the row total is needed to pre-set the validity bitmap
+    NTH_CUDA(cudaMemcpyAsync(&B.memset_rows, d_koff + n_reads, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     NTH_CUDA(cudaStreamSynchronize(st));
   }
-  KmerParams P;
-  P.bases = d_bases;
-  P.n_bases = n_bases_readable;
-  P.k = k;
-  P.h = num_hashes;
-  P.out = d_out;
-  P.valid_bits = d_valid_bits;
-  P.out_fwd = d_out_fwd;
-  P.out_rev = d_out_rev;
-  RaggedItems R;
-  if (int rc = plan_ragged(d_read_off, d_koff, n_reads, max_read_len, k, TILE_BUDGET, st, R)) return rc;
-  P.g = R.g;
-  P.tile_cap = R.tile_cap;
-  if (kmer_smem_bytes(P.tile_cap) > SMEM_MAX) {
-    if (R.d_items) cudaFreeAsync(R.d_items, st);
-    return fail(NTHASH_ERR_UNSUPPORTED, "k=%u needs a %u-byte tile for ragged long reads", k, P.tile_cap);
-  }
-  int rc = run_kmer(P, rows, st);
-  if (R.d_items) cudaFreeAsync(R.d_items, st);
-  return rc;
+  B.d_bases = d_bases;
+  B.n_bases = n_bases_readable;
+  B.d_read_off = d_read_off;
+  B.d_koff = d_koff;
+  B.n_reads = n_reads;
+  B.max_len = max_read_len;
+  B.d_out = d_out;
+  B.d_valid = d_valid_bits;
+  B.d_fwd = d_out_fwd;
+  B.d_rev = d_out_rev;
+  return kmer_dev_run(B, k, num_hashes, st);
 }
 
 int nthash_kmer_batch(const char* bases, const uint64_t* read_off, uint64_t n_reads, uint32_t k,
@@ -386,20 +546,8 @@ int nthash_kmer_batch(const char* bases, const uint64_t* read_off, uint64_t n_re
   if (int rc = check_outputs(out, out_fwd, out_rev)) return rc;
   if (cudaSetDevice(device) != cudaSuccess) return fail(NTHASH_ERR_NO_DEVICE, "cannot select CUDA device %d", device);
   if (int rc = check_device_ready()) return rc;
-  std::vector<uint64_t> koff(n_reads + 1);
-  const uint64_t rows = nthash_window_rows(read_off, n_reads, k, koff.data());
-  if (rows == 0) return NTHASH_OK;
-  uint64_t max_len = 0;
-  for (uint64_t r = 0; r < n_reads; ++r) max_len = std::max(max_len, read_off[r + 1] - read_off[r]);
-  const uint64_t n_bases = read_off[n_reads], nb_pad = (n_bases + 31) & ~15ull;
-  const uint64_t H = num_hashes, vwords = (rows + 31) / 32;
-  HostStaging hs;
-  int rc = hs.open(bases, n_bases, nb_pad, read_off, koff.data(), n_reads, rows, H, valid_bits != nullptr, out_fwd ? 1 : 0);
-  if (rc == NTHASH_OK)
-    rc = nthash_kmer_batch_dev(hs.d_bases, nb_pad, hs.d_off, hs.d_off + n_reads + 1, n_reads, max_len, k, num_hashes,
-                               hs.d_out, hs.d_valid, hs.d_fwd, hs.d_rev, hs.st);
-  if (rc == NTHASH_OK) rc = hs.fetch(out, valid_bits, out_fwd, out_rev, rows, H, vwords, out_fwd ? 1 : 0);
-  return rc;
+  const HostBatch hb = { bases, read_off, n_reads, k, num_hashes, out_fwd ? 1ull : 0ull, out, valid_bits, out_fwd, out_rev };
+  return host_pipeline(hb, [&](const DevBatch& B, cudaStream_t st) { return kmer_dev_run(B, k, num_hashes, st); });
 }
 
 // ---- SeedNtHash -------------------------------------------------------------------------------
@@ -467,17 +615,17 @@ int nthash_seed_batch_uniform_dev(const nthash_seed_plan* plan, const uint8_t* d
   if (n_bases_readable < n_reads * (uint64_t)read_len)
     return fail(NTHASH_ERR_INVALID_ARG, "n_bases_readable smaller than n_reads*read_len");
   if (int rc = check_device_ready()) return rc;
-  SeedParams P;
-  fill_seed_params(plan, P);
-  if (!plan_uniform(n_reads, read_len, k, P.g, P.tile_cap))
-    return fail(NTHASH_ERR_UNSUPPORTED, "k=%u with read_len=%u needs a %u-byte tile", k, read_len, P.tile_cap);
-  P.bases = d_bases;
-  P.n_bases = n_bases_readable;
-  P.out = d_out;
-  P.valid_bits = d_valid_bits;
-  P.out_fwd = d_out_fwd;
-  P.out_rev = d_out_rev;
-  return run_seed(plan, P, n_reads, n_reads * (uint64_t)P.g.nk, (cudaStream_t)stream);
+  DevBatch B;
+  B.d_bases = d_bases;
+  B.n_bases = n_bases_readable;
+  B.n_reads = n_reads;
+  B.uniform_len = read_len;
+  B.d_out = d_out;
+  B.d_valid = d_valid_bits;
+  B.memset_rows = n_reads * (uint64_t)(read_len - k + 1);
+  B.d_fwd = d_out_fwd;
+  B.d_rev = d_out_rev;
+  return seed_dev_run(plan, B, (cudaStream_t)stream);
 }
 
 int nthash_seed_batch_dev(const nthash_seed_plan* plan, const uint8_t* d_bases, uint64_t n_bases_readable,
@@ -493,30 +641,22 @@ int nthash_seed_batch_dev(const nthash_seed_plan* plan, const uint8_t* d_bases, 
   if (!d_read_off || !d_koff) return fail(NTHASH_ERR_INVALID_ARG, "d_read_off and d_koff must not be NULL");
   if (int rc = check_device_ready()) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  uint64_t rows = 0;
+  DevBatch B;
   if (d_valid_bits) {
-    NTH_CUDA(cudaMemcpyAsync(&rows, d_koff + n_reads, sizeof rows, cudaMemcpyDeviceToHost, st));
+    NTH_CUDA(cudaMemcpyAsync(&B.memset_rows, d_koff + n_reads, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     NTH_CUDA(cudaStreamSynchronize(st));
   }
-  SeedParams P;
-  fill_seed_params(plan, P);
-  P.bases = d_bases;
-  P.n_bases = n_bases_readable;
-  P.read_off = d_read_off;
-  P.koff = d_koff;
-  P.out = d_out;
-  P.valid_bits = d_valid_bits;
-  P.out_fwd = d_out_fwd;
-  P.out_rev = d_out_rev;
-  RaggedItems R;
-  const uint32_t budget = TILE_BUDGET > P.plan_smem_bytes / 2 ? TILE_BUDGET - P.plan_smem_bytes / 2 : 0;
-  if (int rc = plan_ragged(d_read_off, d_koff, n_reads, max_read_len, k, budget, st, R)) return rc;
-  P.g = R.g;
-  P.tile_cap = R.tile_cap;
-  P.item_read = R.item_read;
-  int rc = run_seed(plan, P, n_reads, rows, st);
-  if (R.d_items) cudaFreeAsync(R.d_items, st);
-  return rc;
+  B.d_bases = d_bases;
+  B.n_bases = n_bases_readable;
+  B.d_read_off = d_read_off;
+  B.d_koff = d_koff;
+  B.n_reads = n_reads;
+  B.max_len = max_read_len;
+  B.d_out = d_out;
+  B.d_valid = d_valid_bits;
+  B.d_fwd = d_out_fwd;
+  B.d_rev = d_out_rev;
+  return seed_dev_run(plan, B, st);
 }
 
 int nthash_seed_batch(const char* bases, const uint64_t* read_off, uint64_t n_reads, const char* const* seeds,
@@ -530,22 +670,9 @@ int nthash_seed_batch(const char* bases, const uint64_t* read_off, uint64_t n_re
   if (cudaSetDevice(device) != cudaSuccess) return fail(NTHASH_ERR_NO_DEVICE, "cannot select CUDA device %d", device);
   nthash_seed_plan* plan = nullptr;
   if (int rc = nthash_seed_plan_create(seeds, n_seeds, k, num_hashes_per_seed, &plan)) return rc;
-  std::vector<uint64_t> koff(n_reads + 1);
-  const uint64_t rows = nthash_window_rows(read_off, n_reads, k, koff.data());
-  uint64_t max_len = 0;
-  for (uint64_t r = 0; r < n_reads; ++r) max_len = std::max(max_len, read_off[r + 1] - read_off[r]);
-  const uint64_t n_bases = read_off[n_reads], nb_pad = (n_bases + 31) & ~15ull;
-  const uint64_t H = (uint64_t)n_seeds * num_hashes_per_seed, vwords = (rows + 31) / 32;
-  int rc = NTHASH_OK;
-  if (rows) {
-    HostStaging hs;
-    rc = hs.open(bases, n_bases, nb_pad, read_off, koff.data(), n_reads, rows, H, valid_bits != nullptr,
-                 out_fwd ? n_seeds : 0);
-    if (rc == NTHASH_OK)
-      rc = nthash_seed_batch_dev(plan, hs.d_bases, nb_pad, hs.d_off, hs.d_off + n_reads + 1, n_reads, max_len, hs.d_out,
-                                 hs.d_valid, hs.d_fwd, hs.d_rev, hs.st);
-    if (rc == NTHASH_OK) rc = hs.fetch(out, valid_bits, out_fwd, out_rev, rows, H, vwords, out_fwd ? n_seeds : 0);
-  }
+  const HostBatch hb = { bases, read_off, n_reads, k, (uint64_t)n_seeds * num_hashes_per_seed, out_fwd ? (uint64_t)n_seeds : 0ull,
+                         out, valid_bits, out_fwd, out_rev };
+  const int rc = host_pipeline(hb, [&](const DevBatch& B, cudaStream_t st) { return seed_dev_run(plan, B, st); });
   nthash_seed_plan_destroy(plan);
   return rc;
 }

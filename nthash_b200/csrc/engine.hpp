@@ -31,6 +31,7 @@ struct KmerParams
   uint32_t k = 0, h = 0;
   uint64_t* out = nullptr;
   uint32_t* valid_bits = nullptr;
+  uint64_t valid_row0 = 0; // bit index of this batch's row 0 inside valid_bits (chunked host pipeline)
   uint64_t* out_fwd = nullptr;
   uint64_t* out_rev = nullptr;
   uint32_t tile_cap = 0; // bytes of base tile a CTA may stage
@@ -58,6 +59,7 @@ struct SeedParams
   uint32_t k = 0, h = 0, n_seeds = 0;
   uint64_t* out = nullptr;
   uint32_t* valid_bits = nullptr;
+  uint64_t valid_row0 = 0; // bit index of this batch's row 0 inside valid_bits (chunked host pipeline)
   uint64_t* out_fwd = nullptr;
   uint64_t* out_rev = nullptr;
   uint8_t* read_dirty = nullptr; // one byte per read, zeroed by the caller

@@ -310,7 +310,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
       if (j >= k - 1 && run < k) {
         const uint64_t w = my_out + (j - (k - 1));
         for (uint32_t q = 0; q < H; ++q) P.out[w * H + q] = 0;
-        if (P.valid_bits) atomicAnd(&P.valid_bits[w >> 5], ~(1u << (w & 31)));
+        if (P.valid_bits) atomicAnd(&P.valid_bits[(P.valid_row0 + w) >> 5], ~(1u << ((P.valid_row0 + w) & 31)));
       }
     }
   }

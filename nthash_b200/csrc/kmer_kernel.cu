@@ -65,7 +65,7 @@ scrub_item(const KmerParams& P, const uint4* tab_in, const uint8_t* ps, uint64_t
         P.out_fwd[w] = 0;
         P.out_rev[w] = 0;
       }
-      if (P.valid_bits) atomicAnd(&P.valid_bits[w >> 5], ~(1u << (w & 31)));
+      if (P.valid_bits) atomicAnd(&P.valid_bits[(P.valid_row0 + w) >> 5], ~(1u << ((P.valid_row0 + w) & 31)));
     }
   }
 }

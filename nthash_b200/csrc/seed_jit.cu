@@ -6,8 +6,8 @@
 // per window (profiles/r01_ncu_seed_c4_v1.txt).  Here the seed set is baked into the code:
 //  * the window's 2-bit base codes live in registers (a shift register of ceil(k/16) words; one funnel
 //    shift per word per window), so a group index is two rotates and two masks — no byte loads;
-//  * positions are looked up two at a time in 16-entry tables replicated 8x across bank groups
-//    ([entry][lane & 7]): any mix of indices within a quarter-warp is conflict-free (4 wavefronts);
+//  * positions are looked up two at a time in 16-entry tables kept as two 128-byte halves (forward /
+//    reverse strand): every entry in its own bank pair, so the per-lane LDS.64 never conflict;
 //  * ignore-mode seeds start from the full-window hash, rolled with the k-mer kernel's pair table;
 //  * hashes leave through TMA tile stores: each warp fills a [32 items] x [TW windows * H] u64 tile.
 // Exactness for non-ACGTU bytes is handled as in seed_kernel.cu: windows holding one are recomputed
@@ -18,6 +18,7 @@
 #include "seed_plan.hpp"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cuda.h>
 #include <dlfcn.h>
@@ -92,6 +93,7 @@ DI void sts_v2(uint32_t a, uint64_t x, uint64_t y) { asm volatile("st.shared.v2.
 DI void sts_u64(uint32_t a, uint64_t x) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(x) : "memory"); }
 DI void sts_u8(uint32_t a, uint32_t x) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(x) : "memory"); }
 DI uint32_t rotr(uint32_t x, uint32_t r) { return __funnelshift_r(x, x, r); }
+DI uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 struct State { uint32_t flo, fhi, rlo, rhi; };
 // F <- srol(F) ^ e.xy ; R <- sror(R ^ e.zw)   (src/internal.hpp:41-47, :83-88)
 DI void roll_step(State& s, const uint4 e)
@@ -126,7 +128,7 @@ DI uint64_t seed_of_byte(unsigned c)
 )JIT";
 
 const char* const JIT_KERNEL = R"JIT(
-extern "C" __global__ void __launch_bounds__(256, 2)
+extern "C" __global__ void __launch_bounds__(NT, 2)
 seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ TensorMap omap)
 {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -134,8 +136,8 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
   const uint32_t sbase = smem_u32(smem);
   const uint32_t lut = sbase + TABLE_BYTES, bar = lut + 256, tile = bar + 16;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint64_t i0 = (uint64_t)blockIdx.x * 256;
-  const uint64_t i1 = i0 + 256 < P.n_items ? i0 + 256 : P.n_items;
+  const uint64_t i0 = (uint64_t)blockIdx.x * NT;
+  const uint64_t i1 = i0 + NT < P.n_items ? i0 + NT : P.n_items;
   const uint32_t n = P.seg;
 
   auto item_byte = [&](uint64_t i) {
@@ -163,15 +165,14 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
     if (bulk_bytes) bulk_g2s(tile + 16, P.bases + g0, bulk_bytes, bar);
     bulk_g2s(sbase, P.tables, TABLE_BYTES, bar);
   }
-  sts_u8(lut + tid, seed_of_byte(tid) != 0 ? 0u : 1u);
-  for (uint64_t g = (bulk_end > g0 ? bulk_end : g0) + tid; g < g1; g += 256) sts_u8(tile + 16 + (uint32_t)(g - g0), P.bases[g]);
+  for (uint32_t c = tid; c < 256; c += NT) sts_u8(lut + c, seed_of_byte(c) != 0 ? 0u : 1u);
+  for (uint64_t g = (bulk_end > g0 ? bulk_end : g0) + tid; g < g1; g += NT) sts_u8(tile + 16 + (uint32_t)(g - g0), P.bases[g]);
   mbar_wait(bar, 0);
   __syncthreads();
 
   const uint32_t ps = tile + 16 + (uint32_t)(my_byte - g0); // shared address of the item's base 0
-  const uint32_t tb = sbase + (lane & 7) * 16;               // this lane's replica of every group table
-  const uint32_t ot = ((tile + 16 + P.tile_cap + 16 + 1023u) & ~1023u) + warp * OT_BYTES;
-  const uint32_t rowaddr = ot + lane * ROW_BYTES;
+  const uint32_t tb = sbase;                                 // group tables: two conflict-free 128-byte halves each
+  const uint32_t ot0 = ((tile + 16 + P.tile_cap + 16 + 1023u) & ~1023u) + warp * (NBUF * OT_BYTES);
   const int row0 = (int)(i0 + warp * 32);
 
   // warm-up: shift bases -1 .. k-2 into the code window; roll the full-window hash over them (in-only)
@@ -187,11 +188,9 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
 #endif
   }
 
+  uint32_t buf = 0;
   for (uint32_t p0 = 0; p0 < n; p0 += TW) {
-    if (p0) {
-      if (lane == 0) bulk_wait_read0();
-      __syncwarp();
-    }
+    const uint32_t ot = ot0 + buf * OT_BYTES, rowaddr = ot + lane * ROW_BYTES;
 #pragma unroll
     for (uint32_t i = 0; i < TW; ++i) {
       if (p0 + i < n) {
@@ -207,6 +206,10 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
         SHIFT_IN(c >> 1)
         uint64_t hv[HT];
         WINDOW_BODY
+        if (i == 0 && p0 >= NBUF * TW) { // this buffer's previous tile must have left shared memory; waiting
+          if (lane == 0) BULK_WAIT_READ  // only now hides the TMA read behind the first window's arithmetic
+          __syncwarp();
+        }
         STORE_WINDOW(rowaddr + i * (HT * 8))
       }
     }
@@ -216,6 +219,7 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
       tma_store_2d(&omap, ot, (int)(p0 * HT), row0);
       bulk_commit();
     }
+    buf = buf + 1 == NBUF ? 0 : buf + 1;
   }
 
   const bool dirty = active && bad != 0;
@@ -304,7 +308,7 @@ struct SeedJit
   cudaLibrary_t lib = nullptr;
   cudaKernel_t kernel = nullptr;
   uint8_t* d_tables = nullptr;
-  uint32_t table_bytes = 0, tw = 0, row_bytes = 0, ot_bytes = 0, ht = 0;
+  uint32_t table_bytes = 0, tw = 0, row_bytes = 0, ot_bytes = 0, ht = 0, nt = 256, nbuf = 1;
   std::string source; // kept for inspection (nthash_seed_plan_jit_source)
 };
 
@@ -327,7 +331,8 @@ SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
   if (ht > 64) { why = "more than 64 hashes per window"; return nullptr; }
   const uint32_t kw = (k + 15) / 16, off = 16 * kw - k; // window base j sits at code position off + j
 
-  // ---- tables: [pair F 128][pair R 128][in-only 64][group tables: entries x 8 replicas x 16 B] ----
+  // ---- tables: [pair F 128][pair R 128][in-only 64][group tables: F half 128 B | R half 128 B] ----
+  // 16 entries x 8 bytes = 128 bytes = every entry in its own bank pair: LDS.64 with any mix of indices is conflict-free
   const uint64_t seed_of_code[4] = { SEED_A, SEED_C, SEED_T, SEED_G };
   std::vector<uint8_t> tab(320, 0);
   for (unsigned ci = 0; ci < 4; ++ci) {
@@ -352,7 +357,7 @@ SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
       const uint32_t qa = lp[a], qb = two ? lp[a + 1] : 0;
       const uint32_t tab_off = (uint32_t)tab.size();
       const uint32_t n_entries = two ? 16 : 4;
-      tab.resize(tab.size() + n_entries * 128, 0);
+      tab.resize(tab.size() + 256, 0);
       for (uint32_t e = 0; e < n_entries; ++e) {
         const uint32_t ca = e & 3, cb = e >> 2;
         uint64_t f = srol_n(seed_of_code[ca], k - 1 - qa), r = srol_n(seed_of_code[ca ^ 2], qa);
@@ -360,17 +365,25 @@ SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
           f ^= srol_n(seed_of_code[cb], k - 1 - qb);
           r ^= srol_n(seed_of_code[cb ^ 2], qb);
         }
-        for (uint32_t rep = 0; rep < 8; ++rep) {
-          memcpy(&tab[tab_off + e * 128 + rep * 16], &f, 8);
-          memcpy(&tab[tab_off + e * 128 + rep * 16 + 8], &r, 8);
-        }
+        memcpy(&tab[tab_off + e * 8], &f, 8);
+        memcpy(&tab[tab_off + 128 + e * 8], &r, 8);
       }
-      // code of position q sits at bit 2*((off+q) % 16) of word (off+q)/16; rotate it to bit 7 (first) / 9 (second)
+      // code of position q sits at bit 2*((off+q) % 16) of word (off+q)/16; rotate it to bit 3 (first) / 5 (second)
       const uint32_t pa = off + qa, pb = off + qb;
-      body << "    { const uint4 e = lds_v4(tb + " << tab_off << "u + ((rotr(W" << pa / 16 << ", " << ((2 * (pa % 16) + 32 - 7) % 32)
-           << "u) & 0x180u)";
-      if (two) body << " | (rotr(W" << pb / 16 << ", " << ((2 * (pb % 16) + 32 - 9) % 32) << "u) & 0x600u)";
-      body << ")); flo ^= e.x; fhi ^= e.y; rlo ^= e.z; rhi ^= e.w; } \\\n";
+      const size_t gi = a / 2;
+      body << "    const uint32_t ix" << gi << " = (rotr(W" << pa / 16 << ", " << ((2 * (pa % 16) + 32 - 3) % 32) << "u) & 0x18u)";
+      if (two) body << " | (rotr(W" << pb / 16 << ", " << ((2 * (pb % 16) + 32 - 5) % 32) << "u) & 0x60u)";
+      body << "; const uint2 ef" << gi << " = lds_v2(tb + " << tab_off << "u + ix" << gi << "), er" << gi << " = lds_v2(tb + " << tab_off + 128
+           << "u + ix" << gi << "); \\\n";
+    }
+    { // fold the group entries into the accumulators two at a time (one 3-input LOP3 per word)
+      const size_t ng = (lp.size() + 1) / 2;
+      size_t gi = 0;
+      for (; gi + 1 < ng; gi += 2)
+        body << "    flo = xor3(flo, ef" << gi << ".x, ef" << gi + 1 << ".x); fhi = xor3(fhi, ef" << gi << ".y, ef" << gi + 1 << ".y); rlo = xor3(rlo, er"
+             << gi << ".x, er" << gi + 1 << ".x); rhi = xor3(rhi, er" << gi << ".y, er" << gi + 1 << ".y); \\\n";
+      if (gi < ng)
+        body << "    flo ^= ef" << gi << ".x; fhi ^= ef" << gi << ".y; rlo ^= er" << gi << ".x; rhi ^= er" << gi << ".y; \\\n";
     }
     body << "    const uint64_t h0 = (((uint64_t)fhi << 32) | flo) + (((uint64_t)rhi << 32) | rlo); \\\n";
     body << "    hv[" << s * hps << "] = h0; \\\n";
@@ -390,9 +403,16 @@ SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
   }
   if (!tw) { why = "no tile row shape for this number of hashes"; return nullptr; }
   const uint32_t row_bytes = tw * ht * 8, ot_bytes = (32 * row_bytes + 127) & ~127u;
+  // CTA size / output buffering: defaults found on C4 (profiles/), overridable for experiments
+  uint32_t nt = 256, nbuf = 2;
+  if (const char* e = getenv("NTHASH_B200_SEED_JIT_NT")) nt = (uint32_t)atoi(e);
+  if (const char* e = getenv("NTHASH_B200_SEED_JIT_NBUF")) nbuf = (uint32_t)atoi(e);
+  if (nt < 32 || nt > 1024 || nt % 32 || nbuf < 1 || nbuf > 2) { why = "bad NT/NBUF override"; return nullptr; }
 
   std::ostringstream src;
   src << JIT_PRELUDE;
+  src << "#define NT " << nt << "u\n#define NBUF " << nbuf << "u\n#define BULK_WAIT_READ asm volatile(\"cp.async.bulk.wait_group.read "
+      << nbuf - 1 << ";\" ::: \"memory\");\n";
   src << "#define K " << k << "u\n#define M " << m << "u\n#define HPS " << hps << "u\n#define HT " << ht << "u\n#define TW " << tw
       << "u\n#define ROW_BYTES " << row_bytes << "u\n#define OT_BYTES " << ot_bytes << "u\n#define TABLE_BYTES " << table_bytes
       << "u\n#define ANY_IGNORE " << (plan.any_ignore ? 1 : 0) << "\n#define PAIRF_OFF 0u\n#define PAIRR_OFF 128u\n#define INTAB_OFF 256u\n";
@@ -422,6 +442,8 @@ SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
   j->row_bytes = row_bytes;
   j->ot_bytes = ot_bytes;
   j->ht = ht;
+  j->nt = nt;
+  j->nbuf = nbuf;
   nvrtcProgram prog = nullptr;
   if (rt.create(&prog, j->source.c_str(), "seed_jit_kernel.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
     why = "nvrtcCreateProgram failed";
@@ -461,7 +483,15 @@ SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
 
 uint32_t seed_jit_smem_bytes(const SeedJit* j, uint32_t tile_cap)
 {
-  return j->table_bytes + 256 + 16 + 16 + tile_cap + 16 + 1024 + (KMER_NT / 32) * j->ot_bytes;
+  return j->table_bytes + 256 + 16 + 16 + tile_cap + 16 + 1024 + (j->nt / 32) * j->nbuf * j->ot_bytes;
+}
+
+// Bytes of bases one CTA of the specialised kernel stages (its CTA size may differ from KMER_NT).
+static uint32_t seed_jit_tile_cap(const SeedJit* j, const KmerGeom& g, uint32_t k)
+{
+  const uint64_t b = g.segs == 1 ? (uint64_t)j->nt * g.read_len + 64
+                                 : (uint64_t)j->nt * g.seg + ((uint64_t)j->nt / g.segs + 2) * (k - 1) + 64;
+  return b > 0xffffffffull ? 0xffffffffu : (uint32_t)b;
 }
 
 // Uniform batches whose items are all full and whose rows are 16-byte multiples.
@@ -470,7 +500,7 @@ bool seed_jit_applies(const SeedJit* j, const SeedParams& P)
   const KmerGeom& g = P.g;
   return j && !g.item_byte && !P.out_fwd && g.seg && g.nk % g.seg == 0 && ((uint64_t)g.seg * j->ht) % 2 == 0 &&
          g.n_items > 0 && g.n_items < 0x7fffffffull && ((uintptr_t)P.out & 15) == 0 &&
-         seed_jit_smem_bytes(j, P.tile_cap) <= 227u * 1024u;
+         seed_jit_smem_bytes(j, seed_jit_tile_cap(j, g, P.k)) <= 227u * 1024u;
 }
 
 cudaError_t launch_seed_jit(const SeedJit* j, const SeedParams& P, cudaStream_t st)
@@ -508,14 +538,14 @@ cudaError_t launch_seed_jit(const SeedJit* j, const SeedParams& P, cudaStream_t 
   jp.read_dirty = P.read_dirty;
   jp.tables = j->d_tables;
   jp.care = reinterpret_cast<const uint32_t*>(P.plan_blob + P.care_off);
-  jp.tile_cap = P.tile_cap;
+  jp.tile_cap = seed_jit_tile_cap(j, P.g, P.k);
   jp.care_words = P.care_words;
-  const uint32_t smem = seed_jit_smem_bytes(j, P.tile_cap);
+  const uint32_t smem = seed_jit_smem_bytes(j, jp.tile_cap);
   cudaError_t e = cudaFuncSetAttribute((const void*)j->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   void* args[] = { &jp, &map };
-  const uint64_t ctas = (P.g.n_items + KMER_NT - 1) / KMER_NT;
-  return cudaLaunchKernel((const void*)j->kernel, dim3((unsigned)ctas), dim3(KMER_NT), args, smem, st);
+  const uint64_t ctas = (P.g.n_items + j->nt - 1) / j->nt;
+  return cudaLaunchKernel((const void*)j->kernel, dim3((unsigned)ctas), dim3(j->nt), args, smem, st);
 }
 
 } // namespace nthb

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(128) seed_emit_kernel(const __grid_constant__ 
           P.out_fwd[row * m + q] = 0;
           P.out_rev[row * m + q] = 0;
         }
-      if (P.valid_bits) atomicAnd(&P.valid_bits[row >> 5], ~(1u << (row & 31)));
+      if (P.valid_bits) atomicAnd(&P.valid_bits[(P.valid_row0 + row) >> 5], ~(1u << ((P.valid_row0 + row) & 31)));
     }
   };
   // ntmsm64 (base) fails only on a NUL byte at a block position, scanning seeds, blocks, positions in order

@@ -130,3 +130,25 @@ def test_strand_symmetry_and_rna_at_scale():
     ora = ORACLE.kmer_batch(fwd.reshape(-1), np.arange(n + 1, dtype=np.uint64) * L, k, 1, want=(), threads=8)
     got = int(u64(outs[0]).sum(dtype=np.uint64))
     assert got == ora["sum"] and ora["n_emit"] == n * (L - k + 1)
+
+
+def test_host_pipeline_many_chunks(monkeypatch):
+    # the host-buffer entry streams the batch in chunks over three CUDA streams; force tiny chunks
+    monkeypatch.setenv("NTHASH_B200_HOST_CHUNK_VALUES", "3000")
+    rng = np.random.default_rng(21)
+    for lens in (rng.integers(0, 300, 400), np.full(300, 150)):          # ragged, then fixed-length (fast kernel per chunk)
+        off = ragged_offsets(lens).astype(np.uint64)
+        bases = synth(rng, int(off[-1]), p_bad=0.003)
+        for k, h in ((31, 1), (21, 4)):
+            ora = ORACLE.kmer_batch(bases, off, k, h)
+            rows = ora["out"].shape[0]
+            out = np.full((rows, h), 0xCD, np.uint64); fw = np.zeros(rows, np.uint64); rv = np.zeros(rows, np.uint64)
+            vb = np.zeros((rows + 31) // 32, np.uint32)
+            rc = nthash_b200.LIB.nthash_kmer_batch(bases.ctypes.data, off.ctypes.data, len(off) - 1, k, h, out.ctypes.data,
+                                                   vb.ctypes.data, fw.ctypes.data, rv.ctypes.data, 0)
+            assert rc == 0, nthash_b200.LIB.nthash_last_error()
+            bits = ((vb[:, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(-1)[:rows]
+            assert (bits == ora["valid"]).all() and (out == ora["out"]).all() and (fw == ora["fwd"]).all() and (rv == ora["rev"]).all()
+            out2 = np.zeros((rows, h), np.uint64)   # without the optional outputs
+            assert nthash_b200.LIB.nthash_kmer_batch(bases.ctypes.data, off.ctypes.data, len(off) - 1, k, h, out2.ctypes.data, None, None, None, 0) == 0
+            assert (out2 == ora["out"]).all()

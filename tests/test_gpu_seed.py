@@ -196,3 +196,25 @@ def test_blind_roll_and_peek_batches():
             assert (got == np.stack([w[1][t] for w in want])).all()
             assert (u64(fwd) == np.array([w[2][t] for w in want], np.uint64)).all()
             assert (u64(rev) == np.array([w[3][t] for w in want], np.uint64)).all()
+
+
+def test_seed_host_pipeline_many_chunks(monkeypatch):
+    monkeypatch.setenv("NTHASH_B200_HOST_CHUNK_VALUES", "5000")
+    rng = np.random.default_rng(22)
+    seeds, h = [SEED_A31, SEED_B31], 2
+    arr = (C.c_char_p * 2)(*[s.encode() for s in seeds])
+    for lens in (rng.integers(0, 300, 300), np.full(200, 150)):
+        off = ragged_offsets(lens).astype(np.uint64)
+        bases = synth(rng, int(off[-1]), p_bad=0.004)
+        ora = ORACLE.seed_batch(bases, off, seeds, h)
+        rows = ora["out"].shape[0]
+        out = np.zeros((rows, 4), np.uint64); fw = np.zeros((rows, 2), np.uint64); rv = np.zeros((rows, 2), np.uint64)
+        vb = np.zeros((rows + 31) // 32, np.uint32)
+        rc = nthash_b200.LIB.nthash_seed_batch(bases.ctypes.data, off.ctypes.data, len(off) - 1, arr, 2, 31, h, out.ctypes.data,
+                                               vb.ctypes.data, fw.ctypes.data, rv.ctypes.data, 0)
+        assert rc == 0, nthash_b200.LIB.nthash_last_error()
+        bits = ((vb[:, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(-1)[:rows]
+        assert (bits == ora["valid"]).all() and (out == ora["out"]).all() and (fw == ora["fwd"]).all() and (rv == ora["rev"]).all()
+        out2 = np.zeros((rows, 4), np.uint64); vb2 = np.zeros_like(vb)   # no strands: fixed-length chunks take the specialised kernel
+        assert nthash_b200.LIB.nthash_seed_batch(bases.ctypes.data, off.ctypes.data, len(off) - 1, arr, 2, 31, h, out2.ctypes.data, vb2.ctypes.data, None, None, 0) == 0
+        assert (out2 == ora["out"]).all() and (vb2 == vb).all()
