@@ -270,6 +270,36 @@ def main():
            "d2h_bytes_per_step": int(h_out.numel() * 8 + h_valid.numel() * 4), "reads_per_step": e2e_reads,
            "ms_per_step": e_dt * 1e3, "matches_device_path": same}
 
+    # ---- fused consumer (count/sum/xor on the device: what the reference's own benchmark loop computes) ----
+    consumer = None
+    if not seeds:
+        red = nthash_b200.kmer_reduce_uniform(bases, n_reads, L, k, h)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(args.steps):
+            red = nthash_b200.kmer_reduce_uniform(bases, n_reads, L, k, h)
+        r1.record()
+        torch.cuda.synchronize()
+        red_ms = r0.elapsed_time(r1) / args.steps
+        h_res = torch.zeros(3, dtype=torch.int64)
+
+        def e2e_reduce_step():
+            check(LIB.nthash_kmer_reduce(h_bases.data_ptr(), h_off.data_ptr(), e2e_reads, k, h, h_res.data_ptr(), local))
+
+        e2e_reduce_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_reduce_step()
+        er_dt = (time.perf_counter() - t0) / args.e2e_steps
+        red_ms, er_dt = nd.max_over_ranks([red_ms, er_dt])
+        consumer = {"kind": "count/sum/xor of all hashes (nthash_kmer_reduce*), no hash leaves the GPU",
+                    "value": world * rows / (red_ms * 1e-3), "unit": UNIT, "ms_per_step": red_ms,
+                    "e2e": {"value": world * e_rows / er_dt, "unit": UNIT, "ms_per_step": er_dt * 1e3,
+                            "h2d_bytes_per_step": int(h_bases.numel() + h_off.numel() * 8), "d2h_bytes_per_step": 24},
+                    "windows": int(red[0]), "sum": int(red[1]) & (2**64 - 1)}
+
     if rank != 0:
         nd.finalize()
         return
@@ -309,8 +339,10 @@ def main():
                      "traffic": (load_traffic(args.config) or {}).get("dram_bytes_per_launch") if not args.reads else None,
                      "traffic_source": (load_traffic(args.config) or {}).get("source"), "peak_source": peak_src, "kernel": ("seed_kernel" if seeds else "kmer_fast_kernel<%d>" % h), "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_launch": abytes},
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu, "fused_consumer": consumer,
     }
+    if consumer and cpu and sample_reads == n_reads:
+        consumer["matches_cpu_reference"] = consumer["sum"] == s and consumer["windows"] == ne
     print(json.dumps(line))
     nd.finalize()
 

@@ -93,6 +93,21 @@ int nthash_kmer_batch(const char* bases, const uint64_t* read_off, uint64_t n_re
                       uint32_t num_hashes, uint64_t* out, uint32_t* valid_bits, uint64_t* out_fwd,
                       uint64_t* out_rev, int device);
 
+/* ---- fused consumer (first of the "next" rows: the step after the hash path) --------------------
+ * What the reference's own benchmark does with the hashes (examples/benchmark.cpp:34-39: a running
+ * sum over `while (h.roll())`), done on the device so that no hash ever leaves the SM:
+ *   result[0] = number of windows the reference's loop visits over the whole batch
+ *   result[1] = 64-bit wrap-around sum, result[2] = xor, of ALL num_hashes values of those windows.
+ * The device forms zero d_result themselves; the host form only uploads the bases.              */
+int nthash_kmer_reduce_uniform_dev(const uint8_t* d_bases, uint64_t n_bases_readable, uint64_t n_reads,
+                                   uint32_t read_len, uint32_t k, uint32_t num_hashes, uint64_t* d_result,
+                                   void* stream);
+int nthash_kmer_reduce_dev(const uint8_t* d_bases, uint64_t n_bases_readable, const uint64_t* d_read_off,
+                           const uint64_t* d_koff, uint64_t n_reads, uint64_t max_read_len, uint32_t k,
+                           uint32_t num_hashes, uint64_t* d_result, void* stream);
+int nthash_kmer_reduce(const char* bases, const uint64_t* read_off, uint64_t n_reads, uint32_t k,
+                       uint32_t num_hashes, uint64_t* result, int device);
+
 /* ---- SeedNtHash: spaced seeds ----------------------------------------------------------------
  * Replaces `nthash::SeedNtHash it(seq, len, seeds, h, k); while (it.roll()) use(it.hashes())`
  * (nthash.hpp:313-521; SeedNtHash::init/roll src/seed.cpp:493-544; ntmsm64 :130-270).

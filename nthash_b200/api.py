@@ -176,3 +176,26 @@ def blind_peek4(fwd, rev, out_base, k, num_hashes=1, stream=None) -> torch.Tenso
         check(LIB.nthash_blind_peek4_batch_dev(_ptr(fwd), _ptr(rev), _ptr(out_base), n, k, num_hashes, _ptr(out),
                                                _stream_ptr(stream)))
     return out
+
+
+def kmer_reduce_uniform(bases, n_reads, read_len, k, num_hashes=1, stream=None) -> torch.Tensor:
+    """Fused consumer (nthash_kmer_reduce_uniform_dev): int64 tensor [windows visited, sum, xor] on the GPU."""
+    _check_bases(bases)
+    res = torch.empty(3, dtype=torch.int64, device=bases.device)
+    with torch.cuda.device(bases.device):
+        check(LIB.nthash_kmer_reduce_uniform_dev(_ptr(bases), bases.numel(), n_reads, read_len, k, num_hashes, _ptr(res), _stream_ptr(stream)))
+    return res
+
+
+def kmer_reduce(bases, read_off, k, num_hashes=1, stream=None) -> torch.Tensor:
+    """Fused consumer over ragged reads (nthash_kmer_plan_dev + nthash_kmer_reduce_dev)."""
+    _check_bases(bases)
+    n_reads = read_off.numel() - 1
+    res = torch.empty(3, dtype=torch.int64, device=bases.device)
+    with torch.cuda.device(bases.device):
+        koff = torch.empty(n_reads + 1, dtype=torch.int64, device=bases.device)
+        rows, max_len = C.c_uint64(0), C.c_uint64(0)
+        check(LIB.nthash_kmer_plan_dev(_ptr(read_off), n_reads, k, _ptr(koff), C.byref(rows), C.byref(max_len), _stream_ptr(stream)))
+        check(LIB.nthash_kmer_reduce_dev(_ptr(bases), bases.numel(), _ptr(read_off), _ptr(koff), n_reads, max_len.value, k, num_hashes,
+                                         _ptr(res), _stream_ptr(stream)))
+    return res

@@ -5,6 +5,7 @@
 #include "engine.hpp"
 #include "seed_plan.hpp"
 
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -59,6 +60,10 @@ bool plan_uniform(uint64_t n_reads, uint32_t read_len, uint32_t k, KmerGeom& g, 
     // Cut reads into items.  Prefer a segment length that divides nk (all items full => the TMA tile
     // store applies) and whose byte stride spreads lanes over shared-memory banks.
     uint32_t best = 0, best_score = 0;
+    if (const char* e = getenv("NTHASH_B200_SEG")) { // experiments: force the segment length
+      const uint32_t v = (uint32_t)atoi(e);
+      if (v >= 16 && v % 2 == 0 && g.nk % v == 0) best = v, best_score = 0xffffffffu;
+    }
     for (uint32_t seg = 160; seg <= 384; seg += 2) {
       if (g.nk % seg) continue;
       const uint32_t score = (seg % 8 == 4 ? 4 : seg % 4 == 2 ? 3 : seg % 16 == 8 ? 2 : 1) * 1000 - (seg > SEG_LONG ? seg - SEG_LONG : SEG_LONG - seg);
@@ -225,6 +230,7 @@ struct DevBatch
   uint64_t valid_row0 = 0; // row 0 of this batch is bit valid_row0 of d_valid
   uint64_t memset_rows = 0; // > 0: pre-set that many validity bits first
   uint64_t *d_fwd = nullptr, *d_rev = nullptr;
+  uint64_t* d_reduce = nullptr; // fused consumer output {windows, sum, xor}; then d_out etc. are NULL
 };
 
 static int kmer_dev_run(const DevBatch& B, uint32_t k, uint32_t h, cudaStream_t st)
@@ -239,6 +245,7 @@ static int kmer_dev_run(const DevBatch& B, uint32_t k, uint32_t h, cudaStream_t 
   P.valid_row0 = B.valid_row0;
   P.out_fwd = B.d_fwd;
   P.out_rev = B.d_rev;
+  P.reduce_out = B.d_reduce;
   RaggedItems R;
   if (B.uniform_len) {
     if (!plan_uniform(B.n_reads, B.uniform_len, k, P.g, P.tile_cap))
@@ -297,6 +304,7 @@ struct HostBatch
   uint64_t* out;
   uint32_t* valid_bits;
   uint64_t *out_fwd, *out_rev;
+  uint64_t* reduce_result = nullptr; // fused consumer: 3 u64 on the host; then out == NULL and nothing else is copied back
 };
 
 template<class Launch>
@@ -307,25 +315,45 @@ static int host_pipeline(const HostBatch& hb, Launch&& launch)
   const uint64_t CH_BASES = 256ull << 20;
   if (const char* e = getenv("NTHASH_B200_HOST_CHUNK_VALUES")) CH_VALUES = std::max<uint64_t>(1, strtoull(e, nullptr, 10)); // tests
   const uint64_t n = hb.n_reads;
-  std::vector<uint64_t> koff(n + 1);
-  const uint64_t rows = nthash_window_rows(hb.read_off, n, hb.k, koff.data());
-  if (rows == 0) return NTHASH_OK;
+  const bool timing = getenv("NTHASH_B200_HOST_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
+  // fixed-length batches (the common case) need no per-read bookkeeping at all
   bool uniform = true;
   const uint64_t len0 = hb.read_off[1] - hb.read_off[0];
   for (uint64_t r = 1; r < n && uniform; ++r) uniform = hb.read_off[r + 1] - hb.read_off[r] == len0;
   if (len0 > 0xffffffffull) uniform = false;
+  const uint64_t nk0 = len0 >= hb.k ? len0 - hb.k + 1 : 0;
+  std::vector<uint64_t> koff_v;
+  uint64_t rows;
+  if (uniform) {
+    rows = n * nk0;
+  } else {
+    koff_v.resize(n + 1);
+    rows = nthash_window_rows(hb.read_off, n, hb.k, koff_v.data());
+  }
+  if (rows == 0) return NTHASH_OK;
+  auto koff = [&](uint64_t r) { return uniform ? r * nk0 : koff_v[r]; };
 
   // chunk boundaries at read granularity
   std::vector<uint64_t> cut(1, 0);
   uint64_t max_reads = 0, max_bases = 0, max_rows = 0;
-  for (uint64_t r = 0; r < n;) {
-    uint64_t e = r;
-    while (e < n && (e == r || ((koff[e + 1] - koff[r]) * hb.H <= CH_VALUES && hb.read_off[e + 1] - hb.read_off[r] <= CH_BASES))) ++e;
-    cut.push_back(e);
-    max_reads = std::max(max_reads, e - r);
-    max_bases = std::max(max_bases, hb.read_off[e] - hb.read_off[r]);
-    max_rows = std::max(max_rows, koff[e] - koff[r]);
-    r = e;
+  if (uniform) {
+    const uint64_t per = std::max<uint64_t>(1, std::min(CH_VALUES / std::max<uint64_t>(1, nk0 * hb.H), CH_BASES / std::max<uint64_t>(1, len0)));
+    for (uint64_t r = 0; r < n; r += per) cut.push_back(std::min(n, r + per));
+    max_reads = std::min(per, n);
+    max_bases = max_reads * len0;
+    max_rows = max_reads * nk0;
+  } else {
+    for (uint64_t r = 0; r < n;) {
+      uint64_t e = r;
+      while (e < n && (e == r || ((koff_v[e + 1] - koff_v[r]) * hb.H <= CH_VALUES && hb.read_off[e + 1] - hb.read_off[r] <= CH_BASES))) ++e;
+      cut.push_back(e);
+      max_reads = std::max(max_reads, e - r);
+      max_bases = std::max(max_bases, hb.read_off[e] - hb.read_off[r]);
+      max_rows = std::max(max_rows, koff_v[e] - koff_v[r]);
+      r = e;
+    }
   }
   const size_t n_chunks = cut.size() - 1;
   const int ns = (int)std::min<size_t>(NS, n_chunks);
@@ -338,14 +366,17 @@ static int host_pipeline(const HostBatch& hb, Launch&& launch)
     std::vector<uint64_t> h_off;
   } slot[NS];
   uint32_t* d_valid = nullptr;
+  uint64_t* d_reduce = nullptr;
   cudaEvent_t ev_valid = nullptr;
   auto cleanup = [&]() {
     for (int i = 0; i < NS; ++i) {
       if (slot[i].st) cudaStreamSynchronize(slot[i].st);
-      cudaFree(slot[i].d_bases); cudaFree(slot[i].d_off); cudaFree(slot[i].d_out); cudaFree(slot[i].d_fwd); cudaFree(slot[i].d_rev);
+      for (void* q : { (void*)slot[i].d_bases, (void*)slot[i].d_off, (void*)slot[i].d_out, (void*)slot[i].d_fwd, (void*)slot[i].d_rev })
+        if (q) cudaFreeAsync(q, slot[i].st);
+      if (i == 0 && d_valid) cudaFreeAsync(d_valid, slot[0].st);
+      if (i == 0 && d_reduce) cudaFreeAsync(d_reduce, slot[0].st);
       if (slot[i].st) cudaStreamDestroy(slot[i].st);
     }
-    cudaFree(d_valid);
     if (ev_valid) cudaEventDestroy(ev_valid);
   };
 #define NTH_TRY(expr)                                                                          \
@@ -358,28 +389,41 @@ static int host_pipeline(const HostBatch& hb, Launch&& launch)
     }                                                                                          \
   } while (0)
   const uint64_t vwords = (rows + 31) / 32;
+  { // staging buffers come from the device's stream-ordered pool, told to keep freed memory for the next call
+    int dev = 0;
+    cudaMemPool_t pool = nullptr;
+    uint64_t keep = ~0ull;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   for (int i = 0; i < ns; ++i) {
     NTH_TRY(cudaStreamCreateWithFlags(&slot[i].st, cudaStreamNonBlocking));
-    NTH_TRY(cudaMalloc(&slot[i].d_bases, max_bases + 96));
-    if (!uniform) NTH_TRY(cudaMalloc(&slot[i].d_off, 2 * (max_reads + 1) * sizeof(uint64_t)));
-    NTH_TRY(cudaMalloc(&slot[i].d_out, max_rows * hb.H * sizeof(uint64_t)));
+    NTH_TRY(cudaMallocAsync(&slot[i].d_bases, max_bases + 96, slot[i].st));
+    if (!uniform) NTH_TRY(cudaMallocAsync(&slot[i].d_off, 2 * (max_reads + 1) * sizeof(uint64_t), slot[i].st));
+    if (hb.out) NTH_TRY(cudaMallocAsync(&slot[i].d_out, max_rows * hb.H * sizeof(uint64_t), slot[i].st));
     if (hb.strand_cols) {
-      NTH_TRY(cudaMalloc(&slot[i].d_fwd, max_rows * hb.strand_cols * sizeof(uint64_t)));
-      NTH_TRY(cudaMalloc(&slot[i].d_rev, max_rows * hb.strand_cols * sizeof(uint64_t)));
+      NTH_TRY(cudaMallocAsync(&slot[i].d_fwd, max_rows * hb.strand_cols * sizeof(uint64_t), slot[i].st));
+      NTH_TRY(cudaMallocAsync(&slot[i].d_rev, max_rows * hb.strand_cols * sizeof(uint64_t), slot[i].st));
     }
   }
+  if (hb.reduce_result) {
+    NTH_TRY(cudaMallocAsync(&d_reduce, 3 * sizeof(uint64_t), slot[0].st));
+    NTH_TRY(cudaMemsetAsync(d_reduce, 0, 3 * sizeof(uint64_t), slot[0].st));
+    NTH_TRY(cudaStreamSynchronize(slot[0].st)); // chunks on the other streams accumulate into it
+  }
   if (hb.valid_bits) {
-    NTH_TRY(cudaMalloc(&d_valid, vwords * 4));
+    NTH_TRY(cudaMallocAsync(&d_valid, vwords * 4, slot[0].st));
     NTH_TRY(cudaEventCreateWithFlags(&ev_valid, cudaEventDisableTiming));
     NTH_TRY(cudaMemsetAsync(d_valid, 0xFF, vwords * 4, slot[0].st));
     NTH_TRY(cudaEventRecord(ev_valid, slot[0].st));
     for (int i = 1; i < ns; ++i) NTH_TRY(cudaStreamWaitEvent(slot[i].st, ev_valid, 0));
   }
+  const double t1 = now();
   for (size_t c = 0; c < n_chunks; ++c) {
     Slot& s = slot[c % ns];
     if (c >= (size_t)ns) NTH_TRY(cudaStreamSynchronize(s.st)); // the slot's previous chunk has been copied out
     const uint64_t r0 = cut[c], r1 = cut[c + 1], nr = r1 - r0;
-    const uint64_t b0 = hb.read_off[r0], nbytes = hb.read_off[r1] - b0, row0 = koff[r0], nrows = koff[r1] - row0;
+    const uint64_t b0 = hb.read_off[r0], nbytes = hb.read_off[r1] - b0, row0 = koff(r0), nrows = koff(r1) - row0;
     if (nrows == 0) continue;
     // chunk bytes sit 16 bytes into the slot so that "the base before the first one" is addressable
     NTH_TRY(cudaMemcpyAsync(s.d_bases + 16, hb.bases + b0, nbytes, cudaMemcpyHostToDevice, s.st));
@@ -390,6 +434,7 @@ static int host_pipeline(const HostBatch& hb, Launch&& launch)
     B.valid_row0 = row0;
     B.d_fwd = s.d_fwd;
     B.d_rev = s.d_rev;
+    B.d_reduce = d_reduce;
     if (uniform) {
       B.d_bases = s.d_bases + 16;
       B.n_bases = nbytes + 64;
@@ -399,7 +444,7 @@ static int host_pipeline(const HostBatch& hb, Launch&& launch)
       uint64_t mx = 0;
       for (uint64_t i = 0; i <= nr; ++i) {
         s.h_off[i] = hb.read_off[r0 + i] - b0 + 16;
-        s.h_off[nr + 1 + i] = koff[r0 + i] - row0;
+        s.h_off[nr + 1 + i] = koff_v[r0 + i] - row0;
         if (i < nr) mx = std::max(mx, hb.read_off[r0 + i + 1] - hb.read_off[r0 + i]);
       }
       NTH_TRY(cudaMemcpyAsync(s.d_off, s.h_off.data(), 2 * (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.st));
@@ -413,15 +458,21 @@ static int host_pipeline(const HostBatch& hb, Launch&& launch)
       cleanup();
       return rc;
     }
-    NTH_TRY(cudaMemcpyAsync(hb.out + row0 * hb.H, s.d_out, nrows * hb.H * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.st));
+    if (hb.out) NTH_TRY(cudaMemcpyAsync(hb.out + row0 * hb.H, s.d_out, nrows * hb.H * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.st));
     if (hb.strand_cols) {
       NTH_TRY(cudaMemcpyAsync(hb.out_fwd + row0 * hb.strand_cols, s.d_fwd, nrows * hb.strand_cols * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.st));
       NTH_TRY(cudaMemcpyAsync(hb.out_rev + row0 * hb.strand_cols, s.d_rev, nrows * hb.strand_cols * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.st));
     }
   }
+  const double t2 = now();
   for (int i = 0; i < ns; ++i) NTH_TRY(cudaStreamSynchronize(slot[i].st));
   if (hb.valid_bits) NTH_TRY(cudaMemcpy(hb.valid_bits, d_valid, vwords * 4, cudaMemcpyDeviceToHost));
+  if (hb.reduce_result) NTH_TRY(cudaMemcpy(hb.reduce_result, d_reduce, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  const double t3 = now();
   cleanup();
+  if (timing)
+    fprintf(stderr, "[nthash_b200 host pipeline] %zu chunks: plan+alloc %.1f ms, enqueue %.1f ms, drain %.1f ms, free %.1f ms\n", n_chunks,
+            t1 - t0, t2 - t1, t3 - t2, now() - t3);
 #undef NTH_TRY
   return NTHASH_OK;
 }
@@ -547,6 +598,68 @@ int nthash_kmer_batch(const char* bases, const uint64_t* read_off, uint64_t n_re
   if (cudaSetDevice(device) != cudaSuccess) return fail(NTHASH_ERR_NO_DEVICE, "cannot select CUDA device %d", device);
   if (int rc = check_device_ready()) return rc;
   const HostBatch hb = { bases, read_off, n_reads, k, num_hashes, out_fwd ? 1ull : 0ull, out, valid_bits, out_fwd, out_rev };
+  return host_pipeline(hb, [&](const DevBatch& B, cudaStream_t st) { return kmer_dev_run(B, k, num_hashes, st); });
+}
+
+
+// ---- fused consumer: count / sum / xor of every hash value ------------------------------------
+
+int nthash_kmer_reduce_uniform_dev(const uint8_t* d_bases, uint64_t n_bases_readable, uint64_t n_reads,
+                                   uint32_t read_len, uint32_t k, uint32_t num_hashes, uint64_t* d_result, void* stream)
+{
+  if (int rc = check_kh(k, num_hashes)) return rc;
+  if (!d_result) return fail(NTHASH_ERR_INVALID_ARG, "d_result must not be NULL");
+  if (int rc = check_device_ready()) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  NTH_CUDA(cudaMemsetAsync(d_result, 0, 3 * sizeof(uint64_t), st));
+  if (n_reads == 0 || read_len < k) return NTHASH_OK;
+  if (!d_bases || ((uintptr_t)d_bases & 15)) return fail(NTHASH_ERR_INVALID_ARG, "d_bases must be 16-byte aligned");
+  if (n_bases_readable < n_reads * (uint64_t)read_len)
+    return fail(NTHASH_ERR_INVALID_ARG, "n_bases_readable smaller than n_reads*read_len");
+  DevBatch B;
+  B.d_bases = d_bases;
+  B.n_bases = n_bases_readable;
+  B.n_reads = n_reads;
+  B.uniform_len = read_len;
+  B.d_reduce = d_result;
+  return kmer_dev_run(B, k, num_hashes, st);
+}
+
+int nthash_kmer_reduce_dev(const uint8_t* d_bases, uint64_t n_bases_readable, const uint64_t* d_read_off,
+                           const uint64_t* d_koff, uint64_t n_reads, uint64_t max_read_len, uint32_t k,
+                           uint32_t num_hashes, uint64_t* d_result, void* stream)
+{
+  if (int rc = check_kh(k, num_hashes)) return rc;
+  if (!d_result) return fail(NTHASH_ERR_INVALID_ARG, "d_result must not be NULL");
+  if (int rc = check_device_ready()) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  NTH_CUDA(cudaMemsetAsync(d_result, 0, 3 * sizeof(uint64_t), st));
+  if (n_reads == 0 || max_read_len < k) return NTHASH_OK;
+  if (!d_bases || ((uintptr_t)d_bases & 15)) return fail(NTHASH_ERR_INVALID_ARG, "d_bases must be 16-byte aligned");
+  if (!d_read_off || !d_koff) return fail(NTHASH_ERR_INVALID_ARG, "d_read_off and d_koff must not be NULL");
+  DevBatch B;
+  B.d_bases = d_bases;
+  B.n_bases = n_bases_readable;
+  B.d_read_off = d_read_off;
+  B.d_koff = d_koff;
+  B.n_reads = n_reads;
+  B.max_len = max_read_len;
+  B.d_reduce = d_result;
+  return kmer_dev_run(B, k, num_hashes, st);
+}
+
+int nthash_kmer_reduce(const char* bases, const uint64_t* read_off, uint64_t n_reads, uint32_t k, uint32_t num_hashes,
+                       uint64_t* result, int device)
+{
+  if (int rc = check_kh(k, num_hashes)) return rc;
+  if (!result) return fail(NTHASH_ERR_INVALID_ARG, "result must not be NULL");
+  result[0] = result[1] = result[2] = 0;
+  if (n_reads == 0) return NTHASH_OK;
+  if (!bases || !read_off) return fail(NTHASH_ERR_INVALID_ARG, "bases and read_off must not be NULL");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(NTHASH_ERR_NO_DEVICE, "cannot select CUDA device %d", device);
+  if (int rc = check_device_ready()) return rc;
+  HostBatch hb = { bases, read_off, n_reads, k, num_hashes, 0ull, nullptr, nullptr, nullptr, nullptr };
+  hb.reduce_result = result;
   return host_pipeline(hb, [&](const DevBatch& B, cudaStream_t st) { return kmer_dev_run(B, k, num_hashes, st); });
 }
 

@@ -34,6 +34,7 @@ struct KmerParams
   uint64_t valid_row0 = 0; // bit index of this batch's row 0 inside valid_bits (chunked host pipeline)
   uint64_t* out_fwd = nullptr;
   uint64_t* out_rev = nullptr;
+  uint64_t* reduce_out = nullptr; // fused consumer: {windows visited, sum, xor} instead of out (all other outputs NULL)
   uint32_t tile_cap = 0; // bytes of base tile a CTA may stage
   bool use_tma = true;   // allow the TMA tile-store output path when the geometry permits
   uint64_t s[4], sk[4], mult[4]; // filled by launch_kmer

@@ -128,7 +128,9 @@ NTH_D uint64_t canonical2(const State& s)
   return ((uint64_t)hi << 32) | lo;
 }
 
-template<int H>
+// REDUCE: fused consumer (the loop of the reference's examples/benchmark.cpp:34-39): instead of storing
+// the hashes, count the visited windows and accumulate the 64-bit sum and xor of all their hash values.
+template<int H, bool REDUCE>
 __global__ void __launch_bounds__(KMER_NT, 3)
 kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ CUtensorMap omap)
 {
@@ -203,6 +205,9 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   // ---- four bases per step through the tetramer table, then k % 4 single steps               ----
   State s = { 0u, 0u, 0u, 0u };
   uint32_t bad = 0;
+  uint32_t run = 0;                   // REDUCE: hashable bases in a row, ending at the newest one
+  uint64_t acc_sum = 0, acc_xor = 0;  // REDUCE accumulators
+  uint32_t acc_cnt = 0;
   const uint32_t ot = ot_base + warp * OT_BYTES;
   {
     const uint32_t a_w = ps - 1;
@@ -216,15 +221,24 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
       const uint32_t x = __byte_perm(w0, w1, sel);
       w0 = w1;
       // base -1 is checked along with the rest: a false alarm only costs the (exact) scrub pass
-      bad |= lds_u8(lut + __byte_perm(x, 0u, 0x4440u)) | lds_u8(lut + __byte_perm(x, 0u, 0x4441u));
-      bad |= lds_u8(lut + __byte_perm(x, 0u, 0x4442u)) | lds_u8(lut + (x >> 24));
+      const uint32_t v0 = lds_u8(lut + __byte_perm(x, 0u, 0x4440u)), v1 = lds_u8(lut + __byte_perm(x, 0u, 0x4441u));
+      const uint32_t v2 = lds_u8(lut + __byte_perm(x, 0u, 0x4442u)), v3 = lds_u8(lut + (x >> 24));
+      bad |= v0 | v1 | v2 | v3;
+      if (REDUCE) {
+        run = v0 ? 0 : run + 1;
+        run = v1 ? 0 : run + 1;
+        run = v2 ? 0 : run + 1;
+        run = v3 ? 0 : run + 1;
+      }
       const uint32_t y2 = (x >> 1) & 0x03030303u;          // 2-bit codes, first base in byte 0
       const uint32_t off = ((y2 * 0x40100401u) >> 20) & 0xFF0u; // 16 * (c0<<6 | c1<<4 | c2<<2 | c3)
       roll4_in(s, lds_v4(ot_base + off));
     }
     for (uint32_t j = 4 * nq; j < k; ++j) {
       const uint32_t c = lds_u8(a_w + j);
-      bad |= lds_u8(lut + c);
+      const uint32_t v = lds_u8(lut + c);
+      bad |= v;
+      if (REDUCE) run = v ? 0 : run + 1;
       roll_step(s, lds_v4(sbase + F_IN_OFF + ((c & 6u) << 3)));
     }
   }
@@ -254,13 +268,45 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (i >= 2 && cnt < 4) break; // warp-uniform
-      bad |= lds_u8(lut + __byte_perm(x_in, 0u, 0x4440u | i));
+      const uint32_t v = lds_u8(lut + __byte_perm(x_in, 0u, 0x4440u | i));
+      bad |= v;
+      if (REDUCE) run = v ? 0 : run + 1;
       const uint32_t ea = __byte_perm(c4, 0u, 0x4440u | i) + pair;
       const uint2 ef = lds_v2(ea), er = lds_v2(ea + (F_PAIR_R_OFF - F_PAIR_OFF));
       roll_step(s, make_uint4(ef.x, ef.y, er.x, er.y));
       hv[i] = canonical2(s);
+      if (REDUCE && run >= k) { // the window is one the reference visits
+        ++acc_cnt;
+        acc_sum += hv[i];
+        acc_xor ^= hv[i];
+#pragma unroll
+        for (int q = 1; q < H; ++q) {
+          const uint64_t e = ext_hash(hv[i], P.mult[q]);
+          acc_sum += e;
+          acc_xor ^= e;
+        }
+      }
     }
   };
+
+  if constexpr (REDUCE) {
+    for (uint32_t p0 = 0; p0 < n; p0 += 4) {
+      uint64_t hv[4];
+      roll4(hv, n - p0);
+    }
+    if (!active) acc_cnt = 0, acc_sum = 0, acc_xor = 0;
+    for (int o = 16; o; o >>= 1) {
+      acc_cnt += __shfl_down_sync(0xffffffffu, acc_cnt, o);
+      acc_sum += __shfl_down_sync(0xffffffffu, acc_sum, o);
+      acc_xor ^= __shfl_down_sync(0xffffffffu, acc_xor, o);
+    }
+    if (lane == 0) {
+      atomicAdd(reinterpret_cast<unsigned long long*>(P.reduce_out), (unsigned long long)acc_cnt);
+      atomicAdd(reinterpret_cast<unsigned long long*>(P.reduce_out) + 1, (unsigned long long)acc_sum);
+      atomicXor(reinterpret_cast<unsigned long long*>(P.reduce_out) + 2, (unsigned long long)acc_xor);
+    }
+    return;
+  }
 
   constexpr uint32_t STEPS = 16 / H; // windows per tile row
   for (uint32_t p0 = 0; p0 < n; p0 += STEPS) {
@@ -316,9 +362,9 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   }
 }
 
-uint32_t fast_smem_bytes(uint32_t tile_cap)
+uint32_t fast_smem_bytes(uint32_t tile_cap, bool reduce)
 {
-  return F_TILE_OFF + F_TILE_PAD + tile_cap + 16 + 1024 + (KMER_NT / 32) * OT_BYTES;
+  return F_TILE_OFF + F_TILE_PAD + tile_cap + 16 + 1024 + (reduce ? 1 : KMER_NT / 32) * OT_BYTES;
 }
 
 // Tensor map of the output seen as [n_items rows] x [seg*h u64], boxes of 32 rows x 16 u64.
@@ -387,11 +433,11 @@ cudaError_t get_t4_table(uint32_t k, const uint4** out)
   return cudaSuccess;
 }
 
-template<int H>
+template<int H, bool REDUCE>
 cudaError_t launch_fast_t(const KmerParams& P, const CUtensorMap& map, cudaStream_t st)
 {
-  auto fn = kmer_fast_kernel<H>;
-  const uint32_t smem_bytes = fast_smem_bytes(P.tile_cap);
+  auto fn = kmer_fast_kernel<H, REDUCE>;
+  const uint32_t smem_bytes = fast_smem_bytes(P.tile_cap, REDUCE);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return e;
   const uint64_t ctas = (P.g.n_items + KMER_NT - 1) / KMER_NT;
@@ -405,8 +451,8 @@ bool kmer_fast_ok(const KmerParams& P)
 {
   const KmerGeom& g = P.g;
   return !g.item_byte && !P.out_fwd && (P.h == 1 || P.h == 2 || P.h == 4) && g.seg && ((uint64_t)g.seg * P.h) % 2 == 0 && g.seg % 2 == 0 &&
-         g.nk % g.seg == 0 && g.n_items > 0 && g.n_items < 0x7fffffffull && ((uintptr_t)P.out & 15) == 0 &&
-         fast_smem_bytes(P.tile_cap) <= 227u * 1024u;
+         g.nk % g.seg == 0 && g.n_items > 0 && g.n_items < 0x7fffffffull && (P.reduce_out || ((uintptr_t)P.out & 15) == 0) &&
+         fast_smem_bytes(P.tile_cap, P.reduce_out != nullptr) <= 227u * 1024u;
 }
 
 cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
@@ -414,7 +460,7 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
   KmerParams P = Pin;
   CUtensorMap map;
   memset(&map, 0, sizeof map);
-  cudaError_t e = make_out_map(P, &map);
+  cudaError_t e = P.reduce_out ? cudaSuccess : make_out_map(P, &map);
   if (e != cudaSuccess) return e;
   e = get_t4_table(P.k, &P.t4);
   if (e != cudaSuccess) return e;
@@ -425,10 +471,17 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
     const char* env = getenv("NTHASH_B200_PREFETCH_CTAS");
     P.prefetch_ctas = env ? (uint32_t)atoi(env) : (uint32_t)sms * 3; // one residency wave ahead
   }
+  if (P.reduce_out) {
+    switch (P.h) {
+      case 1: return launch_fast_t<1, true>(P, map, st);
+      case 2: return launch_fast_t<2, true>(P, map, st);
+      default: return launch_fast_t<4, true>(P, map, st);
+    }
+  }
   switch (P.h) {
-    case 1: return launch_fast_t<1>(P, map, st);
-    case 2: return launch_fast_t<2>(P, map, st);
-    default: return launch_fast_t<4>(P, map, st);
+    case 1: return launch_fast_t<1, false>(P, map, st);
+    case 2: return launch_fast_t<2, false>(P, map, st);
+    default: return launch_fast_t<4, false>(P, map, st);
   }
 }
 

@@ -170,6 +170,30 @@ __global__ void __launch_bounds__(KMER_NT) kmer_kernel(const __grid_constant__ K
     }
   };
 
+  if (P.reduce_out) { // fused consumer (only instantiated work when H == 0 && !STRANDS is launched with reduce_out)
+    uint32_t run = 0, cnt = 0;
+    uint64_t sum = 0, xr = 0;
+    for (uint32_t j = 0; j + 1 < k; ++j) run = tab_in[ps[j]].x != 0 ? run + 1 : 0;
+    for (uint32_t p = 0; p < n; ++p) {
+      run = tab_in[pin[p]].x != 0 ? run + 1 : 0;
+      const uint64_t h0 = roll(p);
+      if (run >= k) {
+        ++cnt;
+        sum += h0;
+        xr ^= h0;
+        for (uint32_t q = 1; q < h; ++q) {
+          const uint64_t e = ext_hash(h0, ext_mult(q, k));
+          sum += e;
+          xr ^= e;
+        }
+      }
+    }
+    atomicAdd(reinterpret_cast<unsigned long long*>(P.reduce_out), (unsigned long long)cnt);
+    atomicAdd(reinterpret_cast<unsigned long long*>(P.reduce_out) + 1, (unsigned long long)sum);
+    atomicXor(reinterpret_cast<unsigned long long*>(P.reduce_out) + 2, (unsigned long long)xr);
+    return;
+  }
+
   uint32_t p = 0;
   if (H == 1 && !STRANDS) {
     // four consecutive windows = one 32-byte sector; peel to sector alignment first
@@ -214,6 +238,7 @@ cudaError_t launch_kmer(KmerParams P, cudaStream_t st)
   if (P.use_tma && kmer_fast_ok(P)) return launch_kmer_fast(P, st);
   const uint32_t smem = kmer_smem_bytes(P.tile_cap);
   const bool strands = P.out_fwd != nullptr;
+  if (P.reduce_out) return launch_t<0, false>(P, smem, st);
   if (strands) {
     switch (P.h) {
       case 1: return launch_t<1, true>(P, smem, st);

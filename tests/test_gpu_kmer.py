@@ -152,3 +152,25 @@ def test_host_pipeline_many_chunks(monkeypatch):
             out2 = np.zeros((rows, h), np.uint64)   # without the optional outputs
             assert nthash_b200.LIB.nthash_kmer_batch(bases.ctypes.data, off.ctypes.data, len(off) - 1, k, h, out2.ctypes.data, None, None, None, 0) == 0
             assert (out2 == ora["out"]).all()
+
+
+def test_fused_reduce_consumer():
+    # count / sum / xor of every visited window's hashes without materialising them (reference examples/benchmark.cpp:34-39)
+    rng = np.random.default_rng(31)
+    for (n, L, k, h, p_bad) in ((5000, 150, 31, 1, 0.001), (3000, 150, 31, 4, 0.0), (2000, 151, 21, 3, 0.002), (40, 9000, 63, 2, 0.0005)):
+        bases = synth(rng, n * L, p_bad=p_bad)
+        d_b, _keep = to_dev(bases)
+        got = u64(nthash_b200.kmer_reduce_uniform(d_b, n, L, k, h))
+        ora = ORACLE.kmer_batch(bases, np.arange(n + 1, dtype=np.uint64) * L, k, h, want=(), threads=8)
+        assert (int(got[0]), int(got[1]), int(got[2])) == (ora["n_emit"], ora["sum"], ora["xor"]), (n, L, k, h)
+    lens = rng.integers(0, 400, 3000)
+    off = ragged_offsets(lens)
+    bases = synth(rng, int(off[-1]), p_bad=0.002)
+    d_b, _keep = to_dev(bases)
+    got = u64(nthash_b200.kmer_reduce(d_b, torch.from_numpy(off).cuda(), 31, 2))
+    ora = ORACLE.kmer_batch(bases, off.astype(np.uint64), 31, 2, want=())
+    assert (int(got[0]), int(got[1]), int(got[2])) == (ora["n_emit"], ora["sum"], ora["xor"])
+    res = np.zeros(3, np.uint64)   # host entry: bases up, three words back
+    offu = off.astype(np.uint64)
+    assert nthash_b200.LIB.nthash_kmer_reduce(bases.ctypes.data, offu.ctypes.data, len(lens), 31, 2, res.ctypes.data, 0) == 0
+    assert (int(res[0]), int(res[1]), int(res[2])) == (ora["n_emit"], ora["sum"], ora["xor"])
