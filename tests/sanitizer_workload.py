@@ -1,0 +1,28 @@
+# small end-to-end exercise of every kernel for compute-sanitizer (memcheck): sizes kept tiny
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np, torch
+import nthash_b200
+from gpu_util import synth, to_dev, ragged_offsets
+rng = np.random.default_rng(1)
+for L, n, k, h in ((150, 700, 31, 1), (151, 300, 31, 3), (2000, 40, 63, 4), (150, 300, 31, 4)):
+    b = synth(rng, n * L, p_bad=0.002); d, keep = to_dev(b)
+    nthash_b200.kmer_hashes_uniform(d, n, L, k, h); nthash_b200.kmer_hashes_uniform(d, n, L, k, 1, want_strands=True)
+    nthash_b200.kmer_reduce_uniform(d, n, L, k, h)
+lens = rng.integers(0, 400, 500); off = ragged_offsets(lens); b = synth(rng, int(off[-1]), p_bad=0.003); d, keep = to_dev(b, pad=16)
+o = torch.from_numpy(off).cuda()
+nthash_b200.kmer_hashes(d, o, 31, 2, want_strands=True); nthash_b200.kmer_reduce(d, o, 31, 2)
+lens = [30000, 3, 9000, 62]; off = ragged_offsets(lens); b = synth(rng, int(off[-1]), p_bad=0.0003); d, keep = to_dev(b, pad=16)
+nthash_b200.kmer_hashes(d, torch.from_numpy(off).cuda(), 63, 1)
+plan = nthash_b200.SeedPlan(["1010101010101010101010101010101", "1101101101101101011011011011011"], 3)
+b = synth(rng, 400 * 150, p_bad=0.002); d, keep = to_dev(b)
+nthash_b200.seed_hashes_uniform(plan, d, 400, 150); nthash_b200.seed_hashes_uniform(plan, d, 400, 150, want_strands=True)
+nthash_b200.seed_hashes(plan, d, torch.arange(0, 401, dtype=torch.int64).cuda() * 150, want_strands=True)
+init = nthash_b200.kmer_hashes_uniform(d, 100, 31, 31, 2, want_strands=True)
+nthash_b200.blind_roll(init.fwd, init.rev, d[:100].contiguous(), d[100:200].contiguous(), 31, 2)
+nthash_b200.blind_peek4(init.fwd, init.rev, d[:100].contiguous(), 31, 2)
+off = ragged_offsets(rng.integers(0, 300, 200)).astype(np.uint64); b = synth(rng, int(off[-1]), p_bad=0.002)
+out = np.zeros((int(nthash_b200.LIB.nthash_window_rows(off.ctypes.data, 200, 31, None)), 1), np.uint64)
+assert nthash_b200.LIB.nthash_kmer_batch(b.ctypes.data, off.ctypes.data, 200, 31, 1, out.ctypes.data, None, None, None, 0) == 0
+torch.cuda.synchronize(); print("sanitizer workload done")
