@@ -105,6 +105,21 @@ DI void roll_step(State& s, const uint4 e)
   s.rlo = __funnelshift_r(rl, rh, 1);
   s.rhi = (__funnelshift_r(rh, rh >> 1, 1) & ~1u) | (rl & 1u);
 }
+// Strided care block, stride D: F <- srol^D(F) ^ ef ; R <- sror^D(R ^ er).  srol^D (D <= 31) is a 64-bit rotate
+// followed by a swap of the D bits that crossed the 33|31 split (src/internal.hpp:56-66); sror^D is its inverse.
+template<int D>
+DI void blk_step(State& a, const uint2 ef, const uint2 er)
+{
+  const uint32_t vlo = __funnelshift_l(a.fhi, a.flo, D), vhi = __funnelshift_l(a.flo, a.fhi, D);
+  const uint32_t y = (vlo ^ (vhi >> 1)) & ((1u << D) - 1u);
+  a.flo = xor3(vlo, y, ef.x);
+  a.fhi = xor3(vhi, y << 1, ef.y);
+  const uint32_t xlo = a.rlo ^ er.x, xhi = a.rhi ^ er.y;
+  const uint32_t y2 = (xlo ^ (xhi >> 1)) & ((1u << D) - 1u);
+  const uint32_t zlo = xlo ^ y2, zhi = xhi ^ (y2 << 1);
+  a.rlo = __funnelshift_r(zlo, zhi, D);
+  a.rhi = __funnelshift_r(zhi, zlo, D);
+}
 DI uint64_t ext_hash(uint64_t h0, uint64_t mult) { const uint64_t t = h0 * mult; return t ^ (t >> 27); }
 DI uint64_t srol_n(uint64_t x, unsigned d)
 {
@@ -146,9 +161,9 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
   };
   const bool active = i0 + tid < i1;
   const uint64_t lo_byte = item_byte(i0), g1 = item_byte(i1 - 1) + n + K - 1;
-  const uint64_t g0 = (lo_byte ? lo_byte - 1 : 0) & ~15ull;
+  const uint64_t g0 = (lo_byte > 16 ? lo_byte - 16 : 0) & ~15ull; // up to 16 bases before the first item are staged too
   if (g1 - g0 > P.tile_cap) __trap();
-  const uint64_t my_byte = active ? item_byte(i0 + tid) : g0 + 1;
+  const uint64_t my_byte = active ? item_byte(i0 + tid) : g0 + 16;
   const uint64_t my_out = (i0 + tid) * (uint64_t)n;
 
   if (tid == 0) {
@@ -175,51 +190,25 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
   const uint32_t ot0 = ((tile + 16 + P.tile_cap + 16 + 1023u) & ~1023u) + warp * (NBUF * OT_BYTES);
   const int row0 = (int)(i0 + warp * 32);
 
-  // warm-up: shift bases -1 .. k-2 into the code window; roll the full-window hash over them (in-only)
+  // warm-up: shift bases -OLDER .. k-2 into the code window (the bases before the item only serve strided blocks,
+  // where they cancel); roll the full-window hash over bases -1 .. k-2 (in-only)
   DECL_W
+  DECL_BLOCKS
   State full = { 0u, 0u, 0u, 0u };
   uint32_t bad = 0;
-  for (int j = -1; j < (int)K - 1; ++j) {
-    const uint32_t c = lds_u8(ps + j);
+  for (int j = -(int)OLDER; j < (int)K - 1; ++j) {
+    const uint32_t c = lds_u8(ps + (uint32_t)j);
     if (j >= 0) bad |= lds_u8(lut + c);
     SHIFT_IN(c >> 1)
 #if ANY_IGNORE
-    roll_step(full, lds_v4(sbase + INTAB_OFF + ((c & 6u) << 3)));
+    if (j >= -1) roll_step(full, lds_v4(sbase + INTAB_OFF + ((c & 6u) << 3)));
 #endif
   }
+  WARMUP_BLOCKS
 
   uint32_t buf = 0;
-  for (uint32_t p0 = 0; p0 < n; p0 += TW) {
-    const uint32_t ot = ot0 + buf * OT_BYTES, rowaddr = ot + lane * ROW_BYTES;
-#pragma unroll
-    for (uint32_t i = 0; i < TW; ++i) {
-      if (p0 + i < n) {
-        const uint32_t c = lds_u8(ps + (K - 1) + p0 + i);
-        bad |= lds_u8(lut + c);
-#if ANY_IGNORE
-        {
-          const uint32_t po = ((c << 4) & 0x60u) | (rotr(OUT_WORD, OUT_ROT) & 0x18u); // 8 * (4*code_in + code_out)
-          const uint2 ef = lds_v2(sbase + PAIRF_OFF + po), er = lds_v2(sbase + PAIRR_OFF + po);
-          roll_step(full, make_uint4(ef.x, ef.y, er.x, er.y));
-        }
-#endif
-        SHIFT_IN(c >> 1)
-        uint64_t hv[HT];
-        WINDOW_BODY
-        if (i == 0 && p0 >= NBUF * TW) { // this buffer's previous tile must have left shared memory; waiting
-          if (lane == 0) BULK_WAIT_READ  // only now hides the TMA read behind the first window's arithmetic
-          __syncwarp();
-        }
-        STORE_WINDOW(rowaddr + i * (HT * 8))
-      }
-    }
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      tma_store_2d(&omap, ot, (int)(p0 * HT), row0);
-      bulk_commit();
-    }
-    buf = buf + 1 == NBUF ? 0 : buf + 1;
+  for (uint32_t p0 = 0; p0 < n; p0 += UNROLL) {
+    MAIN_TILES
   }
 
   const bool dirty = active && bad != 0;
@@ -329,10 +318,52 @@ SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
   const uint32_t k = plan.k, m = plan.n_seeds, hps = plan.h, ht = m * hps;
   if (k > 128) { why = "k > 128"; return nullptr; }
   if (ht > 64) { why = "more than 64 hashes per window"; return nullptr; }
-  const uint32_t kw = (k + 15) / 16, off = 16 * kw - k; // window base j sits at code position off + j
+  // ---- decomposition of every seed's lookup positions: strided blocks (arithmetic progressions of >= 6
+  //      positions, stride 1..4, rolled like the whole window) + pairs for the rest ----
+  struct Block { uint32_t seed, q0, d, m, id; };
+  std::vector<Block> blocks;
+  std::vector<std::vector<uint32_t>> rest(m);
+  uint32_t phases = 0, older = 1;
+  const bool use_blocks = !getenv("NTHASH_B200_SEED_JIT_NO_BLOCKS");
+  for (uint32_t s = 0; s < m; ++s) {
+    std::vector<char> in(k, 0);
+    for (uint32_t q : plan.lookups[s]) in[q] = 1;
+    while (use_blocks) {
+      Block best = { s, 0, 0, 0, 0 };
+      for (uint32_t d = 1; d <= 4; ++d)
+        for (uint32_t q = 0; q < k; ++q) {
+          if (!in[q] || (q >= d && in[q - d])) continue; // not the start of a maximal progression
+          uint32_t len = 0;
+          while (q + len * d < k && in[q + len * d]) ++len;
+          if (len > best.m) best = { s, q, d, len, 0 };
+        }
+      if (best.m < 6 || phases + best.d > 8) break;
+      best.id = (uint32_t)blocks.size();
+      blocks.push_back(best);
+      phases += best.d;
+      if (best.q0 < best.d) older = std::max(older, best.d - best.q0);
+      for (uint32_t j = 0; j < best.m; ++j) in[best.q0 + j * best.d] = 0;
+    }
+    for (uint32_t q = 0; q < k; ++q)
+      if (in[q]) rest[s].push_back(q);
+  }
+  // window base j sits at code position off + j of a shift register of kw words; `older` positions below it
+  const uint32_t kw = (k + older + 15) / 16, off = 16 * kw - k;
+  auto rot_to = [&](int j, uint32_t target_bit) { // expression that brings the code of window offset j to bits target_bit..+1
+    const uint32_t pos = (uint32_t)((int)off + j);
+    std::ostringstream o;
+    o << "rotr(W" << pos / 16 << ", " << ((2 * (pos % 16) + 32 - target_bit) % 32) << "u)";
+    return o.str();
+  };
+  uint32_t lcm_d = 1;
+  for (const Block& bk : blocks) {
+    uint32_t a = lcm_d, b2 = bk.d;
+    while (b2) { const uint32_t t = a % b2; a = b2; b2 = t; }
+    lcm_d = lcm_d / a * bk.d;
+  }
 
-  // ---- tables: [pair F 128][pair R 128][in-only 64][group tables: F half 128 B | R half 128 B] ----
-  // 16 entries x 8 bytes = 128 bytes = every entry in its own bank pair: LDS.64 with any mix of indices is conflict-free
+  // ---- tables: [pair F 128][pair R 128][in-only 64] then per block / per pair group: F half 128 B | R half 128 B
+  //      (16 entries x 8 bytes = every entry in its own bank pair: LDS.64 with any mix of indices is conflict-free) ----
   const uint64_t seed_of_code[4] = { SEED_A, SEED_C, SEED_T, SEED_G };
   std::vector<uint8_t> tab(320, 0);
   for (unsigned ci = 0; ci < 4; ++ci) {
@@ -346,49 +377,53 @@ SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
     memcpy(&tab[256 + ci * 16], &fi, 8);
     memcpy(&tab[256 + ci * 16 + 8], &ri, 8);
   }
-  std::ostringstream body;
+  auto put = [&](uint32_t base, uint32_t e, uint64_t f, uint64_t r) {
+    memcpy(&tab[base + e * 8], &f, 8);
+    memcpy(&tab[base + 128 + e * 8], &r, 8);
+  };
+  // block tables: roll table indexed (in << 2 | out), in-only table indexed (in)
+  std::vector<uint32_t> blk_roll_off(blocks.size()), blk_in_off(blocks.size());
+  std::ostringstream decl_blocks, warm_blocks;
+  for (const Block& bk : blocks) {
+    const uint32_t q0 = bk.q0, d = bk.d, mm = bk.m;
+    blk_roll_off[bk.id] = (uint32_t)tab.size();
+    tab.resize(tab.size() + 256, 0);
+    blk_in_off[bk.id] = (uint32_t)tab.size();
+    tab.resize(tab.size() + 256, 0);
+    for (uint32_t e = 0; e < 16; ++e) {
+      const uint32_t co = e & 3, ci = e >> 2;
+      put(blk_roll_off[bk.id], e, srol_n(seed_of_code[co], d + k - 1 - q0) ^ srol_n(seed_of_code[ci], k - 1 - q0 - (mm - 1) * d),
+          srol_n(seed_of_code[co ^ 2], q0) ^ srol_n(seed_of_code[ci ^ 2], q0 + mm * d));
+    }
+    for (uint32_t ci = 0; ci < 4; ++ci)
+      put(blk_in_off[bk.id], ci, srol_n(seed_of_code[ci], k - 1 - q0 - (mm - 1) * d), srol_n(seed_of_code[ci ^ 2], q0 + mm * d));
+    for (uint32_t ph = 0; ph < d; ++ph) {
+      decl_blocks << " State b" << bk.id << "_" << ph << " = { 0u, 0u, 0u, 0u };";
+      // G(ph - d) by m in-only steps over bases ph - d + q0 + t*d (t = 0..m-1)
+      warm_blocks << "  for (uint32_t t = 0; t < " << mm << "u; ++t) { const uint32_t ix = (lds_u8(ps + (uint32_t)(" << (int)ph - (int)d + (int)q0
+                  << ") + t * " << d << "u) & 6u) << 2; blk_step<" << d << ">(b" << bk.id << "_" << ph << ", lds_v2(tb + " << blk_in_off[bk.id]
+                  << "u + ix), lds_v2(tb + " << blk_in_off[bk.id] + 128 << "u + ix)); } \\\n";
+    }
+  }
+  // pair groups of the remaining positions
+  struct Pair { uint32_t qa, qb, off; bool two; };
+  std::vector<std::vector<Pair>> pairs(m);
   for (uint32_t s = 0; s < m; ++s) {
-    body << "  { /* seed " << s << (plan.ignore_mode[s] ? " (ignore-mode)" : " (care-mode)") << " */ \\\n";
-    if (plan.ignore_mode[s]) body << "    uint32_t flo = full.flo, fhi = full.fhi, rlo = full.rlo, rhi = full.rhi; \\\n";
-    else body << "    uint32_t flo = 0u, fhi = 0u, rlo = 0u, rhi = 0u; \\\n";
-    const std::vector<uint32_t>& lp = plan.lookups[s];
-    for (size_t a = 0; a < lp.size(); a += 2) {
-      const bool two = a + 1 < lp.size();
-      const uint32_t qa = lp[a], qb = two ? lp[a + 1] : 0;
-      const uint32_t tab_off = (uint32_t)tab.size();
-      const uint32_t n_entries = two ? 16 : 4;
+    const std::vector<uint32_t>& lp = rest[s];
+    for (size_t a2 = 0; a2 < lp.size(); a2 += 2) {
+      Pair pr = { lp[a2], a2 + 1 < lp.size() ? lp[a2 + 1] : 0, (uint32_t)tab.size(), a2 + 1 < lp.size() };
       tab.resize(tab.size() + 256, 0);
-      for (uint32_t e = 0; e < n_entries; ++e) {
+      for (uint32_t e = 0; e < (pr.two ? 16u : 4u); ++e) {
         const uint32_t ca = e & 3, cb = e >> 2;
-        uint64_t f = srol_n(seed_of_code[ca], k - 1 - qa), r = srol_n(seed_of_code[ca ^ 2], qa);
-        if (two) {
-          f ^= srol_n(seed_of_code[cb], k - 1 - qb);
-          r ^= srol_n(seed_of_code[cb ^ 2], qb);
+        uint64_t f = srol_n(seed_of_code[ca], k - 1 - pr.qa), r = srol_n(seed_of_code[ca ^ 2], pr.qa);
+        if (pr.two) {
+          f ^= srol_n(seed_of_code[cb], k - 1 - pr.qb);
+          r ^= srol_n(seed_of_code[cb ^ 2], pr.qb);
         }
-        memcpy(&tab[tab_off + e * 8], &f, 8);
-        memcpy(&tab[tab_off + 128 + e * 8], &r, 8);
+        put(pr.off, e, f, r);
       }
-      // code of position q sits at bit 2*((off+q) % 16) of word (off+q)/16; rotate it to bit 3 (first) / 5 (second)
-      const uint32_t pa = off + qa, pb = off + qb;
-      const size_t gi = a / 2;
-      body << "    const uint32_t ix" << gi << " = (rotr(W" << pa / 16 << ", " << ((2 * (pa % 16) + 32 - 3) % 32) << "u) & 0x18u)";
-      if (two) body << " | (rotr(W" << pb / 16 << ", " << ((2 * (pb % 16) + 32 - 5) % 32) << "u) & 0x60u)";
-      body << "; const uint2 ef" << gi << " = lds_v2(tb + " << tab_off << "u + ix" << gi << "), er" << gi << " = lds_v2(tb + " << tab_off + 128
-           << "u + ix" << gi << "); \\\n";
+      pairs[s].push_back(pr);
     }
-    { // fold the group entries into the accumulators two at a time (one 3-input LOP3 per word)
-      const size_t ng = (lp.size() + 1) / 2;
-      size_t gi = 0;
-      for (; gi + 1 < ng; gi += 2)
-        body << "    flo = xor3(flo, ef" << gi << ".x, ef" << gi + 1 << ".x); fhi = xor3(fhi, ef" << gi << ".y, ef" << gi + 1 << ".y); rlo = xor3(rlo, er"
-             << gi << ".x, er" << gi + 1 << ".x); rhi = xor3(rhi, er" << gi << ".y, er" << gi + 1 << ".y); \\\n";
-      if (gi < ng)
-        body << "    flo ^= ef" << gi << ".x; fhi ^= ef" << gi << ".y; rlo ^= er" << gi << ".x; rhi ^= er" << gi << ".y; \\\n";
-    }
-    body << "    const uint64_t h0 = (((uint64_t)fhi << 32) | flo) + (((uint64_t)rhi << 32) | rlo); \\\n";
-    body << "    hv[" << s * hps << "] = h0; \\\n";
-    for (uint32_t q = 1; q < hps; ++q) body << "    hv[" << s * hps + q << "] = ext_hash(h0, " << hex64(ext_mult(q, k)) << "); \\\n";
-    body << "  } \\\n";
   }
   const uint32_t table_bytes = (uint32_t)((tab.size() + 15) & ~size_t(15));
   tab.resize(table_bytes, 0);
@@ -398,39 +433,108 @@ SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
   for (uint32_t t = 1; t <= 16; ++t) {
     const uint32_t rb = t * ht * 8;
     if (rb % 16 || rb > 512 || t * ht > 256) continue;
-    const uint32_t score = ((rb / 16) % 2 ? 1000 : 0) + (rb >= 128 ? 500 : rb) - (rb > 288 ? rb - 288 : 0);
+    const uint32_t score = ((rb / 16) % 2 ? 1000 : 0) + (rb <= 256 ? rb : 512 - rb); // long rows write better (DRAM), up to ~256 B
     if (score > best) { best = score; tw = t; }
+  }
+  if (const char* e = getenv("NTHASH_B200_SEED_JIT_TW")) { // experiments
+    const uint32_t t = (uint32_t)atoi(e);
+    if (t >= 1 && (t * ht * 8) % 16 == 0 && t * ht <= 256) tw = t;
   }
   if (!tw) { why = "no tile row shape for this number of hashes"; return nullptr; }
   const uint32_t row_bytes = tw * ht * 8, ot_bytes = (32 * row_bytes + 127) & ~127u;
-  // CTA size / output buffering: defaults found on C4 (profiles/), overridable for experiments
-  uint32_t nt = 256, nbuf = 2;
+  uint32_t unroll = tw; // windows per generated loop body: a multiple of the tile and of every block stride
+  {
+    uint32_t a = unroll, b2 = lcm_d;
+    while (b2) { const uint32_t t = a % b2; a = b2; b2 = t; }
+    unroll = unroll / a * lcm_d;
+  }
+  if (unroll > 24) { why = "strided blocks with incompatible strides"; return nullptr; }
+  // CTA size / output buffering: defaults found on C4 (profiles/r01_seed_jit_sweeps.txt), overridable for experiments
+  uint32_t nt = 256, nbuf = 1;
   if (const char* e = getenv("NTHASH_B200_SEED_JIT_NT")) nt = (uint32_t)atoi(e);
   if (const char* e = getenv("NTHASH_B200_SEED_JIT_NBUF")) nbuf = (uint32_t)atoi(e);
   if (nt < 32 || nt > 1024 || nt % 32 || nbuf < 1 || nbuf > 2) { why = "bad NT/NBUF override"; return nullptr; }
+
+  // ---- the per-window body, one text per position u in the unrolled loop (block phases are static there) ----
+  auto window_body = [&](uint32_t u) {
+    std::ostringstream body;
+    for (uint32_t s = 0; s < m; ++s) {
+      body << "        { /* seed " << s << (plan.ignore_mode[s] ? " (ignore-mode)" : " (care-mode)") << " */ \\\n";
+      if (plan.ignore_mode[s]) body << "          uint32_t flo = full.flo, fhi = full.fhi, rlo = full.rlo, rhi = full.rhi; \\\n";
+      else body << "          uint32_t flo = 0u, fhi = 0u, rlo = 0u, rhi = 0u; \\\n";
+      for (const Block& bk : blocks) {
+        if (bk.seed != s) continue;
+        const uint32_t ph = u % bk.d;
+        body << "          { const uint32_t ix = (" << rot_to((int)bk.q0 - (int)bk.d, 3) << " & 0x18u) | (" << rot_to((int)(bk.q0 + (bk.m - 1) * bk.d), 5)
+             << " & 0x60u); blk_step<" << bk.d << ">(b" << bk.id << "_" << ph << ", lds_v2(tb + " << blk_roll_off[bk.id] << "u + ix), lds_v2(tb + "
+             << blk_roll_off[bk.id] + 128 << "u + ix)); flo ^= b" << bk.id << "_" << ph << ".flo; fhi ^= b" << bk.id << "_" << ph << ".fhi; rlo ^= b"
+             << bk.id << "_" << ph << ".rlo; rhi ^= b" << bk.id << "_" << ph << ".rhi; } \\\n";
+      }
+      const std::vector<Pair>& pv = pairs[s];
+      for (size_t gi = 0; gi < pv.size(); ++gi) {
+        body << "          const uint32_t ix" << gi << " = (" << rot_to((int)pv[gi].qa, 3) << " & 0x18u)";
+        if (pv[gi].two) body << " | (" << rot_to((int)pv[gi].qb, 5) << " & 0x60u)";
+        body << "; const uint2 ef" << gi << " = lds_v2(tb + " << pv[gi].off << "u + ix" << gi << "), er" << gi << " = lds_v2(tb + " << pv[gi].off + 128
+             << "u + ix" << gi << "); \\\n";
+      }
+      size_t gi = 0;
+      for (; gi + 1 < pv.size(); gi += 2)
+        body << "          flo = xor3(flo, ef" << gi << ".x, ef" << gi + 1 << ".x); fhi = xor3(fhi, ef" << gi << ".y, ef" << gi + 1 << ".y); rlo = xor3(rlo, er"
+             << gi << ".x, er" << gi + 1 << ".x); rhi = xor3(rhi, er" << gi << ".y, er" << gi + 1 << ".y); \\\n";
+      if (gi < pv.size())
+        body << "          flo ^= ef" << gi << ".x; fhi ^= ef" << gi << ".y; rlo ^= er" << gi << ".x; rhi ^= er" << gi << ".y; \\\n";
+      body << "          const uint64_t h0 = (((uint64_t)fhi << 32) | flo) + (((uint64_t)rhi << 32) | rlo); \\\n";
+      body << "          hv[" << s * hps << "] = h0; \\\n";
+      for (uint32_t q = 1; q < hps; ++q) body << "          hv[" << s * hps + q << "] = ext_hash(h0, " << hex64(ext_mult(q, k)) << "); \\\n";
+      body << "        } \\\n";
+    }
+    return body.str();
+  };
 
   std::ostringstream src;
   src << JIT_PRELUDE;
   src << "#define NT " << nt << "u\n#define NBUF " << nbuf << "u\n#define BULK_WAIT_READ asm volatile(\"cp.async.bulk.wait_group.read "
       << nbuf - 1 << ";\" ::: \"memory\");\n";
   src << "#define K " << k << "u\n#define M " << m << "u\n#define HPS " << hps << "u\n#define HT " << ht << "u\n#define TW " << tw
-      << "u\n#define ROW_BYTES " << row_bytes << "u\n#define OT_BYTES " << ot_bytes << "u\n#define TABLE_BYTES " << table_bytes
-      << "u\n#define ANY_IGNORE " << (plan.any_ignore ? 1 : 0) << "\n#define PAIRF_OFF 0u\n#define PAIRR_OFF 128u\n#define INTAB_OFF 256u\n";
-  src << "#define OUT_WORD W" << off / 16 << "\n#define OUT_ROT " << ((2 * (off % 16) + 32 - 3) % 32) << "u\n";
+      << "u\n#define UNROLL " << unroll << "u\n#define OLDER " << std::min<uint32_t>(off, 16) << "u\n#define ROW_BYTES " << row_bytes
+      << "u\n#define OT_BYTES " << ot_bytes << "u\n#define TABLE_BYTES " << table_bytes << "u\n#define ANY_IGNORE " << (plan.any_ignore ? 1 : 0)
+      << "\n#define PAIRF_OFF 0u\n#define PAIRR_OFF 128u\n#define INTAB_OFF 256u\n";
   src << "__device__ const uint64_t MULT[" << (hps > 1 ? hps : 1) << "] = { 0";
   for (uint32_t q = 1; q < hps; ++q) src << ", " << hex64(ext_mult(q, k));
   src << " };\n#define DECL_W";
   for (uint32_t w = 0; w < kw; ++w) src << " uint32_t W" << w << " = 0u;";
-  src << "\n#define SHIFT_IN(t) {";
+  src << "\n#define DECL_BLOCKS" << decl_blocks.str() << "\n";
+  src << "#define WARMUP_BLOCKS \\\n" << warm_blocks.str() << "\n";
+  src << "#define SHIFT_IN(t) {";
   for (uint32_t w = 0; w + 1 < kw; ++w) src << " W" << w << " = __funnelshift_r(W" << w << ", W" << w + 1 << ", 2);";
   src << " W" << kw - 1 << " = __funnelshift_r(W" << kw - 1 << ", (t), 2); }\n";
-  src << "#define WINDOW_BODY \\\n" << body.str() << "\n";
+  // full-window roll for ignore-mode seeds: the outgoing base is the previous window's base 0 (position off, before the shift)
+  src << "#define FULL_ROLL";
+  if (plan.any_ignore)
+    src << " { const uint32_t po = ((c << 4) & 0x60u) | (rotr(W" << off / 16 << ", " << ((2 * (off % 16) + 32 - 3) % 32)
+        << "u) & 0x18u); const uint2 ef = lds_v2(sbase + PAIRF_OFF + po), er = lds_v2(sbase + PAIRR_OFF + po);"
+           " roll_step(full, make_uint4(ef.x, ef.y, er.x, er.y)); }";
+  src << "\n#define WIN_PRE(P) const uint32_t c = lds_u8(ps + (K - 1) + (P)); bad |= lds_u8(lut + c); FULL_ROLL SHIFT_IN(c >> 1)\n";
   src << "#define STORE_WINDOW(addr) {";
   if (ht % 2 == 0)
     for (uint32_t q = 0; q < ht; q += 2) src << " sts_v2((addr) + " << q * 8 << "u, hv[" << q << "], hv[" << q + 1 << "]);";
   else
     for (uint32_t q = 0; q < ht; ++q) src << " sts_u64((addr) + " << q * 8 << "u, hv[" << q << "]);";
   src << " }\n";
+  src << "#define MAIN_TILES \\\n";
+  for (uint32_t t = 0; t < unroll / tw; ++t) {
+    src << "    if (p0 + " << t * tw << "u < n) { \\\n      const uint32_t ot = ot0 + buf * OT_BYTES, rowaddr = ot + lane * ROW_BYTES; \\\n";
+    for (uint32_t i = 0; i < tw; ++i) {
+      const uint32_t u = t * tw + i;
+      src << "      if (p0 + " << u << "u < n) { \\\n        WIN_PRE(p0 + " << u << "u) \\\n        uint64_t hv[HT]; \\\n" << window_body(u);
+      if (i == 0) // this buffer's previous tile must have left shared memory; waiting only now hides the TMA read behind one window
+        src << "        if (p0 + " << t * tw << "u >= NBUF * TW) { if (lane == 0) BULK_WAIT_READ __syncwarp(); } \\\n";
+      src << "        STORE_WINDOW(rowaddr + " << i * ht * 8 << "u) \\\n      } \\\n";
+    }
+    src << "      fence_proxy_async_smem(); __syncwarp(); \\\n      if (lane == 0) { tma_store_2d(&omap, ot, (int)((p0 + " << t * tw
+        << "u) * HT), row0); bulk_commit(); } \\\n      buf = buf + 1 == NBUF ? 0 : buf + 1; \\\n    } \\\n";
+  }
+  src << "\n";
   src << JIT_KERNEL;
 
   const Nvrtc& rt = nvrtc();
@@ -467,6 +571,10 @@ SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
   std::vector<char> cubin(cs);
   rt.cubin(prog, cubin.data());
   rt.destroy(&prog);
+  if (const char* dump = getenv("NTHASH_B200_SEED_JIT_DUMP")) { // inspection: <prefix>.cu and <prefix>.cubin
+    if (FILE* f = fopen((std::string(dump) + ".cu").c_str(), "w")) { fputs(j->source.c_str(), f); fclose(f); }
+    if (FILE* f = fopen((std::string(dump) + ".cubin").c_str(), "wb")) { fwrite(cubin.data(), 1, cubin.size(), f); fclose(f); }
+  }
   if (!load) return j; // build check on a machine without a GPU
   cudaError_t e = cudaLibraryLoadData(&j->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
   if (e == cudaSuccess) e = cudaLibraryGetKernel(&j->kernel, j->lib, "seed_jit_kernel");
@@ -489,8 +597,8 @@ uint32_t seed_jit_smem_bytes(const SeedJit* j, uint32_t tile_cap)
 // Bytes of bases one CTA of the specialised kernel stages (its CTA size may differ from KMER_NT).
 static uint32_t seed_jit_tile_cap(const SeedJit* j, const KmerGeom& g, uint32_t k)
 {
-  const uint64_t b = g.segs == 1 ? (uint64_t)j->nt * g.read_len + 64
-                                 : (uint64_t)j->nt * g.seg + ((uint64_t)j->nt / g.segs + 2) * (k - 1) + 64;
+  const uint64_t b = g.segs == 1 ? (uint64_t)j->nt * g.read_len + 96
+                                 : (uint64_t)j->nt * g.seg + ((uint64_t)j->nt / g.segs + 2) * (k - 1) + 96;
   return b > 0xffffffffull ? 0xffffffffu : (uint32_t)b;
 }
 
