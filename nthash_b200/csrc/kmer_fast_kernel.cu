@@ -23,6 +23,7 @@
 #include <cuda.h>
 #include <map>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 namespace nthb {
@@ -37,9 +38,10 @@ constexpr int F_PAIR_R_OFF = 128; // 16 x 8 B : [code_in][code_out] -> Skc[in]^S
 constexpr int F_IN_OFF = 256;     //  4 x 16 B : [code_in] -> {S[in], Skc[in]}  (warm-up)
 constexpr int F_LUT_OFF = 320;    // 256 x 1 B : 0 for ACGTUacgtu, 1 otherwise
 constexpr int F_BAR_OFF = 576;    // mbarrier
-constexpr int F_TILE_OFF = 592;   // 16-byte pad + staged bases
+constexpr int F_RANGE_OFF = 592;  // 2 x u64: byte range of the CTA's items
+constexpr int F_TILE_OFF = 608;   // 16-byte pad + staged bases
 constexpr int F_TILE_PAD = 16;
-constexpr int OT_BYTES = 32 * 128; // one warp's output tile: 32 rows x 16 u64
+constexpr int T4_BYTES = 256 * 16; // tetramer warm-up table
 
 NTH_D uint32_t lds_u8(uint32_t a)
 {
@@ -66,6 +68,29 @@ NTH_D uint4 lds_v4(uint32_t a)
   return v;
 }
 
+NTH_D uint64_t lds_u64(uint32_t a)
+{
+  uint64_t v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
+// 1-D bulk copy shared -> global through the TMA engine (SASS: UBLKCP); 16-byte aligned, 16-byte multiple
+NTH_D void bulk_s2g(void* dst_gmem, uint32_t src_smem, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem), "r"(bytes) : "memory");
+}
+NTH_D void tma_store_3d(const void* tmap, uint32_t saddr, int c0, int c1, int c2)
+{
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap), "r"(c0),
+               "r"(c1), "r"(c2), "r"(saddr)
+               : "memory");
+}
+template<int N>
+NTH_D void bulk_wait_read()
+{
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
 template<int LUT>
 NTH_D uint32_t lop3(uint32_t a, uint32_t b, uint32_t c)
 {
@@ -74,6 +99,25 @@ NTH_D uint32_t lop3(uint32_t a, uint32_t b, uint32_t c)
   return d;
 }
 // LUT bytes: a = 0xF0, b = 0xCC, c = 0xAA
+
+// Makes a value opaque to the compiler so that it stays in a register instead of being re-derived (the shared
+// window base costs an S2R SR_CgaCtaId + LEA every time it is rematerialised; ncu showed one per four windows).
+NTH_D uint32_t keep(uint32_t v)
+{
+  asm volatile("" : "+r"(v));
+  return v;
+}
+
+// Per byte of x: non-zero iff the byte is not one of ACGTUacgtu (what NtHash hashes, src/internal.hpp:132-165).
+// A byte is hashable iff bit7 = 0, bit6 = 1, bit3 = 0, bit4 == (bit2 & ~bit1) and (bit4 | bit0) = 1.
+NTH_D uint32_t swar_bad(uint32_t x)
+{
+  const uint32_t t1 = lop3<(0xF0 & ~0xCC) & 0xFF>(x, x << 1, 0u);                 // x & ~(x << 1): bit2 = b2 & ~b1
+  const uint32_t e1 = lop3<(0xF0 ^ 0xCC) & 0xAA>(t1, x >> 2, 0x04040404u);        // b4 != (b2 & ~b1)
+  const uint32_t e2 = lop3<(~(0xF0 | 0xCC)) & 0xAA & 0xFF>(x, x >> 4, 0x01010101u); // !(b0 | b4)
+  const uint32_t e3 = lop3<(0xF0 ^ 0xCC) & 0xAA>(x, 0x40404040u, 0xC8C8C8C8u);    // bit7, bit3 set or bit6 clear
+  return lop3<0xF0 | 0xCC | 0xAA>(e1, e2, e3);
+}
 
 constexpr int LUT_SEL_C = (0xF0 & ~0xAA & 0xFF) | (0xCC & 0xAA); // (a & ~c) | (b & c)
 constexpr int LUT_OR_AND = 0xF0 | (0xCC & 0xAA);                 // a | (b & c)
@@ -86,7 +130,7 @@ NTH_D void roll_step(State& s, const uint4 e)
   {
     const uint32_t lo = s.flo, hi = s.fhi;
     const uint32_t hi1 = __funnelshift_l(lo, hi, 1);              // (hi:lo << 1) high word
-    const uint32_t nhi = lop3<LUT_SEL_C>(hi1, hi >> 30, 2u);      // bit 33 <- old bit 63
+    const uint32_t nhi = lop3<LUT_SEL_C>(hi1, __umulhi(hi, 4u), 2u); // bit 33 <- old bit 63 (hi >> 30 as IMAD.HI: FMA pipe)
     const uint32_t nlo = lop3<LUT_OR_AND>(lo + lo, hi, 1u);       // bit 0  <- old bit 32
     s.flo = nlo ^ e.x;
     s.fhi = nhi ^ e.y;
@@ -94,7 +138,7 @@ NTH_D void roll_step(State& s, const uint4 e)
   {
     const uint32_t lo = s.rlo ^ e.z, hi = s.rhi ^ e.w;
     s.rlo = __funnelshift_r(lo, hi, 1);                           // bit 31 <- old bit 32
-    const uint32_t y = __funnelshift_r(hi, hi >> 1, 1);           // bit 31 <- old bit 33 (hi bit 1)
+    const uint32_t y = __funnelshift_r(hi, __umulhi(hi, 0x80000000u), 1); // bit 31 <- old bit 33 (hi bit 1); hi >> 1 as IMAD.HI
     s.rhi = lop3<LUT_SEL_C>(y, lo, 1u);                           // bit 32 <- old bit 0
   }
 }
@@ -128,33 +172,84 @@ NTH_D uint64_t canonical2(const State& s)
   return ((uint64_t)hi << 32) | lo;
 }
 
+// Geometry of item i (shared with kmer_kernel.cu's item_geom, restated here with the last item of a cut-up
+// read allowed to be short).
+NTH_D void fast_item_geom(const KmerGeom& g, uint64_t i, uint64_t& byte, uint64_t& out, uint32_t& n)
+{
+  if (g.item_byte) { // ragged: arrays are read_off/koff themselves when every read is one item
+    byte = g.item_byte[i];
+    out = g.item_out[i];
+    n = (uint32_t)(g.item_out[i + 1] - out);
+  } else {
+    uint64_t r = i;
+    uint32_t s = 0;
+    if (g.segs > 1) {
+      r = i / g.segs;
+      s = (uint32_t)(i - r * g.segs);
+    }
+    byte = r * g.read_len + (uint64_t)s * g.seg;
+    out = r * g.nk + (uint64_t)s * g.seg;
+    n = min(g.seg, g.nk - s * g.seg);
+  }
+}
+
+// exact clean-up of one item: windows touching a non-ACGTU byte are not emitted (kmer.cpp:232-235, :255-258)
+template<int H>
+__device__ __noinline__ void scrub_lane(const KmerParams& P, uint32_t lut, uint32_t ps, uint64_t my_out, uint32_t n)
+{
+  const uint32_t k = P.k;
+  uint32_t run = 0;
+  for (uint32_t j = 0; j < n + k - 1; ++j) {
+    run = lds_u8(lut + lds_u8(ps + j)) ? 0 : run + 1;
+    if (j >= k - 1 && run < k) {
+      const uint64_t w = my_out + (j - (k - 1));
+      for (uint32_t q = 0; q < H; ++q) P.out[w * H + q] = 0;
+      if (P.valid_bits) atomicAnd(&P.valid_bits[(P.valid_row0 + w) >> 5], ~(1u << ((P.valid_row0 + w) & 31)));
+    }
+  }
+}
+
+// bytes of one lane's row buffer: WS windows x H u64, padded to an odd number of 16-byte chunks so that the
+// per-lane STS.128 of a quarter-warp fall into distinct bank groups
+__host__ __device__ constexpr uint32_t row_buf_bytes(int H, int WS) { return (uint32_t)(WS * H * 8 + (((WS * H / 2) & 1) ? 0 : 16)); }
+
 // REDUCE: fused consumer (the loop of the reference's examples/benchmark.cpp:34-39): instead of storing
 // the hashes, count the visited windows and accumulate the 64-bit sum and xor of all their hash values.
-template<int H, bool REDUCE>
-__global__ void __launch_bounds__(KMER_NT, 3)
+//
+// Output path (REDUCE == false): every lane owns a private row buffer of WS windows in shared memory
+// (NBUF of them, used in turn); when it is full the lane itself pushes it to its row of `out` with one
+// 1-D bulk copy (cp.async.bulk.global.shared::cta -> UBLKCP): WS*H*8 contiguous bytes per store, which is
+// what the HBM write path wants (profiles/r01_microbench_tma_store_patterns.txt: 128-byte pieces 5.1-5.4 TB/s,
+// 320-byte pieces 6.2-6.5, 480-byte pieces 6.9).  Stores start on 32-byte (sector) boundaries: the first
+// (-row) mod (4/H) windows of an item and an odd last one go out as plain stores.
+//
+// BOX == true (uniform batches of whole-read items whose rows are multiples of 64 bytes): the 32 lanes of a warp
+// share one tile laid out [WS*H/8 blocks][32 rows][8 u64] under the 64-byte TMA swizzle (conflict-free STS.128),
+// and ONE elected lane issues a 3-D tensor store (cp.async.bulk.tensor.3d -> UTMASTG) of box 8 x 32 x blocks:
+// the same WS*H*8 contiguous bytes per row, without the 32-iteration issue loop a per-lane bulk copy costs.
+template<int H, bool REDUCE, int WS, int NBUF, bool BOX>
+__global__ void __launch_bounds__(256)
 kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ CUtensorMap omap)
 {
-  extern __shared__ __align__(16) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + F_BAR_OFF);
+  uint64_t* s_range = reinterpret_cast<uint64_t*>(smem + F_RANGE_OFF);
   uint8_t* tile = smem + F_TILE_OFF;
 
+  const uint32_t NT = blockDim.x;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint64_t i0 = (uint64_t)blockIdx.x * KMER_NT;
-  const uint64_t i1 = min(i0 + (uint64_t)KMER_NT, P.g.n_items);
-  const uint32_t k = P.k, n = P.g.seg; // every item has exactly seg windows
+  const uint64_t i0 = (uint64_t)blockIdx.x * NT;
+  const uint64_t i1 = min(i0 + (uint64_t)NT, P.g.n_items);
+  const uint32_t k = P.k;
 
-  // uniform geometry: item i = (read i / segs, segment i % segs)
-  auto item_byte = [&](uint64_t i) {
-    const uint64_t r = P.g.segs > 1 ? i / P.g.segs : i;
-    return r * P.g.read_len + (i - r * P.g.segs) * (uint64_t)n;
-  };
-  const bool active = i0 + tid < i1;
-  const uint64_t lo_byte = item_byte(i0), hi_byte = item_byte(i1 - 1) + n + k - 1;
-  const uint64_t g0 = (lo_byte ? lo_byte - 1 : 0) & ~15ull, g1 = hi_byte;
-  if (g1 - g0 > P.tile_cap) __trap();
-  const uint64_t my_byte = active ? item_byte(i0 + tid) : g0 + 1; // idle lanes hash a dummy row that TMA clips
-  const uint64_t my_out = (i0 + tid) * (uint64_t)n;
+  uint64_t my_byte = 0, my_out = 0;
+  uint32_t n = 0;
+  if (i0 + tid < i1) {
+    fast_item_geom(P.g, i0 + tid, my_byte, my_out, n);
+    if (tid == 0) s_range[0] = my_byte;
+    if (i0 + tid == i1 - 1) s_range[1] = my_byte + (n ? n + k - 1 : 0);
+  }
 
   // ---- stage the CTA's byte range (TMA bulk copy) and build the tables -------------------------
   if (tid == 0) {
@@ -163,20 +258,17 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   }
   if (tid < F_TILE_PAD) tile[tid] = 'A';
   __syncthreads();
+  const uint64_t lo_byte = s_range[0], g1 = max(s_range[1], lo_byte);
+  const uint64_t g0 = (lo_byte ? lo_byte - 1 : 0) & ~15ull;
+  if (g1 - g0 > P.tile_cap) __trap();
   const uint64_t bulk_end = min((g1 + 15) & ~15ull, P.n_bases & ~15ull);
   const uint32_t bulk_bytes = bulk_end > g0 ? (uint32_t)(bulk_end - g0) : 0u;
-  // the 4 KB tetramer table is parked in warp 0's (still unused) output tile for the warm-up phase
-  const uint32_t ot_base = (sbase + F_TILE_OFF + F_TILE_PAD + P.tile_cap + 16 + 1023u) & ~1023u;
+  // row buffers follow the staged bases; the 4 KB tetramer table is parked in them for the warm-up phase
+  const uint32_t rb_base = (sbase + F_TILE_OFF + F_TILE_PAD + P.tile_cap + 16 + 1023u) & ~1023u;
   if (tid == 0) {
-    mbar_expect_tx(bar, bulk_bytes + OT_BYTES);
+    mbar_expect_tx(bar, bulk_bytes + T4_BYTES);
     if (bulk_bytes) bulk_g2s(tile + F_TILE_PAD, P.bases + g0, bulk_bytes, bar);
-    bulk_g2s(smem + (ot_base - sbase), P.t4, OT_BYTES, bar);
-    // pull the tile of the CTA that will run on this SM slot a few waves from now into L2
-    const uint64_t i_nxt = i0 + (uint64_t)P.prefetch_ctas * KMER_NT;
-    if (P.prefetch_ctas && i_nxt < P.g.n_items) {
-      const uint64_t nxt = item_byte(i_nxt) & ~15ull, len = (g1 - g0 + 15) & ~15ull;
-      if (nxt + len <= (P.n_bases & ~15ull)) bulk_prefetch_l2(P.bases + nxt, (uint32_t)len);
-    }
+    bulk_g2s(smem + (rb_base - sbase), P.t4, T4_BYTES, bar);
   }
   {
     // code (byte >> 1) & 3 : 0 = A, 1 = C, 2 = T/U, 3 = G ; complement = code ^ 2
@@ -192,14 +284,20 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
       const uint64_t f = P.s[code2base(ci)], r = P.sk[code2base(ci ^ 2)];
       reinterpret_cast<uint4*>(smem + F_IN_OFF)[ci] = make_uint4((uint32_t)f, (uint32_t)(f >> 32), (uint32_t)r, (uint32_t)(r >> 32));
     }
-    smem[F_LUT_OFF + tid] = is_acgtu(tid) ? 0 : 1; // KMER_NT == 256 threads, one LUT byte each
+    for (uint32_t c = tid; c < 256; c += NT) smem[F_LUT_OFF + c] = is_acgtu(c) ? 0 : 1;
   }
-  for (uint64_t g = max(bulk_end, g0) + tid; g < g1; g += KMER_NT) tile[F_TILE_PAD + (g - g0)] = P.bases[g];
+  for (uint64_t g = max(bulk_end, g0) + tid; g < g1; g += NT) tile[F_TILE_PAD + (g - g0)] = P.bases[g];
   mbar_wait(bar, 0);
   __syncthreads();
 
-  const uint32_t ps = sbase + F_TILE_OFF + F_TILE_PAD + (uint32_t)(my_byte - g0); // shared address of base 0
-  const uint32_t lut = sbase + F_LUT_OFF;
+  const bool active = n != 0;
+  if (BOX && !REDUCE && !active) { // warp-synchronous output path: idle lanes hash a dummy row that the TMA store clips
+    my_byte = g0 + 1;
+    n = P.g.nk;
+  }
+  const uint32_t ps = keep(sbase + F_TILE_OFF + F_TILE_PAD + (uint32_t)(my_byte - g0)); // shared address of base 0
+  const uint32_t lut = keep(sbase + F_LUT_OFF);
+  const uint32_t pair = keep(sbase + F_PAIR_OFF); // 256-byte aligned: a table offset (< 128) can be spliced in with one PRMT
 
   // ---- warm-up: k in-only steps over bases -1 .. k-2 (base -1 is cancelled by the first roll), ----
   // ---- four bases per step through the tetramer table, then k % 4 single steps               ----
@@ -208,8 +306,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   uint32_t run = 0;                   // REDUCE: hashable bases in a row, ending at the newest one
   uint64_t acc_sum = 0, acc_xor = 0;  // REDUCE accumulators
   uint32_t acc_cnt = 0;
-  const uint32_t ot = ot_base + warp * OT_BYTES;
-  {
+  if (n) {
     const uint32_t a_w = ps - 1;
     uint32_t wp = a_w & ~3u;
     const uint32_t sel = 0x3210u + 0x1111u * (a_w & 3u);
@@ -232,7 +329,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
       }
       const uint32_t y2 = (x >> 1) & 0x03030303u;          // 2-bit codes, first base in byte 0
       const uint32_t off = ((y2 * 0x40100401u) >> 20) & 0xFF0u; // 16 * (c0<<6 | c1<<4 | c2<<2 | c3)
-      roll4_in(s, lds_v4(ot_base + off));
+      roll4_in(s, lds_v4(rb_base + off));
     }
     for (uint32_t j = 4 * nq; j < k; ++j) {
       const uint32_t c = lds_u8(a_w + j);
@@ -242,59 +339,99 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
       roll_step(s, lds_v4(sbase + F_IN_OFF + ((c & 6u) << 3)));
     }
   }
-  __syncthreads(); // the tetramer table is dead from here on: its bytes become warp 0's output tile
+  __syncthreads(); // the tetramer table is dead from here on: its bytes become row buffers
 
-  // ---- main loop: word streams + pair table, 16 u64 per tile row ---------------------------------
-  // in-stream starts at base k-1, out-stream at base -1; both are read as aligned words + PRMT realign
-  const uint32_t a_in = ps + k - 1, a_out = ps - 1;
-  uint32_t wp_in = a_in & ~3u, wp_out = a_out & ~3u;
-  const uint32_t sel_in = 0x3210u + 0x1111u * (a_in & 3u), sel_out = 0x3210u + 0x1111u * (a_out & 3u);
-  uint32_t w_in = lds_u32(wp_in), w_out = lds_u32(wp_out);
-
-  const uint32_t rbx = (ot + lane * 128) ^ ((lane & 7) << 4); // row base with the 128B-swizzle term folded in
-  const int row0 = (int)(i0 + warp * 32);
-  const uint32_t pair = sbase + F_PAIR_OFF;
-
-  // up to four windows (cnt = 4, or 2 at the very end of a row): consumes one realigned word of each stream
-  auto roll4 = [&](uint64_t (&hv)[4], uint32_t cnt) {
-    wp_in += 4;
-    wp_out += 4;
-    const uint32_t w_in_n = lds_u32(wp_in), w_out_n = lds_u32(wp_out);
-    const uint32_t x_in = __byte_perm(w_in, w_in_n, sel_in), x_out = __byte_perm(w_out, w_out_n, sel_out);
-    w_in = w_in_n;
-    w_out = w_out_n;
-    // per byte: code_in at bits 5-6, code_out at bits 3-4  =>  byte = 8 * (4*code_in + code_out) = table offset
-    const uint32_t c4 = lop3<LUT_SEL_C>(x_out << 2, x_in << 4, 0x60606060u) & 0x78787878u;
+  // one window through single-byte loads (alignment peel)
+  auto roll1 = [&](uint32_t p) -> uint64_t {
+    const uint32_t ci = lds_u8(ps + k - 1 + p), co = lds_u8(ps - 1 + p);
+    const uint32_t v = lds_u8(lut + ci);
+    bad |= v;
+    if (REDUCE) run = v ? 0 : run + 1;
+    const uint32_t ea = pair + (((ci & 6u) << 4) | ((co & 6u) << 2));
+    const uint2 ef = lds_v2(ea), er = lds_v2(ea + (F_PAIR_R_OFF - F_PAIR_OFF));
+    roll_step(s, make_uint4(ef.x, ef.y, er.x, er.y));
+    return canonical2(s);
+  };
+  auto reduce_add = [&](uint64_t h0) {
+    if (run >= k) { // the window is one the reference visits
+      ++acc_cnt;
+      acc_sum += h0;
+      acc_xor ^= h0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (i >= 2 && cnt < 4) break; // warp-uniform
-      const uint32_t v = lds_u8(lut + __byte_perm(x_in, 0u, 0x4440u | i));
-      bad |= v;
-      if (REDUCE) run = v ? 0 : run + 1;
-      const uint32_t ea = __byte_perm(c4, 0u, 0x4440u | i) + pair;
-      const uint2 ef = lds_v2(ea), er = lds_v2(ea + (F_PAIR_R_OFF - F_PAIR_OFF));
-      roll_step(s, make_uint4(ef.x, ef.y, er.x, er.y));
-      hv[i] = canonical2(s);
-      if (REDUCE && run >= k) { // the window is one the reference visits
-        ++acc_cnt;
-        acc_sum += hv[i];
-        acc_xor ^= hv[i];
-#pragma unroll
-        for (int q = 1; q < H; ++q) {
-          const uint64_t e = ext_hash(hv[i], P.mult[q]);
-          acc_sum += e;
-          acc_xor ^= e;
-        }
+      for (int q = 1; q < H; ++q) {
+        const uint64_t e = ext_hash(h0, P.mult[q]);
+        acc_sum += e;
+        acc_xor ^= e;
       }
     }
   };
 
-  if constexpr (REDUCE) {
-    for (uint32_t p0 = 0; p0 < n; p0 += 4) {
-      uint64_t hv[4];
-      roll4(hv, n - p0);
+  // ---- alignment peel: plain stores until the lane's next output u64 sits on a 32-byte boundary ----
+  uint32_t p = 0;
+  if (!REDUCE) {
+    const uint32_t peel = min(n, (uint32_t)((0 - my_out) & (uint64_t)(4 / H - 1)));
+    for (; p < peel; ++p) {
+      const uint64_t h0 = roll1(p);
+      uint64_t* o = P.out + (my_out + p) * H;
+      o[0] = h0;
+#pragma unroll
+      for (int q = 1; q < H; ++q) o[q] = ext_hash(h0, P.mult[q]);
     }
-    if (!active) acc_cnt = 0, acc_sum = 0, acc_xor = 0;
+  }
+
+  // ---- main loop: word streams + pair table ------------------------------------------------------
+  // in-stream starts at base k-1+p, out-stream at base p-1; both are read as aligned words + PRMT realign
+  const uint32_t a_in = ps + k - 1 + p, a_out = ps - 1 + p;
+  uint32_t wp_in = a_in & ~3u, wp_out = a_out & ~3u;
+  const uint32_t sel_in = 0x3210u + 0x1111u * (a_in & 3u), sel_out = 0x3210u + 0x1111u * (a_out & 3u);
+  uint32_t w_in = n ? lds_u32(wp_in) : 0u, w_out = n ? lds_u32(wp_out) : 0u;
+
+  uint32_t w_in_n = n ? lds_u32(wp_in + 4) : 0u, w_out_n = n ? lds_u32(wp_out + 4) : 0u; // one word ahead
+  wp_in += 4;
+  wp_out += 4;
+
+  // Four windows (FULL) or the first cnt < 4 of them: consumes one realigned word of each stream.  The next
+  // words are requested before the current ones are used, so their latency hides behind the four rolls.
+  auto roll4 = [&](uint64_t (&hv)[4], auto full, uint32_t cnt) {
+    constexpr bool FULL = decltype(full)::value;
+    const uint32_t x_in = __byte_perm(w_in, w_in_n, sel_in), x_out = __byte_perm(w_out, w_out_n, sel_out);
+    w_in = w_in_n;
+    w_out = w_out_n;
+    wp_in += 4;
+    wp_out += 4;
+    w_in_n = lds_u32(wp_in);
+    w_out_n = lds_u32(wp_out);
+    // per byte: code_in at bits 5-6, code_out at bits 3-4  =>  byte = 8 * (4*code_in + code_out) = table offset
+    const uint32_t c4 = lop3<LUT_SEL_C>(x_out << 2, x_in << 4, 0x60606060u) & 0x78787878u;
+    const uint32_t bw = swar_bad(x_in); // bytes past cnt may flag a false alarm: that only costs the exact scrub
+    if (!REDUCE) bad |= bw;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (!FULL && i && (uint32_t)i >= cnt) break;
+      if (REDUCE) {
+        const uint32_t v = __byte_perm(bw, 0u, 0x4440u | i);
+        bad |= v;
+        run = v ? 0 : run + 1;
+      }
+      const uint32_t ea = __byte_perm(c4, pair, 0x7650u | i); // (pair & ~0xFF) | byte i of c4
+      const uint2 ef = lds_v2(ea), er = lds_v2(ea + (F_PAIR_R_OFF - F_PAIR_OFF));
+      roll_step(s, make_uint4(ef.x, ef.y, er.x, er.y));
+      hv[i] = canonical2(s);
+      if (REDUCE) reduce_add(hv[i]);
+    }
+  };
+  using full_t = std::true_type;
+  using part_t = std::false_type;
+
+  if constexpr (REDUCE) {
+    for (; p + 4 <= n; p += 4) {
+      uint64_t hv[4];
+      roll4(hv, full_t(), 4u);
+    }
+    if (p < n) {
+      uint64_t hv[4];
+      roll4(hv, part_t(), n - p);
+    }
     for (int o = 16; o; o >>= 1) {
       acc_cnt += __shfl_down_sync(0xffffffffu, acc_cnt, o);
       acc_sum += __shfl_down_sync(0xffffffffu, acc_sum, o);
@@ -306,90 +443,126 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
       atomicXor(reinterpret_cast<unsigned long long*>(P.reduce_out) + 2, (unsigned long long)acc_xor);
     }
     return;
-  }
-
-  constexpr uint32_t STEPS = 16 / H; // windows per tile row
-  for (uint32_t p0 = 0; p0 < n; p0 += STEPS) {
-#pragma unroll
-    for (uint32_t q = 0; q < STEPS / 4; ++q) {
-      if (p0 + 4 * q < n) { // n is even on this path: a row ends with a group of 4 or of 2
+  } else if constexpr (BOX) {
+    constexpr uint32_t TILE = (uint32_t)(WS * H / 8) * 2048u; // blocks x 32 rows x 64 bytes
+    const uint32_t tb0 = rb_base + warp * (NBUF * TILE);
+    // SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3; tiles are 2048-byte multiples, so the lane term can be OR-ed in
+    const uint32_t lterm = keep(lane * 64 + (((lane >> 1) & 3) << 4));
+    const int row0 = (int)(i0 + warp * 32);
+    auto chunk_addr = [&](uint32_t tbl, uint32_t cc) { return (tbl ^ ((cc & 3u) << 4)) + (cc >> 2) * 2048u; };
+    uint32_t t = 0, b = 0;
+    for (; p < n; p += WS) { // n is the same for every lane here
+      const uint32_t cnt = min((uint32_t)WS, n - p);
+      const uint32_t tb_raw = tb0 + b * TILE, tb = tb_raw + lterm;
+      // one group of four windows -> the tile (FULL: all four, no per-window branches)
+      auto group = [&](uint32_t q, auto full, uint32_t c4n) {
         uint64_t hv[4];
-        roll4(hv, n - (p0 + 4 * q));
-        if (q == 0 && p0) { // the previous tile must have left shared memory before it is overwritten;
-          if (lane == 0) bulk_wait_read0(); // waiting here (not at the top) hides the TMA read behind 4 rolls
+        roll4(hv, full, c4n);
+        if (q == 0 && t >= (uint32_t)NBUF) { // the tile stored NBUF steps ago must have left shared memory
+          if (lane == 0) bulk_wait_read<NBUF - 1>();
           __syncwarp();
         }
         if (H == 1) {
-          st_shared_v2_u64(rbx ^ ((2 * q) << 4), hv[0], hv[1]);
-          st_shared_v2_u64(rbx ^ ((2 * q + 1) << 4), hv[2], hv[3]);
+          st_shared_v2_u64(chunk_addr(tb, 2 * q), hv[0], hv[1]);
+          st_shared_v2_u64(chunk_addr(tb, 2 * q + 1), hv[2], hv[3]);
         } else if (H == 2) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) st_shared_v2_u64(rbx ^ ((4 * q + i) << 4), hv[i], ext_hash(hv[i], P.mult[1]));
+          for (int i = 0; i < 4; ++i) st_shared_v2_u64(chunk_addr(tb, 4 * q + i), hv[i], ext_hash(hv[i], P.mult[1]));
         } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            st_shared_v2_u64(rbx ^ ((2 * i) << 4), hv[i], ext_hash(hv[i], P.mult[1]));
-            st_shared_v2_u64(rbx ^ ((2 * i + 1) << 4), ext_hash(hv[i], P.mult[2]), ext_hash(hv[i], P.mult[3]));
+            st_shared_v2_u64(chunk_addr(tb, 8 * q + 2 * i), hv[i], ext_hash(hv[i], P.mult[1]));
+            st_shared_v2_u64(chunk_addr(tb, 8 * q + 2 * i + 1), ext_hash(hv[i], P.mult[2]), ext_hash(hv[i], P.mult[3]));
           }
         }
+      };
+      if (cnt == (uint32_t)WS) {
+#pragma unroll
+        for (uint32_t q = 0; q < (uint32_t)WS / 4; ++q) group(q, full_t(), 4u);
+      } else {
+#pragma unroll
+        for (uint32_t q = 0; q < (uint32_t)WS / 4; ++q) {
+          if (4 * q + 4 <= cnt) group(q, full_t(), 4u);
+          else if (4 * q < cnt) group(q, part_t(), cnt - 4 * q);
+        }
       }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&omap, tb_raw, 0, row0, (int)(p * H / 8));
+        bulk_commit();
+      }
+      ++t;
+      b = (b + 1 == (uint32_t)NBUF) ? 0 : b + 1;
     }
-    fence_proxy_async_smem();
-    __syncwarp();
+    const bool dirty = active && bad != 0;
+    const bool any_dirty = __any_sync(0xffffffffu, dirty);
     if (lane == 0) {
-      tma_store_2d(&omap, ot, (int)(p0 * H), row0);
-      bulk_commit();
+      if (any_dirty) bulk_wait_all0(); // zeros must land after the tile they overwrite
+      else bulk_wait_read0();          // shared memory must outlive the TMA read
     }
-  }
-
-  const bool dirty = active && bad != 0;
-  const bool any_dirty = __any_sync(0xffffffffu, dirty);
-  if (lane == 0) {
-    if (any_dirty) bulk_wait_all0(); // zeros must land after the tile they overwrite
-    else bulk_wait_read0();          // shared memory must outlive the TMA read
-  }
-  __syncwarp();
-  if (dirty) { // exact clean-up: windows touching a non-ACGTU byte are not emitted (kmer.cpp:232-235, :255-258)
-    uint32_t run = 0;
-    for (uint32_t j = 0; j < n + k - 1; ++j) {
-      run = lds_u8(lut + lds_u8(ps + j)) ? 0 : run + 1;
-      if (j >= k - 1 && run < k) {
-        const uint64_t w = my_out + (j - (k - 1));
-        for (uint32_t q = 0; q < H; ++q) P.out[w * H + q] = 0;
-        if (P.valid_bits) atomicAnd(&P.valid_bits[(P.valid_row0 + w) >> 5], ~(1u << ((P.valid_row0 + w) & 31)));
+    __syncwarp();
+    if (dirty) scrub_lane<H>(P, lut, ps, my_out, n);
+  } else {
+    constexpr uint32_t ROWB = row_buf_bytes(H, WS);
+    const uint32_t rb0 = rb_base + tid * ROWB; // buffer b of this lane: rb0 + b * NT * ROWB
+    uint32_t t = 0, b = 0;
+    while (p < n) {
+      const uint32_t cnt = min((uint32_t)WS, n - p);
+      const uint32_t rb = rb0 + b * (NT * ROWB);
+      auto group = [&](uint32_t q, auto full, uint32_t c4n) {
+        uint64_t hv[4];
+        roll4(hv, full, c4n);
+        // buffer b was handed to the copy engine NBUF tiles ago: it must have been read out by now
+        // (waiting here, not at the top, hides the wait behind four rolls)
+        if (q == 0 && t >= (uint32_t)NBUF) bulk_wait_read<NBUF - 1>();
+        if (H == 1) {
+          st_shared_v2_u64(rb + (2 * q) * 16, hv[0], hv[1]);
+          st_shared_v2_u64(rb + (2 * q + 1) * 16, hv[2], hv[3]);
+        } else if (H == 2) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) st_shared_v2_u64(rb + (4 * q + i) * 16, hv[i], ext_hash(hv[i], P.mult[1]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            st_shared_v2_u64(rb + (8 * q + 2 * i) * 16, hv[i], ext_hash(hv[i], P.mult[1]));
+            st_shared_v2_u64(rb + (8 * q + 2 * i + 1) * 16, ext_hash(hv[i], P.mult[2]), ext_hash(hv[i], P.mult[3]));
+          }
+        }
+      };
+      if (cnt == (uint32_t)WS) {
+#pragma unroll
+        for (uint32_t q = 0; q < (uint32_t)WS / 4; ++q) group(q, full_t(), 4u);
+      } else {
+#pragma unroll
+        for (uint32_t q = 0; q < (uint32_t)WS / 4; ++q) {
+          if (4 * q + 4 <= cnt) group(q, full_t(), 4u);
+          else if (4 * q < cnt) group(q, part_t(), cnt - 4 * q);
+        }
       }
+      uint64_t* o = P.out + (my_out + p) * H;
+      const uint32_t bytes = (cnt * H * 8) & ~15u;
+      if (bytes) {
+        fence_proxy_async_smem();
+        bulk_s2g(o, rb, bytes);
+      }
+      bulk_commit();
+      if (H == 1 && (cnt & 1)) o[cnt - 1] = lds_u64(rb + (cnt - 1) * 8); // odd last window of the item
+      p += cnt;
+      ++t;
+      b = (b + 1 == (uint32_t)NBUF) ? 0 : b + 1;
     }
+
+    const bool dirty = bad != 0;
+    if (dirty) bulk_wait_all0(); // zeros must land after the bytes they overwrite
+    else bulk_wait_read0();      // shared memory must outlive the copy engine's reads
+    if (dirty) scrub_lane<H>(P, lut, ps, my_out, n);
   }
 }
 
-uint32_t fast_smem_bytes(uint32_t tile_cap, bool reduce)
+uint32_t fast_smem_bytes(uint32_t tile_cap, uint32_t buf_bytes)
 {
-  return F_TILE_OFF + F_TILE_PAD + tile_cap + 16 + 1024 + (reduce ? 1 : KMER_NT / 32) * OT_BYTES;
-}
-
-// Tensor map of the output seen as [n_items rows] x [seg*h u64], boxes of 32 rows x 16 u64.
-cudaError_t make_out_map(const KmerParams& P, CUtensorMap* map)
-{
-  using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeFn encode = nullptr;
-  if (!encode) {
-    void* fp = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qr);
-    if (e != cudaSuccess) return e;
-    if (!fp || qr != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
-    encode = (EncodeFn)fp;
-  }
-  const cuuint64_t dims[2] = { (cuuint64_t)P.g.seg * P.h, P.g.n_items };
-  const cuuint64_t strides[1] = { (cuuint64_t)P.g.seg * P.h * 8 };
-  const cuuint32_t box[2] = { 16, 32 };
-  const cuuint32_t estr[2] = { 1, 1 };
-  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, P.out, dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+  return F_TILE_OFF + F_TILE_PAD + tile_cap + 16 + 1024 + (buf_bytes > (uint32_t)T4_BYTES ? buf_bytes : (uint32_t)T4_BYTES);
 }
 
 // 256 x {TF, TR}: combined in-only contribution of four consecutive bases c0..c3 (codes, c0 first):
@@ -421,9 +594,9 @@ cudaError_t get_t4_table(uint32_t k, const uint4** out)
     tab[idx] = make_uint4((uint32_t)tf, (uint32_t)(tf >> 32), (uint32_t)tr, (uint32_t)(tr >> 32));
   }
   uint4* d = nullptr;
-  e = cudaMalloc(&d, OT_BYTES);
+  e = cudaMalloc(&d, T4_BYTES);
   if (e != cudaSuccess) return e;
-  e = cudaMemcpy(d, tab.data(), OT_BYTES, cudaMemcpyHostToDevice);
+  e = cudaMemcpy(d, tab.data(), T4_BYTES, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     cudaFree(d);
     return e;
@@ -433,16 +606,93 @@ cudaError_t get_t4_table(uint32_t k, const uint4** out)
   return cudaSuccess;
 }
 
-template<int H, bool REDUCE>
-cudaError_t launch_fast_t(const KmerParams& P, const CUtensorMap& map, cudaStream_t st)
+struct FastCfg
 {
-  auto fn = kmer_fast_kernel<H, REDUCE>;
-  const uint32_t smem_bytes = fast_smem_bytes(P.tile_cap, REDUCE);
-  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  uint32_t nt, ws, nbuf;
+  bool box;
+};
+
+// Tensor map of the output seen as [rows*H/8 blocks][n_items rows][8 u64] (blocks outermost), boxes of
+// `blocks` x 32 rows x 8 u64 under the 64-byte swizzle.
+cudaError_t make_out_map(const KmerParams& P, uint32_t blocks, CUtensorMap* map)
+{
+  using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qr);
+    if (e != cudaSuccess) return e;
+    if (!fp || qr != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+    encode = (EncodeFn)fp;
+  }
+  const uint64_t row_u64 = (uint64_t)P.g.seg * P.h;
+  const cuuint64_t dims[3] = { 8, P.g.n_items, row_u64 / 8 };
+  const cuuint64_t strides[2] = { row_u64 * 8, 64 };
+  const cuuint32_t box[3] = { 8, 32, blocks };
+  const cuuint32_t estr[3] = { 1, 1, 1 };
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, P.out, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template<int H, bool REDUCE, int WS, int NBUF, bool BOX>
+cudaError_t launch_fast_t(const KmerParams& P, uint32_t nt, cudaStream_t st)
+{
+  auto fn = kmer_fast_kernel<H, REDUCE, WS, NBUF, BOX>;
+  const uint32_t buf = BOX ? (nt / 32) * NBUF * (uint32_t)(WS * H / 8) * 2048u : nt * NBUF * row_buf_bytes(H, WS);
+  uint32_t smem_bytes = fast_smem_bytes(P.tile_cap, REDUCE ? 0u : buf);
+  if (const char* e = getenv("NTHASH_B200_SMEM_PAD")) smem_bytes += (uint32_t)atoi(e); // experiments: lower the occupancy
+  if (smem_bytes > 227u * 1024u) return cudaErrorInvalidConfiguration;
+  CUtensorMap map;
+  memset(&map, 0, sizeof map);
+  cudaError_t e = (BOX && !REDUCE) ? make_out_map(P, (uint32_t)(WS * H / 8), &map) : cudaSuccess;
   if (e != cudaSuccess) return e;
-  const uint64_t ctas = (P.g.n_items + KMER_NT - 1) / KMER_NT;
-  fn<<<(unsigned)ctas, KMER_NT, smem_bytes, st>>>(P, map);
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e != cudaSuccess) return e;
+  const uint64_t ctas = (P.g.n_items + nt - 1) / nt;
+  if (ctas > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+  fn<<<(unsigned)ctas, nt, smem_bytes, st>>>(P, map);
   return cudaGetLastError();
+}
+
+template<int H, int WS>
+cudaError_t launch_fast_nbuf(const KmerParams& P, const FastCfg& c, cudaStream_t st)
+{
+  if (c.box) return c.nbuf >= 2 ? launch_fast_t<H, false, WS, 2, true>(P, c.nt, st) : launch_fast_t<H, false, WS, 1, true>(P, c.nt, st);
+  return c.nbuf >= 2 ? launch_fast_t<H, false, WS, 2, false>(P, c.nt, st) : launch_fast_t<H, false, WS, 1, false>(P, c.nt, st);
+}
+
+// windows per store: index 0/1/2 = short / medium / long pieces (192-256 / 320-384 / 512 bytes per row)
+template<int H>
+constexpr int fast_ws(int idx)
+{
+  return H == 1 ? (idx == 0 ? 24 : idx == 1 ? 40 : 64) : H == 2 ? (idx == 0 ? 12 : idx == 1 ? 20 : 32) : (idx == 0 ? 8 : idx == 1 ? 12 : 16);
+}
+
+int fast_ws_rt(uint32_t h, uint32_t idx)
+{
+  return h == 1 ? fast_ws<1>((int)idx) : h == 2 ? fast_ws<2>((int)idx) : fast_ws<4>((int)idx);
+}
+
+template<int H>
+cudaError_t launch_fast_h(const KmerParams& P, const FastCfg& c, cudaStream_t st)
+{
+  if (P.reduce_out) return launch_fast_t<H, true, fast_ws<H>(1), 1, false>(P, c.nt, st);
+  switch (c.ws) {
+    case 0: return launch_fast_nbuf<H, fast_ws<H>(0)>(P, c, st);
+    case 1: return launch_fast_nbuf<H, fast_ws<H>(1)>(P, c, st);
+    default: return launch_fast_nbuf<H, fast_ws<H>(2)>(P, c, st);
+  }
+}
+
+uint32_t env_u32(const char* name, uint32_t dflt)
+{
+  const char* e = getenv(name);
+  return e ? (uint32_t)atoi(e) : dflt;
 }
 
 } // namespace
@@ -450,38 +700,59 @@ cudaError_t launch_fast_t(const KmerParams& P, const CUtensorMap& map, cudaStrea
 bool kmer_fast_ok(const KmerParams& P)
 {
   const KmerGeom& g = P.g;
-  return !g.item_byte && !P.out_fwd && (P.h == 1 || P.h == 2 || P.h == 4) && g.seg && ((uint64_t)g.seg * P.h) % 2 == 0 && g.seg % 2 == 0 &&
-         g.nk % g.seg == 0 && g.n_items > 0 && g.n_items < 0x7fffffffull && (P.reduce_out || ((uintptr_t)P.out & 15) == 0) &&
-         fast_smem_bytes(P.tile_cap, P.reduce_out != nullptr) <= 227u * 1024u;
+  return !P.out_fwd && (P.h == 1 || P.h == 2 || P.h == 4) && g.n_items > 0 && (P.reduce_out || ((uintptr_t)P.out & 31) == 0) &&
+         (g.item_byte || (g.seg && g.segs));
 }
 
+// Launch configuration.  Uniform batches get their own item geometry here (reads longer than FAST_WHOLE_READ
+// bases are cut into ~FAST_SEG-window items, the last one short); ragged batches keep the caller's item arrays.
 cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
 {
   KmerParams P = Pin;
-  CUtensorMap map;
-  memset(&map, 0, sizeof map);
-  cudaError_t e = P.reduce_out ? cudaSuccess : make_out_map(P, &map);
-  if (e != cudaSuccess) return e;
-  e = get_t4_table(P.k, &P.t4);
-  if (e != cudaSuccess) return e;
-  {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const char* env = getenv("NTHASH_B200_PREFETCH_CTAS");
-    P.prefetch_ctas = env ? (uint32_t)atoi(env) : (uint32_t)sms * 3; // one residency wave ahead
-  }
-  if (P.reduce_out) {
-    switch (P.h) {
-      case 1: return launch_fast_t<1, true>(P, map, st);
-      case 2: return launch_fast_t<2, true>(P, map, st);
-      default: return launch_fast_t<4, true>(P, map, st);
+  FastCfg c;
+  // defaults from profiles/sweeps/ (round 1): what matters most is resident warps per SM (small pieces win over
+  // long ones that cost occupancy), then CTA size (fewer prologues)
+  const bool box_shape = !P.g.item_byte && P.g.read_len <= env_u32("NTHASH_B200_FAST_WHOLE_READ", 400) &&
+                         ((uint64_t)P.g.nk * P.h) % 8 == 0 && !P.reduce_out;
+  c.ws = env_u32("NTHASH_B200_FAST_WS", box_shape ? 0 : 1);
+  c.nbuf = env_u32("NTHASH_B200_FAST_NBUF", 1);
+  c.nt = 128;
+  if (box_shape) { // largest CTA that still leaves >= 16 warps resident
+    const uint32_t tile_per_warp = c.nbuf * (uint32_t)(fast_ws_rt(P.h, c.ws) * P.h / 8) * 2048u;
+    for (uint32_t nt : { 256u, 192u, 128u, 96u }) {
+      const uint32_t smem = fast_smem_bytes(nt * P.g.read_len + 64, (nt / 32) * tile_per_warp) + 1024;
+      c.nt = nt;
+      if ((227u * 1024u / smem) * (nt / 32) >= 16) break;
     }
   }
+  c.nt = env_u32("NTHASH_B200_FAST_NT", c.nt);
+  if (c.nt < 32 || c.nt > 256 || c.nt % 32) return cudaErrorInvalidValue;
+  if (!P.g.item_byte) {
+    const uint64_t n_reads = P.g.n_items / P.g.segs;
+    const uint32_t whole = env_u32("NTHASH_B200_FAST_WHOLE_READ", 400), seg_t = env_u32("NTHASH_B200_FAST_SEG", 240);
+    if (P.g.read_len <= whole) {
+      P.g.seg = P.g.nk;
+      P.g.segs = 1;
+      P.tile_cap = c.nt * P.g.read_len + 64;
+    } else {
+      const uint32_t segs = (P.g.nk + seg_t - 1) / seg_t;
+      P.g.seg = (((P.g.nk + segs - 1) / segs) + 7u) & ~7u; // balanced items, 64-byte multiples of output
+      P.g.segs = (P.g.nk + P.g.seg - 1) / P.g.seg;
+      P.tile_cap = (uint32_t)((uint64_t)c.nt * P.g.seg + ((uint64_t)c.nt / P.g.segs + 2) * (P.k - 1) + 64);
+    }
+    P.g.n_items = n_reads * P.g.segs;
+    // warp-level 3-D tile stores need rows that are whole 64-byte blocks (then every row is 64-byte aligned too)
+    c.box = P.g.segs == 1 && ((uint64_t)P.g.nk * P.h) % 8 == 0 && !P.reduce_out && !getenv("NTHASH_B200_FAST_NO_BOX");
+  } else {
+    // the caller sized tile_cap for KMER_NT consecutive items
+    P.tile_cap = (uint32_t)(((uint64_t)P.tile_cap * c.nt + KMER_NT - 1) / KMER_NT) + 2 * P.k + 64;
+  }
+  cudaError_t e = get_t4_table(P.k, &P.t4);
+  if (e != cudaSuccess) return e;
   switch (P.h) {
-    case 1: return launch_fast_t<1, false>(P, map, st);
-    case 2: return launch_fast_t<2, false>(P, map, st);
-    default: return launch_fast_t<4, false>(P, map, st);
+    case 1: return launch_fast_h<1>(P, c, st);
+    case 2: return launch_fast_h<2>(P, c, st);
+    default: return launch_fast_h<4>(P, c, st);
   }
 }
 
