@@ -74,11 +74,6 @@ NTH_D uint64_t lds_u64(uint32_t a)
   asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
   return v;
 }
-// 1-D bulk copy shared -> global through the TMA engine (SASS: UBLKCP); 16-byte aligned, 16-byte multiple
-NTH_D void bulk_s2g(void* dst_gmem, uint32_t src_smem, uint32_t bytes)
-{
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem), "r"(bytes) : "memory");
-}
 NTH_D void tma_store_3d(const void* tmap, uint32_t saddr, int c0, int c1, int c2)
 {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap), "r"(c0),
@@ -209,19 +204,19 @@ __device__ __noinline__ void scrub_lane(const KmerParams& P, uint32_t lut, uint3
   }
 }
 
-// bytes of one lane's row buffer: WS windows x H u64, padded to an odd number of 16-byte chunks so that the
-// per-lane STS.128 of a quarter-warp fall into distinct bank groups
-__host__ __device__ constexpr uint32_t row_buf_bytes(int H, int WS) { return (uint32_t)(WS * H * 8 + (((WS * H / 2) & 1) ? 0 : 16)); }
+// General output path: one lane's shared-memory row = 256 bytes of hashes + 16 bytes of padding (an odd number of
+// 16-byte chunks, so the per-lane STS.128 of a quarter-warp fall into distinct bank groups)
+constexpr uint32_t ROW1_BYTES = 272;
 
 // REDUCE: fused consumer (the loop of the reference's examples/benchmark.cpp:34-39): instead of storing
 // the hashes, count the visited windows and accumulate the 64-bit sum and xor of all their hash values.
 //
-// Output path (REDUCE == false): every lane owns a private row buffer of WS windows in shared memory
-// (NBUF of them, used in turn); when it is full the lane itself pushes it to its row of `out` with one
-// 1-D bulk copy (cp.async.bulk.global.shared::cta -> UBLKCP): WS*H*8 contiguous bytes per store, which is
-// what the HBM write path wants (profiles/r01_microbench_tma_store_patterns.txt: 128-byte pieces 5.1-5.4 TB/s,
-// 320-byte pieces 6.2-6.5, 480-byte pieces 6.9).  Stores start on 32-byte (sector) boundaries: the first
-// (-row) mod (4/H) windows of an item and an odd last one go out as plain stores.
+// Output (REDUCE == false): hashes leave the SM as contiguous pieces of 192-256 bytes per row, which is what the
+// HBM write path wants (profiles/r01_microbench_tma_store_patterns_v2.txt: 128-byte pieces 5.1-5.4 TB/s, 192-byte
+// 5.6, 320-byte 6.3-7.0), staged through shared memory; pieces start on 32-byte (sector) boundaries: the first
+// (-row) mod (4/H) windows of an item go out as plain stores.  (A per-lane cp.async.bulk per piece was tried and
+// dropped: UBLKCP is a uniform-datapath instruction, so the compiler serialises it over the 32 lanes at ~12
+// instructions each; profiles/r01_sweep_kmer_fast_v5a_1d_bulk.txt.)
 //
 // BOX == true (uniform batches of whole-read items whose rows are multiples of 64 bytes): the 32 lanes of a warp
 // share one tile laid out [WS*H/8 blocks][32 rows][8 u64] under the 64-byte TMA swizzle (conflict-free STS.128),
@@ -504,18 +499,20 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     __syncwarp();
     if (dirty) scrub_lane<H>(P, lut, ps, my_out, n);
   } else {
-    constexpr uint32_t ROWB = row_buf_bytes(H, WS);
-    const uint32_t rb0 = rb_base + tid * ROWB; // buffer b of this lane: rb0 + b * NT * ROWB
-    uint32_t t = 0, b = 0;
-    while (p < n) {
-      const uint32_t cnt = min((uint32_t)WS, n - p);
-      const uint32_t rb = rb0 + b * (NT * ROWB);
+    // General output path (ragged batches, cut-up reads, rows that are not 64-byte multiples): every lane collects
+    // 256 bytes of its row (32/H windows) in a private shared-memory row, then the warp copies the 32 rows out
+    // with coalesced 16-byte stores, two rows per instruction (a half-warp per row).  Each row's global address
+    // and byte count travel through a 16-byte descriptor, so lanes may differ in length and alignment.
+    constexpr uint32_t WS1 = 32 / H;
+    const uint32_t wbase = rb_base + (tid & ~31u) * (ROW1_BYTES + 16); // this warp: [32 descriptors][32 rows]
+    const uint32_t desc0 = wbase, rows0 = wbase + 32 * 16;
+    const uint32_t rb = rows0 + lane * ROW1_BYTES;
+    const uint32_t hw = lane >> 4, c16 = (lane & 15) * 16;
+    while (__any_sync(0xffffffffu, p < n)) {
+      const uint32_t cnt = p < n ? min(WS1, n - p) : 0u;
       auto group = [&](uint32_t q, auto full, uint32_t c4n) {
         uint64_t hv[4];
         roll4(hv, full, c4n);
-        // buffer b was handed to the copy engine NBUF tiles ago: it must have been read out by now
-        // (waiting here, not at the top, hides the wait behind four rolls)
-        if (q == 0 && t >= (uint32_t)NBUF) bulk_wait_read<NBUF - 1>();
         if (H == 1) {
           st_shared_v2_u64(rb + (2 * q) * 16, hv[0], hv[1]);
           st_shared_v2_u64(rb + (2 * q + 1) * 16, hv[2], hv[3]);
@@ -530,33 +527,35 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
           }
         }
       };
-      if (cnt == (uint32_t)WS) {
+      if (cnt == WS1) {
 #pragma unroll
-        for (uint32_t q = 0; q < (uint32_t)WS / 4; ++q) group(q, full_t(), 4u);
+        for (uint32_t q = 0; q < WS1 / 4; ++q) group(q, full_t(), 4u);
       } else {
 #pragma unroll
-        for (uint32_t q = 0; q < (uint32_t)WS / 4; ++q) {
+        for (uint32_t q = 0; q < WS1 / 4; ++q) {
           if (4 * q + 4 <= cnt) group(q, full_t(), 4u);
           else if (4 * q < cnt) group(q, part_t(), cnt - 4 * q);
         }
       }
-      uint64_t* o = P.out + (my_out + p) * H;
-      const uint32_t bytes = (cnt * H * 8) & ~15u;
-      if (bytes) {
-        fence_proxy_async_smem();
-        bulk_s2g(o, rb, bytes);
+      st_shared_v2_u64(desc0 + lane * 16, (uint64_t)(uintptr_t)(P.out + (my_out + p) * H), (uint64_t)(cnt * H * 8));
+      __syncwarp();
+#pragma unroll 4
+      for (uint32_t rr = 0; rr < 16; ++rr) {
+        const uint32_t row = 2 * rr + hw;
+        const uint4 d = lds_v4(desc0 + row * 16); // {address lo, address hi, bytes, 0}
+        uint8_t* ga = reinterpret_cast<uint8_t*>(((uint64_t)d.y << 32) | d.x) + c16;
+        const uint32_t src = rows0 + row * ROW1_BYTES + c16;
+        if (c16 + 16 <= d.z) {
+          const uint4 v = lds_v4(src);
+          asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(ga), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        } else if (c16 + 8 == d.z) { // odd last u64 of an item (H == 1 only)
+          *reinterpret_cast<uint64_t*>(ga) = lds_u64(src);
+        }
       }
-      bulk_commit();
-      if (H == 1 && (cnt & 1)) o[cnt - 1] = lds_u64(rb + (cnt - 1) * 8); // odd last window of the item
+      __syncwarp(); // rows are rewritten next; also orders these stores before the scrub's zeros
       p += cnt;
-      ++t;
-      b = (b + 1 == (uint32_t)NBUF) ? 0 : b + 1;
     }
-
-    const bool dirty = bad != 0;
-    if (dirty) bulk_wait_all0(); // zeros must land after the bytes they overwrite
-    else bulk_wait_read0();      // shared memory must outlive the copy engine's reads
-    if (dirty) scrub_lane<H>(P, lut, ps, my_out, n);
+    if (bad != 0) scrub_lane<H>(P, lut, ps, my_out, n);
   }
 }
 
@@ -643,7 +642,7 @@ template<int H, bool REDUCE, int WS, int NBUF, bool BOX>
 cudaError_t launch_fast_t(const KmerParams& P, uint32_t nt, cudaStream_t st)
 {
   auto fn = kmer_fast_kernel<H, REDUCE, WS, NBUF, BOX>;
-  const uint32_t buf = BOX ? (nt / 32) * NBUF * (uint32_t)(WS * H / 8) * 2048u : nt * NBUF * row_buf_bytes(H, WS);
+  const uint32_t buf = BOX ? (nt / 32) * NBUF * (uint32_t)(WS * H / 8) * 2048u : nt * (ROW1_BYTES + 16);
   uint32_t smem_bytes = fast_smem_bytes(P.tile_cap, REDUCE ? 0u : buf);
   if (const char* e = getenv("NTHASH_B200_SMEM_PAD")) smem_bytes += (uint32_t)atoi(e); // experiments: lower the occupancy
   if (smem_bytes > 227u * 1024u) return cudaErrorInvalidConfiguration;
@@ -662,8 +661,7 @@ cudaError_t launch_fast_t(const KmerParams& P, uint32_t nt, cudaStream_t st)
 template<int H, int WS>
 cudaError_t launch_fast_nbuf(const KmerParams& P, const FastCfg& c, cudaStream_t st)
 {
-  if (c.box) return c.nbuf >= 2 ? launch_fast_t<H, false, WS, 2, true>(P, c.nt, st) : launch_fast_t<H, false, WS, 1, true>(P, c.nt, st);
-  return c.nbuf >= 2 ? launch_fast_t<H, false, WS, 2, false>(P, c.nt, st) : launch_fast_t<H, false, WS, 1, false>(P, c.nt, st);
+  return c.nbuf >= 2 ? launch_fast_t<H, false, WS, 2, true>(P, c.nt, st) : launch_fast_t<H, false, WS, 1, true>(P, c.nt, st);
 }
 
 // windows per store: index 0/1/2 = short / medium / long pieces (192-256 / 320-384 / 512 bytes per row)
@@ -681,7 +679,8 @@ int fast_ws_rt(uint32_t h, uint32_t idx)
 template<int H>
 cudaError_t launch_fast_h(const KmerParams& P, const FastCfg& c, cudaStream_t st)
 {
-  if (P.reduce_out) return launch_fast_t<H, true, fast_ws<H>(1), 1, false>(P, c.nt, st);
+  if (P.reduce_out) return launch_fast_t<H, true, fast_ws<H>(0), 1, false>(P, c.nt, st);
+  if (!c.box) return launch_fast_t<H, false, fast_ws<H>(0), 1, false>(P, c.nt, st); // WS / NBUF are unused there
   switch (c.ws) {
     case 0: return launch_fast_nbuf<H, fast_ws<H>(0)>(P, c, st);
     case 1: return launch_fast_nbuf<H, fast_ws<H>(1)>(P, c, st);
@@ -710,43 +709,48 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
 {
   KmerParams P = Pin;
   FastCfg c;
-  // defaults from profiles/sweeps/ (round 1): what matters most is resident warps per SM (small pieces win over
-  // long ones that cost occupancy), then CTA size (fewer prologues)
-  const bool box_shape = !P.g.item_byte && P.g.read_len <= env_u32("NTHASH_B200_FAST_WHOLE_READ", 400) &&
-                         ((uint64_t)P.g.nk * P.h) % 8 == 0 && !P.reduce_out;
-  c.ws = env_u32("NTHASH_B200_FAST_WS", box_shape ? 0 : 1);
+  c.box = false;
   c.nbuf = env_u32("NTHASH_B200_FAST_NBUF", 1);
-  c.nt = 128;
-  if (box_shape) { // largest CTA that still leaves >= 16 warps resident
-    const uint32_t tile_per_warp = c.nbuf * (uint32_t)(fast_ws_rt(P.h, c.ws) * P.h / 8) * 2048u;
-    for (uint32_t nt : { 256u, 192u, 128u, 96u }) {
-      const uint32_t smem = fast_smem_bytes(nt * P.g.read_len + 64, (nt / 32) * tile_per_warp) + 1024;
-      c.nt = nt;
-      if ((227u * 1024u / smem) * (nt / 32) >= 16) break;
+  c.ws = env_u32("NTHASH_B200_FAST_WS", 0);
+  const bool uniform = !P.g.item_byte;
+  if (uniform) {
+    KmerGeom& g = P.g;
+    const uint64_t n_reads = g.n_items / g.segs;
+    const uint32_t whole = env_u32("NTHASH_B200_FAST_WHOLE_READ", 400), seg_t = env_u32("NTHASH_B200_FAST_SEG", 240);
+    if (g.read_len <= whole) { // one item per read
+      g.seg = g.nk;
+      g.segs = 1;
+      // tensor stores need rows that are whole 64-byte blocks (then every row is 64-byte aligned too)
+      c.box = !P.reduce_out && ((uint64_t)g.nk * P.h) % 8 == 0 && !getenv("NTHASH_B200_FAST_NO_BOX");
+    } else {
+      // balanced items, the last one shorter.  seg = 4 (mod 8): an odd number of 32-bit words between the rows of
+      // neighbouring lanes keeps their LDS.32 on distinct banks (seg = 256 ran 1.7x slower than 244), and a
+      // multiple of 4 windows keeps every item's output on a 32-byte boundary when the read's is.
+      const uint32_t segs = (g.nk + seg_t - 1) / seg_t, x = (g.nk + segs - 1) / segs;
+      g.seg = (x & ~7u) + ((x & 7u) <= 4 ? 4u : 12u);
+      g.segs = (g.nk + g.seg - 1) / g.seg;
     }
+    g.n_items = n_reads * g.segs;
+  }
+  auto tile_cap_for = [&](uint32_t nt) -> uint32_t {
+    if (!uniform) return (uint32_t)(((uint64_t)Pin.tile_cap * nt + KMER_NT - 1) / KMER_NT) + 2 * P.k + 64; // sized for KMER_NT items
+    if (P.g.segs == 1) return nt * P.g.read_len + 64;
+    return (uint32_t)((uint64_t)nt * P.g.seg + ((uint64_t)nt / P.g.segs + 2) * (P.k - 1) + 64);
+  };
+  // defaults from profiles/sweeps/ (round 1): what matters most is resident warps per SM (small pieces win over
+  // long ones that cost occupancy), then CTA size (fewer prologues): the largest CTA that leaves >= 16 warps resident
+  const uint32_t buf_per_warp = P.reduce_out ? 0u
+                                : c.box    ? c.nbuf * (uint32_t)(fast_ws_rt(P.h, c.ws) * P.h / 8) * 2048u
+                                           : 32u * (ROW1_BYTES + 16);
+  c.nt = 96;
+  for (uint32_t nt : { 256u, 192u, 128u, 96u }) {
+    const uint32_t smem = fast_smem_bytes(tile_cap_for(nt), (nt / 32) * buf_per_warp) + 1024;
+    c.nt = nt;
+    if (smem <= 227u * 1024u && (227u * 1024u / smem) * (nt / 32) >= 16) break;
   }
   c.nt = env_u32("NTHASH_B200_FAST_NT", c.nt);
   if (c.nt < 32 || c.nt > 256 || c.nt % 32) return cudaErrorInvalidValue;
-  if (!P.g.item_byte) {
-    const uint64_t n_reads = P.g.n_items / P.g.segs;
-    const uint32_t whole = env_u32("NTHASH_B200_FAST_WHOLE_READ", 400), seg_t = env_u32("NTHASH_B200_FAST_SEG", 240);
-    if (P.g.read_len <= whole) {
-      P.g.seg = P.g.nk;
-      P.g.segs = 1;
-      P.tile_cap = c.nt * P.g.read_len + 64;
-    } else {
-      const uint32_t segs = (P.g.nk + seg_t - 1) / seg_t;
-      P.g.seg = (((P.g.nk + segs - 1) / segs) + 7u) & ~7u; // balanced items, 64-byte multiples of output
-      P.g.segs = (P.g.nk + P.g.seg - 1) / P.g.seg;
-      P.tile_cap = (uint32_t)((uint64_t)c.nt * P.g.seg + ((uint64_t)c.nt / P.g.segs + 2) * (P.k - 1) + 64);
-    }
-    P.g.n_items = n_reads * P.g.segs;
-    // warp-level 3-D tile stores need rows that are whole 64-byte blocks (then every row is 64-byte aligned too)
-    c.box = P.g.segs == 1 && ((uint64_t)P.g.nk * P.h) % 8 == 0 && !P.reduce_out && !getenv("NTHASH_B200_FAST_NO_BOX");
-  } else {
-    // the caller sized tile_cap for KMER_NT consecutive items
-    P.tile_cap = (uint32_t)(((uint64_t)P.tile_cap * c.nt + KMER_NT - 1) / KMER_NT) + 2 * P.k + 64;
-  }
+  P.tile_cap = tile_cap_for(c.nt);
   cudaError_t e = get_t4_table(P.k, &P.t4);
   if (e != cudaSuccess) return e;
   switch (P.h) {

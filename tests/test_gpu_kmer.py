@@ -86,6 +86,43 @@ def test_uniform_batches(read_len, k, h):
     assert_batch_equal(res, ORACLE.kmer_batch(bases, off, k, h, threads=8), h, check_strands=(h == 1))
 
 
+FAST_SHAPES = [
+    # (reads, read_len, k, h)           output path the launch picks (csrc/kmer_fast_kernel.cu)
+    (3000, 150, 31, 1), (1000, 150, 31, 2), (1000, 150, 31, 4),   # 3-D tensor stores, one item per read
+    (33, 150, 31, 1), (1, 150, 31, 1), (257, 102, 31, 1),         # partly filled warps / CTAs
+    (2000, 149, 31, 1), (2000, 152, 31, 1), (700, 151, 31, 2),    # rows not 64-byte multiples: per-lane bulk stores + peel
+    (300, 1000, 31, 1), (300, 1000, 31, 4), (200, 1230, 31, 2),   # cut-up reads, 4-D tensor stores (overlapping / exact last item)
+    (301, 401, 31, 2), (60, 5003, 32, 1), (9, 50000, 63, 1),      # two items per read; 21 items; configs[4] shape
+    (150, 1001, 31, 1), (64, 3001, 21, 1),                        # odd row length: cut-up reads through per-lane stores
+]
+
+
+@pytest.mark.parametrize("n,read_len,k,h", FAST_SHAPES)
+@pytest.mark.parametrize("no_box", [False, True])
+def test_fast_kernel_output_paths(n, read_len, k, h, no_box, monkeypatch):
+    """Uniform batches without strand outputs take kmer_fast_kernel; every output path must match the oracle,
+    including rows the reference skips (non-ACGTU bytes) and rows written twice by overlapping items."""
+    if no_box:
+        monkeypatch.setenv("NTHASH_B200_FAST_NO_BOX", "1")
+    rng = np.random.default_rng(n * 131 + read_len * 7 + k + h)
+    bases = synth(rng, n * read_len, p_bad=0.0004, lower=0.05)
+    bases[-1] = ord("N")                      # the very last window is one the reference skips
+    if read_len > 400:
+        bases[read_len - k - 3] = ord("n")    # inside the overlap of the last two items of read 0
+    d_b, _keep = to_dev(bases)
+    res = nthash_b200.kmer_hashes_uniform(d_b, n, read_len, k, h)
+    torch.cuda.synchronize()
+    off = np.arange(n + 1, dtype=np.uint64) * read_len
+    assert_batch_equal(res, ORACLE.kmer_batch(bases, off, k, h, threads=8), h)
+    for ws, nt, nbuf in ((1, 96, 2), (2, 160, 1)):   # the other launch knobs (sweeps use them)
+        monkeypatch.setenv("NTHASH_B200_FAST_WS", str(ws))
+        monkeypatch.setenv("NTHASH_B200_FAST_NT", str(nt))
+        monkeypatch.setenv("NTHASH_B200_FAST_NBUF", str(nbuf))
+        res2 = nthash_b200.kmer_hashes_uniform(d_b, n, read_len, k, h)
+        torch.cuda.synchronize()
+        assert torch.equal(res2.out, res.out) and torch.equal(res2.valid_bits, res.valid_bits)
+
+
 def test_ragged_long_reads_use_item_table():
     rng = np.random.default_rng(5)
     lens = [70000, 10, 30000, 62, 63, 64, 12345, 0, 999]
