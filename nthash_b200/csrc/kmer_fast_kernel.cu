@@ -18,6 +18,7 @@
 //    (UTMASTG): the output leaves the SM as full 128-byte row segments (7.2 TB/s pattern).
 #include "kmer_common.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <cuda.h>
@@ -68,12 +69,6 @@ NTH_D uint4 lds_v4(uint32_t a)
   return v;
 }
 
-NTH_D uint64_t lds_u64(uint32_t a)
-{
-  uint64_t v;
-  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
-  return v;
-}
 NTH_D void tma_store_3d(const void* tmap, uint32_t saddr, int c0, int c1, int c2)
 {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap), "r"(c0),
@@ -264,6 +259,13 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     mbar_expect_tx(bar, bulk_bytes + T4_BYTES);
     if (bulk_bytes) bulk_g2s(tile + F_TILE_PAD, P.bases + g0, bulk_bytes, bar);
     bulk_g2s(smem + (rb_base - sbase), P.t4, T4_BYTES, bar);
+    // pull the bases of the CTA that will take this SM slot next into L2 (same extent, one residency wave ahead),
+    // so that its start-up wait is an L2 hit instead of a DRAM read queued behind the output stream
+    if (P.prefetch_ctas) {
+      const uint64_t nxt = g0 + (uint64_t)P.prefetch_ctas * ((g1 - g0) & ~15ull);
+      const uint64_t len = (g1 - g0 + 15) & ~15ull;
+      if (len && nxt + len <= (P.n_bases & ~15ull)) bulk_prefetch_l2(P.bases + nxt, (uint32_t)len);
+    }
   }
   {
     // code (byte >> 1) & 3 : 0 = A, 1 = C, 2 = T/U, 3 = G ; complement = code ^ 2
@@ -539,17 +541,23 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
       }
       st_shared_v2_u64(desc0 + lane * 16, (uint64_t)(uintptr_t)(P.out + (my_out + p) * H), (uint64_t)(cnt * H * 8));
       __syncwarp();
-#pragma unroll 4
-      for (uint32_t rr = 0; rr < 16; ++rr) {
-        const uint32_t row = 2 * rr + hw;
-        const uint4 d = lds_v4(desc0 + row * 16); // {address lo, address hi, bytes, 0}
-        uint8_t* ga = reinterpret_cast<uint8_t*>(((uint64_t)d.y << 32) | d.x) + c16;
-        const uint32_t src = rows0 + row * ROW1_BYTES + c16;
-        if (c16 + 16 <= d.z) {
-          const uint4 v = lds_v4(src);
-          asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(ga), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-        } else if (c16 + 8 == d.z) { // odd last u64 of an item (H == 1 only)
-          *reinterpret_cast<uint64_t*>(ga) = lds_u64(src);
+      // all loads of a batch of rows first (they do not depend on each other), then the stores
+#pragma unroll
+      for (uint32_t r0 = 0; r0 < 16; r0 += 8) {
+        uint4 d[8], v[8];
+#pragma unroll
+        for (uint32_t rr = 0; rr < 8; ++rr) {
+          const uint32_t row = 2 * (r0 + rr) + hw;
+          d[rr] = lds_v4(desc0 + row * 16); // {address lo, address hi, bytes, 0}
+          v[rr] = lds_v4(rows0 + row * ROW1_BYTES + c16);
+        }
+#pragma unroll
+        for (uint32_t rr = 0; rr < 8; ++rr) {
+          uint8_t* ga = reinterpret_cast<uint8_t*>(((uint64_t)d[rr].y << 32) | d[rr].x) + c16;
+          if (c16 + 16 <= d[rr].z)
+            asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(ga), "r"(v[rr].x), "r"(v[rr].y), "r"(v[rr].z), "r"(v[rr].w) : "memory");
+          else if (c16 + 8 == d[rr].z) // odd last u64 of an item (H == 1 only)
+            asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(ga), "r"(v[rr].x), "r"(v[rr].y) : "memory");
         }
       }
       __syncwarp(); // rows are rewritten next; also orders these stores before the scrub's zeros
@@ -753,6 +761,16 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
   P.tile_cap = tile_cap_for(c.nt);
   cudaError_t e = get_t4_table(P.k, &P.t4);
   if (e != cudaSuccess) return e;
+  {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t smem = fast_smem_bytes(P.tile_cap, (c.nt / 32) * buf_per_warp) + 1024;
+    const uint32_t resident = std::max(1u, 227u * 1024u / smem) * (uint32_t)sms;
+    // measured (profiles/r01_prefetch_sweep.txt): the prefetch costs 1-10 % on every config, so it stays off
+    P.prefetch_ctas = env_u32("NTHASH_B200_PREFETCH_CTAS", 0);
+    if (P.prefetch_ctas == 1) P.prefetch_ctas = resident;
+  }
   switch (P.h) {
     case 1: return launch_fast_h<1>(P, c, st);
     case 2: return launch_fast_h<2>(P, c, st);
