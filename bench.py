@@ -61,25 +61,62 @@ def load_peak():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons during the timed region: NVML every 2 ms (nvidia_ml_py), or
+    `nvidia-smi` every 100 ms when NVML cannot be loaded."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.sm, self.mx, self.reasons, self._stop, self._t, self.source = index, [], [], set(), threading.Event(), None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # torch's device index follows CUDA_VISIBLE_DEVICES; NVML's does not
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nv = pynvml
+            self.source = "nvml"
+        except Exception:
+            self._nv = None
+            self.source = "nvidia-smi"
 
-    def _run(self):
+    def _poll_nvml(self):
+        nv = self._nv
+        bits = [(getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_slowdown"),
+                (getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40), "hw_thermal_slowdown"),
+                (getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_thermal_slowdown"),
+                (getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4), "sw_power_cap")]
+        try:
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        except Exception:
+            pass
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                r = get_reasons(self._h)
+                self.reasons.update(name for bit, name in bits if r & bit)
+            except Exception:
+                pass
+            self._stop.wait(0.002)
+
+    def _poll_smi(self):
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                r = [x.strip() for x in out.split(",")]
+                if len(r) >= 7:
+                    self.sm.append(float(r[0]))
+                    self.mx.append(float(r[1]))
+                    self.reasons.update(self.NAMES[i] for i in range(4) if r[3 + i].lower().startswith("active"))
             except Exception:
                 pass
             self._stop.wait(0.1)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t = threading.Thread(target=self._poll_nvml if self._nv else self._poll_smi, daemon=True)
         self._t.start()
         return self
 
@@ -88,12 +125,8 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
 def synth_reads_device(torch, n_bases, seed):
@@ -337,7 +370,7 @@ def main():
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (load_traffic(args.config) or {}).get("dram_bytes_per_launch") if not args.reads else None,
-                     "traffic_source": (load_traffic(args.config) or {}).get("source"), "peak_source": peak_src, "kernel": ("seed_kernel" if seeds else "kmer_fast_kernel<%d>" % h), "kernel_ms": kernel_ms,
+                     "traffic_source": (load_traffic(args.config) or {}).get("source"), "peak_source": peak_src, "kernel": ("seed_jit_kernel (NVRTC-specialised)" if seeds else "kmer_fast_kernel<H=%d>" % h), "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_launch": abytes},
         "cpu_baseline": cpu, "fused_consumer": consumer,
     }
