@@ -22,6 +22,7 @@
 #include <cstring>
 #include <cuda.h>
 #include <dlfcn.h>
+#include <mutex>
 #include <nvrtc.h>
 #include <sstream>
 
@@ -81,6 +82,10 @@ DI void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
 DI void tma_store_2d(const void* tmap, uint32_t saddr, int c0, int c1)
 {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(saddr) : "memory");
+}
+DI void tma_store_3d(const void* tmap, uint32_t saddr, int c0, int c1, int c2)
+{
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(saddr) : "memory");
 }
 DI void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 DI void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -189,6 +194,7 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
   const uint32_t tb = sbase;                                 // group tables: two conflict-free 128-byte halves each
   const uint32_t ot0 = ((tile + 16 + P.tile_cap + 16 + 1023u) & ~1023u) + warp * (NBUF * OT_BYTES);
   const int row0 = (int)(i0 + warp * 32);
+  const uint32_t lterm = lane * 64 + (((lane >> 1) & 3) << 4); // box3: row inside a block + its 64-byte-swizzle term
 
   // warm-up: shift bases -OLDER .. k-2 into the code window (the bases before the item only serve strided blocks,
   // where they cancel); roll the full-window hash over bases -1 .. k-2 (in-only)
@@ -298,12 +304,17 @@ struct SeedJit
   cudaKernel_t kernel = nullptr;
   uint8_t* d_tables = nullptr;
   uint32_t table_bytes = 0, tw = 0, row_bytes = 0, ot_bytes = 0, ht = 0, nt = 256, nbuf = 1;
+  bool box3 = false;            // output through 3-D tensor stores of 64-byte blocks (rows must be 64-byte multiples)
+  const SeedPlanHost* plan = nullptr;
+  mutable SeedJit* alt = nullptr; // the 2-D tile variant for other row lengths, compiled on first use
+  mutable std::mutex mu;
   std::string source; // kept for inspection (nthash_seed_plan_jit_source)
 };
 
 void seed_jit_destroy(SeedJit* j)
 {
   if (!j) return;
+  seed_jit_destroy(j->alt);
   if (j->lib) cudaLibraryUnload(j->lib);
   cudaFree(j->d_tables);
   delete j;
@@ -313,7 +324,14 @@ const char* seed_jit_source(const SeedJit* j) { return j ? j->source.c_str() : "
 
 // Generates, compiles and loads the kernel for one seed set.  Returns nullptr (with a reason) when the
 // specialised path does not apply; the caller then uses the generic kernel.
+static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& why, bool load, bool box3);
+
 SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
+{
+  return seed_jit_build_variant(plan, why, load, !getenv("NTHASH_B200_SEED_JIT_NO_BOX"));
+}
+
+static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& why, bool load, bool box3)
 {
   const uint32_t k = plan.k, m = plan.n_seeds, hps = plan.h, ht = m * hps;
   if (k > 128) { why = "k > 128"; return nullptr; }
@@ -428,20 +446,30 @@ SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
   const uint32_t table_bytes = (uint32_t)((tab.size() + 15) & ~size_t(15));
   tab.resize(table_bytes, 0);
 
-  // ---- output tile geometry: TW windows per tile row; prefer an odd number of 16-byte chunks per row ----
+  // ---- output tile geometry: TW windows per tile row ----
+  //  box3: rows of whole 64-byte blocks ([blocks][32 rows][8 u64] under the TMA 64-byte swizzle), 192-256 bytes preferred
+  //        (the k-mer kernel's finding: longer pieces cost more occupancy than they gain on the write path);
+  //  else: one dense [32 rows][TW*HT u64] tile, an odd number of 16-byte chunks per row preferred (conflict-free STS.128)
   uint32_t tw = 0, best = 0;
-  for (uint32_t t = 1; t <= 16; ++t) {
+  for (uint32_t t = 1; t <= 32; ++t) {
     const uint32_t rb = t * ht * 8;
-    if (rb % 16 || rb > 512 || t * ht > 256) continue;
-    const uint32_t score = ((rb / 16) % 2 ? 1000 : 0) + (rb <= 256 ? rb : 512 - rb); // long rows write better (DRAM), up to ~256 B
+    if (rb > 512 || t * ht > 256) continue;
+    uint32_t score;
+    if (box3) {
+      if (rb % 64) continue;
+      score = 1000 - (rb >= 192 ? rb - 192 : 2 * (192 - rb));
+    } else {
+      if (rb % 16) continue;
+      score = ((rb / 16) % 2 ? 1000 : 0) + (rb <= 256 ? rb : 512 - rb); // long rows write better (DRAM), up to ~256 B
+    }
     if (score > best) { best = score; tw = t; }
   }
   if (const char* e = getenv("NTHASH_B200_SEED_JIT_TW")) { // experiments
     const uint32_t t = (uint32_t)atoi(e);
-    if (t >= 1 && (t * ht * 8) % 16 == 0 && t * ht <= 256) tw = t;
+    if (t >= 1 && (t * ht * 8) % (box3 ? 64 : 16) == 0 && t * ht <= 256) tw = t;
   }
   if (!tw) { why = "no tile row shape for this number of hashes"; return nullptr; }
-  const uint32_t row_bytes = tw * ht * 8, ot_bytes = (32 * row_bytes + 127) & ~127u;
+  const uint32_t row_bytes = tw * ht * 8, ot_bytes = box3 ? (row_bytes / 64) * 2048u : (32 * row_bytes + 127) & ~127u;
   uint32_t unroll = tw; // windows per generated loop body: a multiple of the tile and of every block stride
   {
     uint32_t a = unroll, b2 = lcm_d;
@@ -450,10 +478,11 @@ SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
   }
   if (unroll > 24) { why = "strided blocks with incompatible strides"; return nullptr; }
   // CTA size / output buffering: defaults found on C4 (profiles/r01_seed_jit_sweeps.txt), overridable for experiments
-  uint32_t nt = 256, nbuf = 1;
+  // (box3: 128 threads and two 6 KB tiles per warp = 0.82 of the HBM peak on C4; one tile 0.76; 2-D tiles 0.63)
+  uint32_t nt = box3 ? 128 : 256, nbuf = box3 ? 2 : 1;
   if (const char* e = getenv("NTHASH_B200_SEED_JIT_NT")) nt = (uint32_t)atoi(e);
   if (const char* e = getenv("NTHASH_B200_SEED_JIT_NBUF")) nbuf = (uint32_t)atoi(e);
-  if (nt < 32 || nt > 1024 || nt % 32 || nbuf < 1 || nbuf > 2) { why = "bad NT/NBUF override"; return nullptr; }
+  if (nt < 32 || nt > 1024 || nt % 32 || nbuf < 1 || nbuf > 4) { why = "bad NT/NBUF override"; return nullptr; }
 
   // ---- the per-window body, one text per position u in the unrolled loop (block phases are static there) ----
   auto window_body = [&](uint32_t u) {
@@ -515,24 +544,39 @@ SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
         << "u) & 0x18u); const uint2 ef = lds_v2(sbase + PAIRF_OFF + po), er = lds_v2(sbase + PAIRR_OFF + po);"
            " roll_step(full, make_uint4(ef.x, ef.y, er.x, er.y)); }";
   src << "\n#define WIN_PRE(P) const uint32_t c = lds_u8(ps + (K - 1) + (P)); bad |= lds_u8(lut + c); FULL_ROLL SHIFT_IN(c >> 1)\n";
-  src << "#define STORE_WINDOW(addr) {";
-  if (ht % 2 == 0)
-    for (uint32_t q = 0; q < ht; q += 2) src << " sts_v2((addr) + " << q * 8 << "u, hv[" << q << "], hv[" << q + 1 << "]);";
-  else
-    for (uint32_t q = 0; q < ht; ++q) src << " sts_u64((addr) + " << q * 8 << "u, hv[" << q << "]);";
-  src << " }\n";
+  // STORE_WINDOW_i(base): window i of the tile row -> shared memory
+  for (uint32_t i = 0; i < tw; ++i) {
+    src << "#define STORE_WINDOW_" << i << "(base) {";
+    for (uint32_t q = 0; q < ht;) {
+      const uint32_t col = i * ht + q;           // u64 column inside the tile row
+      const bool two = col % 2 == 0 && q + 1 < ht; // a whole 16-byte chunk
+      std::ostringstream addr;
+      if (box3) { // block col/8 of the lane's row; 16-byte chunk (col/2)&3 XOR-swizzled with the lane term folded into `base`
+        addr << "((base) ^ " << (((col / 2) & 3u) << 4) << "u) + " << (col / 8) * 2048u + (col & 1u) * 8u << "u";
+      } else {
+        addr << "(base) + " << col * 8 << "u";
+      }
+      if (two) src << " sts_v2(" << addr.str() << ", hv[" << q << "], hv[" << q + 1 << "]);";
+      else src << " sts_u64(" << addr.str() << ", hv[" << q << "]);";
+      q += two ? 2 : 1;
+    }
+    src << " }\n";
+  }
   src << "#define MAIN_TILES \\\n";
   for (uint32_t t = 0; t < unroll / tw; ++t) {
-    src << "    if (p0 + " << t * tw << "u < n) { \\\n      const uint32_t ot = ot0 + buf * OT_BYTES, rowaddr = ot + lane * ROW_BYTES; \\\n";
+    src << "    if (p0 + " << t * tw << "u < n) { \\\n      const uint32_t ot = ot0 + buf * OT_BYTES, rowaddr = ot + "
+        << (box3 ? "lterm" : "lane * ROW_BYTES") << "; \\\n";
     for (uint32_t i = 0; i < tw; ++i) {
       const uint32_t u = t * tw + i;
       src << "      if (p0 + " << u << "u < n) { \\\n        WIN_PRE(p0 + " << u << "u) \\\n        uint64_t hv[HT]; \\\n" << window_body(u);
       if (i == 0) // this buffer's previous tile must have left shared memory; waiting only now hides the TMA read behind one window
         src << "        if (p0 + " << t * tw << "u >= NBUF * TW) { if (lane == 0) BULK_WAIT_READ __syncwarp(); } \\\n";
-      src << "        STORE_WINDOW(rowaddr + " << i * ht * 8 << "u) \\\n      } \\\n";
+      src << "        STORE_WINDOW_" << i << "(rowaddr) \\\n      } \\\n";
     }
-    src << "      fence_proxy_async_smem(); __syncwarp(); \\\n      if (lane == 0) { tma_store_2d(&omap, ot, (int)((p0 + " << t * tw
-        << "u) * HT), row0); bulk_commit(); } \\\n      buf = buf + 1 == NBUF ? 0 : buf + 1; \\\n    } \\\n";
+    src << "      fence_proxy_async_smem(); __syncwarp(); \\\n      if (lane == 0) { ";
+    if (box3) src << "tma_store_3d(&omap, ot, 0, row0, (int)((p0 + " << t * tw << "u) * HT / 8u));";
+    else src << "tma_store_2d(&omap, ot, (int)((p0 + " << t * tw << "u) * HT), row0);";
+    src << " bulk_commit(); } \\\n      buf = buf + 1 == NBUF ? 0 : buf + 1; \\\n    } \\\n";
   }
   src << "\n";
   src << JIT_KERNEL;
@@ -548,6 +592,8 @@ SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
   j->ht = ht;
   j->nt = nt;
   j->nbuf = nbuf;
+  j->box3 = box3;
+  j->plan = &plan;
   nvrtcProgram prog = nullptr;
   if (rt.create(&prog, j->source.c_str(), "seed_jit_kernel.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
     why = "nvrtcCreateProgram failed";
@@ -602,17 +648,34 @@ static uint32_t seed_jit_tile_cap(const SeedJit* j, const KmerGeom& g, uint32_t 
   return b > 0xffffffffull ? 0xffffffffu : (uint32_t)b;
 }
 
-// Uniform batches whose items are all full and whose rows are 16-byte multiples.
-bool seed_jit_applies(const SeedJit* j, const SeedParams& P)
+// The variant of the compiled kernel that fits the geometry: the 3-D box stores need rows of whole 64-byte blocks;
+// other (even) row lengths take the 2-D tile variant, compiled on first use.
+static const SeedJit* seed_jit_variant(const SeedJit* j, const KmerGeom& g)
 {
-  const KmerGeom& g = P.g;
-  return j && !g.item_byte && !P.out_fwd && g.seg && g.nk % g.seg == 0 && ((uint64_t)g.seg * j->ht) % 2 == 0 &&
-         g.n_items > 0 && g.n_items < 0x7fffffffull && ((uintptr_t)P.out & 15) == 0 &&
-         seed_jit_smem_bytes(j, seed_jit_tile_cap(j, g, P.k)) <= 227u * 1024u;
+  if (!j || !j->box3 || ((uint64_t)g.seg * j->ht) % 8 == 0) return j;
+  std::lock_guard<std::mutex> lock(j->mu);
+  if (!j->alt) {
+    std::string why;
+    j->alt = seed_jit_build_variant(*j->plan, why, true, false);
+  }
+  return j->alt;
 }
 
-cudaError_t launch_seed_jit(const SeedJit* j, const SeedParams& P, cudaStream_t st)
+// Uniform batches whose items are all full and whose rows are 16-byte multiples.
+bool seed_jit_applies(const SeedJit* j0, const SeedParams& P)
 {
+  const KmerGeom& g = P.g;
+  if (!j0 || g.item_byte || P.out_fwd || !g.seg || g.nk % g.seg || ((uint64_t)g.seg * j0->ht) % 2 || !g.n_items ||
+      g.n_items >= 0x7fffffffull || ((uintptr_t)P.out & 15))
+    return false;
+  const SeedJit* j = seed_jit_variant(j0, g);
+  return j && seed_jit_smem_bytes(j, seed_jit_tile_cap(j, g, P.k)) <= 227u * 1024u;
+}
+
+cudaError_t launch_seed_jit(const SeedJit* j0, const SeedParams& P, cudaStream_t st)
+{
+  const SeedJit* j = seed_jit_variant(j0, P.g);
+  if (!j) return cudaErrorNotSupported;
   using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -626,13 +689,24 @@ cudaError_t launch_seed_jit(const SeedJit* j, const SeedParams& P, cudaStream_t 
     encode = (EncodeFn)fp;
   }
   CUtensorMap map;
-  const cuuint64_t dims[2] = { (cuuint64_t)P.g.seg * j->ht, P.g.n_items };
-  const cuuint64_t strides[1] = { (cuuint64_t)P.g.seg * j->ht * 8 };
-  const cuuint32_t box[2] = { j->tw * j->ht, 32 };
-  const cuuint32_t estr[2] = { 1, 1 };
-  if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, P.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return cudaErrorInvalidValue;
+  const uint64_t row_u64 = (uint64_t)P.g.seg * j->ht;
+  CUresult cr;
+  if (j->box3) { // [row blocks][items][8 u64], boxes of (row_bytes / 64) x 32 x 8 under the 64-byte swizzle
+    const cuuint64_t dims[3] = { 8, P.g.n_items, row_u64 / 8 };
+    const cuuint64_t strides[2] = { row_u64 * 8, 64 };
+    const cuuint32_t box[3] = { 8, 32, j->row_bytes / 64 };
+    const cuuint32_t estr[3] = { 1, 1, 1 };
+    cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, P.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t dims[2] = { row_u64, P.g.n_items };
+    const cuuint64_t strides[1] = { row_u64 * 8 };
+    const cuuint32_t box[2] = { j->tw * j->ht, 32 };
+    const cuuint32_t estr[2] = { 1, 1 };
+    cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, P.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
   JitParams jp;
   jp.bases = P.bases;
   jp.n_bases = P.n_bases;
