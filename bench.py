@@ -115,6 +115,14 @@ class ClockSampler:
                 pass
             self._stop.wait(0.1)
 
+    def sample_now(self):
+        """One sample from the calling thread (work is queued on the GPU at this point)."""
+        if self._nv:
+            try:
+                self.sm.append(float(self._nv.nvmlDeviceGetClockInfo(self._h, self._nv.NVML_CLOCK_SM)))
+            except Exception:
+                pass
+
     def __enter__(self):
         self._t = threading.Thread(target=self._poll_nvml if self._nv else self._poll_smi, daemon=True)
         self._t.start()
@@ -238,25 +246,28 @@ def main():
     # ---- device-resident throughput (value) -------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         step()
+    torch.cuda.synchronize()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:  # clocks are sampled (NVML, ~5 ms per sample) over both timed loops below
         ev0.record()
         for _ in range(args.steps):
             step()
         ev1.record()
+        clk.sample_now()
         torch.cuda.synchronize()
-    barrier()
-    ms = ev0.elapsed_time(ev1) / args.steps
-    # ---- dominant kernel alone (roofline): same launch without the bitmap memset ------------
-    step(False)
-    torch.cuda.synchronize()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for _ in range(args.steps):
+        barrier()
+        # ---- dominant kernel alone (roofline): same launch without the bitmap memset ----
         step(False)
-    k1.record()
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        k0.record()
+        for _ in range(args.steps):
+            step(False)
+        k1.record()
+        clk.sample_now()
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
     kernel_ms = k0.elapsed_time(k1) / args.steps
     ms, kernel_ms = nd.max_over_ranks([ms, kernel_ms])
 

@@ -478,8 +478,8 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
   }
   if (unroll > 24) { why = "strided blocks with incompatible strides"; return nullptr; }
   // CTA size / output buffering: defaults found on C4 (profiles/r01_seed_jit_sweeps.txt), overridable for experiments
-  // (box3: 128 threads and two 6 KB tiles per warp = 0.82 of the HBM peak on C4; one tile 0.76; 2-D tiles 0.63)
-  uint32_t nt = box3 ? 128 : 256, nbuf = box3 ? 2 : 1;
+  // (box3 on C4: 128 threads with three 6 KB tiles per warp 0.89 of the HBM peak, two 0.85, one 0.76; 2-D tiles 0.63)
+  uint32_t nt = box3 ? 128 : 256, nbuf = box3 ? 3 : 1;
   if (const char* e = getenv("NTHASH_B200_SEED_JIT_NT")) nt = (uint32_t)atoi(e);
   if (const char* e = getenv("NTHASH_B200_SEED_JIT_NBUF")) nbuf = (uint32_t)atoi(e);
   if (nt < 32 || nt > 1024 || nt % 32 || nbuf < 1 || nbuf > 4) { why = "bad NT/NBUF override"; return nullptr; }
