@@ -344,6 +344,30 @@ def main():
                             "h2d_bytes_per_step": int(h_bases.numel() + h_off.numel() * 8), "d2h_bytes_per_step": 24},
                     "windows": int(red[0]), "sum": int(red[1]) & (2**64 - 1)}
 
+        # second fused consumer: Bloom filter insert / query (the caller nthash.hpp:14-17 names), 3 hashes per
+        # k-mer into a 1 GiB (2^33 bit) device-resident filter; bound by random 32-byte atomics, not by streaming
+        try:
+            bits = 1 << 33
+            filt = nthash_b200.bloom_filter(bits)
+            b0, b1, b2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            nthash_b200.kmer_bloom_uniform(bases, min(n_reads, 100_000), L, k, 3, filt, bits)  # warm-up
+            filt.zero_()
+            torch.cuda.synchronize()
+            b0.record()
+            ins = nthash_b200.kmer_bloom_uniform(bases, n_reads, L, k, 3, filt, bits)
+            b1.record()
+            qry = nthash_b200.kmer_bloom_uniform(bases, n_reads, L, k, 3, filt, bits, query=True)
+            b2.record()
+            torch.cuda.synchronize()
+            ins_ms, qry_ms = nd.max_over_ranks([b0.elapsed_time(b1), b1.elapsed_time(b2)])
+            consumer["bloom"] = {"filter_bits": bits, "hashes_per_kmer": 3,
+                                 "insert": {"value": world * rows / (ins_ms * 1e-3), "unit": UNIT, "ms_per_step": ins_ms},
+                                 "query": {"value": world * rows / (qry_ms * 1e-3), "unit": UNIT, "ms_per_step": qry_ms},
+                                 "windows": int(ins[0]), "query_hits": int(qry[1])}
+            del filt
+        except Exception as e:  # the filter did not fit next to the batch
+            consumer["bloom"] = {"skipped": str(e)[:80]}
+
     if rank != 0:
         nd.finalize()
         return

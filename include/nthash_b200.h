@@ -108,6 +108,24 @@ int nthash_kmer_reduce_dev(const uint8_t* d_bases, uint64_t n_bases_readable, co
 int nthash_kmer_reduce(const char* bases, const uint64_t* read_off, uint64_t n_reads, uint32_t k,
                        uint32_t num_hashes, uint64_t* result, int device);
 
+/* ---- fused consumer: Bloom filter (the caller the reference's header names, nthash.hpp:14-17: k-mer
+ * hashes feeding Bloom filters) ------------------------------------------------------------------
+ * For every window the reference's `while (h.roll())` loop visits, the num_hashes values of h.hashes()
+ * (any 1..255, extend_hashes src/internal.hpp:104-118) address bits `hash % filter_bits` of a device-resident
+ * filter; bit b is bit (b & 31) of 32-bit word b >> 5, i.e. bit (b & 7) of byte b >> 3.  query == 0 sets the
+ * bits (atomically; the filter is the result and is order-independent), query != 0 only tests them.
+ *   d_result[0] = windows visited
+ *   d_result[1] = windows whose num_hashes bits were all set already (query: exact; insert: depends on the
+ *                 order in which colliding k-mers of the same batch arrive)
+ * d_result (3 x uint64, the third is 0) is zeroed by the call.  d_filter_words holds (filter_bits+31)/32 words. */
+int nthash_kmer_bloom_uniform_dev(const uint8_t* d_bases, uint64_t n_bases_readable, uint64_t n_reads,
+                                  uint32_t read_len, uint32_t k, uint32_t num_hashes, uint32_t* d_filter_words,
+                                  uint64_t filter_bits, int query, uint64_t* d_result, void* stream);
+int nthash_kmer_bloom_dev(const uint8_t* d_bases, uint64_t n_bases_readable, const uint64_t* d_read_off,
+                          const uint64_t* d_koff, uint64_t n_reads, uint64_t max_read_len, uint32_t k,
+                          uint32_t num_hashes, uint32_t* d_filter_words, uint64_t filter_bits, int query,
+                          uint64_t* d_result, void* stream);
+
 /* ---- SeedNtHash: spaced seeds ----------------------------------------------------------------
  * Replaces `nthash::SeedNtHash it(seq, len, seeds, h, k); while (it.roll()) use(it.hashes())`
  * (nthash.hpp:313-521; SeedNtHash::init/roll src/seed.cpp:493-544; ntmsm64 :130-270).

@@ -199,3 +199,34 @@ def kmer_reduce(bases, read_off, k, num_hashes=1, stream=None) -> torch.Tensor:
         check(LIB.nthash_kmer_reduce_dev(_ptr(bases), bases.numel(), _ptr(read_off), _ptr(koff), n_reads, max_len.value, k, num_hashes,
                                          _ptr(res), _stream_ptr(stream)))
     return res
+
+
+def bloom_filter(bits, device="cuda") -> torch.Tensor:
+    """An empty device-resident Bloom filter of `bits` bits (int32 words; bit b = bit b & 31 of word b >> 5)."""
+    return torch.zeros((int(bits) + 31) // 32, dtype=torch.int32, device=device)
+
+
+def kmer_bloom_uniform(bases, n_reads, read_len, k, num_hashes, filt, bits, query=False, stream=None) -> torch.Tensor:
+    """Fused Bloom-filter consumer (nthash_kmer_bloom_uniform_dev): every visited window's num_hashes values set
+    (query=False) or test (query=True) bits `hash % bits` of `filt`.  Returns int64 [windows visited, windows whose
+    bits were all set already, 0] on the GPU."""
+    _check_bases(bases)
+    res = torch.empty(3, dtype=torch.int64, device=bases.device)
+    with torch.cuda.device(bases.device):
+        check(LIB.nthash_kmer_bloom_uniform_dev(_ptr(bases), bases.numel(), n_reads, read_len, k, num_hashes, _ptr(filt), int(bits),
+                                                1 if query else 0, _ptr(res), _stream_ptr(stream)))
+    return res
+
+
+def kmer_bloom(bases, read_off, k, num_hashes, filt, bits, query=False, stream=None) -> torch.Tensor:
+    """Fused Bloom-filter consumer over ragged reads (nthash_kmer_plan_dev + nthash_kmer_bloom_dev)."""
+    _check_bases(bases)
+    n_reads = read_off.numel() - 1
+    res = torch.empty(3, dtype=torch.int64, device=bases.device)
+    with torch.cuda.device(bases.device):
+        koff = torch.empty(n_reads + 1, dtype=torch.int64, device=bases.device)
+        rows, max_len = C.c_uint64(0), C.c_uint64(0)
+        check(LIB.nthash_kmer_plan_dev(_ptr(read_off), n_reads, k, _ptr(koff), C.byref(rows), C.byref(max_len), _stream_ptr(stream)))
+        check(LIB.nthash_kmer_bloom_dev(_ptr(bases), bases.numel(), _ptr(read_off), _ptr(koff), n_reads, max_len.value, k, num_hashes,
+                                        _ptr(filt), int(bits), 1 if query else 0, _ptr(res), _stream_ptr(stream)))
+    return res

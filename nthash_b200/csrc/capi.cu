@@ -231,6 +231,9 @@ struct DevBatch
   uint64_t memset_rows = 0; // > 0: pre-set that many validity bits first
   uint64_t *d_fwd = nullptr, *d_rev = nullptr;
   uint64_t* d_reduce = nullptr; // fused consumer output {windows, sum, xor}; then d_out etc. are NULL
+  uint32_t* d_bloom = nullptr;  // Bloom-filter consumer: filter words, size in bits, 1 = insert / 2 = query
+  uint64_t bloom_bits = 0;
+  uint32_t bloom_mode = 0;
 };
 
 static int kmer_dev_run(const DevBatch& B, uint32_t k, uint32_t h, cudaStream_t st)
@@ -246,6 +249,9 @@ static int kmer_dev_run(const DevBatch& B, uint32_t k, uint32_t h, cudaStream_t 
   P.out_fwd = B.d_fwd;
   P.out_rev = B.d_rev;
   P.reduce_out = B.d_reduce;
+  P.bloom_words = B.d_bloom;
+  P.bloom_bits = B.bloom_bits;
+  P.bloom_mode = B.bloom_mode;
   RaggedItems R;
   if (B.uniform_len) {
     if (!plan_uniform(B.n_reads, B.uniform_len, k, P.g, P.tile_cap))
@@ -661,6 +667,65 @@ int nthash_kmer_reduce(const char* bases, const uint64_t* read_off, uint64_t n_r
   HostBatch hb = { bases, read_off, n_reads, k, num_hashes, 0ull, nullptr, nullptr, nullptr, nullptr };
   hb.reduce_result = result;
   return host_pipeline(hb, [&](const DevBatch& B, cudaStream_t st) { return kmer_dev_run(B, k, num_hashes, st); });
+}
+
+// ---- fused consumer: Bloom filter insert / query ------------------------------------------------
+
+static int bloom_args(uint32_t k, uint32_t h, const uint32_t* d_filter, uint64_t bits, const uint64_t* d_result)
+{
+  if (int rc = check_kh(k, h)) return rc;
+  if (!d_filter || bits == 0) return fail(NTHASH_ERR_INVALID_ARG, "the filter must not be NULL or empty");
+  if ((uintptr_t)d_filter & 3) return fail(NTHASH_ERR_INVALID_ARG, "d_filter_words must be 4-byte aligned");
+  if (!d_result) return fail(NTHASH_ERR_INVALID_ARG, "d_result must not be NULL");
+  return check_device_ready();
+}
+
+int nthash_kmer_bloom_uniform_dev(const uint8_t* d_bases, uint64_t n_bases_readable, uint64_t n_reads, uint32_t read_len,
+                                  uint32_t k, uint32_t num_hashes, uint32_t* d_filter_words, uint64_t filter_bits,
+                                  int query, uint64_t* d_result, void* stream)
+{
+  if (int rc = bloom_args(k, num_hashes, d_filter_words, filter_bits, d_result)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  NTH_CUDA(cudaMemsetAsync(d_result, 0, 3 * sizeof(uint64_t), st));
+  if (n_reads == 0 || read_len < k) return NTHASH_OK;
+  if (!d_bases || ((uintptr_t)d_bases & 15)) return fail(NTHASH_ERR_INVALID_ARG, "d_bases must be 16-byte aligned");
+  if (n_bases_readable < n_reads * (uint64_t)read_len)
+    return fail(NTHASH_ERR_INVALID_ARG, "n_bases_readable smaller than n_reads*read_len");
+  DevBatch B;
+  B.d_bases = d_bases;
+  B.n_bases = n_bases_readable;
+  B.n_reads = n_reads;
+  B.uniform_len = read_len;
+  B.d_reduce = d_result;
+  B.d_bloom = d_filter_words;
+  B.bloom_bits = filter_bits;
+  B.bloom_mode = query ? 2 : 1;
+  return kmer_dev_run(B, k, num_hashes, st);
+}
+
+int nthash_kmer_bloom_dev(const uint8_t* d_bases, uint64_t n_bases_readable, const uint64_t* d_read_off,
+                          const uint64_t* d_koff, uint64_t n_reads, uint64_t max_read_len, uint32_t k,
+                          uint32_t num_hashes, uint32_t* d_filter_words, uint64_t filter_bits, int query,
+                          uint64_t* d_result, void* stream)
+{
+  if (int rc = bloom_args(k, num_hashes, d_filter_words, filter_bits, d_result)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  NTH_CUDA(cudaMemsetAsync(d_result, 0, 3 * sizeof(uint64_t), st));
+  if (n_reads == 0 || max_read_len < k) return NTHASH_OK;
+  if (!d_bases || ((uintptr_t)d_bases & 15)) return fail(NTHASH_ERR_INVALID_ARG, "d_bases must be 16-byte aligned");
+  if (!d_read_off || !d_koff) return fail(NTHASH_ERR_INVALID_ARG, "d_read_off and d_koff must not be NULL");
+  DevBatch B;
+  B.d_bases = d_bases;
+  B.n_bases = n_bases_readable;
+  B.d_read_off = d_read_off;
+  B.d_koff = d_koff;
+  B.n_reads = n_reads;
+  B.max_len = max_read_len;
+  B.d_reduce = d_result;
+  B.d_bloom = d_filter_words;
+  B.bloom_bits = filter_bits;
+  B.bloom_mode = query ? 2 : 1;
+  return kmer_dev_run(B, k, num_hashes, st);
 }
 
 // ---- SeedNtHash -------------------------------------------------------------------------------

@@ -35,6 +35,10 @@ struct KmerParams
   uint64_t* out_fwd = nullptr;
   uint64_t* out_rev = nullptr;
   uint64_t* reduce_out = nullptr; // fused consumer: {windows visited, sum, xor} instead of out (all other outputs NULL)
+  // fused Bloom-filter consumer (reduce_out = {windows visited, windows whose bits were all set already, 0}):
+  uint32_t* bloom_words = nullptr; // bit b of the filter = bit (b & 31) of word b >> 5
+  uint64_t bloom_bits = 0;         // filter size in bits; bit index = hash % bloom_bits
+  uint32_t bloom_mode = 0;         // 0: none, 1: insert (atomicOr), 2: query
   uint32_t tile_cap = 0; // bytes of base tile a CTA may stage
   bool use_tma = true;   // allow the TMA tile-store output path when the geometry permits
   uint64_t s[4], sk[4], mult[4]; // filled by launch_kmer

@@ -217,7 +217,10 @@ constexpr uint32_t ROW1_BYTES = 272;
 // share one tile laid out [WS*H/8 blocks][32 rows][8 u64] under the 64-byte TMA swizzle (conflict-free STS.128),
 // and ONE elected lane issues a 3-D tensor store (cp.async.bulk.tensor.3d -> UTMASTG) of box 8 x 32 x blocks:
 // the same WS*H*8 contiguous bytes per row, without the 32-iteration issue loop a per-lane bulk copy costs.
-template<int H, bool REDUCE, int WS, int NBUF, bool BOX>
+//
+// CONS: 0 = store the hashes; 1 = REDUCE (count / sum / xor); 2 / 3 = Bloom-filter insert / query (runtime number
+// of hashes P.h; position = hash % P.bloom_bits; counts the windows whose positions were all set already).
+template<int H, int CONS, int WS, int NBUF, bool BOX>
 __global__ void __launch_bounds__(256)
 kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ CUtensorMap omap)
 {
@@ -227,6 +230,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   uint64_t* s_range = reinterpret_cast<uint64_t*>(smem + F_RANGE_OFF);
   uint8_t* tile = smem + F_TILE_OFF;
 
+  constexpr bool REDUCE = CONS != 0;
   const uint32_t NT = blockDim.x;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t i0 = (uint64_t)blockIdx.x * NT;
@@ -352,13 +356,27 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   auto reduce_add = [&](uint64_t h0) {
     if (run >= k) { // the window is one the reference visits
       ++acc_cnt;
-      acc_sum += h0;
-      acc_xor ^= h0;
+      if (CONS == 1) {
+        acc_sum += h0;
+        acc_xor ^= h0;
 #pragma unroll
-      for (int q = 1; q < H; ++q) {
-        const uint64_t e = ext_hash(h0, P.mult[q]);
-        acc_sum += e;
-        acc_xor ^= e;
+        for (int q = 1; q < H; ++q) {
+          const uint64_t e = ext_hash(h0, P.mult[q]);
+          acc_sum += e;
+          acc_xor ^= e;
+        }
+      } else { // Bloom filter: P.h positions per window (extend_hashes, src/internal.hpp:104-118, with a runtime count)
+        const uint64_t kmul = P.mult[0]; // k * MULTISEED
+        const bool pow2 = (P.bloom_bits & (P.bloom_bits - 1)) == 0;
+        bool all = true;
+        for (uint32_t q = 0; q < P.h; ++q) {
+          const uint64_t hq = q ? ext_hash(h0, (uint64_t)q ^ kmul) : h0;
+          const uint64_t pos = pow2 ? hq & (P.bloom_bits - 1) : hq % P.bloom_bits;
+          const uint32_t bit = 1u << (pos & 31);
+          const uint32_t old = CONS == 2 ? atomicOr(P.bloom_words + (pos >> 5), bit) : __ldg(P.bloom_words + (pos >> 5));
+          all = all && (old & bit);
+        }
+        acc_sum += all ? 1u : 0u;
       }
     }
   };
@@ -646,10 +664,11 @@ cudaError_t make_out_map(const KmerParams& P, uint32_t blocks, CUtensorMap* map)
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-template<int H, bool REDUCE, int WS, int NBUF, bool BOX>
+template<int H, int CONS, int WS, int NBUF, bool BOX>
 cudaError_t launch_fast_t(const KmerParams& P, uint32_t nt, cudaStream_t st)
 {
-  auto fn = kmer_fast_kernel<H, REDUCE, WS, NBUF, BOX>;
+  constexpr bool REDUCE = CONS != 0;
+  auto fn = kmer_fast_kernel<H, CONS, WS, NBUF, BOX>;
   const uint32_t buf = BOX ? (nt / 32) * NBUF * (uint32_t)(WS * H / 8) * 2048u : nt * (ROW1_BYTES + 16);
   uint32_t smem_bytes = fast_smem_bytes(P.tile_cap, REDUCE ? 0u : buf);
   if (const char* e = getenv("NTHASH_B200_SMEM_PAD")) smem_bytes += (uint32_t)atoi(e); // experiments: lower the occupancy
@@ -669,7 +688,7 @@ cudaError_t launch_fast_t(const KmerParams& P, uint32_t nt, cudaStream_t st)
 template<int H, int WS>
 cudaError_t launch_fast_nbuf(const KmerParams& P, const FastCfg& c, cudaStream_t st)
 {
-  return c.nbuf >= 2 ? launch_fast_t<H, false, WS, 2, true>(P, c.nt, st) : launch_fast_t<H, false, WS, 1, true>(P, c.nt, st);
+  return c.nbuf >= 2 ? launch_fast_t<H, 0, WS, 2, true>(P, c.nt, st) : launch_fast_t<H, 0, WS, 1, true>(P, c.nt, st);
 }
 
 // windows per store: index 0/1/2 = short / medium / long pieces (192-256 / 320-384 / 512 bytes per row)
@@ -687,8 +706,8 @@ int fast_ws_rt(uint32_t h, uint32_t idx)
 template<int H>
 cudaError_t launch_fast_h(const KmerParams& P, const FastCfg& c, cudaStream_t st)
 {
-  if (P.reduce_out) return launch_fast_t<H, true, fast_ws<H>(0), 1, false>(P, c.nt, st);
-  if (!c.box) return launch_fast_t<H, false, fast_ws<H>(0), 1, false>(P, c.nt, st); // WS / NBUF are unused there
+  if (P.reduce_out) return launch_fast_t<H, 1, fast_ws<H>(0), 1, false>(P, c.nt, st);
+  if (!c.box) return launch_fast_t<H, 0, fast_ws<H>(0), 1, false>(P, c.nt, st); // WS / NBUF are unused there
   switch (c.ws) {
     case 0: return launch_fast_nbuf<H, fast_ws<H>(0)>(P, c, st);
     case 1: return launch_fast_nbuf<H, fast_ws<H>(1)>(P, c, st);
@@ -707,8 +726,8 @@ uint32_t env_u32(const char* name, uint32_t dflt)
 bool kmer_fast_ok(const KmerParams& P)
 {
   const KmerGeom& g = P.g;
-  return !P.out_fwd && (P.h == 1 || P.h == 2 || P.h == 4) && g.n_items > 0 && (P.reduce_out || ((uintptr_t)P.out & 31) == 0) &&
-         (g.item_byte || (g.seg && g.segs));
+  return !P.out_fwd && (P.h == 1 || P.h == 2 || P.h == 4 || P.bloom_mode) && g.n_items > 0 &&
+         (P.reduce_out || ((uintptr_t)P.out & 31) == 0) && (g.item_byte || (g.seg && g.segs));
 }
 
 // Launch configuration.  Uniform batches get their own item geometry here (reads longer than FAST_WHOLE_READ
@@ -770,6 +789,11 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
     // measured (profiles/r01_prefetch_sweep.txt): the prefetch costs 1-10 % on every config, so it stays off
     P.prefetch_ctas = env_u32("NTHASH_B200_PREFETCH_CTAS", 0);
     if (P.prefetch_ctas == 1) P.prefetch_ctas = resident;
+  }
+  if (P.bloom_mode) { // runtime number of hashes; mult[0] carries k * MULTISEED
+    P.mult[0] = (uint64_t)P.k * MULTISEED;
+    return P.bloom_mode == 1 ? launch_fast_t<1, 2, fast_ws<1>(0), 1, false>(P, c.nt, st)
+                             : launch_fast_t<1, 3, fast_ws<1>(0), 1, false>(P, c.nt, st);
   }
   switch (P.h) {
     case 1: return launch_fast_h<1>(P, c, st);

@@ -211,3 +211,52 @@ def test_fused_reduce_consumer():
     offu = off.astype(np.uint64)
     assert nthash_b200.LIB.nthash_kmer_reduce(bases.ctypes.data, offu.ctypes.data, len(lens), 31, 2, res.ctypes.data, 0) == 0
     assert (int(res[0]), int(res[1]), int(res[2])) == (ora["n_emit"], ora["sum"], ora["xor"])
+
+
+def _bloom_oracle(ora, h, bits):
+    """numpy restatement of the Bloom consumer from the oracle's hashes: filter words + per-window positions."""
+    vals = ora["out"][ora["valid"].astype(bool)]            # rows the reference visits, all h values
+    pos = vals % np.uint64(bits)
+    words = np.zeros((bits + 31) // 32, np.uint32)
+    np.bitwise_or.at(words, (pos >> np.uint64(5)).astype(np.int64).reshape(-1),
+                     (np.uint32(1) << (pos & np.uint64(31)).astype(np.uint32)).reshape(-1))
+    return words, pos
+
+
+@pytest.mark.parametrize("h,bits", [(1, 1 << 20), (3, 1 << 22), (5, 3_000_017), (4, 999_983)])
+def test_fused_bloom_consumer(h, bits):
+    # the caller the reference's header names (nthash.hpp:14-17): hashes() feeding a Bloom filter
+    rng = np.random.default_rng(h * 1000 + bits % 97)
+    n, L, k = 4000, 150, 31
+    bases = synth(rng, n * L, p_bad=0.001)
+    off = np.arange(n + 1, dtype=np.uint64) * L
+    ora = ORACLE.kmer_batch(bases, off, k, h, threads=8)
+    want_words, pos = _bloom_oracle(ora, h, bits)
+    d_b, _keep = to_dev(bases)
+    filt = nthash_b200.bloom_filter(bits)
+    ins = u64(nthash_b200.kmer_bloom_uniform(d_b, n, L, k, h, filt, bits))
+    assert int(ins[0]) == int(ora["n_emit"])
+    assert (filt.cpu().numpy().view(np.uint32) == want_words).all(), "filter contents differ from the oracle's"
+    # querying the same reads: every window hits; a second insert changes nothing and reports all windows as present
+    q = u64(nthash_b200.kmer_bloom_uniform(d_b, n, L, k, h, filt, bits, query=True))
+    assert (int(q[0]), int(q[1])) == (int(ora["n_emit"]), int(ora["n_emit"]))
+    again = u64(nthash_b200.kmer_bloom_uniform(d_b, n, L, k, h, filt, bits))
+    assert int(again[1]) == int(ora["n_emit"]) and (filt.cpu().numpy().view(np.uint32) == want_words).all()
+    # other reads against that filter: the hit count is exact (false positives included)
+    other = synth(rng, 1000 * L, p_bad=0.001)
+    ora2 = ORACLE.kmer_batch(other, np.arange(1001, dtype=np.uint64) * L, k, h, threads=8)
+    _, pos2 = _bloom_oracle(ora2, h, bits)
+    isset = (want_words[(pos2 >> np.uint64(5)).astype(np.int64)] >> (pos2 & np.uint64(31)).astype(np.uint32)) & 1
+    d_o, _keep2 = to_dev(other)
+    q2 = u64(nthash_b200.kmer_bloom_uniform(d_o, 1000, L, k, h, filt, bits, query=True))
+    assert (int(q2[0]), int(q2[1])) == (int(ora2["n_emit"]), int(isset.all(axis=1).sum()))
+    # ragged reads into a fresh filter
+    lens = rng.integers(0, 500, 800)
+    roff = ragged_offsets(lens)
+    rb = synth(rng, int(roff[-1]), p_bad=0.002)
+    ora3 = ORACLE.kmer_batch(rb, roff.astype(np.uint64), k, h)
+    words3, _ = _bloom_oracle(ora3, h, bits)
+    d_r, _keep3 = to_dev(rb)
+    f3 = nthash_b200.bloom_filter(bits)
+    r3 = u64(nthash_b200.kmer_bloom(d_r, torch.from_numpy(roff).cuda(), k, h, f3, bits))
+    assert int(r3[0]) == int(ora3["n_emit"]) and (f3.cpu().numpy().view(np.uint32) == words3).all()
