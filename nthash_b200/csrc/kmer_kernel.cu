@@ -235,7 +235,12 @@ cudaError_t launch_kmer(KmerParams P, cudaStream_t st)
     P.sk[x] = srol_n(base[x], P.k);
   }
   for (unsigned q = 0; q < 4; ++q) P.mult[q] = ext_mult(q, P.k);
-  if (P.use_tma && kmer_fast_ok(P)) return launch_kmer_fast(P, st);
+  if (P.use_tma && kmer_fast_ok(P)) {
+    const cudaError_t e = launch_kmer_fast(P, st);
+    if (e != cudaErrorInvalidConfiguration) return e; // does not fit shared memory (huge k): the general kernel below
+    cudaGetLastError();
+  }
+  if (P.bloom_mode) return cudaErrorNotSupported; // the Bloom consumer only exists in the fast kernel
   const uint32_t smem = kmer_smem_bytes(P.tile_cap);
   const bool strands = P.out_fwd != nullptr;
   if (P.reduce_out) return launch_t<0, false>(P, smem, st);
