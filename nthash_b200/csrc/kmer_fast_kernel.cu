@@ -494,12 +494,9 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
       if (cnt == (uint32_t)WS) {
 #pragma unroll
         for (uint32_t q = 0; q < (uint32_t)WS / 4; ++q) group(q, full_t(), 4u);
-      } else {
-#pragma unroll
-        for (uint32_t q = 0; q < (uint32_t)WS / 4; ++q) {
-          if (4 * q + 4 <= cnt) group(q, full_t(), 4u);
-          else if (4 * q < cnt) group(q, part_t(), cnt - 4 * q);
-        }
+      } else { // the last, shorter tile of a row: kept rolled up (small code for the instruction cache)
+#pragma unroll 1
+        for (uint32_t q = 0; 4 * q < cnt; ++q) group(q, part_t(), cnt - 4 * q);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -550,12 +547,9 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
       if (cnt == WS1) {
 #pragma unroll
         for (uint32_t q = 0; q < WS1 / 4; ++q) group(q, full_t(), 4u);
-      } else {
-#pragma unroll
-        for (uint32_t q = 0; q < WS1 / 4; ++q) {
-          if (4 * q + 4 <= cnt) group(q, full_t(), 4u);
-          else if (4 * q < cnt) group(q, part_t(), cnt - 4 * q);
-        }
+      } else { // the last piece of an item: kept rolled up (once per item; the code stays small for the instruction cache)
+#pragma unroll 1
+        for (uint32_t q = 0; 4 * q < cnt; ++q) group(q, part_t(), cnt - 4 * q);
       }
       st_shared_v2_u64(desc0 + lane * 16, (uint64_t)(uintptr_t)(P.out + (my_out + p) * H), (uint64_t)(cnt * H * 8));
       __syncwarp();
