@@ -112,7 +112,13 @@ static int run_kmer(KmerParams& P, uint64_t rows, cudaStream_t st)
   if (getenv("NTHASH_B200_DISABLE_TMA_STORE")) P.use_tma = false; // A/B switch for tests and profiling
   if (P.valid_bits && rows) NTH_CUDA(cudaMemsetAsync(P.valid_bits, 0xFF, ((rows + 31) / 32) * 4, st));
   if (P.g.n_items == 0) return NTHASH_OK;
-  NTH_CUDA(launch_kmer(P, st));
+  const cudaError_t e = launch_kmer(P, st);
+  if (e == cudaErrorInvalidConfiguration || e == cudaErrorNotSupported) {
+    cudaGetLastError();
+    return fail(NTHASH_ERR_UNSUPPORTED, "k=%u, num_hashes=%u on reads of up to %u bases: no kernel fits this request in shared memory%s", P.k,
+                P.h, P.g.read_len, P.bloom_mode ? " (the Bloom consumer has no general-kernel form)" : "");
+  }
+  NTH_CUDA(e);
   return NTHASH_OK;
 }
 
@@ -254,16 +260,13 @@ static int kmer_dev_run(const DevBatch& B, uint32_t k, uint32_t h, cudaStream_t 
   P.bloom_mode = B.bloom_mode;
   RaggedItems R;
   if (B.uniform_len) {
-    if (!plan_uniform(B.n_reads, B.uniform_len, k, P.g, P.tile_cap))
-      return fail(NTHASH_ERR_UNSUPPORTED, "k=%u with read_len=%u needs a %u-byte tile", k, B.uniform_len, P.tile_cap);
+    // the fast kernel plans its own (smaller) CTAs, so a tile too large for the general kernel is not fatal yet
+    P.general_fits = plan_uniform(B.n_reads, B.uniform_len, k, P.g, P.tile_cap);
   } else {
     if (int rc = plan_ragged(B.d_read_off, B.d_koff, B.n_reads, B.max_len, k, TILE_BUDGET, st, R)) return rc;
     P.g = R.g;
     P.tile_cap = R.tile_cap;
-    if (kmer_smem_bytes(P.tile_cap) > SMEM_MAX) {
-      if (R.d_items) cudaFreeAsync(R.d_items, st);
-      return fail(NTHASH_ERR_UNSUPPORTED, "k=%u needs a %u-byte tile for ragged long reads", k, P.tile_cap);
-    }
+    P.general_fits = kmer_smem_bytes(P.tile_cap) <= SMEM_MAX;
   }
   int rc = run_kmer(P, B.memset_rows, st);
   if (R.d_items) cudaFreeAsync(R.d_items, st);

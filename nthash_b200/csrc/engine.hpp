@@ -40,7 +40,8 @@ struct KmerParams
   uint64_t bloom_bits = 0;         // filter size in bits; bit index = hash % bloom_bits
   uint32_t bloom_mode = 0;         // 0: none, 1: insert (atomicOr), 2: query
   uint32_t tile_cap = 0; // bytes of base tile a CTA may stage
-  bool use_tma = true;   // allow the TMA tile-store output path when the geometry permits
+  bool use_tma = true;   // allow the fast kernel (kmer_fast_kernel.cu) when the request permits
+  bool general_fits = true; // false: the general kernel's CTA tile would not fit shared memory (huge k) - fast kernel or nothing
   uint64_t s[4], sk[4], mult[4]; // filled by launch_kmer
   uint32_t prefetch_ctas = 0;    // fast kernel: L2-prefetch the base tile this many CTAs ahead (0 = off)
   const uint4* t4 = nullptr;     // tetramer warm-up table (fast kernel only), filled by launch_kmer_fast

@@ -753,25 +753,28 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
     }
     g.n_items = n_reads * g.segs;
   }
-  auto tile_cap_for = [&](uint32_t nt) -> uint32_t {
-    if (!uniform) return (uint32_t)(((uint64_t)Pin.tile_cap * nt + KMER_NT - 1) / KMER_NT) + 2 * P.k + 64; // sized for KMER_NT items
-    if (P.g.segs == 1) return nt * P.g.read_len + 64;
-    return (uint32_t)((uint64_t)nt * P.g.seg + ((uint64_t)nt / P.g.segs + 2) * (P.k - 1) + 64);
+  auto tile_cap_for = [&](uint32_t nt) -> uint64_t {
+    if (!uniform) return ((uint64_t)Pin.tile_cap * nt + KMER_NT - 1) / KMER_NT + 2 * (uint64_t)P.k + 64; // sized for KMER_NT items
+    if (P.g.segs == 1) return (uint64_t)nt * P.g.read_len + 64;
+    return (uint64_t)nt * P.g.seg + ((uint64_t)nt / P.g.segs + 2) * (P.k - 1) + 64;
   };
   // defaults from profiles/sweeps/ (round 1): what matters most is resident warps per SM (small pieces win over
   // long ones that cost occupancy), then CTA size (fewer prologues): the largest CTA that leaves >= 16 warps resident
   const uint32_t buf_per_warp = P.reduce_out ? 0u
                                 : c.box    ? c.nbuf * (uint32_t)(fast_ws_rt(P.h, c.ws) * P.h / 8) * 2048u
                                            : 32u * (ROW1_BYTES + 16);
-  c.nt = 96;
-  for (uint32_t nt : { 256u, 192u, 128u, 96u }) {
-    const uint32_t smem = fast_smem_bytes(tile_cap_for(nt), (nt / 32) * buf_per_warp) + 1024;
+  c.nt = 32;
+  for (uint32_t nt : { 256u, 192u, 128u, 96u, 64u, 32u }) { // the small ones only matter for huge k
+    const uint64_t cap = tile_cap_for(nt);
+    if (cap > 227u * 1024u) continue;
+    const uint32_t smem = fast_smem_bytes((uint32_t)cap, (nt / 32) * buf_per_warp) + 1024;
     c.nt = nt;
-    if (smem <= 227u * 1024u && (227u * 1024u / smem) * (nt / 32) >= 16) break;
+    if (smem <= 227u * 1024u && ((227u * 1024u / smem) * (nt / 32) >= 16 || nt <= 96)) break;
   }
   c.nt = env_u32("NTHASH_B200_FAST_NT", c.nt);
   if (c.nt < 32 || c.nt > 256 || c.nt % 32) return cudaErrorInvalidValue;
-  P.tile_cap = tile_cap_for(c.nt);
+  if (tile_cap_for(c.nt) > 227u * 1024u) return cudaErrorInvalidConfiguration;
+  P.tile_cap = (uint32_t)tile_cap_for(c.nt);
   cudaError_t e = get_t4_table(P.k, &P.t4);
   if (e != cudaSuccess) return e;
   {

@@ -241,6 +241,7 @@ cudaError_t launch_kmer(KmerParams P, cudaStream_t st)
     cudaGetLastError();
   }
   if (P.bloom_mode) return cudaErrorNotSupported; // the Bloom consumer only exists in the fast kernel
+  if (!P.general_fits) return cudaErrorInvalidConfiguration;
   const uint32_t smem = kmer_smem_bytes(P.tile_cap);
   const bool strands = P.out_fwd != nullptr;
   if (P.reduce_out) return launch_t<0, false>(P, smem, st);

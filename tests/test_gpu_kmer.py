@@ -123,6 +123,27 @@ def test_fast_kernel_output_paths(n, read_len, k, h, no_box, monkeypatch):
         assert torch.equal(res2.out, res.out) and torch.equal(res2.valid_bits, res.valid_bits)
 
 
+@pytest.mark.parametrize("n,read_len,k,h", [(40, 6000, 2000, 1), (6, 70000, 65535, 2), (300, 1300, 1023, 4)])
+def test_huge_k_uniform(n, read_len, k, h):
+    # k up to uint16 max (the reference's k is a uint16_t, nthash.hpp:74); the general kernel's CTA tile no longer
+    # fits shared memory there, the fast kernel's smaller CTAs do
+    rng = np.random.default_rng(k)
+    bases = synth(rng, n * read_len, p_bad=0.00002)
+    d_b, _keep = to_dev(bases)
+    res = nthash_b200.kmer_hashes_uniform(d_b, n, read_len, k, h)
+    torch.cuda.synchronize()
+    off = np.arange(n + 1, dtype=np.uint64) * read_len
+    assert_batch_equal(res, ORACLE.kmer_batch(bases, off, k, h, threads=8), h)
+
+
+def test_huge_k_ragged():
+    rng = np.random.default_rng(77)
+    lens = [5000, 100, 999, 1000, 1001, 20000, 0, 3000]
+    off = ragged_offsets(lens)
+    bases = synth(rng, int(off[-1]), p_bad=0.0001)
+    assert_batch_equal(run_ragged(bases, off, 1000, 2), ORACLE.kmer_batch(bases, off.astype(np.uint64), 1000, 2, threads=4), 2)
+
+
 def test_ragged_long_reads_use_item_table():
     rng = np.random.default_rng(5)
     lens = [70000, 10, 30000, 62, 63, 64, 12345, 0, 999]
