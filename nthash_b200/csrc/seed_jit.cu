@@ -562,21 +562,29 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
     }
     src << " }\n";
   }
-  src << "#define MAIN_TILES \\\n";
-  for (uint32_t t = 0; t < unroll / tw; ++t) {
-    src << "    if (p0 + " << t * tw << "u < n) { \\\n      const uint32_t ot = ot0 + buf * OT_BYTES, rowaddr = ot + "
-        << (box3 ? "lterm" : "lane * ROW_BYTES") << "; \\\n";
+  // one tile = TW windows; a full tile (the common case: rows are usually a multiple of TW) runs without the
+  // per-window bound checks, a partial one (end of a row) keeps them
+  auto tile_text = [&](uint32_t t, bool full) {
+    std::ostringstream o;
+    o << "      const uint32_t ot = ot0 + buf * OT_BYTES, rowaddr = ot + " << (box3 ? "lterm" : "lane * ROW_BYTES") << "; \\\n";
     for (uint32_t i = 0; i < tw; ++i) {
       const uint32_t u = t * tw + i;
-      src << "      if (p0 + " << u << "u < n) { \\\n        WIN_PRE(p0 + " << u << "u) \\\n        uint64_t hv[HT]; \\\n" << window_body(u);
+      o << "      " << (full ? "{" : "if (p0 + " + std::to_string(u) + "u < n) {") << " \\\n        WIN_PRE(p0 + " << u << "u) \\\n        uint64_t hv[HT]; \\\n"
+        << window_body(u);
       if (i == 0) // this buffer's previous tile must have left shared memory; waiting only now hides the TMA read behind one window
-        src << "        if (p0 + " << t * tw << "u >= NBUF * TW) { if (lane == 0) BULK_WAIT_READ __syncwarp(); } \\\n";
-      src << "        STORE_WINDOW_" << i << "(rowaddr) \\\n      } \\\n";
+        o << "        if (p0 + " << t * tw << "u >= NBUF * TW) { if (lane == 0) BULK_WAIT_READ __syncwarp(); } \\\n";
+      o << "        STORE_WINDOW_" << i << "(rowaddr) \\\n      } \\\n";
     }
-    src << "      fence_proxy_async_smem(); __syncwarp(); \\\n      if (lane == 0) { ";
-    if (box3) src << "tma_store_3d(&omap, ot, 0, row0, (int)((p0 + " << t * tw << "u) * HT / 8u));";
-    else src << "tma_store_2d(&omap, ot, (int)((p0 + " << t * tw << "u) * HT), row0);";
-    src << " bulk_commit(); } \\\n      buf = buf + 1 == NBUF ? 0 : buf + 1; \\\n    } \\\n";
+    o << "      fence_proxy_async_smem(); __syncwarp(); \\\n      if (lane == 0) { ";
+    if (box3) o << "tma_store_3d(&omap, ot, 0, row0, (int)((p0 + " << t * tw << "u) * HT / 8u));";
+    else o << "tma_store_2d(&omap, ot, (int)((p0 + " << t * tw << "u) * HT), row0);";
+    o << " bulk_commit(); } \\\n      buf = buf + 1 == NBUF ? 0 : buf + 1; \\\n";
+    return o.str();
+  };
+  src << "#define MAIN_TILES \\\n";
+  for (uint32_t t = 0; t < unroll / tw; ++t) {
+    src << "    if (p0 + " << (t + 1) * tw << "u <= n) { \\\n" << tile_text(t, true) << "    } else if (p0 + " << t * tw << "u < n) { \\\n"
+        << tile_text(t, false) << "    } \\\n";
   }
   src << "\n";
   src << JIT_KERNEL;
