@@ -10,9 +10,16 @@ for L, n, k, h in ((150, 700, 31, 1), (151, 300, 31, 3), (2000, 40, 63, 4), (150
     b = synth(rng, n * L, p_bad=0.002); d, keep = to_dev(b)
     nthash_b200.kmer_hashes_uniform(d, n, L, k, h); nthash_b200.kmer_hashes_uniform(d, n, L, k, 1, want_strands=True)
     nthash_b200.kmer_reduce_uniform(d, n, L, k, h)
+# fast kernel: tensor-store path with a partial last tile, general path (odd rows, cut-up reads), huge k, Bloom consumer
+for L, n, k, h in ((102, 300, 31, 1), (149, 300, 31, 1), (1000, 40, 31, 2), (5003, 9, 32, 1), (3000, 6, 2500, 1)):
+    b = synth(rng, n * L, p_bad=0.001); d, keep = to_dev(b)
+    nthash_b200.kmer_hashes_uniform(d, n, L, k, h)
+    filt = nthash_b200.bloom_filter(1 << 16)
+    nthash_b200.kmer_bloom_uniform(d, n, L, k, 3, filt, 1 << 16); nthash_b200.kmer_bloom_uniform(d, n, L, k, 3, filt, 1 << 16, query=True)
 lens = rng.integers(0, 400, 500); off = ragged_offsets(lens); b = synth(rng, int(off[-1]), p_bad=0.003); d, keep = to_dev(b, pad=16)
 o = torch.from_numpy(off).cuda()
-nthash_b200.kmer_hashes(d, o, 31, 2, want_strands=True); nthash_b200.kmer_reduce(d, o, 31, 2)
+nthash_b200.kmer_hashes(d, o, 31, 2, want_strands=True); nthash_b200.kmer_reduce(d, o, 31, 2); nthash_b200.kmer_hashes(d, o, 31, 1)
+nthash_b200.kmer_bloom(d, o, 31, 2, nthash_b200.bloom_filter(99991), 99991)
 lens = [30000, 3, 9000, 62]; off = ragged_offsets(lens); b = synth(rng, int(off[-1]), p_bad=0.0003); d, keep = to_dev(b, pad=16)
 nthash_b200.kmer_hashes(d, torch.from_numpy(off).cuda(), 63, 1)
 plan = nthash_b200.SeedPlan(["1010101010101010101010101010101", "1101101101101101011011011011011"], 3)
