@@ -353,9 +353,9 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     roll_step(s, make_uint4(ef.x, ef.y, er.x, er.y));
     return canonical2(s);
   };
-  auto reduce_add = [&](uint64_t h0) {
-    if (run >= k) { // the window is one the reference visits
-      ++acc_cnt;
+  auto consume = [&](uint64_t h0) { // one window the reference visits
+    {
+      {
       if (CONS == 1) {
         acc_sum += h0;
         acc_xor ^= h0;
@@ -378,6 +378,13 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
         }
         acc_sum += all ? 1u : 0u;
       }
+      }
+    }
+  };
+  auto reduce_add = [&](uint64_t h0) {
+    if (run >= k) { // the window is one the reference visits
+      ++acc_cnt;
+      consume(h0);
     }
   };
 
@@ -420,6 +427,18 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     const uint32_t c4 = lop3<LUT_SEL_C>(x_out << 2, x_in << 4, 0x60606060u) & 0x78787878u;
     const uint32_t bw = swar_bad(x_in); // bytes past cnt may flag a false alarm: that only costs the exact scrub
     if (!REDUCE) bad |= bw;
+    if (REDUCE && FULL && bw == 0 && run + 1 >= k) { // consumer, steady state: all four windows are visited ones
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t ea = __byte_perm(c4, pair, 0x7650u | i);
+        const uint2 ef = lds_v2(ea), er = lds_v2(ea + (F_PAIR_R_OFF - F_PAIR_OFF));
+        roll_step(s, make_uint4(ef.x, ef.y, er.x, er.y));
+        consume(canonical2(s));
+      }
+      run += 4;
+      acc_cnt += 4;
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (!FULL && i && (uint32_t)i >= cnt) break;

@@ -26,7 +26,7 @@ def ragged_offsets(lens):
 def to_dev(a, pad=32):
     """uint8 numpy -> CUDA tensor whose allocation is readable `pad` bytes past the data."""
     t = torch.zeros(len(a) + pad, dtype=torch.uint8, device="cuda")
-    t[: len(a)] = torch.from_numpy(np.ascontiguousarray(a))
+    t[: len(a)] = torch.from_numpy(np.array(a, dtype=np.uint8, copy=True))
     return t[: len(a)], t
 
 
