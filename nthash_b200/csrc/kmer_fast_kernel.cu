@@ -515,7 +515,10 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
         for (uint32_t q = 0; q < (uint32_t)WS / 4; ++q) group(q, full_t(), 4u);
       } else { // the last, shorter tile of a row: kept rolled up (small code for the instruction cache)
 #pragma unroll 1
-        for (uint32_t q = 0; 4 * q < cnt; ++q) group(q, part_t(), cnt - 4 * q);
+        for (uint32_t q = 0; 4 * q < cnt; ++q) {
+          if (4 * q + 4 <= cnt) group(q, full_t(), 4u);
+          else group(q, part_t(), cnt - 4 * q);
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -568,7 +571,10 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
         for (uint32_t q = 0; q < WS1 / 4; ++q) group(q, full_t(), 4u);
       } else { // the last piece of an item: kept rolled up (once per item; the code stays small for the instruction cache)
 #pragma unroll 1
-        for (uint32_t q = 0; 4 * q < cnt; ++q) group(q, part_t(), cnt - 4 * q);
+        for (uint32_t q = 0; 4 * q < cnt; ++q) {
+          if (4 * q + 4 <= cnt) group(q, full_t(), 4u);
+          else group(q, part_t(), cnt - 4 * q);
+        }
       }
       st_shared_v2_u64(desc0 + lane * 16, (uint64_t)(uintptr_t)(P.out + (my_out + p) * H), (uint64_t)(cnt * H * 8));
       __syncwarp();
@@ -704,11 +710,11 @@ cudaError_t launch_fast_nbuf(const KmerParams& P, const FastCfg& c, cudaStream_t
   return c.nbuf >= 2 ? launch_fast_t<H, 0, WS, 2, true>(P, c.nt, st) : launch_fast_t<H, 0, WS, 1, true>(P, c.nt, st);
 }
 
-// windows per store: index 0/1/2 = short / medium / long pieces (192-256 / 320-384 / 512 bytes per row)
+// windows per tensor store: index 0/1/2 = 192-256 / 256-384 / 320-512 bytes per row
 template<int H>
 constexpr int fast_ws(int idx)
 {
-  return H == 1 ? (idx == 0 ? 24 : idx == 1 ? 40 : 64) : H == 2 ? (idx == 0 ? 12 : idx == 1 ? 20 : 32) : (idx == 0 ? 8 : idx == 1 ? 12 : 16);
+  return H == 1 ? (idx == 0 ? 24 : idx == 1 ? 32 : 40) : H == 2 ? (idx == 0 ? 12 : idx == 1 ? 16 : 20) : (idx == 0 ? 8 : idx == 1 ? 12 : 16);
 }
 
 int fast_ws_rt(uint32_t h, uint32_t idx)
