@@ -66,8 +66,9 @@ def kmer_hashes_uniform(bases, n_reads, read_len, k, num_hashes=1, want_valid=Tr
     return HashBatch(out, valid_bits, None, rows, fwd, rev)
 
 
-def kmer_hashes(bases, read_off, k, num_hashes=1, want_valid=True, want_strands=False, stream=None) -> HashBatch:
-    """NtHash over ragged reads: read r is bases[read_off[r]:read_off[r+1]] (nthash_kmer_plan_dev + nthash_kmer_batch_dev)."""
+def kmer_hashes(bases, read_off, k, num_hashes=1, want_valid=True, want_strands=False, stream=None, out=None) -> HashBatch:
+    """NtHash over ragged reads: read r is bases[read_off[r]:read_off[r+1]] (nthash_kmer_plan_dev + nthash_kmer_batch_dev).
+    `out`: optional preallocated int64 CUDA tensor with at least rows * num_hashes elements (reused across calls)."""
     _check_bases(bases)
     if not (read_off.is_cuda and read_off.dtype == torch.int64 and read_off.is_contiguous()):
         raise ValueError("read_off must be a contiguous int64 CUDA tensor")
@@ -79,7 +80,12 @@ def kmer_hashes(bases, read_off, k, num_hashes=1, want_valid=True, want_strands=
         max_len = C.c_uint64(0)
         check(LIB.nthash_kmer_plan_dev(_ptr(read_off), n_reads, k, _ptr(koff), C.byref(rows), C.byref(max_len), _stream_ptr(stream)))
         rows = rows.value
-        out = torch.empty((rows, num_hashes), dtype=torch.int64, device=dev)
+        if out is None:
+            out = torch.empty((rows, num_hashes), dtype=torch.int64, device=dev)
+        else:
+            if not (out.is_cuda and out.dtype == torch.int64 and out.is_contiguous() and out.numel() >= rows * num_hashes):
+                raise ValueError("out must be a contiguous int64 CUDA tensor with at least rows * num_hashes elements")
+            out = out.view(-1)[: rows * num_hashes].view(rows, num_hashes)
         valid_bits = torch.empty(int(LIB.nthash_valid_words(rows)), dtype=torch.int32, device=dev) if want_valid else None
         fwd = torch.empty(rows, dtype=torch.int64, device=dev) if want_strands else None
         rev = torch.empty(rows, dtype=torch.int64, device=dev) if want_strands else None

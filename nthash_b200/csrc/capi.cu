@@ -5,6 +5,7 @@
 #include "engine.hpp"
 #include "seed_plan.hpp"
 
+#include <atomic>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -104,6 +105,16 @@ static int check_device_ready()
   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   if (major != 10)
     return fail(NTHASH_ERR_NO_DEVICE, "device %d is sm_%d?: the engine is built for sm_100a only", dev, major);
+  // Scratch (item tables, staging buffers) comes from the device's stream-ordered pool; tell it once to keep freed
+  // memory for the next call instead of returning it to the driver at every synchronisation (a 200 MB item table
+  // for ragged long reads cost ~20 ms per call that way).
+  static std::atomic<uint64_t> pool_tuned{ 0 };
+  if (dev < 64 && !(pool_tuned.load() >> dev & 1)) {
+    cudaMemPool_t pool = nullptr;
+    uint64_t keep = ~0ull;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    pool_tuned.fetch_or(1ull << dev);
+  }
   return NTHASH_OK;
 }
 

@@ -244,6 +244,38 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     if (tid == 0) s_range[0] = my_byte;
     if (i0 + tid == i1 - 1) s_range[1] = my_byte + (n ? n + k - 1 : 0);
   }
+  if (P.g.item_byte) {
+    // Ragged batch: a warp runs as long as its longest item, so hand the CTA's items out by length class
+    // (32 classes, longest first; counting sort through shared memory that the tables overwrite later).
+    // 10 M reads of 100-150 bases: 3.10 -> 2.63 ms per call, of 36-150 bases: 3.55 -> 2.25 ms (profiles/r01_ragged_bench.txt);
+    // nothing else depends on which lane owns which item.
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem + F_PAIR_OFF); // 32 class counters + the CTA's longest item
+    uint8_t* perm = smem + F_LUT_OFF;                               // slot -> thread that first held the item
+    if (tid < 33) cnt[tid] = 0;
+    __syncthreads();
+    atomicMax(&cnt[32], n);
+    __syncthreads();
+    const uint32_t cls = 31u - (uint32_t)(((uint64_t)n * 32u) / ((uint64_t)cnt[32] + 1u));
+    const uint32_t pos = atomicAdd(&cnt[cls], 1u);
+    __syncthreads();
+    if (tid < 32) { // exclusive scan of the class counters
+      const uint32_t c = cnt[tid];
+      uint32_t x = c;
+      for (uint32_t o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      cnt[tid] = x - c;
+    }
+    __syncthreads();
+    perm[cnt[cls] + pos] = (uint8_t)tid;
+    __syncthreads();
+    const uint32_t src = perm[tid];
+    my_byte = my_out = 0;
+    n = 0;
+    if (i0 + src < i1) fast_item_geom(P.g, i0 + src, my_byte, my_out, n);
+    __syncthreads(); // the scratch is reused for the tables below
+  }
 
   // ---- stage the CTA's byte range (TMA bulk copy) and build the tables -------------------------
   if (tid == 0) {
