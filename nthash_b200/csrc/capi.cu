@@ -787,9 +787,7 @@ int nthash_seed_jit_selftest(const char* const* seeds, uint32_t n_seeds, uint32_
   const std::string err = build_seed_plan(seeds, n_seeds, k, num_hashes_per_seed, host);
   if (!err.empty()) return fail(NTHASH_ERR_INVALID_ARG, "%s", err.c_str());
   std::string why;
-  SeedJit* j = seed_jit_build(host, why, false);
-  if (!j) return fail(NTHASH_ERR_UNSUPPORTED, "%s", why.c_str());
-  seed_jit_destroy(j);
+  if (!seed_jit_compile_all(host, why)) return fail(NTHASH_ERR_UNSUPPORTED, "%s", why.c_str());
   return NTHASH_OK;
 }
 

@@ -84,6 +84,7 @@ struct SeedJit;
 struct SeedPlanHost;
 SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load);
 void seed_jit_destroy(SeedJit* j);
+bool seed_jit_compile_all(const SeedPlanHost& plan, std::string& why); // every variant, compile only (no GPU needed)
 const char* seed_jit_source(const SeedJit* j);
 bool seed_jit_applies(const SeedJit* j, const SeedParams& P);
 cudaError_t launch_seed_jit(const SeedJit* j, const SeedParams& P, cudaStream_t st);

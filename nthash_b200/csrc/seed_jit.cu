@@ -43,6 +43,9 @@ struct JitParams
   const uint8_t* tables;
   const uint32_t* care;
   uint32_t tile_cap, care_words;
+  const uint64_t* item_byte; // ragged batches (RAGGED variant): item i starts at byte item_byte[i], its windows are
+  const uint64_t* item_out;  // dense rows [item_out[i], item_out[i+1]); item_read[i] = its read (NULL: items are reads)
+  const uint64_t* item_read;
 };
 
 const char* const JIT_PRELUDE = R"JIT(
@@ -62,6 +65,9 @@ struct JitParams
   const uint8_t* tables;
   const uint32_t* care;
   uint32_t tile_cap, care_words;
+  const uint64_t* item_byte; // ragged batches (RAGGED variant): item i starts at byte item_byte[i], its windows are
+  const uint64_t* item_out;  // dense rows [item_out[i], item_out[i+1]); item_read[i] = its read (NULL: items are reads)
+  const uint64_t* item_read;
 };
 #define DI __device__ __forceinline__
 DI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -94,6 +100,9 @@ DI void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;"
 DI uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 DI uint2 lds_v2(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 DI uint4 lds_v4(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+DI uint2 lds_u2x(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+DI void stg_v4(void* p, uint4 v) { asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+DI void stg_v2(void* p, uint2 v) { asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory"); }
 DI void sts_v2(uint32_t a, uint64_t x, uint64_t y) { asm volatile("st.shared.v2.u64 [%0], {%1,%2};" ::"r"(a), "l"(x), "l"(y) : "memory"); }
 DI void sts_u64(uint32_t a, uint64_t x) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(x) : "memory"); }
 DI void sts_u8(uint32_t a, uint32_t x) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(x) : "memory"); }
@@ -158,25 +167,80 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t i0 = (uint64_t)blockIdx.x * NT;
   const uint64_t i1 = i0 + NT < P.n_items ? i0 + NT : P.n_items;
+  bool active = i0 + tid < i1;
+  uint64_t item = i0 + tid; // the item this thread hashes (ragged batches re-deal the CTA's items by length below)
+#if RAGGED
+  // items of any length: geometry from the item arrays, the CTA's byte range through shared memory
+  __shared__ uint64_t s_range[2];
+  uint64_t my_byte = 0, my_out = 0;
+  uint32_t n = 0;
+  if (active) {
+    my_byte = P.item_byte[i0 + tid];
+    my_out = P.item_out[i0 + tid];
+    n = (uint32_t)(P.item_out[i0 + tid + 1] - my_out);
+    if (tid == 0) s_range[0] = my_byte;
+    if (i0 + tid == i1 - 1) s_range[1] = my_byte + (n ? n + K - 1 : 0);
+  }
+  {
+    // A warp runs as long as its longest item: hand the CTA's items out by length class (32 classes, longest first;
+    // counting sort in shared memory that the tables and the validity LUT overwrite afterwards).
+    uint32_t* cnt = (uint32_t*)smem;        // 32 class counters + the CTA's longest item
+    uint8_t* perm = smem + TABLE_BYTES;     // slot -> thread that first held the item (NT <= 256)
+    if (tid < 33) cnt[tid] = 0;
+    __syncthreads();
+    atomicMax(&cnt[32], n);
+    __syncthreads();
+    const uint32_t cls = 31u - (uint32_t)(((uint64_t)n * 32u) / ((uint64_t)cnt[32] + 1u));
+    const uint32_t pos = atomicAdd(&cnt[cls], 1u);
+    __syncthreads();
+    if (tid < 32) {
+      const uint32_t c = cnt[tid];
+      uint32_t x = c;
+      for (uint32_t o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      cnt[tid] = x - c;
+    }
+    __syncthreads();
+    perm[cnt[cls] + pos] = (uint8_t)tid;
+    __syncthreads();
+    item = i0 + perm[tid];
+    active = item < i1;
+    my_byte = my_out = 0;
+    n = 0;
+    if (active) {
+      my_byte = P.item_byte[item];
+      my_out = P.item_out[item];
+      n = (uint32_t)(P.item_out[item + 1] - my_out);
+    }
+    __syncthreads(); // the scratch becomes tables / LUT below
+  }
+#else
   const uint32_t n = P.seg;
-
   auto item_byte = [&](uint64_t i) {
     const uint64_t r = P.segs > 1 ? i / P.segs : i;
     return r * P.read_len + (i - r * P.segs) * (uint64_t)n;
   };
-  const bool active = i0 + tid < i1;
-  const uint64_t lo_byte = item_byte(i0), g1 = item_byte(i1 - 1) + n + K - 1;
-  const uint64_t g0 = (lo_byte > 16 ? lo_byte - 16 : 0) & ~15ull; // up to 16 bases before the first item are staged too
-  if (g1 - g0 > P.tile_cap) __trap();
-  const uint64_t my_byte = active ? item_byte(i0 + tid) : g0 + 16;
-  const uint64_t my_out = (i0 + tid) * (uint64_t)n;
-
+#endif
   if (tid == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
   }
   if (tid < 16) sts_u8(tile + tid, 'A');
   __syncthreads();
+#if RAGGED
+  const uint64_t lo_byte = s_range[0], g1 = s_range[1] > lo_byte ? s_range[1] : lo_byte;
+  const uint64_t g0 = (lo_byte > 16 ? lo_byte - 16 : 0) & ~15ull; // up to 16 bases before the first item are staged too
+  if (g1 - g0 > P.tile_cap) __trap();
+  if (!n) my_byte = g0 + 16; // nothing to hash: the warm-up below still runs, on bytes that exist
+#else
+  const uint64_t lo_byte = item_byte(i0), g1 = item_byte(i1 - 1) + n + K - 1;
+  const uint64_t g0 = (lo_byte > 16 ? lo_byte - 16 : 0) & ~15ull; // up to 16 bases before the first item are staged too
+  if (g1 - g0 > P.tile_cap) __trap();
+  const uint64_t my_byte = active ? item_byte(i0 + tid) : g0 + 16;
+  const uint64_t my_out = (i0 + tid) * (uint64_t)n;
+#endif
   const uint64_t nb16 = P.n_bases & ~15ull;
   const uint64_t bulk_end = ((g1 + 15) & ~15ull) < nb16 ? ((g1 + 15) & ~15ull) : nb16;
   const uint32_t bulk_bytes = bulk_end > g0 ? (uint32_t)(bulk_end - g0) : 0u;
@@ -192,9 +256,43 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
 
   const uint32_t ps = tile + 16 + (uint32_t)(my_byte - g0); // shared address of the item's base 0
   const uint32_t tb = sbase;                                 // group tables: two conflict-free 128-byte halves each
+#if RAGGED
+  // per warp: [32 descriptors x 16 B][32 private rows x ROW_PITCH]; rows go out through coalesced stores (see MAIN_TILES)
+  const uint32_t desc0 = ((tile + 16 + P.tile_cap + 16 + 15u) & ~15u) + warp * (32u * (ROW_PITCH + 16u)), rows0 = desc0 + 32u * 16u;
+  const uint32_t hw = lane / LANES_PER_ROW, cpos = (lane % LANES_PER_ROW) * CHUNK;
+  // the warp's 32 row pieces -> global memory: a group of LANES_PER_ROW lanes per row, CHUNK bytes per lane; each row's
+  // address and byte count come from its 16-byte descriptor; loads are issued in batches of eight before the stores
+  auto copy_out = [&]() {
+    constexpr uint32_t RPI = 32u / LANES_PER_ROW; // rows per store instruction
+#pragma unroll
+    for (uint32_t r0 = 0; r0 < 32u; r0 += 8u * RPI) {
+      uint4 d[8], v[8];
+#pragma unroll
+      for (uint32_t j = 0; j < 8u; ++j) {
+        const uint32_t row = r0 + j * RPI + hw;
+        d[j] = lds_v4(desc0 + row * 16u);
+        if (CHUNK == 16u) {
+          v[j] = lds_v4(rows0 + row * ROW_PITCH + cpos);
+        } else {
+          const uint2 t2 = lds_v2(rows0 + row * ROW_PITCH + cpos);
+          v[j] = make_uint4(t2.x, t2.y, 0u, 0u);
+        }
+      }
+#pragma unroll
+      for (uint32_t j = 0; j < 8u; ++j) {
+        uint8_t* ga = (uint8_t*)(((uint64_t)d[j].y << 32) | d[j].x) + cpos;
+        if (cpos + CHUNK <= d[j].z) {
+          if (CHUNK == 16u) stg_v4(ga, v[j]);
+          else stg_v2(ga, make_uint2(v[j].x, v[j].y));
+        }
+      }
+    }
+  };
+#else
   const uint32_t ot0 = ((tile + 16 + P.tile_cap + 16 + 1023u) & ~1023u) + warp * (NBUF * OT_BYTES);
   const int row0 = (int)(i0 + warp * 32);
   const uint32_t lterm = lane * 64 + (((lane >> 1) & 3) << 4); // box3: row inside a block + its 64-byte-swizzle term
+#endif
 
   // warm-up: shift bases -OLDER .. k-2 into the code window (the bases before the item only serve strided blocks,
   // where they cancel); roll the full-window hash over bases -1 .. k-2 (in-only)
@@ -212,6 +310,12 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
   }
   WARMUP_BLOCKS
 
+#if RAGGED
+  for (uint32_t p0 = 0; __any_sync(0xffffffffu, p0 < n); p0 += UNROLL) {
+    MAIN_TILES
+  }
+  const bool dirty = active && n != 0 && bad != 0;
+#else
   uint32_t buf = 0;
   for (uint32_t p0 = 0; p0 < n; p0 += UNROLL) {
     MAIN_TILES
@@ -224,6 +328,7 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
     else bulk_wait_read0();
   }
   __syncwarp();
+#endif
   if (dirty) {
     // windows holding a zero-seed byte: byte-exact values (seed.cpp:149-166); then flag the read for the replay
     uint32_t run = 0;
@@ -248,8 +353,12 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
         }
       }
     }
-    const uint64_t i = i0 + tid;
+    const uint64_t i = item;
+#if RAGGED
+    P.read_dirty[P.item_read ? P.item_read[i] : i] = 1;
+#else
     P.read_dirty[P.segs > 1 ? i / P.segs : i] = 1;
+#endif
   }
 }
 )JIT";
@@ -305,8 +414,11 @@ struct SeedJit
   uint8_t* d_tables = nullptr;
   uint32_t table_bytes = 0, tw = 0, row_bytes = 0, ot_bytes = 0, ht = 0, nt = 256, nbuf = 1;
   bool box3 = false;            // output through 3-D tensor stores of 64-byte blocks (rows must be 64-byte multiples)
+  bool ragged = false;          // ragged-batch variant (item arrays, per-lane rows, coalesced stores)
+  uint32_t row_pitch = 0;       // ragged variant: bytes between the lanes' private rows
   const SeedPlanHost* plan = nullptr;
-  mutable SeedJit* alt = nullptr; // the 2-D tile variant for other row lengths, compiled on first use
+  mutable SeedJit* alt = nullptr;  // the 2-D tile variant for other row lengths, compiled on first use
+  mutable SeedJit* alt_ragged = nullptr; // the ragged variant, compiled on first use
   mutable std::mutex mu;
   std::string source; // kept for inspection (nthash_seed_plan_jit_source)
 };
@@ -315,6 +427,7 @@ void seed_jit_destroy(SeedJit* j)
 {
   if (!j) return;
   seed_jit_destroy(j->alt);
+  seed_jit_destroy(j->alt_ragged);
   if (j->lib) cudaLibraryUnload(j->lib);
   cudaFree(j->d_tables);
   delete j;
@@ -324,15 +437,18 @@ const char* seed_jit_source(const SeedJit* j) { return j ? j->source.c_str() : "
 
 // Generates, compiles and loads the kernel for one seed set.  Returns nullptr (with a reason) when the
 // specialised path does not apply; the caller then uses the generic kernel.
-static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& why, bool load, bool box3);
+// mode 0: dense 2-D tiles (TMA 2-D tensor stores), 1: [blocks][rows][8 u64] tiles (TMA 3-D tensor stores; the default
+// for uniform batches), 2: ragged batches (per-lane rows, coalesced stores, item arrays)
+static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& why, bool load, int mode);
 
 SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
 {
-  return seed_jit_build_variant(plan, why, load, !getenv("NTHASH_B200_SEED_JIT_NO_BOX"));
+  return seed_jit_build_variant(plan, why, load, getenv("NTHASH_B200_SEED_JIT_NO_BOX") ? 0 : 1);
 }
 
-static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& why, bool load, bool box3)
+static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& why, bool load, int mode)
 {
+  const bool box3 = mode == 1, ragged = mode == 2;
   const uint32_t k = plan.k, m = plan.n_seeds, hps = plan.h, ht = m * hps;
   if (k > 128) { why = "k > 128"; return nullptr; }
   if (ht > 64) { why = "more than 64 hashes per window"; return nullptr; }
@@ -458,6 +574,9 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
     if (box3) {
       if (rb % 64) continue;
       score = 1000 - (rb >= 192 ? rb - 192 : 2 * (192 - rb));
+    } else if (ragged) { // a row piece is copied out by 16 (or, for odd hash counts, 32) lanes: at most 256 bytes
+      if (rb > 256 || rb % (ht % 2 ? 8 : 16)) continue;
+      score = rb;
     } else {
       if (rb % 16) continue;
       score = ((rb / 16) % 2 ? 1000 : 0) + (rb <= 256 ? rb : 512 - rb); // long rows write better (DRAM), up to ~256 B
@@ -466,7 +585,7 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
   }
   if (const char* e = getenv("NTHASH_B200_SEED_JIT_TW")) { // experiments
     const uint32_t t = (uint32_t)atoi(e);
-    if (t >= 1 && (t * ht * 8) % (box3 ? 64 : 16) == 0 && t * ht <= 256) tw = t;
+    if (!ragged && t >= 1 && (t * ht * 8) % (box3 ? 64 : 16) == 0 && t * ht <= 256) tw = t;
   }
   if (!tw) { why = "no tile row shape for this number of hashes"; return nullptr; }
   const uint32_t row_bytes = tw * ht * 8, ot_bytes = box3 ? (row_bytes / 64) * 2048u : (32 * row_bytes + 127) & ~127u;
@@ -479,7 +598,7 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
   if (unroll > 24) { why = "strided blocks with incompatible strides"; return nullptr; }
   // CTA size / output buffering: defaults found on C4 (profiles/r01_seed_jit_sweeps.txt), overridable for experiments
   // (box3 on C4: 128 threads with three 6 KB tiles per warp 0.89 of the HBM peak, two 0.85, one 0.76; 2-D tiles 0.63)
-  uint32_t nt = box3 ? 128 : 256, nbuf = box3 ? 3 : 1;
+  uint32_t nt = box3 || ragged ? 128 : 256, nbuf = box3 ? 3 : 1;
   if (const char* e = getenv("NTHASH_B200_SEED_JIT_NT")) nt = (uint32_t)atoi(e);
   if (const char* e = getenv("NTHASH_B200_SEED_JIT_NBUF")) nbuf = (uint32_t)atoi(e);
   if (nt < 32 || nt > 1024 || nt % 32 || nbuf < 1 || nbuf > 4) { why = "bad NT/NBUF override"; return nullptr; }
@@ -528,6 +647,12 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
       << "u\n#define UNROLL " << unroll << "u\n#define OLDER " << std::min<uint32_t>(off, 16) << "u\n#define ROW_BYTES " << row_bytes
       << "u\n#define OT_BYTES " << ot_bytes << "u\n#define TABLE_BYTES " << table_bytes << "u\n#define ANY_IGNORE " << (plan.any_ignore ? 1 : 0)
       << "\n#define PAIRF_OFF 0u\n#define PAIRR_OFF 128u\n#define INTAB_OFF 256u\n";
+  {
+    // ragged variant: 16-byte chunks, two rows per store instruction when rows are 16-byte aligned (even hash count),
+    // else 8-byte chunks, one row per instruction; rows padded to an odd number of 16-byte chunks (conflict-free STS.128)
+    const uint32_t chunk = ht % 2 ? 8 : 16, pitch = (row_bytes + 15) / 16 * 16 + ((((row_bytes + 15) / 16) % 2) ? 0 : 16);
+    src << "#define RAGGED " << (ragged ? 1 : 0) << "\n#define CHUNK " << chunk << "u\n#define LANES_PER_ROW " << 256 / chunk << "u\n#define ROW_PITCH " << pitch << "u\n";
+  }
   src << "__device__ const uint64_t MULT[" << (hps > 1 ? hps : 1) << "] = { 0";
   for (uint32_t q = 1; q < hps; ++q) src << ", " << hex64(ext_mult(q, k));
   src << " };\n#define DECL_W";
@@ -581,8 +706,24 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
     o << " bulk_commit(); } \\\n      buf = buf + 1 == NBUF ? 0 : buf + 1; \\\n";
     return o.str();
   };
+  // ragged variant: lanes differ in length; every lane fills its private row, then the warp copies the rows out
+  auto ragged_tile_text = [&](uint32_t t) {
+    std::ostringstream o;
+    o << "      const uint32_t rowaddr = rows0 + lane * ROW_PITCH; \\\n";
+    for (uint32_t i = 0; i < tw; ++i) {
+      const uint32_t u = t * tw + i;
+      o << "      if (p0 + " << u << "u < n) { \\\n        WIN_PRE(p0 + " << u << "u) \\\n        uint64_t hv[HT]; \\\n" << window_body(u)
+        << "        STORE_WINDOW_" << i << "(rowaddr) \\\n      } \\\n";
+    }
+    o << "      { const uint32_t w0 = p0 + " << t * tw << "u, cntw = w0 < n ? (n - w0 < TW ? n - w0 : TW) : 0u; \\\n"
+      << "        sts_v2(desc0 + lane * 16u, (uint64_t)(P.out + (my_out + w0) * HT), (uint64_t)(cntw * HT * 8u)); } \\\n"
+      << "      __syncwarp(); \\\n      copy_out(); \\\n      __syncwarp(); \\\n";
+    return o.str();
+  };
   src << "#define MAIN_TILES \\\n";
-  for (uint32_t t = 0; t < unroll / tw; ++t) {
+  for (uint32_t t = 0; ragged && t < unroll / tw; ++t)
+    src << "    if (__any_sync(0xffffffffu, p0 + " << t * tw << "u < n)) { \\\n" << ragged_tile_text(t) << "    } \\\n";
+  for (uint32_t t = 0; !ragged && t < unroll / tw; ++t) {
     src << "    if (p0 + " << (t + 1) * tw << "u <= n) { \\\n" << tile_text(t, true) << "    } else if (p0 + " << t * tw << "u < n) { \\\n"
         << tile_text(t, false) << "    } \\\n";
   }
@@ -601,6 +742,8 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
   j->nt = nt;
   j->nbuf = nbuf;
   j->box3 = box3;
+  j->ragged = ragged;
+  j->row_pitch = (row_bytes + 15) / 16 * 16 + ((((row_bytes + 15) / 16) % 2) ? 0 : 16);
   j->plan = &plan;
   nvrtcProgram prog = nullptr;
   if (rt.create(&prog, j->source.c_str(), "seed_jit_kernel.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
@@ -645,39 +788,69 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
 
 uint32_t seed_jit_smem_bytes(const SeedJit* j, uint32_t tile_cap)
 {
-  return j->table_bytes + 256 + 16 + 16 + tile_cap + 16 + 1024 + (j->nt / 32) * j->nbuf * j->ot_bytes;
+  const uint32_t out_bytes = j->ragged ? (j->nt / 32) * 32u * (j->row_pitch + 16u) + 256u : (j->nt / 32) * j->nbuf * j->ot_bytes;
+  return j->table_bytes + 256 + 16 + 16 + tile_cap + 16 + 1024 + out_bytes;
 }
 
 // Bytes of bases one CTA of the specialised kernel stages (its CTA size may differ from KMER_NT).
-static uint32_t seed_jit_tile_cap(const SeedJit* j, const KmerGeom& g, uint32_t k)
+static uint32_t seed_jit_tile_cap(const SeedJit* j, const SeedParams& P)
 {
-  const uint64_t b = g.segs == 1 ? (uint64_t)j->nt * g.read_len + 96
-                                 : (uint64_t)j->nt * g.seg + ((uint64_t)j->nt / g.segs + 2) * (k - 1) + 96;
+  const KmerGeom& g = P.g;
+  uint64_t b;
+  if (g.item_byte) b = ((uint64_t)P.tile_cap * j->nt + KMER_NT - 1) / KMER_NT + 2 * (uint64_t)P.k + 96; // the caller sized it for KMER_NT items
+  else if (g.segs == 1) b = (uint64_t)j->nt * g.read_len + 96;
+  else b = (uint64_t)j->nt * g.seg + ((uint64_t)j->nt / g.segs + 2) * (P.k - 1) + 96;
   return b > 0xffffffffull ? 0xffffffffu : (uint32_t)b;
 }
 
-// The variant of the compiled kernel that fits the geometry: the 3-D box stores need rows of whole 64-byte blocks;
-// other (even) row lengths take the 2-D tile variant, compiled on first use.
+// Build check without a GPU: compiles every variant (3-D box, 2-D tiles, ragged) for sm_100a.
+bool seed_jit_compile_all(const SeedPlanHost& plan, std::string& why)
+{
+  for (int mode : { 1, 0, 2 }) {
+    if (mode == 2 && plan.n_seeds * plan.h > 32) continue;
+    std::string w;
+    SeedJit* j = seed_jit_build_variant(plan, w, false, mode);
+    if (!j && (mode == 1 || w.rfind("NVRTC compilation failed", 0) == 0)) { // "does not apply" is fine for the side variants
+      why = "variant " + std::to_string(mode) + ": " + w;
+      return false;
+    }
+    seed_jit_destroy(j);
+  }
+  return true;
+}
+
+// The variant of the compiled kernel that fits the geometry: ragged batches take the ragged variant; uniform ones the
+// 3-D box stores when rows are whole 64-byte blocks, else the 2-D tile variant.  Variants other than the one built with
+// the plan are compiled on first use.
 static const SeedJit* seed_jit_variant(const SeedJit* j, const KmerGeom& g)
 {
-  if (!j || !j->box3 || ((uint64_t)g.seg * j->ht) % 8 == 0) return j;
+  if (!j) return j;
+  if (g.item_byte) {
+    if (j->ht > 32 || getenv("NTHASH_B200_SEED_JIT_NO_RAGGED")) return nullptr; // a window must fit a 256-byte row piece
+    std::lock_guard<std::mutex> lock(j->mu);
+    if (!j->alt_ragged) {
+      std::string why;
+      j->alt_ragged = seed_jit_build_variant(*j->plan, why, true, 2);
+    }
+    return j->alt_ragged;
+  }
+  if (!j->box3 || ((uint64_t)g.seg * j->ht) % 8 == 0) return j;
   std::lock_guard<std::mutex> lock(j->mu);
   if (!j->alt) {
     std::string why;
-    j->alt = seed_jit_build_variant(*j->plan, why, true, false);
+    j->alt = seed_jit_build_variant(*j->plan, why, true, 0);
   }
   return j->alt;
 }
 
-// Uniform batches whose items are all full and whose rows are 16-byte multiples.
+// Uniform batches whose items are all full and whose rows are 16-byte multiples; ragged batches without strand outputs.
 bool seed_jit_applies(const SeedJit* j0, const SeedParams& P)
 {
   const KmerGeom& g = P.g;
-  if (!j0 || g.item_byte || P.out_fwd || !g.seg || g.nk % g.seg || ((uint64_t)g.seg * j0->ht) % 2 || !g.n_items ||
-      g.n_items >= 0x7fffffffull || ((uintptr_t)P.out & 15))
-    return false;
+  if (!j0 || P.out_fwd || !g.n_items || g.n_items >= 0x7fffffffull || ((uintptr_t)P.out & 15)) return false;
+  if (!g.item_byte && (!g.seg || g.nk % g.seg || ((uint64_t)g.seg * j0->ht) % 2)) return false;
   const SeedJit* j = seed_jit_variant(j0, g);
-  return j && seed_jit_smem_bytes(j, seed_jit_tile_cap(j, g, P.k)) <= 227u * 1024u;
+  return j && seed_jit_smem_bytes(j, seed_jit_tile_cap(j, P)) <= 227u * 1024u;
 }
 
 cudaError_t launch_seed_jit(const SeedJit* j0, const SeedParams& P, cudaStream_t st)
@@ -697,9 +870,12 @@ cudaError_t launch_seed_jit(const SeedJit* j0, const SeedParams& P, cudaStream_t
     encode = (EncodeFn)fp;
   }
   CUtensorMap map;
+  memset(&map, 0, sizeof map);
   const uint64_t row_u64 = (uint64_t)P.g.seg * j->ht;
-  CUresult cr;
-  if (j->box3) { // [row blocks][items][8 u64], boxes of (row_bytes / 64) x 32 x 8 under the 64-byte swizzle
+  CUresult cr = CUDA_SUCCESS;
+  if (j->ragged) {
+    // no tensor map: rows leave through plain coalesced stores
+  } else if (j->box3) { // [row blocks][items][8 u64], boxes of (row_bytes / 64) x 32 x 8 under the 64-byte swizzle
     const cuuint64_t dims[3] = { 8, P.g.n_items, row_u64 / 8 };
     const cuuint64_t strides[2] = { row_u64 * 8, 64 };
     const cuuint32_t box[3] = { 8, 32, j->row_bytes / 64 };
@@ -728,8 +904,11 @@ cudaError_t launch_seed_jit(const SeedJit* j0, const SeedParams& P, cudaStream_t
   jp.read_dirty = P.read_dirty;
   jp.tables = j->d_tables;
   jp.care = reinterpret_cast<const uint32_t*>(P.plan_blob + P.care_off);
-  jp.tile_cap = seed_jit_tile_cap(j, P.g, P.k);
+  jp.tile_cap = seed_jit_tile_cap(j, P);
   jp.care_words = P.care_words;
+  jp.item_byte = P.g.item_byte;
+  jp.item_out = P.g.item_out;
+  jp.item_read = P.item_read;
   const uint32_t smem = seed_jit_smem_bytes(j, jp.tile_cap);
   cudaError_t e = cudaFuncSetAttribute((const void*)j->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

@@ -102,6 +102,28 @@ def test_uniform_config4_shape(read_len, n, p_bad):
     assert_batch_equal(res, ora, 6, check_strands=True)
 
 
+@pytest.mark.parametrize("seeds,h", SEED_SETS, ids=lambda v: v[0][:10] if isinstance(v, list) else str(v))
+def test_ragged_specialised_kernel(seeds, h, capfd, monkeypatch):
+    # ragged batches without strand outputs take the ragged variant of the NVRTC-specialised kernel (per-lane rows,
+    # coalesced stores); same rows as the oracle and as the generic interpreter, dirty bytes and NULs included
+    k = len(seeds[0])
+    rng = np.random.default_rng(len(seeds) * 77 + k)
+    for lens in (rng.integers(0, 3 * k + 100, 500), [40000, 3, k, 9000, k + 1, 0, 777]):
+        lens = np.asarray(lens)
+        off = ragged_offsets(lens)
+        bases = synth(rng, int(off[-1]), p_bad=0.004, lower=0.1)
+        bases[rng.integers(0, len(bases), 4)] = 0
+        plan = nthash_b200.SeedPlan(seeds, h)
+        res = run_ragged(plan, bases, off, strands=False)
+        ora = ORACLE.seed_batch(bases, off.astype(np.uint64), seeds, h, threads=4)
+        assert_batch_equal(res, ora, len(seeds) * h)
+        monkeypatch.setenv("NTHASH_B200_DISABLE_SEED_JIT", "1")
+        slow = run_ragged(plan, bases, off, strands=False)
+        monkeypatch.delenv("NTHASH_B200_DISABLE_SEED_JIT")
+        assert torch.equal(res.out, slow.out) and torch.equal(res.valid_bits, slow.valid_bits)
+    capfd.readouterr()
+
+
 def test_generic_and_specialised_kernels_agree(monkeypatch):
     # uniform batches take the NVRTC-specialised kernel; the generic interpreter must give the same rows
     rng = np.random.default_rng(12)
