@@ -297,8 +297,7 @@ def main():
             check(LIB.nthash_seed_batch(h_bases.data_ptr(), h_off.data_ptr(), e2e_reads, seed_arr, len(seeds), k, h,
                                         h_out.data_ptr(), h_valid.data_ptr(), None, None, local))
         else:
-            check(LIB.nthash_kmer_batch(h_bases.data_ptr(), h_off.data_ptr(), e2e_reads, k, h, h_out.data_ptr(),
-                                        h_valid.data_ptr(), None, None, local))
+            check(LIB.nthash_kmer_batch_uniform(h_bases.data_ptr(), e2e_reads, L, k, h, h_out.data_ptr(), h_valid.data_ptr(), None, None, local))
 
     e2e_step()
     barrier()
@@ -310,7 +309,7 @@ def main():
     e_dt = nd.max_over_ranks([e_dt])[0]
     # parity of the e2e result with the device-resident one (same reads): checksum of checksums
     same = bool((h_out[: 1000 * nk].cuda() == out[: 1000 * nk]).all())
-    e2e = {"value": world * e_rows / e_dt, "unit": UNIT, "h2d_bytes_per_step": int(h_bases.numel() + h_off.numel() * 8),
+    e2e = {"value": world * e_rows / e_dt, "unit": UNIT, "h2d_bytes_per_step": int(h_bases.numel()),
            "d2h_bytes_per_step": int(h_out.numel() * 8 + h_valid.numel() * 4), "reads_per_step": e2e_reads,
            "ms_per_step": e_dt * 1e3, "matches_device_path": same}
 
@@ -337,11 +336,34 @@ def main():
         for _ in range(args.e2e_steps):
             e2e_reduce_step()
         er_dt = (time.perf_counter() - t0) / args.e2e_steps
-        red_ms, er_dt = nd.max_over_ranks([red_ms, er_dt])
+        # the same consumer fed with 2-bit packed bases from the host (nthash_kmer_reduce_packed2bit): a quarter of the H2D bytes
+        lut2 = torch.zeros(256, dtype=torch.uint8, device="cuda")
+        lut2[torch.tensor(list(b"ACGT"), device="cuda").long()] = torch.arange(4, dtype=torch.uint8, device="cuda")
+        codes = lut2[bases[: e2e_reads * L].long()]
+        if codes.numel() % 4:
+            codes = torch.cat([codes, torch.zeros(4 - codes.numel() % 4, dtype=torch.uint8, device="cuda")])
+        c4 = codes.view(-1, 4)
+        h_packed = (c4[:, 0] | (c4[:, 1] << 2) | (c4[:, 2] << 4) | (c4[:, 3] << 6)).cpu().pin_memory()
+        del codes, c4, lut2
+        h_res2 = torch.zeros(3, dtype=torch.int64)
+
+        def e2e_packed_step():
+            check(LIB.nthash_kmer_reduce_packed2bit(h_packed.data_ptr(), None, None, e2e_reads, L, k, h, h_res2.data_ptr(), local))
+
+        e2e_packed_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_packed_step()
+        ep_dt = (time.perf_counter() - t0) / args.e2e_steps
+        red_ms, er_dt, ep_dt = nd.max_over_ranks([red_ms, er_dt, ep_dt])
         consumer = {"kind": "count/sum/xor of all hashes (nthash_kmer_reduce*), no hash leaves the GPU",
                     "value": world * rows / (red_ms * 1e-3), "unit": UNIT, "ms_per_step": red_ms,
                     "e2e": {"value": world * e_rows / er_dt, "unit": UNIT, "ms_per_step": er_dt * 1e3,
-                            "h2d_bytes_per_step": int(h_bases.numel() + h_off.numel() * 8), "d2h_bytes_per_step": 24},
+                            "h2d_bytes_per_step": int(h_bases.numel()), "d2h_bytes_per_step": 24},
+                    "e2e_packed2bit": {"value": world * e_rows / ep_dt, "unit": UNIT, "ms_per_step": ep_dt * 1e3,
+                                       "h2d_bytes_per_step": int(h_packed.numel()), "d2h_bytes_per_step": 24,
+                                       "matches_ascii_path": bool((h_res2 == h_res).all())},
                     "windows": int(red[0]), "sum": int(red[1]) & (2**64 - 1)}
 
         # second fused consumer: Bloom filter insert / query (the caller nthash.hpp:14-17 names), 3 hashes per

@@ -93,6 +93,11 @@ int nthash_kmer_batch(const char* bases, const uint64_t* read_off, uint64_t n_re
                       uint32_t num_hashes, uint64_t* out, uint32_t* valid_bits, uint64_t* out_fwd,
                       uint64_t* out_rev, int device);
 
+/* Fixed-length batch from host memory (n_reads reads of read_len bases back to back): nthash_kmer_batch without
+ * the offsets array.  Rows are n_reads * (read_len - k + 1); same outputs and optional arguments.            */
+int nthash_kmer_batch_uniform(const char* bases, uint64_t n_reads, uint32_t read_len, uint32_t k, uint32_t num_hashes,
+                              uint64_t* out, uint32_t* valid_bits, uint64_t* out_fwd, uint64_t* out_rev, int device);
+
 /* ---- fused consumer (first of the "next" rows: the step after the hash path) --------------------
  * What the reference's own benchmark does with the hashes (examples/benchmark.cpp:34-39: a running
  * sum over `while (h.roll())`), done on the device so that no hash ever leaves the SM:
@@ -107,6 +112,24 @@ int nthash_kmer_reduce_dev(const uint8_t* d_bases, uint64_t n_bases_readable, co
                            uint32_t num_hashes, uint64_t* d_result, void* stream);
 int nthash_kmer_reduce(const char* bases, const uint64_t* read_off, uint64_t n_reads, uint32_t k,
                        uint32_t num_hashes, uint64_t* result, int device);
+
+/* ---- input format next to the path: 2-bit packed bases ------------------------------------------
+ * The reference takes ASCII; pipelines that already hold 2-bit sequence can hand it over as is and move a quarter of
+ * the bytes across PCIe.  Base g of the batch is bits 2*(g & 3).. of packed[g >> 2], 0 = A, 1 = C, 2 = G, 3 = T;
+ * bit g of invalid_bits (nullable; 32-bit words, bit g & 31 of word g >> 5) marks a base that is not ACGT: it is
+ * expanded to 'N', so every byte-level rule of the reference still applies (NtHash skips such windows,
+ * kmer.cpp:232-235).  read_off indexes BASES exactly as in nthash_kmer_batch.  The device helper expands bases
+ * [first_base, first_base + n_bases) of a packed stream into d_bases_out (16-byte aligned, writable up to the next
+ * 16-byte multiple), ready for the *_dev entry points.  read_off may be NULL for n_reads reads of uniform_read_len
+ * bases back to back (no offsets array to build or scan); uniform_read_len is ignored otherwise.               */
+int nthash_kmer_batch_packed2bit(const uint8_t* packed, const uint32_t* invalid_bits, const uint64_t* read_off,
+                                 uint64_t n_reads, uint32_t uniform_read_len, uint32_t k, uint32_t num_hashes,
+                                 uint64_t* out, uint32_t* valid_bits, int device);
+int nthash_kmer_reduce_packed2bit(const uint8_t* packed, const uint32_t* invalid_bits, const uint64_t* read_off,
+                                  uint64_t n_reads, uint32_t uniform_read_len, uint32_t k, uint32_t num_hashes,
+                                  uint64_t* result, int device);
+int nthash_unpack2bit_dev(const uint8_t* d_packed, const uint32_t* d_invalid_bits, uint64_t first_base, uint64_t n_bases,
+                          uint8_t* d_bases_out, void* stream);
 
 /* ---- fused consumer: Bloom filter (the caller the reference's header names, nthash.hpp:14-17: k-mer
  * hashes feeding Bloom filters) ------------------------------------------------------------------

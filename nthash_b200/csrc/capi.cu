@@ -325,6 +325,10 @@ struct HostBatch
   uint32_t* valid_bits;
   uint64_t *out_fwd, *out_rev;
   uint64_t* reduce_result = nullptr; // fused consumer: 3 u64 on the host; then out == NULL and nothing else is copied back
+  // 2-bit packed input instead of `bases` (then bases == NULL): 4 bases per byte + optional invalid-base bitmap
+  const uint8_t* packed = nullptr;
+  const uint32_t* invalid_bits = nullptr;
+  uint64_t uniform_len = 0; // > 0: n_reads reads of this length back to back, read_off may be NULL (and is not scanned)
 };
 
 template<class Launch>
@@ -340,9 +344,14 @@ static int host_pipeline(const HostBatch& hb, Launch&& launch)
   const double t0 = now();
   // fixed-length batches (the common case) need no per-read bookkeeping at all
   bool uniform = true;
-  const uint64_t len0 = hb.read_off[1] - hb.read_off[0];
-  for (uint64_t r = 1; r < n && uniform; ++r) uniform = hb.read_off[r + 1] - hb.read_off[r] == len0;
+  const uint64_t len0 = hb.uniform_len ? hb.uniform_len : hb.read_off[1] - hb.read_off[0];
+  if (!hb.uniform_len) {
+    uint64_t diff = 0; // branch-free so that the compiler vectorises the scan of 10^7 offsets
+    for (uint64_t r = 1; r < n; ++r) diff |= (hb.read_off[r + 1] - hb.read_off[r]) ^ len0;
+    uniform = diff == 0;
+  }
   if (len0 > 0xffffffffull) uniform = false;
+  const uint64_t base0 = hb.uniform_len ? 0 : hb.read_off[0];
   const uint64_t nk0 = len0 >= hb.k ? len0 - hb.k + 1 : 0;
   std::vector<uint64_t> koff_v;
   uint64_t rows;
@@ -381,7 +390,8 @@ static int host_pipeline(const HostBatch& hb, Launch&& launch)
   struct Slot
   {
     cudaStream_t st = nullptr;
-    uint8_t* d_bases = nullptr;
+    uint8_t *d_bases = nullptr, *d_packed = nullptr;
+    uint32_t* d_inv = nullptr;
     uint64_t *d_off = nullptr, *d_out = nullptr, *d_fwd = nullptr, *d_rev = nullptr;
     std::vector<uint64_t> h_off;
   } slot[NS];
@@ -391,7 +401,8 @@ static int host_pipeline(const HostBatch& hb, Launch&& launch)
   auto cleanup = [&]() {
     for (int i = 0; i < NS; ++i) {
       if (slot[i].st) cudaStreamSynchronize(slot[i].st);
-      for (void* q : { (void*)slot[i].d_bases, (void*)slot[i].d_off, (void*)slot[i].d_out, (void*)slot[i].d_fwd, (void*)slot[i].d_rev })
+      for (void* q : { (void*)slot[i].d_bases, (void*)slot[i].d_packed, (void*)slot[i].d_inv, (void*)slot[i].d_off, (void*)slot[i].d_out,
+                       (void*)slot[i].d_fwd, (void*)slot[i].d_rev })
         if (q) cudaFreeAsync(q, slot[i].st);
       if (i == 0 && d_valid) cudaFreeAsync(d_valid, slot[0].st);
       if (i == 0 && d_reduce) cudaFreeAsync(d_reduce, slot[0].st);
@@ -419,6 +430,8 @@ static int host_pipeline(const HostBatch& hb, Launch&& launch)
   for (int i = 0; i < ns; ++i) {
     NTH_TRY(cudaStreamCreateWithFlags(&slot[i].st, cudaStreamNonBlocking));
     NTH_TRY(cudaMallocAsync(&slot[i].d_bases, max_bases + 96, slot[i].st));
+    if (hb.packed) NTH_TRY(cudaMallocAsync(&slot[i].d_packed, max_bases / 4 + 16, slot[i].st));
+    if (hb.packed && hb.invalid_bits) NTH_TRY(cudaMallocAsync(&slot[i].d_inv, (max_bases / 32 + 4) * 4, slot[i].st));
     if (!uniform) NTH_TRY(cudaMallocAsync(&slot[i].d_off, 2 * (max_reads + 1) * sizeof(uint64_t), slot[i].st));
     if (hb.out) NTH_TRY(cudaMallocAsync(&slot[i].d_out, max_rows * hb.H * sizeof(uint64_t), slot[i].st));
     if (hb.strand_cols) {
@@ -443,10 +456,20 @@ static int host_pipeline(const HostBatch& hb, Launch&& launch)
     Slot& s = slot[c % ns];
     if (c >= (size_t)ns) NTH_TRY(cudaStreamSynchronize(s.st)); // the slot's previous chunk has been copied out
     const uint64_t r0 = cut[c], r1 = cut[c + 1], nr = r1 - r0;
-    const uint64_t b0 = hb.read_off[r0], nbytes = hb.read_off[r1] - b0, row0 = koff(r0), nrows = koff(r1) - row0;
+    const uint64_t b0 = uniform ? base0 + r0 * len0 : hb.read_off[r0], nbytes = uniform ? (r1 - r0) * len0 : hb.read_off[r1] - b0;
+    const uint64_t row0 = koff(r0), nrows = koff(r1) - row0;
     if (nrows == 0) continue;
     // chunk bytes sit 16 bytes into the slot so that "the base before the first one" is addressable
-    NTH_TRY(cudaMemcpyAsync(s.d_bases + 16, hb.bases + b0, nbytes, cudaMemcpyHostToDevice, s.st));
+    if (hb.packed) { // a quarter of the bytes cross PCIe; a small kernel expands them to the ASCII the hash kernels read
+      // both slices start at the bitmap word holding base b0 (base 32*v0), so one offset addresses them
+      const uint64_t v0 = b0 / 32, v1 = (b0 + nbytes + 31) / 32, p0 = 8 * v0, p1 = (b0 + nbytes + 3) / 4;
+      NTH_TRY(cudaMemcpyAsync(s.d_packed, hb.packed + p0, p1 - p0, cudaMemcpyHostToDevice, s.st));
+      if (hb.invalid_bits) NTH_TRY(cudaMemcpyAsync(s.d_inv, hb.invalid_bits + v0, (v1 - v0) * 4, cudaMemcpyHostToDevice, s.st));
+      // the kernel indexes the staged slices with bases counted from their first byte / word
+      NTH_TRY(launch_unpack2bit(s.d_packed, hb.invalid_bits ? s.d_inv : nullptr, b0 - 32 * v0, nbytes, s.d_bases + 16, s.st));
+    } else {
+      NTH_TRY(cudaMemcpyAsync(s.d_bases + 16, hb.bases + b0, nbytes, cudaMemcpyHostToDevice, s.st));
+    }
     DevBatch B;
     B.n_reads = nr;
     B.d_out = s.d_out;
@@ -622,6 +645,21 @@ int nthash_kmer_batch(const char* bases, const uint64_t* read_off, uint64_t n_re
 }
 
 
+// Fixed-length batches from host memory: no offsets array to build, scan or keep (10^7 reads = 80 MB of offsets).
+int nthash_kmer_batch_uniform(const char* bases, uint64_t n_reads, uint32_t read_len, uint32_t k, uint32_t num_hashes, uint64_t* out,
+                              uint32_t* valid_bits, uint64_t* out_fwd, uint64_t* out_rev, int device)
+{
+  if (int rc = check_kh(k, num_hashes)) return rc;
+  if (int rc = check_outputs(out, out_fwd, out_rev)) return rc;
+  if (n_reads == 0 || read_len < k) return NTHASH_OK;
+  if (!bases) return fail(NTHASH_ERR_INVALID_ARG, "bases must not be NULL");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(NTHASH_ERR_NO_DEVICE, "cannot select CUDA device %d", device);
+  if (int rc = check_device_ready()) return rc;
+  HostBatch hb = { bases, nullptr, n_reads, k, num_hashes, out_fwd ? 1ull : 0ull, out, valid_bits, out_fwd, out_rev };
+  hb.uniform_len = read_len;
+  return host_pipeline(hb, [&](const DevBatch& B, cudaStream_t st) { return kmer_dev_run(B, k, num_hashes, st); });
+}
+
 // ---- fused consumer: count / sum / xor of every hash value ------------------------------------
 
 int nthash_kmer_reduce_uniform_dev(const uint8_t* d_bases, uint64_t n_bases_readable, uint64_t n_reads,
@@ -681,6 +719,59 @@ int nthash_kmer_reduce(const char* bases, const uint64_t* read_off, uint64_t n_r
   HostBatch hb = { bases, read_off, n_reads, k, num_hashes, 0ull, nullptr, nullptr, nullptr, nullptr };
   hb.reduce_result = result;
   return host_pipeline(hb, [&](const DevBatch& B, cudaStream_t st) { return kmer_dev_run(B, k, num_hashes, st); });
+}
+
+// ---- 2-bit packed input (host entries): a quarter of the bytes cross PCIe --------------------------
+
+static int packed_args(const uint8_t* packed, const uint64_t* read_off, uint64_t n_reads, uint32_t uniform_read_len, int device)
+{
+  if (n_reads == 0) return NTHASH_OK;
+  if (!packed) return fail(NTHASH_ERR_INVALID_ARG, "packed must not be NULL");
+  if (!read_off && !uniform_read_len) return fail(NTHASH_ERR_INVALID_ARG, "give read_off or a uniform_read_len > 0");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(NTHASH_ERR_NO_DEVICE, "cannot select CUDA device %d", device);
+  return check_device_ready();
+}
+
+int nthash_kmer_batch_packed2bit(const uint8_t* packed, const uint32_t* invalid_bits, const uint64_t* read_off, uint64_t n_reads,
+                                 uint32_t uniform_read_len, uint32_t k, uint32_t num_hashes, uint64_t* out, uint32_t* valid_bits,
+                                 int device)
+{
+  if (int rc = check_kh(k, num_hashes)) return rc;
+  if (int rc = check_outputs(out, nullptr, nullptr)) return rc;
+  if (int rc = packed_args(packed, read_off, n_reads, uniform_read_len, device)) return rc;
+  if (n_reads == 0) return NTHASH_OK;
+  HostBatch hb = { nullptr, read_off, n_reads, k, num_hashes, 0ull, out, valid_bits, nullptr, nullptr };
+  hb.uniform_len = read_off ? 0 : uniform_read_len;
+  hb.packed = packed;
+  hb.invalid_bits = invalid_bits;
+  return host_pipeline(hb, [&](const DevBatch& B, cudaStream_t st) { return kmer_dev_run(B, k, num_hashes, st); });
+}
+
+int nthash_kmer_reduce_packed2bit(const uint8_t* packed, const uint32_t* invalid_bits, const uint64_t* read_off, uint64_t n_reads,
+                                  uint32_t uniform_read_len, uint32_t k, uint32_t num_hashes, uint64_t* result, int device)
+{
+  if (int rc = check_kh(k, num_hashes)) return rc;
+  if (!result) return fail(NTHASH_ERR_INVALID_ARG, "result must not be NULL");
+  result[0] = result[1] = result[2] = 0;
+  if (int rc = packed_args(packed, read_off, n_reads, uniform_read_len, device)) return rc;
+  if (n_reads == 0) return NTHASH_OK;
+  HostBatch hb = { nullptr, read_off, n_reads, k, num_hashes, 0ull, nullptr, nullptr, nullptr, nullptr };
+  hb.uniform_len = read_off ? 0 : uniform_read_len;
+  hb.reduce_result = result;
+  hb.packed = packed;
+  hb.invalid_bits = invalid_bits;
+  return host_pipeline(hb, [&](const DevBatch& B, cudaStream_t st) { return kmer_dev_run(B, k, num_hashes, st); });
+}
+
+int nthash_unpack2bit_dev(const uint8_t* d_packed, const uint32_t* d_invalid_bits, uint64_t first_base, uint64_t n_bases,
+                          uint8_t* d_bases_out, void* stream)
+{
+  if (n_bases == 0) return NTHASH_OK;
+  if (!d_packed || !d_bases_out) return fail(NTHASH_ERR_INVALID_ARG, "d_packed and d_bases_out must not be NULL");
+  if ((uintptr_t)d_bases_out & 15) return fail(NTHASH_ERR_INVALID_ARG, "d_bases_out must be 16-byte aligned");
+  if (int rc = check_device_ready()) return rc;
+  NTH_CUDA(launch_unpack2bit(d_packed, d_invalid_bits, first_base, n_bases, d_bases_out, (cudaStream_t)stream));
+  return NTHASH_OK;
 }
 
 // ---- fused consumer: Bloom filter insert / query ------------------------------------------------

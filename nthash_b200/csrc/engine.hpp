@@ -103,6 +103,10 @@ uint32_t span_bound(uint32_t seg, uint32_t segs, uint32_t k);
 // stats[2] = number of items when reads are cut into seg-window items.  All device pointers.
 cudaError_t launch_koff_scan(const uint64_t* read_off, uint64_t n_reads, uint32_t k, uint32_t seg,
                              uint64_t* koff, uint64_t* stats, cudaStream_t st);
+// 2-bit packed bases (+ optional invalid-base bitmap) -> ASCII; bases [first_base, first_base + n_bases) of the packed
+// stream go to d_out[0 .. n_bases) (16-byte aligned, padded to a 16-byte multiple).
+cudaError_t launch_unpack2bit(const uint8_t* d_packed, const uint32_t* d_invalid, uint64_t first_base, uint64_t n_bases, uint8_t* d_out,
+                              cudaStream_t st);
 // Expands reads into items (only needed when some read exceeds the whole-read tile budget).
 cudaError_t launch_item_fill(const uint64_t* read_off, const uint64_t* koff, uint64_t n_reads, uint32_t k,
                              uint32_t seg, uint64_t* item_byte, uint64_t* item_out, uint64_t* item_read,

@@ -149,7 +149,40 @@ __global__ void item_fill(const uint64_t* read_off, const uint64_t* koff, const 
   }
 }
 
+// 2-bit packed bases -> the ASCII bytes the hash kernels read.  Base g of the packed stream is bits 2*(g & 3).. of byte
+// g >> 2 (0 = A, 1 = C, 2 = G, 3 = T); bit g of `invalid` (optional) marks a base that is not ACGT and comes out as 'N',
+// which is what keeps the reference's byte-level rules (windows with such a base are skipped by NtHash, hashed as a
+// zero seed by SeedNtHash).  Thread t writes output bytes [16 t, 16 t + 16) with one 16-byte store.
+__global__ void unpack2bit_kernel(const uint8_t* packed, const uint32_t* invalid, uint64_t first_base, uint64_t n_bases, uint8_t* out)
+{
+  const uint64_t j0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (j0 >= n_bases) return;
+  uint32_t w[4] = { 0, 0, 0, 0 };
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const uint64_t g = first_base + j0 + j;
+    uint32_t c = 'A';
+    if (j0 + j < n_bases) {
+      const uint32_t code = (packed[g >> 2] >> (2 * (g & 3))) & 3u;
+      c = (0x54474341u >> (8 * code)) & 0xFFu; // "ACGT"
+      if (invalid && (invalid[g >> 5] >> (g & 31) & 1u)) c = 'N';
+    }
+    w[j >> 2] |= c << (8 * (j & 3));
+  }
+  *reinterpret_cast<uint4*>(out + j0) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 } // namespace
+
+// d_out must be 16-byte aligned and writable up to the next multiple of 16 bytes past n_bases.
+cudaError_t launch_unpack2bit(const uint8_t* d_packed, const uint32_t* d_invalid, uint64_t first_base, uint64_t n_bases, uint8_t* d_out,
+                              cudaStream_t st)
+{
+  if (n_bases == 0) return cudaSuccess;
+  const uint64_t threads = (n_bases + 15) / 16;
+  unpack2bit_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_packed, d_invalid, first_base, n_bases, d_out);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_koff_scan(const uint64_t* read_off, uint64_t n_reads, uint32_t k, uint32_t seg, uint64_t* excl,
                              uint64_t* stats, cudaStream_t st)

@@ -281,3 +281,62 @@ def test_fused_bloom_consumer(h, bits):
     f3 = nthash_b200.bloom_filter(bits)
     r3 = u64(nthash_b200.kmer_bloom(d_r, torch.from_numpy(roff).cuda(), k, h, f3, bits))
     assert int(r3[0]) == int(ora3["n_emit"]) and (f3.cpu().numpy().view(np.uint32) == words3).all()
+
+
+def _pack2bit(ascii_bases):
+    """ACGTN bytes -> (packed 2-bit array, invalid-base bitmap) in the layout of include/nthash_b200.h."""
+    code = np.zeros(256, np.uint8); code[list(b"ACGT")] = [0, 1, 2, 3]
+    n = len(ascii_bases)
+    c = np.zeros((n + 3) // 4 * 4, np.uint8); c[:n] = code[ascii_bases]
+    c = c.reshape(-1, 4)
+    packed = (c[:, 0] | (c[:, 1] << 2) | (c[:, 2] << 4) | (c[:, 3] << 6)).astype(np.uint8)
+    inv = np.zeros((n + 31) // 32 * 32, np.uint8); inv[:n] = ascii_bases == ord("N")
+    bits = np.packbits(inv.reshape(-1, 8), axis=1, bitorder="little").reshape(-1).view(np.uint32)
+    return np.ascontiguousarray(packed), np.ascontiguousarray(bits)
+
+
+@pytest.mark.parametrize("tiny_chunks", [False, True])
+def test_packed_2bit_input(tiny_chunks, monkeypatch):
+    # 2-bit packed bases + invalid-base bitmap through the host entries: same rows as the ASCII path / the oracle
+    if tiny_chunks:
+        monkeypatch.setenv("NTHASH_B200_HOST_CHUNK_VALUES", "2500")   # chunk boundaries at every alignment of the packed stream
+    rng = np.random.default_rng(17)
+    for lens, k, h in ((np.full(400, 150), 31, 1), (rng.integers(0, 300, 500), 21, 2), ([5000, 3, 2000, 31, 77], 31, 4)):
+        off = ragged_offsets(lens).astype(np.uint64)
+        bases = rng.choice(np.frombuffer(b"ACGT", np.uint8), int(off[-1]))
+        bases[rng.random(len(bases)) < 0.002] = ord("N")
+        packed, inv = _pack2bit(bases)
+        ora = ORACLE.kmer_batch(bases, off, k, h)
+        rows = ora["out"].shape[0]
+        out = np.full((rows, h), 0xEE, np.uint64); vb = np.zeros((rows + 31) // 32, np.uint32)
+        rc = nthash_b200.LIB.nthash_kmer_batch_packed2bit(packed.ctypes.data, inv.ctypes.data, off.ctypes.data, len(off) - 1, 0, k, h,
+                                                          out.ctypes.data, vb.ctypes.data, 0)
+        assert rc == 0, nthash_b200.LIB.nthash_last_error()
+        bits = ((vb[:, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(-1)[:rows]
+        assert (bits == ora["valid"]).all() and (out == ora["out"]).all()
+        res = np.zeros(3, np.uint64)
+        assert nthash_b200.LIB.nthash_kmer_reduce_packed2bit(packed.ctypes.data, inv.ctypes.data, off.ctypes.data, len(off) - 1, 0, k, h,
+                                                             res.ctypes.data, 0) == 0
+        assert (int(res[0]), int(res[1]), int(res[2])) == (ora["n_emit"], ora["sum"], ora["xor"])
+        if len(set(np.diff(off.astype(np.int64)))) == 1:   # fixed-length batch: the entries without an offsets array
+            L = int(off[1])
+            out2 = np.zeros((rows, h), np.uint64); res2 = np.zeros(3, np.uint64); out3 = np.zeros((rows, h), np.uint64)
+            assert nthash_b200.LIB.nthash_kmer_batch_packed2bit(packed.ctypes.data, inv.ctypes.data, None, len(off) - 1, L, k, h,
+                                                                out2.ctypes.data, None, 0) == 0
+            assert nthash_b200.LIB.nthash_kmer_reduce_packed2bit(packed.ctypes.data, inv.ctypes.data, None, len(off) - 1, L, k, h,
+                                                                 res2.ctypes.data, 0) == 0
+            assert nthash_b200.LIB.nthash_kmer_batch_uniform(bases.ctypes.data, len(off) - 1, L, k, h, out3.ctypes.data, None, None, None, 0) == 0
+            assert (out2 == ora["out"]).all() and (out3 == ora["out"]).all() and (res2 == res).all()
+    # without a bitmap every base is ACGT; and the device helper on an unaligned slice
+    clean = rng.choice(np.frombuffer(b"ACGT", np.uint8), 10_001)
+    packed, _ = _pack2bit(clean)
+    offc = np.array([0, 10_001], np.uint64)
+    orac = ORACLE.kmer_batch(clean, offc, 31, 1)
+    res = np.zeros(3, np.uint64)
+    assert nthash_b200.LIB.nthash_kmer_reduce_packed2bit(packed.ctypes.data, None, offc.ctypes.data, 1, 0, 31, 1, res.ctypes.data, 0) == 0
+    assert (int(res[0]), int(res[1])) == (orac["n_emit"], orac["sum"])
+    d_p = torch.from_numpy(packed).cuda()
+    d_o = torch.zeros(10_016, dtype=torch.uint8, device="cuda")
+    assert nthash_b200.LIB.nthash_unpack2bit_dev(d_p.data_ptr(), None, 37, 9000, d_o.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    assert (d_o[:9000].cpu().numpy() == clean[37:9037]).all()
