@@ -48,3 +48,15 @@ def test_reference_test_scenarios_through_the_gpu():
     out = subprocess.run([build_shim_tests()], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "all blocks: 0 failure(s)" in out.stdout
+
+
+@pytest.mark.gpu
+def test_unmodified_reference_tests_pass_against_the_shim():
+    """oracle/_ref/ref_tests_shim is the reference's own tests/tests.cpp, untouched, compiled against the drop-in header
+    and linked with the CUDA engine (oracle/Makefile builds it where /root/reference exists; the binary travels)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_tests_shim")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_tests_shim not built (needs the reference tree at build time)")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert (out.stdout + out.stderr).count("Testing") == 17
