@@ -220,6 +220,14 @@ def main():
 
     rank, world, local = nd.env_rank()
     torch.cuda.set_device(local)
+    try:  # pin this rank to the CPUs next to its GPU, so that the pinned host buffers land on that NUMA node (best effort)
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else local
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+    except Exception:
+        pass
     nd.init("nccl", torch.device("cuda", local))
     barrier = nd.barrier
 
