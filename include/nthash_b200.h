@@ -93,6 +93,13 @@ int nthash_kmer_batch(const char* bases, const uint64_t* read_off, uint64_t n_re
                       uint32_t num_hashes, uint64_t* out, uint32_t* valid_bits, uint64_t* out_fwd,
                       uint64_t* out_rev, int device);
 
+/* The same batch over several GPUs of one box: contiguous read ranges with about equal
+ * numbers of bases, one host thread and one chunked pipeline per listed device, no exchange between devices.
+ * Outputs are the same dense arrays as nthash_kmer_batch's.                                                  */
+int nthash_kmer_batch_multi(const char* bases, const uint64_t* read_off, uint64_t n_reads, uint32_t k,
+                            uint32_t num_hashes, uint64_t* out, uint32_t* valid_bits, uint64_t* out_fwd,
+                            uint64_t* out_rev, const int* devices, int n_devices);
+
 /* Fixed-length batch from host memory (n_reads reads of read_len bases back to back): nthash_kmer_batch without
  * the offsets array.  Rows are n_reads * (read_len - k + 1); same outputs and optional arguments.            */
 int nthash_kmer_batch_uniform(const char* bases, uint64_t n_reads, uint32_t read_len, uint32_t k, uint32_t num_hashes,

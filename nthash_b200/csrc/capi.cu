@@ -10,7 +10,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace nthb {
@@ -644,6 +646,61 @@ int nthash_kmer_batch(const char* bases, const uint64_t* read_off, uint64_t n_re
   return host_pipeline(hb, [&](const DevBatch& B, cudaStream_t st) { return kmer_dev_run(B, k, num_hashes, st); });
 }
 
+
+// One host batch over several GPUs of the box: contiguous read ranges with about equal numbers of bases, one host
+// thread + the chunked pipeline per device, no exchange between devices.
+int nthash_kmer_batch_multi(const char* bases, const uint64_t* read_off, uint64_t n_reads, uint32_t k, uint32_t num_hashes,
+                            uint64_t* out, uint32_t* valid_bits, uint64_t* out_fwd, uint64_t* out_rev, const int* devices,
+                            int n_devices)
+{
+  if (int rc = check_kh(k, num_hashes)) return rc;
+  if (n_devices < 1 || !devices) return fail(NTHASH_ERR_INVALID_ARG, "give at least one device");
+  if (n_reads == 0) return NTHASH_OK;
+  if (!bases || !read_off) return fail(NTHASH_ERR_INVALID_ARG, "bases and read_off must not be NULL");
+  if (int rc = check_outputs(out, out_fwd, out_rev)) return rc;
+  const uint64_t G = std::min<uint64_t>((uint64_t)n_devices, n_reads);
+  // shard boundaries: the first read starting at or after j/G of the bases
+  std::vector<uint64_t> cut(G + 1, n_reads);
+  cut[0] = 0;
+  const uint64_t total = read_off[n_reads] - read_off[0];
+  for (uint64_t j = 1; j < G; ++j)
+    cut[j] = std::max<uint64_t>(cut[j - 1], std::lower_bound(read_off, read_off + n_reads, read_off[0] + total / G * j) - read_off);
+  // dense row of every boundary (the shards' outputs are slices of the caller's arrays)
+  std::vector<uint64_t> row(G + 1, 0);
+  for (uint64_t j = 0; j < G; ++j) row[j + 1] = row[j] + nthash_window_rows(read_off + cut[j], cut[j + 1] - cut[j], k, nullptr);
+  std::vector<int> rcs(G, NTHASH_OK);
+  std::vector<std::string> errs(G);
+  std::vector<std::vector<uint32_t>> vtmp(G); // per-shard bitmaps start at bit 0; merged below
+  std::vector<std::thread> threads;
+  for (uint64_t j = 0; j < G; ++j) {
+    threads.emplace_back([&, j]() {
+      const uint64_t nr = cut[j + 1] - cut[j], rows = row[j + 1] - row[j];
+      if (nr == 0 || rows == 0) return;
+      if (valid_bits) vtmp[j].assign((rows + 31) / 32, 0u);
+      rcs[j] = nthash_kmer_batch(bases, read_off + cut[j], nr, k, num_hashes, out + row[j] * num_hashes,
+                                 valid_bits ? vtmp[j].data() : nullptr, out_fwd ? out_fwd + row[j] : nullptr,
+                                 out_rev ? out_rev + row[j] : nullptr, devices[j]);
+      if (rcs[j] != NTHASH_OK) errs[j] = g_err; // the message lives in this thread's slot
+    });
+  }
+  for (std::thread& t : threads) t.join();
+  for (uint64_t j = 0; j < G; ++j)
+    if (rcs[j] != NTHASH_OK) return fail(rcs[j], "device %d: %s", devices[j], errs[j].c_str());
+  if (valid_bits) {
+    std::fill(valid_bits, valid_bits + (row[G] + 31) / 32, 0u);
+    for (uint64_t j = 0; j < G; ++j) {
+      const uint64_t rows = row[j + 1] - row[j], b0 = row[j];
+      const uint32_t sh = (uint32_t)(b0 & 31);
+      for (uint64_t w = 0; w < vtmp[j].size(); ++w) {
+        uint32_t v = vtmp[j][w];
+        if (w + 1 == vtmp[j].size() && (rows & 31)) v &= (1u << (rows & 31)) - 1u; // bits past the shard's last row
+        valid_bits[(b0 >> 5) + w] |= v << sh;
+        if (sh && ((b0 >> 5) + w + 1) < (row[G] + 31) / 32) valid_bits[(b0 >> 5) + w + 1] |= v >> (32 - sh);
+      }
+    }
+  }
+  return NTHASH_OK;
+}
 
 // Fixed-length batches from host memory: no offsets array to build, scan or keep (10^7 reads = 80 MB of offsets).
 int nthash_kmer_batch_uniform(const char* bases, uint64_t n_reads, uint32_t read_len, uint32_t k, uint32_t num_hashes, uint64_t* out,

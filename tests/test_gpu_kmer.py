@@ -340,3 +340,23 @@ def test_packed_2bit_input(tiny_chunks, monkeypatch):
     assert nthash_b200.LIB.nthash_unpack2bit_dev(d_p.data_ptr(), None, 37, 9000, d_o.data_ptr(), None) == 0
     torch.cuda.synchronize()
     assert (d_o[:9000].cpu().numpy() == clean[37:9037]).all()
+
+
+def test_multi_device_host_entry():
+    # nthash_kmer_batch_multi shards one host batch over the listed devices; with one GPU the list repeats it, which still
+    # exercises the sharding, the per-shard pipelines in threads and the merge of the validity bitmaps at odd bit offsets
+    rng = np.random.default_rng(23)
+    ndev = torch.cuda.device_count()
+    devs = np.array([i % ndev for i in range(3)], np.int32)
+    for lens, k, h in ((rng.integers(0, 300, 1000), 31, 2), (np.full(777, 151), 21, 1), ([40, 5000, 7], 31, 1)):
+        off = ragged_offsets(lens).astype(np.uint64)
+        bases = synth(rng, int(off[-1]), p_bad=0.003)
+        ora = ORACLE.kmer_batch(bases, off, k, h)
+        rows = ora["out"].shape[0]
+        out = np.full((rows, h), 0xAB, np.uint64); fw = np.zeros(rows, np.uint64); rv = np.zeros(rows, np.uint64)
+        vb = np.full((rows + 31) // 32, 0xFFFFFFFF, np.uint32)
+        rc = nthash_b200.LIB.nthash_kmer_batch_multi(bases.ctypes.data, off.ctypes.data, len(off) - 1, k, h, out.ctypes.data, vb.ctypes.data,
+                                                     fw.ctypes.data, rv.ctypes.data, devs.ctypes.data, len(devs))
+        assert rc == 0, nthash_b200.LIB.nthash_last_error()
+        bits = ((vb[:, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(-1)[:rows]
+        assert (bits == ora["valid"]).all() and (out == ora["out"]).all() and (fw == ora["fwd"]).all() and (rv == ora["rev"]).all()
