@@ -360,3 +360,35 @@ def test_multi_device_host_entry():
         assert rc == 0, nthash_b200.LIB.nthash_last_error()
         bits = ((vb[:, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(-1)[:rows]
         assert (bits == ora["valid"]).all() and (out == ora["out"]).all() and (fw == ora["fwd"]).all() and (rv == ora["rev"]).all()
+
+
+def test_full_size_config2_properties():
+    """BASELINE.json configs[1] at full size (10 M x 150 bp, k=31, h=1; 1.2e9 k-mers) through size-independent properties:
+    strand symmetry of the canonical hash (reference tests.cpp:119-133), agreement of the three output paths' checksums
+    (stored hashes, fused reduce consumer, 2-bit packed input), and a sampled comparison with the oracle."""
+    n, L, k = 10_000_000, 150, 31
+    nk = L - k + 1
+    g = torch.Generator(device="cuda"); g.manual_seed(2024)
+    codes = torch.randint(0, 4, (n, L), dtype=torch.uint8, device="cuda", generator=g)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device="cuda")
+    fwd = torch.zeros(n * L + 64, dtype=torch.uint8, device="cuda"); fwd[: n * L] = lut[codes.long()].view(-1)
+    rc = torch.zeros(n * L + 64, dtype=torch.uint8, device="cuda"); rc[: n * L] = lut[(3 - codes.flip(1)).long()].view(-1)
+    out_f = nthash_b200.kmer_hashes_uniform(fwd[: n * L], n, L, k, 1, want_valid=False).out.view(n, nk)
+    out_r = nthash_b200.kmer_hashes_uniform(rc[: n * L], n, L, k, 1, want_valid=False).out.view(n, nk)
+    torch.cuda.synchronize()
+    assert torch.equal(out_f, out_r.flip(1))                      # window p of a read == window nk-1-p of its reverse complement
+    del out_r, rc
+    total = int(out_f.sum())                                      # wraps modulo 2^64 like the consumer's sum
+    red = nthash_b200.kmer_reduce_uniform(fwd[: n * L], n, L, k, 1)
+    assert int(red[0]) == n * nk and int(red[1]) == total
+    # a sample of reads against the oracle, bit for bit
+    idx = torch.arange(0, n, 9973, device="cuda")
+    sample = fwd[: n * L].view(n, L)[idx].cpu().numpy()
+    ora = ORACLE.kmer_batch(sample.reshape(-1), np.arange(len(idx) + 1, dtype=np.uint64) * L, k, 1, threads=8)
+    assert (u64(out_f[idx]).reshape(-1, 1) == ora["out"]).all()
+    # the packed-input host entry on the first million reads
+    m = 1_000_000
+    packed = (codes[:m].reshape(-1, 4).to(torch.int32) * torch.tensor([1, 4, 16, 64], device="cuda", dtype=torch.int32)).sum(1).to(torch.uint8).cpu().numpy()
+    res = np.zeros(3, np.uint64)
+    assert nthash_b200.LIB.nthash_kmer_reduce_packed2bit(packed.ctypes.data, None, None, m, L, k, 1, res.ctypes.data, 0) == 0
+    assert int(res[0]) == m * nk and int(res[1]) == int(out_f[:m].sum()) & (2**64 - 1)
