@@ -138,6 +138,15 @@ int nthash_kmer_reduce_packed2bit(const uint8_t* packed, const uint32_t* invalid
 int nthash_unpack2bit_dev(const uint8_t* d_packed, const uint32_t* d_invalid_bits, uint64_t first_base, uint64_t n_bases,
                           uint8_t* d_bases_out, void* stream);
 
+/* ---- compacted output -------------------------------------------------------------------------------
+ * The dense layout keeps a (zero) row for every window; the reference's loop only ever sees the windows it
+ * visits.  This keeps exactly those rows (validity bit set), in order: d_compact[n][values_per_row], and
+ * optionally their dense row numbers d_row_index[n] (row = koff[read] + get_pos(), so (read, position) follow
+ * from koff); n goes to *d_count (device memory).  d_compact / d_row_index need room for `rows` entries at most.
+ * Works on the output of the k-mer and the seed entry points alike.                                           */
+int nthash_compact_rows_dev(const uint64_t* d_out, const uint32_t* d_valid_bits, uint64_t rows, uint32_t values_per_row,
+                            uint64_t* d_compact, uint64_t* d_row_index, uint64_t* d_count, void* stream);
+
 /* ---- fused consumer: Bloom filter (the caller the reference's header names, nthash.hpp:14-17: k-mer
  * hashes feeding Bloom filters) ------------------------------------------------------------------
  * For every window the reference's `while (h.roll())` loop visits, the num_hashes values of h.hashes()

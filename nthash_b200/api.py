@@ -207,6 +207,23 @@ def kmer_reduce(bases, read_off, k, num_hashes=1, stream=None) -> torch.Tensor:
     return res
 
 
+def compact(batch, stream=None):
+    """HashBatch -> (hashes [n, H], dense row numbers [n]) of the windows the reference's loop visits, in its order
+    (nthash_compact_rows_dev).  Synchronises to learn n."""
+    if batch.valid_bits is None:
+        raise ValueError("the batch was computed without a validity bitmap")
+    out = batch.out
+    H = out.shape[1]
+    dev = out.device
+    with torch.cuda.device(dev):
+        comp = torch.empty_like(out)
+        idx = torch.empty(batch.rows, dtype=torch.int64, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        check(LIB.nthash_compact_rows_dev(_ptr(out), _ptr(batch.valid_bits), batch.rows, H, _ptr(comp), _ptr(idx), _ptr(cnt), _stream_ptr(stream)))
+        n = int(cnt.item())
+    return comp[:n], idx[:n]
+
+
 def bloom_filter(bits, device="cuda") -> torch.Tensor:
     """An empty device-resident Bloom filter of `bits` bits (int32 words; bit b = bit b & 31 of word b >> 5)."""
     return torch.zeros((int(bits) + 31) // 32, dtype=torch.int32, device=device)

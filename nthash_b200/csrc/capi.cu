@@ -831,6 +831,19 @@ int nthash_unpack2bit_dev(const uint8_t* d_packed, const uint32_t* d_invalid_bit
   return NTHASH_OK;
 }
 
+// ---- compacted output: only the windows the reference's loop visits, in its order ------------------
+
+int nthash_compact_rows_dev(const uint64_t* d_out, const uint32_t* d_valid_bits, uint64_t rows, uint32_t values_per_row,
+                            uint64_t* d_compact, uint64_t* d_row_index, uint64_t* d_count, void* stream)
+{
+  if (!d_count) return fail(NTHASH_ERR_INVALID_ARG, "d_count must not be NULL");
+  if (rows && (!d_out || !d_valid_bits || !d_compact || !values_per_row))
+    return fail(NTHASH_ERR_INVALID_ARG, "d_out, d_valid_bits and d_compact must not be NULL, values_per_row > 0");
+  if (int rc = check_device_ready()) return rc;
+  NTH_CUDA(launch_compact_rows(d_out, d_valid_bits, rows, values_per_row, d_compact, d_row_index, d_count, (cudaStream_t)stream));
+  return NTHASH_OK;
+}
+
 // ---- fused consumer: Bloom filter insert / query ------------------------------------------------
 
 static int bloom_args(uint32_t k, uint32_t h, const uint32_t* d_filter, uint64_t bits, const uint64_t* d_result)

@@ -172,7 +172,106 @@ __global__ void unpack2bit_kernel(const uint8_t* packed, const uint32_t* invalid
   *reinterpret_cast<uint4*>(out + j0) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// ---- compaction of the dense rows to the windows the reference's loop visits, in its order --------------------
+constexpr int CMP_T = 256;                   // threads per block: 8 warps x 32 bitmap words x 32 rows = 8192 rows
+constexpr uint64_t CMP_ROWS = CMP_T * 32ull;
+
+__global__ void compact_count(const uint32_t* valid, uint64_t rows, uint64_t* block_sums)
+{
+  const uint64_t w = (uint64_t)blockIdx.x * CMP_T + threadIdx.x, nw = (rows + 31) / 32;
+  uint32_t v = w < nw ? valid[w] : 0u;
+  if (w + 1 == nw && (rows & 31)) v &= (1u << (rows & 31)) - 1u;
+  uint32_t c = __popc(v);
+  for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  __shared__ uint32_t ws[CMP_T / 32];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int i = 0; i < CMP_T / 32; ++i) t += ws[i];
+    block_sums[blockIdx.x] = t;
+  }
+}
+
+// one block: exclusive scan of the block sums in place, total to *count
+__global__ void compact_scan(uint64_t* block_sums, uint64_t nb, uint64_t* count)
+{
+  __shared__ uint64_t carry;
+  __shared__ uint64_t ws[32];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint64_t base = 0; base < nb; base += blockDim.x) {
+    const uint64_t i = base + threadIdx.x;
+    const uint64_t v = i < nb ? block_sums[i] : 0;
+    uint64_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+    __syncthreads();
+    uint64_t off = carry;
+    for (unsigned w = 0; w < (threadIdx.x >> 5); ++w) off += ws[w];
+    if (i < nb) block_sums[i] = off + x - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = off + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = carry;
+}
+
+// every warp walks its 32 bitmap words; for one word the 32 lanes are 32 consecutive rows (coalesced reads), the kept
+// ones land at consecutive compact rows
+__global__ void compact_write(const uint64_t* out, const uint32_t* valid, uint64_t rows, uint32_t H, const uint64_t* block_off,
+                              uint64_t* compact, uint64_t* row_index)
+{
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t w0 = (uint64_t)blockIdx.x * CMP_T + warp * 32, nw = (rows + 31) / 32;
+  // this lane's word -> popcount -> exclusive scan inside the warp, then across the block's warps
+  uint32_t v = w0 + lane < nw ? valid[w0 + lane] : 0u;
+  if (w0 + lane + 1 == nw && (rows & 31)) v &= (1u << (rows & 31)) - 1u;
+  const uint32_t c = __popc(v);
+  uint32_t x = c;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  __shared__ uint32_t ws[CMP_T / 32];
+  if (lane == 31) ws[warp] = x;
+  __syncthreads();
+  uint64_t base = block_off[blockIdx.x];
+  for (uint32_t i = 0; i < warp; ++i) base += ws[i];
+  const uint32_t excl = x - c;
+  for (uint32_t j = 0; j < 32; ++j) {
+    const uint32_t word = __shfl_sync(0xffffffffu, v, j);
+    if (!word) continue;
+    const uint64_t dst0 = base + __shfl_sync(0xffffffffu, excl, j);
+    if (word >> lane & 1u) {
+      const uint64_t r = (w0 + j) * 32 + lane, d = dst0 + __popc(word & ((1u << lane) - 1u));
+      for (uint32_t q = 0; q < H; ++q) compact[d * H + q] = out[r * H + q];
+      if (row_index) row_index[d] = r;
+    }
+  }
+}
+
 } // namespace
+
+// Keeps the rows whose validity bit is set, in order: compact[n][H] (+ their dense row numbers), n to *d_count.
+cudaError_t launch_compact_rows(const uint64_t* d_out, const uint32_t* d_valid, uint64_t rows, uint32_t H, uint64_t* d_compact,
+                                uint64_t* d_row_index, uint64_t* d_count, cudaStream_t st)
+{
+  if (rows == 0) return cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st);
+  const uint64_t nb = (rows + CMP_ROWS - 1) / CMP_ROWS;
+  uint64_t* sums = nullptr;
+  cudaError_t e = cudaMallocAsync(&sums, nb * sizeof(uint64_t), st);
+  if (e != cudaSuccess) return e;
+  compact_count<<<(unsigned)nb, CMP_T, 0, st>>>(d_valid, rows, sums);
+  compact_scan<<<1, 1024, 0, st>>>(sums, nb, d_count);
+  compact_write<<<(unsigned)nb, CMP_T, 0, st>>>(d_out, d_valid, rows, H, sums, d_compact, d_row_index);
+  e = cudaGetLastError();
+  cudaFreeAsync(sums, st);
+  return e;
+}
 
 // d_out must be 16-byte aligned and writable up to the next multiple of 16 bytes past n_bases.
 cudaError_t launch_unpack2bit(const uint8_t* d_packed, const uint32_t* d_invalid, uint64_t first_base, uint64_t n_bases, uint8_t* d_out,

@@ -392,3 +392,46 @@ def test_full_size_config2_properties():
     res = np.zeros(3, np.uint64)
     assert nthash_b200.LIB.nthash_kmer_reduce_packed2bit(packed.ctypes.data, None, None, m, L, k, 1, res.ctypes.data, 0) == 0
     assert int(res[0]) == m * nk and int(res[1]) == int(out_f[:m].sum()) & (2**64 - 1)
+
+
+def test_compacted_output_is_the_reference_iteration_order():
+    # nthash_compact_rows_dev keeps exactly what `while (h.roll())` yields, in order: per read, the reference iterator's
+    # positions and hashes (ORACLE.kmer_read / seed_read restate NtHash / SeedNtHash as iterators)
+    rng = np.random.default_rng(41)
+    lens = rng.integers(0, 260, 300)
+    off = ragged_offsets(lens)
+    bases = synth(rng, int(off[-1]), p_bad=0.01, lower=0.1)
+    k, h = 21, 2
+    res = run_ragged(bases, off, k, h)
+    comp, idx = nthash_b200.compact(res)
+    koff = ORACLE.koff(off.astype(np.uint64), k)
+    want_rows, want_h = [], []
+    for r in range(len(lens)):
+        it = ORACLE.kmer_read(bases[off[r]:off[r + 1]].tobytes(), k, h) if lens[r] >= k else None
+        if it is not None and len(it[0]):
+            want_rows.append(it[0].astype(np.uint64) + koff[r])
+            want_h.append(it[1])
+    want_rows = np.concatenate(want_rows); want_h = np.concatenate(want_h)
+    assert (u64(idx) == want_rows).all() and (u64(comp).reshape(-1, h) == want_h).all()
+    # SeedNtHash: its own visiting rule (jumps over invalid incoming bases, seed.cpp:524-530)
+    seeds = ["110101011", "101111101"]
+    plan = nthash_b200.SeedPlan(seeds, 2)
+    d_b, _keep = to_dev(bases)
+    sres = nthash_b200.seed_hashes(plan, d_b, torch.from_numpy(off).cuda())
+    scomp, sidx = nthash_b200.compact(sres)
+    koff9 = ORACLE.koff(off.astype(np.uint64), 9)
+    rows_w, h_w = [], []
+    for r in range(len(lens)):
+        if lens[r] < 9:
+            continue
+        it = ORACLE.seed_read(bases[off[r]:off[r + 1]].tobytes(), seeds, 2)
+        if it is not None and len(it[0]):
+            rows_w.append(it[0].astype(np.uint64) + koff9[r]); h_w.append(it[1])
+    assert (u64(sidx) == np.concatenate(rows_w)).all() and (u64(scomp).reshape(-1, 4) == np.concatenate(h_w)).all()
+    # a large clean batch: nothing is dropped, order kept
+    n, L = 100_000, 150
+    clean = synth(rng, n * L)
+    d_c, _k2 = to_dev(clean)
+    big = nthash_b200.kmer_hashes_uniform(d_c, n, L, 31, 1)
+    c2, i2 = nthash_b200.compact(big)
+    assert c2.shape[0] == big.rows and torch.equal(c2, big.out) and torch.equal(i2, torch.arange(big.rows, device="cuda"))
