@@ -221,6 +221,14 @@ int nthash_blind_roll_batch_dev(uint64_t* d_fwd, uint64_t* d_rev, const uint8_t*
 /* peek('A'),('C'),('G'),('T') of every state: d_out[(i*4 + e)*num_hashes + j]; states untouched. */
 int nthash_blind_peek4_batch_dev(const uint64_t* d_fwd, const uint64_t* d_rev, const uint8_t* d_out_base,
                                  uint64_t n, uint32_t k, uint32_t num_hashes, uint64_t* d_out, void* stream);
+/* BlindSeedNtHash::roll(char_in) on n states (nthash.hpp:537-632, src/seed.cpp:701-718).  A state is its k-mer, as in
+ * the reference object (which keeps it in a deque): d_kmers holds n windows of k bytes back to back (16-byte aligned,
+ * n_bytes_readable >= n*k); every window drops its first base and takes d_in_base[i], then d_out[i][n_seeds*h] gets
+ * hashes() (seed-major) and the optional d_out_fwd/d_out_rev [i][n_seeds] the per-seed strand hashes.  Initial
+ * hashes of the windows: nthash_seed_batch_uniform_dev with read_len = k.                                        */
+int nthash_blind_seed_roll_batch_dev(const nthash_seed_plan* plan, uint8_t* d_kmers, uint64_t n_bytes_readable,
+                                     const uint8_t* d_in_base, uint64_t n, uint64_t* d_out, uint64_t* d_out_fwd,
+                                     uint64_t* d_out_rev, void* stream);
 /* Host buffers in/out. */
 int nthash_blind_roll_batch(uint64_t* fwd, uint64_t* rev, const char* out_base, const char* in_base,
                             uint64_t n, uint32_t k, uint32_t num_hashes, uint64_t* out, int device);

@@ -207,6 +207,22 @@ def kmer_reduce(bases, read_off, k, num_hashes=1, stream=None) -> torch.Tensor:
     return res
 
 
+def blind_seed_roll(plan, kmers, in_base, want_strands=False, stream=None):
+    """BlindSeedNtHash::roll(char_in) on n states (nthash_blind_seed_roll_batch_dev): `kmers` (uint8 [n, k], contiguous,
+    updated in place) each drop their first base and take in_base[i]; returns hashes [n, n_seeds * h] (and fwd, rev [n, n_seeds])."""
+    n, k = kmers.shape
+    assert k == plan.k and kmers.is_contiguous() and kmers.dtype == torch.uint8
+    H, m = len(plan.seeds) * plan.h, len(plan.seeds)
+    dev = kmers.device
+    with torch.cuda.device(dev):
+        out = torch.empty((n, H), dtype=torch.int64, device=dev)
+        fwd = torch.empty((n, m), dtype=torch.int64, device=dev) if want_strands else None
+        rev = torch.empty((n, m), dtype=torch.int64, device=dev) if want_strands else None
+        check(LIB.nthash_blind_seed_roll_batch_dev(plan._h, _ptr(kmers), kmers.numel(), _ptr(in_base), n, _ptr(out), _ptr(fwd), _ptr(rev),
+                                                   _stream_ptr(stream)))
+    return (out, fwd, rev) if want_strands else out
+
+
 def compact(batch, stream=None):
     """HashBatch -> (hashes [n, H], dense row numbers [n]) of the windows the reference's loop visits, in its order
     (nthash_compact_rows_dev).  Synchronises to learn n."""

@@ -59,7 +59,28 @@ blind_kernel(uint64_t* __restrict__ fwd, uint64_t* __restrict__ rev, const uint8
   }
 }
 
+// BlindSeedNtHash::roll(char_in) keeps the k-mer itself (seed.cpp:701-718): drop its first base, append char_in.
+// One thread per state; the hashing of the new windows is the SeedNtHash batch path on n reads of length k.
+__global__ void __launch_bounds__(256)
+blind_seed_shift_kernel(uint8_t* __restrict__ kmers, const uint8_t* __restrict__ in_base, uint64_t n, uint32_t k)
+{
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t* w = kmers + i * k;
+  for (uint32_t j = 0; j + 1 < k; ++j) w[j] = w[j + 1];
+  w[k - 1] = in_base[i];
+}
+
 } // namespace
+
+cudaError_t launch_blind_seed_shift(uint8_t* kmers, const uint8_t* in_base, uint64_t n, uint32_t k, cudaStream_t st)
+{
+  if (n == 0) return cudaSuccess;
+  const uint64_t blocks = (n + 255) / 256;
+  if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+  blind_seed_shift_kernel<<<(unsigned)blocks, 256, 0, st>>>(kmers, in_base, n, k);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_blind(uint64_t* fwd, uint64_t* rev, const uint8_t* out_base, const uint8_t* in_base, uint64_t n,
                          uint32_t k, uint32_t h, uint64_t* out, bool peek4, cudaStream_t st)

@@ -979,6 +979,20 @@ int nthash_seed_batch_uniform_dev(const nthash_seed_plan* plan, const uint8_t* d
   return seed_dev_run(plan, B, (cudaStream_t)stream);
 }
 
+int nthash_blind_seed_roll_batch_dev(const nthash_seed_plan* plan, uint8_t* d_kmers, uint64_t n_bytes_readable,
+                                     const uint8_t* d_in_base, uint64_t n, uint64_t* d_out, uint64_t* d_out_fwd,
+                                     uint64_t* d_out_rev, void* stream)
+{
+  if (!plan) return fail(NTHASH_ERR_INVALID_ARG, "plan must not be NULL");
+  if (n == 0) return NTHASH_OK;
+  if (!d_kmers || !d_in_base) return fail(NTHASH_ERR_INVALID_ARG, "d_kmers and d_in_base must not be NULL");
+  if (int rc = check_device_ready()) return rc;
+  NTH_CUDA(launch_blind_seed_shift(d_kmers, d_in_base, n, plan->host.k, (cudaStream_t)stream));
+  // the new windows are n reads of exactly k bases: one row each (SeedNtHash's init hashes whatever bytes it is given,
+  // like BlindSeedNtHash; no validity bitmap is produced)
+  return nthash_seed_batch_uniform_dev(plan, d_kmers, n_bytes_readable, n, plan->host.k, d_out, nullptr, d_out_fwd, d_out_rev, stream);
+}
+
 int nthash_seed_batch_dev(const nthash_seed_plan* plan, const uint8_t* d_bases, uint64_t n_bases_readable,
                           const uint64_t* d_read_off, const uint64_t* d_koff, uint64_t n_reads, uint64_t max_read_len,
                           uint64_t* d_out, uint32_t* d_valid_bits, uint64_t* d_out_fwd, uint64_t* d_out_rev,

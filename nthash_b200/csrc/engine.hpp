@@ -93,6 +93,9 @@ cudaError_t launch_seed_jit(const SeedJit* j, const SeedParams& P, cudaStream_t 
 cudaError_t launch_blind(uint64_t* fwd, uint64_t* rev, const uint8_t* out_base, const uint8_t* in_base, uint64_t n,
                          uint32_t k, uint32_t h, uint64_t* out, bool peek4, cudaStream_t st);
 
+// BlindSeedNtHash::roll: shift every state's k-mer by one base and append in_base[i] (hashing = the seed batch path).
+cudaError_t launch_blind_seed_shift(uint8_t* kmers, const uint8_t* in_base, uint64_t n, uint32_t k, cudaStream_t st);
+
 // Uniform geometry for n_reads reads of read_len bases; returns false if unsupported.
 bool plan_uniform(uint64_t n_reads, uint32_t read_len, uint32_t k, KmerGeom& g, uint32_t& tile_cap);
 // Worst-case staged span of one CTA for a geometry cut into `seg`-window items.

@@ -240,3 +240,26 @@ def test_seed_host_pipeline_many_chunks(monkeypatch):
         out2 = np.zeros((rows, 4), np.uint64); vb2 = np.zeros_like(vb)   # no strands: fixed-length chunks take the specialised kernel
         assert nthash_b200.LIB.nthash_seed_batch(bases.ctypes.data, off.ctypes.data, len(off) - 1, arr, 2, 31, h, out2.ctypes.data, vb2.ctypes.data, None, None, 0) == 0
         assert (out2 == ora["out"]).all() and (vb2 == vb).all()
+
+
+def test_blind_seed_roll_batch():
+    # BlindSeedNtHash::roll(char) on many states (reference tests.cpp "Testing BlindSeedNtHash": after each roll the object
+    # agrees with a SeedNtHash on the same window); invalid letters are hashed like any byte
+    rng = np.random.default_rng(5)
+    seeds, h = ["110101011", "101111101"], 3
+    k, n = 9, 5000
+    plan = nthash_b200.SeedPlan(seeds, h)
+    windows = synth(rng, n * k, p_bad=0.01, lower=0.1).reshape(n, k)
+    d_w = torch.zeros(n * k + 64, dtype=torch.uint8, device="cuda")
+    d_w[: n * k] = torch.from_numpy(windows.reshape(-1).copy())
+    kmers = d_w[: n * k].view(n, k)
+    cur = windows.copy()
+    for step in range(4):
+        feed = synth(rng, n, p_bad=0.02, lower=0.1)
+        out, fwd, rev = nthash_b200.blind_seed_roll(plan, kmers, torch.from_numpy(feed.copy()).cuda(), want_strands=True)
+        torch.cuda.synchronize()
+        cur = np.concatenate([cur[:, 1:], feed[:, None]], axis=1)
+        assert (kmers.cpu().numpy() == cur).all()
+        ora = ORACLE.seed_batch(cur.reshape(-1), np.arange(n + 1, dtype=np.uint64) * k, seeds, h)
+        assert ora["valid"].all()
+        assert (u64(out) == ora["out"]).all() and (u64(fwd) == ora["fwd"]).all() and (u64(rev) == ora["rev"]).all()
