@@ -138,6 +138,17 @@ int nthash_kmer_reduce_packed2bit(const uint8_t* packed, const uint32_t* invalid
 int nthash_unpack2bit_dev(const uint8_t* d_packed, const uint32_t* d_invalid_bits, uint64_t first_base, uint64_t n_bases,
                           uint8_t* d_bases_out, void* stream);
 
+/* ---- FASTQ staging on the device (the caller's side of the path) --------------------------------
+ * FASTQ text already in device memory (plain four-line records, LF or CRLF) -> the concatenated layout the batch
+ * entry points take: d_bases (sequence lines back to back) and d_read_off[n_reads + 1].  No host parsing: newline
+ * positions come from a device-wide select, one warp copies each sequence line.  *n_reads / *n_bases (host) receive
+ * the counts; the call synchronises the stream twice to size its passes.  Capacities: d_bases needs room for every
+ * sequence byte (n_bytes / 2 always suffices), d_read_off for the number of records + 1.  Feed the result to
+ * nthash_kmer_plan_dev + nthash_kmer_batch_dev (or the seed / consumer entries).                              */
+int nthash_fastq_extract_dev(const uint8_t* d_text, uint64_t n_bytes, uint8_t* d_bases, uint64_t bases_capacity,
+                             uint64_t* d_read_off, uint64_t reads_capacity, uint64_t* n_reads, uint64_t* n_bases,
+                             void* stream);
+
 /* ---- compacted output -------------------------------------------------------------------------------
  * The dense layout keeps a (zero) row for every window; the reference's loop only ever sees the windows it
  * visits.  This keeps exactly those rows (validity bit set), in order: d_compact[n][values_per_row], and

@@ -223,6 +223,22 @@ def blind_seed_roll(plan, kmers, in_base, want_strands=False, stream=None):
     return (out, fwd, rev) if want_strands else out
 
 
+def fastq_extract(text, stream=None):
+    """FASTQ text (uint8 CUDA tensor) -> (bases, read_off) in the layout of kmer_hashes / seed_hashes (nthash_fastq_extract_dev).
+    `bases` keeps 64 readable bytes of slack past the last base."""
+    if not (text.is_cuda and text.dtype == torch.uint8 and text.is_contiguous()):
+        raise ValueError("text must be a contiguous uint8 CUDA tensor")
+    nb = text.numel()
+    with torch.cuda.device(text.device):
+        bases = torch.empty(nb // 2 + 80, dtype=torch.uint8, device=text.device)
+        read_off = torch.empty(nb // 8 + 2, dtype=torch.int64, device=text.device)   # a record is at least 8 bytes
+        n_reads, n_bases = C.c_uint64(0), C.c_uint64(0)
+        check(LIB.nthash_fastq_extract_dev(_ptr(text), nb, _ptr(bases), nb // 2, _ptr(read_off), nb // 8 + 1, C.byref(n_reads), C.byref(n_bases),
+                                           _stream_ptr(stream)))
+        bases[n_bases.value: n_bases.value + 64] = 0
+    return bases[: n_bases.value], read_off[: n_reads.value + 1]
+
+
 def compact(batch, stream=None):
     """HashBatch -> (hashes [n, H], dense row numbers [n]) of the windows the reference's loop visits, in its order
     (nthash_compact_rows_dev).  Synchronises to learn n."""

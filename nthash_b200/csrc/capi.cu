@@ -831,6 +831,25 @@ int nthash_unpack2bit_dev(const uint8_t* d_packed, const uint32_t* d_invalid_bit
   return NTHASH_OK;
 }
 
+// ---- FASTQ staging on the device --------------------------------------------------------------------
+
+int nthash_fastq_extract_dev(const uint8_t* d_text, uint64_t n_bytes, uint8_t* d_bases, uint64_t bases_capacity,
+                             uint64_t* d_read_off, uint64_t reads_capacity, uint64_t* n_reads, uint64_t* n_bases, void* stream)
+{
+  if (!n_reads || !n_bases) return fail(NTHASH_ERR_INVALID_ARG, "n_reads and n_bases must not be NULL");
+  *n_reads = *n_bases = 0;
+  if (!d_read_off) return fail(NTHASH_ERR_INVALID_ARG, "d_read_off must not be NULL");
+  if (n_bytes && (!d_text || !d_bases)) return fail(NTHASH_ERR_INVALID_ARG, "d_text and d_bases must not be NULL");
+  if (int rc = check_device_ready()) return rc;
+  const cudaError_t e = fastq_extract(d_text, n_bytes, d_bases, bases_capacity, d_read_off, reads_capacity, n_reads, n_bases, (cudaStream_t)stream);
+  if (e == cudaErrorInvalidValue) {
+    cudaGetLastError();
+    return fail(NTHASH_ERR_INVALID_ARG, "the text holds more reads or bases than the output buffers' capacities");
+  }
+  NTH_CUDA(e);
+  return NTHASH_OK;
+}
+
 // ---- compacted output: only the windows the reference's loop visits, in its order ------------------
 
 int nthash_compact_rows_dev(const uint64_t* d_out, const uint32_t* d_valid_bits, uint64_t rows, uint32_t values_per_row,

@@ -93,6 +93,10 @@ cudaError_t launch_seed_jit(const SeedJit* j, const SeedParams& P, cudaStream_t 
 cudaError_t launch_blind(uint64_t* fwd, uint64_t* rev, const uint8_t* out_base, const uint8_t* in_base, uint64_t n,
                          uint32_t k, uint32_t h, uint64_t* out, bool peek4, cudaStream_t st);
 
+// FASTQ text in device memory -> concatenated bases + read_off (fastq_stage.cu); counts come back through host pointers.
+cudaError_t fastq_extract(const uint8_t* d_text, uint64_t n_bytes, uint8_t* d_bases, uint64_t bases_capacity, uint64_t* d_read_off,
+                          uint64_t reads_capacity, uint64_t* n_reads_out, uint64_t* n_bases_out, cudaStream_t st);
+
 // BlindSeedNtHash::roll: shift every state's k-mer by one base and append in_base[i] (hashing = the seed batch path).
 cudaError_t launch_blind_seed_shift(uint8_t* kmers, const uint8_t* in_base, uint64_t n, uint32_t k, cudaStream_t st);
 

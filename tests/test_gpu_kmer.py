@@ -435,3 +435,26 @@ def test_compacted_output_is_the_reference_iteration_order():
     big = nthash_b200.kmer_hashes_uniform(d_c, n, L, 31, 1)
     c2, i2 = nthash_b200.compact(big)
     assert c2.shape[0] == big.rows and torch.equal(c2, big.out) and torch.equal(i2, torch.arange(big.rows, device="cuda"))
+
+
+@pytest.mark.parametrize("crlf,final_newline", [(False, True), (True, True), (False, False)])
+def test_fastq_staging_on_the_device(crlf, final_newline):
+    # FASTQ text -> bases/read_off on the GPU (nthash_fastq_extract_dev), then the ordinary ragged path
+    rng = np.random.default_rng(3 + crlf)
+    lens = rng.integers(1, 300, 2000)
+    lens[:3] = [1, 30, 31]
+    reads = [bytes(synth(rng, int(n), p_bad=0.01, lower=0.1)) for n in lens]
+    eol = b"\r\n" if crlf else b"\n"
+    rec = [b"@r%d some description" % i + eol + r + eol + b"+" + eol + bytes(rng.integers(33, 74, len(r), dtype=np.uint8)) + eol for i, r in enumerate(reads)]
+    text = b"".join(rec)
+    if not final_newline:
+        text = text[: -len(eol)]
+    d_text = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+    bases, read_off = nthash_b200.fastq_extract(d_text)
+    torch.cuda.synchronize()
+    want_off = ragged_offsets(lens)
+    assert (read_off.cpu().numpy() == want_off).all()
+    want_bases = np.frombuffer(b"".join(reads), np.uint8)
+    assert (bases.cpu().numpy() == want_bases).all()
+    res = nthash_b200.kmer_hashes(bases, read_off, 31, 2)
+    assert_batch_equal(res, ORACLE.kmer_batch(want_bases, want_off.astype(np.uint64), 31, 2), 2)
