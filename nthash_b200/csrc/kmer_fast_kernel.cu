@@ -423,7 +423,8 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   // ---- alignment peel: plain stores until the lane's next output u64 sits on a 32-byte boundary ----
   uint32_t p = 0;
   if (!REDUCE) {
-    const uint32_t peel = min(n, (uint32_t)((0 - my_out) & (uint64_t)(4 / H - 1)));
+    constexpr uint32_t ALIGN_W = H == 4 ? 1 : H == 2 ? 2 : 4; // windows per 32-byte boundary of the row (H = 1, 3: four)
+    const uint32_t peel = min(n, (uint32_t)((0 - my_out) & (uint64_t)(ALIGN_W - 1)));
     for (; p < peel; ++p) {
       const uint64_t h0 = roll1(p);
       uint64_t* o = P.out + (my_out + p) * H;
@@ -534,6 +535,16 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
         } else if (H == 2) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) st_shared_v2_u64(chunk_addr(tb, 4 * q + i), hv[i], ext_hash(hv[i], P.mult[1]));
+        } else if (H == 3) { // 12 u64 per group = 6 chunks; chunks straddle windows
+          uint64_t v[12];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[3 * i] = hv[i];
+            v[3 * i + 1] = ext_hash(hv[i], P.mult[1]);
+            v[3 * i + 2] = ext_hash(hv[i], P.mult[2]);
+          }
+#pragma unroll
+          for (int c = 0; c < 6; ++c) st_shared_v2_u64(chunk_addr(tb, 6 * q + c), v[2 * c], v[2 * c + 1]);
         } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -574,7 +585,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     // 256 bytes of its row (32/H windows) in a private shared-memory row, then the warp copies the 32 rows out
     // with coalesced 16-byte stores, two rows per instruction (a half-warp per row).  Each row's global address
     // and byte count travel through a 16-byte descriptor, so lanes may differ in length and alignment.
-    constexpr uint32_t WS1 = 32 / H;
+    constexpr uint32_t WS1 = H == 3 ? 8 : 32 / H; // windows per row piece: 256 bytes (192 for three hashes)
     const uint32_t wbase = rb_base + (tid & ~31u) * (ROW1_BYTES + 16); // this warp: [32 descriptors][32 rows]
     const uint32_t desc0 = wbase, rows0 = wbase + 32 * 16;
     const uint32_t rb = rows0 + lane * ROW1_BYTES;
@@ -590,6 +601,16 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
         } else if (H == 2) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) st_shared_v2_u64(rb + (4 * q + i) * 16, hv[i], ext_hash(hv[i], P.mult[1]));
+        } else if (H == 3) {
+          uint64_t v[12];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[3 * i] = hv[i];
+            v[3 * i + 1] = ext_hash(hv[i], P.mult[1]);
+            v[3 * i + 2] = ext_hash(hv[i], P.mult[2]);
+          }
+#pragma unroll
+          for (int c = 0; c < 6; ++c) st_shared_v2_u64(rb + (6 * q + c) * 16, v[2 * c], v[2 * c + 1]);
         } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -625,7 +646,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
           uint8_t* ga = reinterpret_cast<uint8_t*>(((uint64_t)d[rr].y << 32) | d[rr].x) + c16;
           if (c16 + 16 <= d[rr].z)
             asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(ga), "r"(v[rr].x), "r"(v[rr].y), "r"(v[rr].z), "r"(v[rr].w) : "memory");
-          else if (c16 + 8 == d[rr].z) // odd last u64 of an item (H == 1 only)
+          else if (c16 + 8 == d[rr].z) // odd last u64 of an item (odd number of hashes only)
             asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(ga), "r"(v[rr].x), "r"(v[rr].y) : "memory");
         }
       }
@@ -746,12 +767,15 @@ cudaError_t launch_fast_nbuf(const KmerParams& P, const FastCfg& c, cudaStream_t
 template<int H>
 constexpr int fast_ws(int idx)
 {
-  return H == 1 ? (idx == 0 ? 24 : idx == 1 ? 32 : 40) : H == 2 ? (idx == 0 ? 12 : idx == 1 ? 16 : 20) : (idx == 0 ? 8 : idx == 1 ? 12 : 16);
+  return H == 1   ? (idx == 0 ? 24 : idx == 1 ? 32 : 40)
+         : H == 2 ? (idx == 0 ? 12 : idx == 1 ? 16 : 20)
+         : H == 3 ? (idx == 0 ? 8 : idx == 1 ? 16 : 24)
+                  : (idx == 0 ? 8 : idx == 1 ? 12 : 16);
 }
 
 int fast_ws_rt(uint32_t h, uint32_t idx)
 {
-  return h == 1 ? fast_ws<1>((int)idx) : h == 2 ? fast_ws<2>((int)idx) : fast_ws<4>((int)idx);
+  return h == 1 ? fast_ws<1>((int)idx) : h == 2 ? fast_ws<2>((int)idx) : h == 3 ? fast_ws<3>((int)idx) : fast_ws<4>((int)idx);
 }
 
 template<int H>
@@ -777,7 +801,7 @@ uint32_t env_u32(const char* name, uint32_t dflt)
 bool kmer_fast_ok(const KmerParams& P)
 {
   const KmerGeom& g = P.g;
-  return !P.out_fwd && (P.h == 1 || P.h == 2 || P.h == 4 || P.bloom_mode) && g.n_items > 0 &&
+  return !P.out_fwd && ((P.h >= 1 && P.h <= 4) || P.bloom_mode) && g.n_items > 0 &&
          (P.reduce_out || ((uintptr_t)P.out & 31) == 0) && (g.item_byte || (g.seg && g.segs));
 }
 
@@ -852,6 +876,7 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
   switch (P.h) {
     case 1: return launch_fast_h<1>(P, c, st);
     case 2: return launch_fast_h<2>(P, c, st);
+    case 3: return launch_fast_h<3>(P, c, st);
     default: return launch_fast_h<4>(P, c, st);
   }
 }
