@@ -9,7 +9,7 @@ LIB = os.path.join(HERE, "libnthash_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-ldl",
+    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-ldl", "--threads", "0",
 ]
 
 
