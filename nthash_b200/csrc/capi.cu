@@ -530,7 +530,7 @@ extern "C" {
 
 const char* nthash_fn_name(void) { return "ntHash_v2"; }
 const char* nthash_last_error(void) { return g_err.c_str(); }
-int nthash_b200_abi_version(void) { return 1; }
+int nthash_b200_abi_version(void) { return 2; } // 2: consumers, packed input, FASTQ staging, compaction, multi-GPU entry
 
 int nthash_device_count(void)
 {

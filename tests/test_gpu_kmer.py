@@ -459,3 +459,39 @@ def test_fastq_staging_on_the_device(crlf, final_newline):
     assert (bases.cpu().numpy() == want_bases).all()
     res = nthash_b200.kmer_hashes(bases, read_off, 31, 2)
     assert_batch_equal(res, ORACLE.kmer_batch(want_bases, want_off.astype(np.uint64), 31, 2), 2)
+
+
+def test_concurrent_host_calls_from_several_threads():
+    # the ABI is thread-safe (per-thread error text, mutex-protected per-device caches): four host threads hash different
+    # batches on the same GPU at once, plus a spaced-seed plan compiled concurrently
+    import threading
+    rng = np.random.default_rng(77)
+    jobs = []
+    for t in range(4):
+        lens = rng.integers(0, 400, 600) if t % 2 else np.full(500, 150)
+        off = ragged_offsets(lens).astype(np.uint64)
+        bases = synth(rng, int(off[-1]), p_bad=0.002)
+        k, h = (31, 1 + t)
+        jobs.append((bases, off, k, h, ORACLE.kmer_batch(bases, off, k, h)))
+    results, errors = [None] * 4, []
+
+    def work(i):
+        bases, off, k, h, ora = jobs[i]
+        try:
+            for _ in range(5):
+                out = np.zeros_like(ora["out"])
+                rc = nthash_b200.LIB.nthash_kmer_batch(bases.ctypes.data, off.ctypes.data, len(off) - 1, k, h, out.ctypes.data, None, None, None, 0)
+                assert rc == 0, nthash_b200.LIB.nthash_last_error()
+                assert (out == ora["out"]).all()
+            if i == 0:
+                nthash_b200.SeedPlan(["110011", "101101"], 2)
+            results[i] = True
+        except Exception as e:  # surfaced below
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors and all(results), errors
