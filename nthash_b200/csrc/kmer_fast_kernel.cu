@@ -69,6 +69,10 @@ NTH_D uint4 lds_v4(uint32_t a)
   return v;
 }
 
+NTH_D void st_shared_u64(uint32_t saddr, uint64_t a)
+{
+  asm volatile("st.shared.u64 [%0], %1;" ::"r"(saddr), "l"(a) : "memory");
+}
 NTH_D void tma_store_3d(const void* tmap, uint32_t saddr, int c0, int c1, int c2)
 {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap), "r"(c0),
@@ -184,10 +188,10 @@ NTH_D void fast_item_geom(const KmerGeom& g, uint64_t i, uint64_t& byte, uint64_
 }
 
 // exact clean-up of one item: windows touching a non-ACGTU byte are not emitted (kmer.cpp:232-235, :255-258)
-template<int H>
+template<int H0>
 __device__ __noinline__ void scrub_lane(const KmerParams& P, uint32_t lut, uint32_t ps, uint64_t my_out, uint32_t n)
 {
-  const uint32_t k = P.k;
+  const uint32_t k = P.k, H = H0 ? (uint32_t)H0 : P.h;
   uint32_t run = 0;
   for (uint32_t j = 0; j < n + k - 1; ++j) {
     run = lds_u8(lut + lds_u8(ps + j)) ? 0 : run + 1;
@@ -231,6 +235,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   uint8_t* tile = smem + F_TILE_OFF;
 
   constexpr bool REDUCE = CONS != 0;
+  const uint32_t HH = H ? (uint32_t)H : P.h; // H == 0: runtime number of hashes (5..8, general output path only)
   const uint32_t NT = blockDim.x;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t i0 = (uint64_t)blockIdx.x * NT;
@@ -423,14 +428,19 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   // ---- alignment peel: plain stores until the lane's next output u64 sits on a 32-byte boundary ----
   uint32_t p = 0;
   if (!REDUCE) {
-    constexpr uint32_t ALIGN_W = H == 4 ? 1 : H == 2 ? 2 : 4; // windows per 32-byte boundary of the row (H = 1, 3: four)
+    // windows per 32-byte boundary of the row: 4 / gcd(h, 4)
+    const uint32_t ALIGN_W = (HH & 3) == 0 ? 1 : (HH & 1) == 0 ? 2 : 4;
     const uint32_t peel = min(n, (uint32_t)((0 - my_out) & (uint64_t)(ALIGN_W - 1)));
     for (; p < peel; ++p) {
       const uint64_t h0 = roll1(p);
-      uint64_t* o = P.out + (my_out + p) * H;
+      uint64_t* o = P.out + (my_out + p) * HH;
       o[0] = h0;
+      if (H) {
 #pragma unroll
-      for (int q = 1; q < H; ++q) o[q] = ext_hash(h0, P.mult[q]);
+        for (int q = 1; q < H; ++q) o[q] = ext_hash(h0, P.mult[q]);
+      } else {
+        for (uint32_t q = 1; q < HH; ++q) o[q] = ext_hash(h0, (uint64_t)q ^ P.mult[0]);
+      }
     }
   }
 
@@ -585,7 +595,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     // 256 bytes of its row (32/H windows) in a private shared-memory row, then the warp copies the 32 rows out
     // with coalesced 16-byte stores, two rows per instruction (a half-warp per row).  Each row's global address
     // and byte count travel through a 16-byte descriptor, so lanes may differ in length and alignment.
-    constexpr uint32_t WS1 = H == 3 ? 8 : 32 / H; // windows per row piece: 256 bytes (192 for three hashes)
+    constexpr uint32_t WS1 = H == 0 ? 4 : H == 3 ? 8 : 32 / (H ? H : 1); // windows per row piece: <= 256 bytes
     const uint32_t wbase = rb_base + (tid & ~31u) * (ROW1_BYTES + 16); // this warp: [32 descriptors][32 rows]
     const uint32_t desc0 = wbase, rows0 = wbase + 32 * 16;
     const uint32_t rb = rows0 + lane * ROW1_BYTES;
@@ -611,6 +621,13 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
           }
 #pragma unroll
           for (int c = 0; c < 6; ++c) st_shared_v2_u64(rb + (6 * q + c) * 16, v[2 * c], v[2 * c + 1]);
+        } else if (H == 0) { // 5..8 hashes: one group of four windows is the whole row piece
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t a = rb + (uint32_t)i * HH * 8u;
+            st_shared_u64(a, hv[i]);
+            for (uint32_t e = 1; e < HH; ++e) st_shared_u64(a + e * 8u, ext_hash(hv[i], (uint64_t)e ^ P.mult[0]));
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -629,7 +646,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
           else group(q, part_t(), cnt - 4 * q);
         }
       }
-      st_shared_v2_u64(desc0 + lane * 16, (uint64_t)(uintptr_t)(P.out + (my_out + p) * H), (uint64_t)(cnt * H * 8));
+      st_shared_v2_u64(desc0 + lane * 16, (uint64_t)(uintptr_t)(P.out + (my_out + p) * HH), (uint64_t)(cnt * HH * 8));
       __syncwarp();
       // all loads of a batch of rows first (they do not depend on each other), then the stores
 #pragma unroll
@@ -801,7 +818,7 @@ uint32_t env_u32(const char* name, uint32_t dflt)
 bool kmer_fast_ok(const KmerParams& P)
 {
   const KmerGeom& g = P.g;
-  return !P.out_fwd && ((P.h >= 1 && P.h <= 4) || P.bloom_mode) && g.n_items > 0 &&
+  return !P.out_fwd && ((P.h >= 1 && P.h <= 4) || (P.h <= 8 && !P.reduce_out) || P.bloom_mode) && g.n_items > 0 &&
          (P.reduce_out || ((uintptr_t)P.out & 31) == 0) && (g.item_byte || (g.seg && g.segs));
 }
 
@@ -823,7 +840,7 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
       g.seg = g.nk;
       g.segs = 1;
       // tensor stores need rows that are whole 64-byte blocks (then every row is 64-byte aligned too)
-      c.box = !P.reduce_out && ((uint64_t)g.nk * P.h) % 8 == 0 && !getenv("NTHASH_B200_FAST_NO_BOX");
+      c.box = !P.reduce_out && P.h <= 4 && ((uint64_t)g.nk * P.h) % 8 == 0 && !getenv("NTHASH_B200_FAST_NO_BOX");
     } else {
       // balanced items, the last one shorter.  seg = 4 (mod 8): an odd number of 32-bit words between the rows of
       // neighbouring lanes keeps their LDS.32 on distinct banks (seg = 256 ran 1.7x slower than 244), and a
@@ -877,7 +894,8 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
     case 1: return launch_fast_h<1>(P, c, st);
     case 2: return launch_fast_h<2>(P, c, st);
     case 3: return launch_fast_h<3>(P, c, st);
-    default: return launch_fast_h<4>(P, c, st);
+    case 4: return launch_fast_h<4>(P, c, st);
+    default: return launch_fast_t<0, 0, 8, 1, false>(P, c.nt, st); // 5..8 hashes: runtime count, general output path
   }
 }
 

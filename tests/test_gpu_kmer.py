@@ -95,6 +95,7 @@ FAST_SHAPES = [
     (301, 401, 31, 2), (60, 5003, 32, 1), (9, 50000, 63, 1),      # two items per read; 21 items; configs[4] shape
     (150, 1001, 31, 1), (64, 3001, 21, 1),                        # odd row length: cut-up reads through per-lane stores
     (1500, 150, 31, 3), (700, 151, 31, 3), (120, 1000, 31, 3),    # three hashes: 24-byte windows straddle the 16-byte chunks
+    (500, 150, 31, 5), (300, 151, 31, 8), (60, 1000, 31, 7), (400, 149, 21, 6),   # 5..8 hashes: runtime count in the general output path
 ]
 
 
