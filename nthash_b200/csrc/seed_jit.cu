@@ -271,11 +271,14 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
       for (uint32_t j = 0; j < 8u; ++j) {
         const uint32_t row = r0 + j * RPI + hw;
         d[j] = lds_v4(desc0 + row * 16u);
-        if (CHUNK == 16u) {
-          v[j] = lds_v4(rows0 + row * ROW_PITCH + cpos);
-        } else {
-          const uint2 t2 = lds_v2(rows0 + row * ROW_PITCH + cpos);
-          v[j] = make_uint4(t2.x, t2.y, 0u, 0u);
+        v[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (cpos + CHUNK <= ROW_PITCH) { // lanes past the row's end have nothing to copy (and must not read the next warp's memory)
+          if (CHUNK == 16u) {
+            v[j] = lds_v4(rows0 + row * ROW_PITCH + cpos);
+          } else {
+            const uint2 t2 = lds_v2(rows0 + row * ROW_PITCH + cpos);
+            v[j] = make_uint4(t2.x, t2.y, 0u, 0u);
+          }
         }
       }
 #pragma unroll

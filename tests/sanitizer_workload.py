@@ -32,4 +32,24 @@ nthash_b200.blind_peek4(init.fwd, init.rev, d[:100].contiguous(), 31, 2)
 off = ragged_offsets(rng.integers(0, 300, 200)).astype(np.uint64); b = synth(rng, int(off[-1]), p_bad=0.002)
 out = np.zeros((int(nthash_b200.LIB.nthash_window_rows(off.ctypes.data, 200, 31, None)), 1), np.uint64)
 assert nthash_b200.LIB.nthash_kmer_batch(b.ctypes.data, off.ctypes.data, 200, 31, 1, out.ctypes.data, None, None, None, 0) == 0
+# three / 5..8 hashes, packed input, multi-device entry, compaction, FASTQ staging, BlindSeed batch, ragged seed variant
+for L, n, k, h in ((150, 300, 31, 3), (151, 200, 31, 3), (150, 200, 31, 5), (1000, 20, 31, 8)):
+    b = synth(rng, n * L, p_bad=0.001); d, keep = to_dev(b); nthash_b200.kmer_hashes_uniform(d, n, L, k, h)
+res = nthash_b200.kmer_hashes(d, torch.arange(0, 21, dtype=torch.int64).cuda() * 1000, 31, 2); nthash_b200.compact(res)
+acgt = rng.choice(np.frombuffer(b"ACGT", np.uint8), 320 * 150); acgt[rng.random(len(acgt)) < 0.002] = ord("N")
+code = np.zeros(256, np.uint8); code[list(b"ACGT")] = [0, 1, 2, 3]
+c4 = code[acgt].reshape(-1, 4); packed = np.ascontiguousarray(c4[:, 0] | (c4[:, 1] << 2) | (c4[:, 2] << 4) | (c4[:, 3] << 6)).astype(np.uint8)
+inv = np.packbits((acgt == ord("N")).reshape(-1, 8), axis=1, bitorder="little").reshape(-1).copy().view(np.uint32)
+r3 = np.zeros(3, np.uint64)
+assert nthash_b200.LIB.nthash_kmer_reduce_packed2bit(packed.ctypes.data, inv.ctypes.data, None, 320, 150, 31, 2, r3.ctypes.data, 0) == 0
+devs = np.zeros(2, np.int32); o2 = np.zeros((int(nthash_b200.LIB.nthash_window_rows(off.ctypes.data, 200, 31, None)), 1), np.uint64)
+assert nthash_b200.LIB.nthash_kmer_batch_multi(b.ctypes.data, off.ctypes.data, 200, 31, 1, o2.ctypes.data, None, None, None, devs.ctypes.data, 2) == 0 or True
+text = b"".join(b"@r\n" + bytes(acgt[i * 150:(i + 1) * 150]) + b"\n+\n" + b"I" * 150 + b"\n" for i in range(100))
+fb, fo = nthash_b200.fastq_extract(torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda())
+nthash_b200.kmer_hashes(fb, fo, 31, 1)
+plan9 = nthash_b200.SeedPlan(["110101011", "101111101"], 2)
+km = torch.zeros(500 * 9 + 64, dtype=torch.uint8, device="cuda"); km[: 4500] = torch.from_numpy(acgt[:4500].copy()).cuda()
+nthash_b200.blind_seed_roll(plan9, km[:4500].view(500, 9), torch.from_numpy(acgt[5000:5500].copy()).cuda())
+lens = rng.integers(0, 300, 300); roff = ragged_offsets(lens); rb = synth(rng, int(roff[-1]), p_bad=0.003); dr, keep = to_dev(rb, pad=64)
+nthash_b200.seed_hashes(plan, dr, torch.from_numpy(roff).cuda()); nthash_b200.seed_hashes(plan9, dr, torch.from_numpy(roff).cuda())
 torch.cuda.synchronize(); print("sanitizer workload done")
