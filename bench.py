@@ -398,6 +398,37 @@ def main():
         except Exception as e:  # the filter did not fit next to the batch
             consumer["bloom"] = {"skipped": str(e)[:80]}
 
+    if seeds:
+        # SeedNtHash consumer: count / sum / xor of every visited window's hashes, two passes on the device (rows to scratch
+        # memory, then a reduction): no hash crosses PCIe
+        red = nthash_b200.seed_reduce_uniform(plan, bases, n_reads, L)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(args.steps):
+            red = nthash_b200.seed_reduce_uniform(plan, bases, n_reads, L)
+        r1.record()
+        torch.cuda.synchronize()
+        red_ms = r0.elapsed_time(r1) / args.steps
+        h_res = torch.zeros(3, dtype=torch.int64)
+
+        def e2e_seed_reduce_step():
+            check(LIB.nthash_seed_reduce(h_bases.data_ptr(), h_off.data_ptr(), e2e_reads, seed_arr, len(seeds), k, h, h_res.data_ptr(), local))
+
+        e2e_seed_reduce_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_seed_reduce_step()
+        er_dt = (time.perf_counter() - t0) / args.e2e_steps
+        red_ms, er_dt = nd.max_over_ranks([red_ms, er_dt])
+        consumer = {"kind": "count/sum/xor of all SeedNtHash hashes (nthash_seed_reduce*: rows to device scratch, then a reduction; not fused)",
+                    "value": world * rows / (red_ms * 1e-3), "unit": UNIT, "ms_per_step": red_ms,
+                    "e2e": {"value": world * e_rows / er_dt, "unit": UNIT, "ms_per_step": er_dt * 1e3,
+                            "h2d_bytes_per_step": int(h_bases.numel()), "d2h_bytes_per_step": 24},
+                    "windows": int(red[0]), "sum": int(red[1]) & (2**64 - 1),
+                    "e2e_matches_device": bool(e2e_reads != n_reads or (h_res.cuda() == red).all())}
+
     if rank != 0:
         nd.finalize()
         return

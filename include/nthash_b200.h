@@ -216,6 +216,14 @@ int nthash_seed_batch(const char* bases, const uint64_t* read_off, uint64_t n_re
                       const char* const* seeds, uint32_t n_seeds, uint32_t k, uint32_t num_hashes_per_seed,
                       uint64_t* out, uint32_t* valid_bits, uint64_t* out_fwd, uint64_t* out_rev, int device);
 
+/* SeedNtHash consumer: {windows the reference's loop visits, sum, xor of all their n_seeds * num_hashes_per_seed values}
+ * without any hash crossing PCIe.  Two passes on the device (the seed kernels write a chunk of rows to scratch memory,
+ * a reduction reads them back) - not yet fused like the k-mer consumers.  The device form zeroes d_result itself.   */
+int nthash_seed_reduce(const char* bases, const uint64_t* read_off, uint64_t n_reads, const char* const* seeds,
+                       uint32_t n_seeds, uint32_t k, uint32_t num_hashes_per_seed, uint64_t* result, int device);
+int nthash_seed_reduce_uniform_dev(const nthash_seed_plan* plan, const uint8_t* d_bases, uint64_t n_bases_readable,
+                                   uint64_t n_reads, uint32_t read_len, uint64_t* d_result, void* stream);
+
 /* ---- BlindNtHash: caller-fed rolling over many independent states -----------------------
  * Replaces `blind.roll(char_in)` / `blind.peek(char_in)` (nthash.hpp:213-311; BlindNtHash::roll
  * src/kmer.cpp:355-364, ::peek :382-393) applied to n states at once, e.g. all frontier nodes of

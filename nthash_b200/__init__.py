@@ -7,6 +7,6 @@ PyTorch only for HBM buffers and streams; host.py drives host-buffer calls and m
 from ._lib import LIB, LIB_PATH, NtHashError  # noqa: F401
 from .api import (HashBatch, SeedPlan, blind_peek4, blind_roll, blind_seed_roll, kmer_hashes, kmer_hashes_uniform,  # noqa: F401
                   bloom_filter, compact, fastq_extract, kmer_bloom, kmer_bloom_uniform, kmer_reduce, kmer_reduce_uniform,
-                  seed_hashes, seed_hashes_uniform)
+                  seed_hashes, seed_hashes_uniform, seed_reduce_uniform)
 
 FN_NAME = LIB.nthash_fn_name().decode()

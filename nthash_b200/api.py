@@ -207,6 +207,15 @@ def kmer_reduce(bases, read_off, k, num_hashes=1, stream=None) -> torch.Tensor:
     return res
 
 
+def seed_reduce_uniform(plan, bases, n_reads, read_len, stream=None) -> torch.Tensor:
+    """SeedNtHash consumer (nthash_seed_reduce_uniform_dev): int64 [windows visited, sum, xor] on the GPU."""
+    _check_bases(bases)
+    res = torch.empty(3, dtype=torch.int64, device=bases.device)
+    with torch.cuda.device(bases.device):
+        check(LIB.nthash_seed_reduce_uniform_dev(plan._h, _ptr(bases), bases.numel(), n_reads, read_len, _ptr(res), _stream_ptr(stream)))
+    return res
+
+
 def blind_seed_roll(plan, kmers, in_base, want_strands=False, stream=None):
     """BlindSeedNtHash::roll(char_in) on n states (nthash_blind_seed_roll_batch_dev): `kmers` (uint8 [n, k], contiguous,
     updated in place) each drop their first base and take in_base[i]; returns hashes [n, n_seeds * h] (and fwd, rev [n, n_seeds])."""

@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -250,6 +252,7 @@ struct DevBatch
   uint64_t memset_rows = 0; // > 0: pre-set that many validity bits first
   uint64_t *d_fwd = nullptr, *d_rev = nullptr;
   uint64_t* d_reduce = nullptr; // fused consumer output {windows, sum, xor}; then d_out etc. are NULL
+  uint64_t rows = 0;            // dense rows of this batch (set by the host pipeline)
   uint32_t* d_bloom = nullptr;  // Bloom-filter consumer: filter words, size in bits, 1 = insert / 2 = query
   uint64_t bloom_bits = 0;
   uint32_t bloom_mode = 0;
@@ -331,6 +334,7 @@ struct HostBatch
   const uint8_t* packed = nullptr;
   const uint32_t* invalid_bits = nullptr;
   uint64_t uniform_len = 0; // > 0: n_reads reads of this length back to back, read_off may be NULL (and is not scanned)
+  bool scratch_rows = false; // rows and validity bitmap are produced on the device but not copied back (two-pass consumers)
 };
 
 template<class Launch>
@@ -435,7 +439,7 @@ static int host_pipeline(const HostBatch& hb, Launch&& launch)
     if (hb.packed) NTH_TRY(cudaMallocAsync(&slot[i].d_packed, max_bases / 4 + 16, slot[i].st));
     if (hb.packed && hb.invalid_bits) NTH_TRY(cudaMallocAsync(&slot[i].d_inv, (max_bases / 32 + 4) * 4, slot[i].st));
     if (!uniform) NTH_TRY(cudaMallocAsync(&slot[i].d_off, 2 * (max_reads + 1) * sizeof(uint64_t), slot[i].st));
-    if (hb.out) NTH_TRY(cudaMallocAsync(&slot[i].d_out, max_rows * hb.H * sizeof(uint64_t), slot[i].st));
+    if (hb.out || hb.scratch_rows) NTH_TRY(cudaMallocAsync(&slot[i].d_out, max_rows * hb.H * sizeof(uint64_t), slot[i].st));
     if (hb.strand_cols) {
       NTH_TRY(cudaMallocAsync(&slot[i].d_fwd, max_rows * hb.strand_cols * sizeof(uint64_t), slot[i].st));
       NTH_TRY(cudaMallocAsync(&slot[i].d_rev, max_rows * hb.strand_cols * sizeof(uint64_t), slot[i].st));
@@ -446,7 +450,7 @@ static int host_pipeline(const HostBatch& hb, Launch&& launch)
     NTH_TRY(cudaMemsetAsync(d_reduce, 0, 3 * sizeof(uint64_t), slot[0].st));
     NTH_TRY(cudaStreamSynchronize(slot[0].st)); // chunks on the other streams accumulate into it
   }
-  if (hb.valid_bits) {
+  if (hb.valid_bits || hb.scratch_rows) {
     NTH_TRY(cudaMallocAsync(&d_valid, vwords * 4, slot[0].st));
     NTH_TRY(cudaEventCreateWithFlags(&ev_valid, cudaEventDisableTiming));
     NTH_TRY(cudaMemsetAsync(d_valid, 0xFF, vwords * 4, slot[0].st));
@@ -480,6 +484,7 @@ static int host_pipeline(const HostBatch& hb, Launch&& launch)
     B.d_fwd = s.d_fwd;
     B.d_rev = s.d_rev;
     B.d_reduce = d_reduce;
+    B.rows = nrows;
     if (uniform) {
       B.d_bases = s.d_bases + 16;
       B.n_bases = nbytes + 64;
@@ -1043,6 +1048,27 @@ int nthash_seed_batch_dev(const nthash_seed_plan* plan, const uint8_t* d_bases, 
   return seed_dev_run(plan, B, st);
 }
 
+// The host entries take seed strings, not a plan: compiled plans (an NVRTC build, ~0.3 s) are kept per (device, seeds, h)
+// for the life of the process so that repeated calls do not recompile.
+static int cached_seed_plan(const char* const* seeds, uint32_t n_seeds, uint32_t k, uint32_t h, const nthash_seed_plan** out)
+{
+  static std::mutex mu;
+  static std::map<std::string, nthash_seed_plan*> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::string key = std::to_string(dev) + "/" + std::to_string(k) + "/" + std::to_string(h);
+  for (uint32_t i = 0; i < n_seeds; ++i) key += std::string("/") + (seeds && seeds[i] ? seeds[i] : "");
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    nthash_seed_plan* plan = nullptr;
+    if (int rc = nthash_seed_plan_create(seeds, n_seeds, k, h, &plan)) return rc;
+    it = cache.emplace(key, plan).first;
+  }
+  *out = it->second;
+  return NTHASH_OK;
+}
+
 int nthash_seed_batch(const char* bases, const uint64_t* read_off, uint64_t n_reads, const char* const* seeds,
                       uint32_t n_seeds, uint32_t k, uint32_t num_hashes_per_seed, uint64_t* out,
                       uint32_t* valid_bits, uint64_t* out_fwd, uint64_t* out_rev, int device)
@@ -1052,12 +1078,78 @@ int nthash_seed_batch(const char* bases, const uint64_t* read_off, uint64_t n_re
   if (!bases || !read_off) return fail(NTHASH_ERR_INVALID_ARG, "bases and read_off must not be NULL");
   if (int rc = check_outputs(out, out_fwd, out_rev)) return rc;
   if (cudaSetDevice(device) != cudaSuccess) return fail(NTHASH_ERR_NO_DEVICE, "cannot select CUDA device %d", device);
-  nthash_seed_plan* plan = nullptr;
-  if (int rc = nthash_seed_plan_create(seeds, n_seeds, k, num_hashes_per_seed, &plan)) return rc;
+  const nthash_seed_plan* plan = nullptr;
+  if (int rc = cached_seed_plan(seeds, n_seeds, k, num_hashes_per_seed, &plan)) return rc;
   const HostBatch hb = { bases, read_off, n_reads, k, (uint64_t)n_seeds * num_hashes_per_seed, out_fwd ? (uint64_t)n_seeds : 0ull,
                          out, valid_bits, out_fwd, out_rev };
-  const int rc = host_pipeline(hb, [&](const DevBatch& B, cudaStream_t st) { return seed_dev_run(plan, B, st); });
-  nthash_seed_plan_destroy(plan);
+  return host_pipeline(hb, [&](const DevBatch& B, cudaStream_t st) { return seed_dev_run(plan, B, st); });
+}
+
+// SeedNtHash consumer (two passes on the device: the seed kernels write a chunk of rows, a reduction reads them back; no
+// hash crosses PCIe).  result = {windows visited, sum, xor} over all n_seeds * num_hashes_per_seed values.
+int nthash_seed_reduce(const char* bases, const uint64_t* read_off, uint64_t n_reads, const char* const* seeds, uint32_t n_seeds,
+                       uint32_t k, uint32_t num_hashes_per_seed, uint64_t* result, int device)
+{
+  if (int rc = check_kh(k, num_hashes_per_seed)) return rc;
+  if (!result) return fail(NTHASH_ERR_INVALID_ARG, "result must not be NULL");
+  result[0] = result[1] = result[2] = 0;
+  if (n_reads == 0) return NTHASH_OK;
+  if (!bases || !read_off) return fail(NTHASH_ERR_INVALID_ARG, "bases and read_off must not be NULL");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(NTHASH_ERR_NO_DEVICE, "cannot select CUDA device %d", device);
+  const nthash_seed_plan* plan = nullptr;
+  if (int rc = cached_seed_plan(seeds, n_seeds, k, num_hashes_per_seed, &plan)) return rc;
+  const uint32_t H = n_seeds * num_hashes_per_seed;
+  HostBatch hb = { bases, read_off, n_reads, k, (uint64_t)H, 0ull, nullptr, nullptr, nullptr, nullptr };
+  hb.reduce_result = result;
+  hb.scratch_rows = true;
+  const int rc = host_pipeline(hb, [&](const DevBatch& B, cudaStream_t st) {
+    if (int r = seed_dev_run(plan, B, st)) return r;
+    NTH_CUDA(launch_reduce_rows(B.d_out, B.d_valid, B.valid_row0, B.rows, H, B.d_reduce, st));
+    return (int)NTHASH_OK;
+  });
+  return rc;
+}
+
+int nthash_seed_reduce_uniform_dev(const nthash_seed_plan* plan, const uint8_t* d_bases, uint64_t n_bases_readable, uint64_t n_reads,
+                                   uint32_t read_len, uint64_t* d_result, void* stream)
+{
+  if (!plan) return fail(NTHASH_ERR_INVALID_ARG, "plan must not be NULL");
+  if (!d_result) return fail(NTHASH_ERR_INVALID_ARG, "d_result must not be NULL");
+  if (int rc = check_device_ready()) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  NTH_CUDA(cudaMemsetAsync(d_result, 0, 3 * sizeof(uint64_t), st));
+  const uint32_t k = plan->host.k, H = plan->host.n_seeds * plan->host.h;
+  if (n_reads == 0 || read_len < k) return NTHASH_OK;
+  if (!d_bases || ((uintptr_t)d_bases & 15)) return fail(NTHASH_ERR_INVALID_ARG, "d_bases must be 16-byte aligned");
+  if (n_bases_readable < n_reads * (uint64_t)read_len)
+    return fail(NTHASH_ERR_INVALID_ARG, "n_bases_readable smaller than n_reads*read_len");
+  // chunks of reads whose rows fit a fixed scratch buffer (~512 MB of hashes); chunk starts stay 16-byte aligned
+  const uint64_t nk = read_len - k + 1;
+  uint64_t per = std::max<uint64_t>(16, ((64ull << 20) / (nk * H)) & ~15ull);
+  per = std::min<uint64_t>(per, (n_reads + 15) & ~(uint64_t)15);
+  uint64_t* d_out = nullptr;
+  uint32_t* d_valid = nullptr;
+  NTH_CUDA(cudaMallocAsync(&d_out, per * nk * H * sizeof(uint64_t), st));
+  cudaError_t e = cudaMallocAsync(&d_valid, ((per * nk + 31) / 32) * 4, st);
+  int rc = e == cudaSuccess ? NTHASH_OK : fail(NTHASH_ERR_CUDA, "cudaMallocAsync: %s", cudaGetErrorString(e));
+  for (uint64_t r0 = 0; r0 < n_reads && rc == NTHASH_OK; r0 += per) {
+    const uint64_t nr = std::min(per, n_reads - r0);
+    DevBatch B;
+    B.d_bases = d_bases + r0 * read_len;
+    B.n_bases = n_bases_readable - r0 * read_len;
+    B.n_reads = nr;
+    B.uniform_len = read_len;
+    B.d_out = d_out;
+    B.d_valid = d_valid;
+    B.memset_rows = nr * nk;
+    rc = seed_dev_run(plan, B, st);
+    if (rc == NTHASH_OK) {
+      e = launch_reduce_rows(d_out, d_valid, 0, nr * nk, H, d_result, st);
+      if (e != cudaSuccess) rc = fail(NTHASH_ERR_CUDA, "launch_reduce_rows: %s", cudaGetErrorString(e));
+    }
+  }
+  if (d_valid) cudaFreeAsync(d_valid, st);
+  cudaFreeAsync(d_out, st);
   return rc;
 }
 

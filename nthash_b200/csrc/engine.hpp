@@ -110,6 +110,9 @@ uint32_t span_bound(uint32_t seg, uint32_t segs, uint32_t k);
 // stats[2] = number of items when reads are cut into seg-window items.  All device pointers.
 cudaError_t launch_koff_scan(const uint64_t* read_off, uint64_t n_reads, uint32_t k, uint32_t seg,
                              uint64_t* koff, uint64_t* stats, cudaStream_t st);
+// {rows with their validity bit set, sum, xor of all their values} accumulated into d_result (3 x u64, not zeroed here).
+cudaError_t launch_reduce_rows(const uint64_t* d_out, const uint32_t* d_valid, uint64_t valid_row0, uint64_t rows, uint32_t H,
+                               uint64_t* d_result, cudaStream_t st);
 // Dense rows -> only the rows whose validity bit is set, in order (what the reference's `while (roll())` loop yields).
 cudaError_t launch_compact_rows(const uint64_t* d_out, const uint32_t* d_valid, uint64_t rows, uint32_t H, uint64_t* d_compact,
                                 uint64_t* d_row_index, uint64_t* d_count, cudaStream_t st);

@@ -4,6 +4,8 @@
 // into seg-window items.  Plain three-pass block scan; this is plumbing, not the hot loop.
 #include "engine.hpp"
 
+#include <algorithm>
+
 namespace nthb {
 
 namespace {
@@ -254,7 +256,53 @@ __global__ void compact_write(const uint64_t* out, const uint32_t* valid, uint64
   }
 }
 
+// count / sum / xor over the rows whose validity bit is set (all H values of a row): the consumer of the reference's
+// benchmark loop for outputs that were written to device memory first (SeedNtHash: no fused form yet)
+__global__ void __launch_bounds__(256)
+reduce_rows_kernel(const uint64_t* out, const uint32_t* valid, uint64_t valid_row0, uint64_t rows, uint32_t H, uint32_t magic,
+                   unsigned long long* res)
+{
+  uint64_t sum = 0, x = 0;
+  uint32_t cnt = 0;
+  const uint32_t lane = threadIdx.x & 31, span = 32 * H; // a warp walks 32 rows = 32*H contiguous values at a time
+  const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5, w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  for (uint64_t r0 = w * 32; r0 < rows; r0 += warps * 32) {
+    const uint64_t nvals = min((uint64_t)span, (rows - r0) * H);
+    for (uint32_t i = lane; i < nvals; i += 32) {
+      const uint32_t q = __umulhi(i, magic); // i / H, exact for i < 2^16
+      const uint64_t row = r0 + q, bit = valid_row0 + row;
+      if (valid[bit >> 5] >> (bit & 31) & 1u) {
+        const uint64_t v = out[r0 * H + i];
+        sum += v;
+        x ^= v;
+        cnt += (i - q * H) == 0;
+      }
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    sum += __shfl_down_sync(0xffffffffu, sum, o);
+    x ^= __shfl_down_sync(0xffffffffu, x, o);
+  }
+  if (lane == 0 && (cnt | sum | x)) {
+    atomicAdd(res, (unsigned long long)cnt);
+    atomicAdd(res + 1, (unsigned long long)sum);
+    atomicXor(res + 2, (unsigned long long)x);
+  }
+}
+
 } // namespace
+
+cudaError_t launch_reduce_rows(const uint64_t* d_out, const uint32_t* d_valid, uint64_t valid_row0, uint64_t rows, uint32_t H,
+                               uint64_t* d_result, cudaStream_t st)
+{
+  if (rows == 0) return cudaSuccess;
+  if (H == 0 || H > 2040) return cudaErrorInvalidValue; // 32*H must stay below 2^16 for the reciprocal division
+  const uint32_t magic = (uint32_t)((0x100000000ull + H - 1) / H);
+  const uint64_t blocks = std::min<uint64_t>((rows + 255) / 256, 148ull * 16);
+  reduce_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_out, d_valid, valid_row0, rows, H, magic, reinterpret_cast<unsigned long long*>(d_result));
+  return cudaGetLastError();
+}
 
 // Keeps the rows whose validity bit is set, in order: compact[n][H] (+ their dense row numbers), n to *d_count.
 cudaError_t launch_compact_rows(const uint64_t* d_out, const uint32_t* d_valid, uint64_t rows, uint32_t H, uint64_t* d_compact,

@@ -263,3 +263,27 @@ def test_blind_seed_roll_batch():
         ora = ORACLE.seed_batch(cur.reshape(-1), np.arange(n + 1, dtype=np.uint64) * k, seeds, h)
         assert ora["valid"].all()
         assert (u64(out) == ora["out"]).all() and (u64(fwd) == ora["fwd"]).all() and (u64(rev) == ora["rev"]).all()
+
+
+def test_seed_reduce_consumer(monkeypatch):
+    # count / sum / xor of every visited window's hashes for SeedNtHash, computed on the device (two passes); dirty reads
+    # follow the reference's own visiting rule
+    rng = np.random.default_rng(15)
+    seeds, h = ["1010101010101010101010101010101", "1101101101101101011011011011011"], 3
+    plan = nthash_b200.SeedPlan(seeds, h)
+    n, L = 6000, 150
+    bases = synth(rng, n * L, p_bad=0.001)
+    d_b, _keep = to_dev(bases)
+    ora = ORACLE.seed_batch(bases, np.arange(n + 1, dtype=np.uint64) * L, seeds, h, want=(), threads=8)
+    got = u64(nthash_b200.seed_reduce_uniform(plan, d_b, n, L))
+    assert (int(got[0]), int(got[1]), int(got[2])) == (ora["n_emit"], ora["sum"], ora["xor"])
+    # host entry, ragged, several pipeline chunks
+    monkeypatch.setenv("NTHASH_B200_HOST_CHUNK_VALUES", "50000")
+    lens = rng.integers(0, 300, 700)
+    off = ragged_offsets(lens).astype(np.uint64)
+    rb = synth(rng, int(off[-1]), p_bad=0.003)
+    ora2 = ORACLE.seed_batch(rb, off, seeds, h, want=())
+    res = np.zeros(3, np.uint64)
+    arr = (C.c_char_p * 2)(*[s.encode() for s in seeds])
+    assert nthash_b200.LIB.nthash_seed_reduce(rb.ctypes.data, off.ctypes.data, len(lens), arr, 2, 31, h, res.ctypes.data, 0) == 0, nthash_b200.LIB.nthash_last_error()
+    assert (int(res[0]), int(res[1]), int(res[2])) == (ora2["n_emit"], ora2["sum"], ora2["xor"])
