@@ -198,6 +198,10 @@ __device__ __noinline__ void scrub_lane(const KmerParams& P, uint32_t lut, uint3
     if (j >= k - 1 && run < k) {
       const uint64_t w = my_out + (j - (k - 1));
       for (uint32_t q = 0; q < H; ++q) P.out[w * H + q] = 0;
+      if (P.out_fwd) {
+        P.out_fwd[w] = 0;
+        P.out_rev[w] = 0;
+      }
       if (P.valid_bits) atomicAnd(&P.valid_bits[(P.valid_row0 + w) >> 5], ~(1u << ((P.valid_row0 + w) & 31)));
     }
   }
@@ -234,7 +238,8 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   uint64_t* s_range = reinterpret_cast<uint64_t*>(smem + F_RANGE_OFF);
   uint8_t* tile = smem + F_TILE_OFF;
 
-  constexpr bool REDUCE = CONS != 0;
+  constexpr bool STR = CONS == 4;                  // CONS == 4: store the hashes AND the strand hashes (general output path)
+  constexpr bool REDUCE = CONS != 0 && CONS != 4;  // consumers proper: nothing is stored
   const uint32_t HH = H ? (uint32_t)H : P.h; // H == 0: runtime number of hashes (5..8, general output path only)
   const uint32_t NT = blockDim.x;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -388,6 +393,10 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     const uint32_t ea = pair + (((ci & 6u) << 4) | ((co & 6u) << 2));
     const uint2 ef = lds_v2(ea), er = lds_v2(ea + (F_PAIR_R_OFF - F_PAIR_OFF));
     roll_step(s, make_uint4(ef.x, ef.y, er.x, er.y));
+    if (STR) { // get_forward_hash() / get_reverse_hash() of this window (nthash.hpp:183-194)
+      P.out_fwd[my_out + p] = ((uint64_t)s.fhi << 32) | s.flo;
+      P.out_rev[my_out + p] = ((uint64_t)s.rhi << 32) | s.rlo;
+    }
     return canonical2(s);
   };
   auto consume = [&](uint64_t h0) { // one window the reference visits
@@ -429,7 +438,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   uint32_t p = 0;
   if (!REDUCE) {
     // windows per 32-byte boundary of the row: 4 / gcd(h, 4)
-    const uint32_t ALIGN_W = (HH & 3) == 0 ? 1 : (HH & 1) == 0 ? 2 : 4;
+    const uint32_t ALIGN_W = STR ? 4 : (HH & 3) == 0 ? 1 : (HH & 1) == 0 ? 2 : 4; // strand rows are 8 bytes per window
     const uint32_t peel = min(n, (uint32_t)((0 - my_out) & (uint64_t)(ALIGN_W - 1)));
     for (; p < peel; ++p) {
       const uint64_t h0 = roll1(p);
@@ -457,6 +466,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
 
   // Four windows (FULL) or the first cnt < 4 of them: consumes one realigned word of each stream.  The next
   // words are requested before the current ones are used, so their latency hides behind the four rolls.
+  uint64_t fw4[4], rv4[4]; // STR: strand hashes of the group's four windows
   auto roll4 = [&](uint64_t (&hv)[4], auto full, uint32_t cnt) {
     constexpr bool FULL = decltype(full)::value;
     const uint32_t x_in = __byte_perm(w_in, w_in_n, sel_in), x_out = __byte_perm(w_out, w_out_n, sel_out);
@@ -494,6 +504,10 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
       const uint2 ef = lds_v2(ea), er = lds_v2(ea + (F_PAIR_R_OFF - F_PAIR_OFF));
       roll_step(s, make_uint4(ef.x, ef.y, er.x, er.y));
       hv[i] = canonical2(s);
+      if (STR) {
+        fw4[i] = ((uint64_t)s.fhi << 32) | s.flo;
+        rv4[i] = ((uint64_t)s.rhi << 32) | s.rlo;
+      }
       if (REDUCE) reduce_add(hv[i]);
     }
   };
@@ -596,15 +610,23 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     // with coalesced 16-byte stores, two rows per instruction (a half-warp per row).  Each row's global address
     // and byte count travel through a 16-byte descriptor, so lanes may differ in length and alignment.
     constexpr uint32_t WS1 = H == 0 ? 4 : H == 3 ? 8 : 32 / (H ? H : 1); // windows per row piece: <= 256 bytes
-    const uint32_t wbase = rb_base + (tid & ~31u) * (ROW1_BYTES + 16); // this warp: [32 descriptors][32 rows]
-    const uint32_t desc0 = wbase, rows0 = wbase + 32 * 16;
+    constexpr uint32_t NARR = STR ? 3 : 1; // output arrays: hashes (+ forward and reverse strand hashes)
+    const uint32_t wbase = rb_base + (tid & ~31u) * NARR * (ROW1_BYTES + 16); // this warp: NARR x [32 descriptors], NARR x [32 rows]
+    const uint32_t desc0 = wbase, rows0 = wbase + NARR * 32 * 16;
     const uint32_t rb = rows0 + lane * ROW1_BYTES;
+    const uint32_t rbf = rb + 32 * ROW1_BYTES, rbr = rb + 64 * ROW1_BYTES; // STR only
     const uint32_t hw = lane >> 4, c16 = (lane & 15) * 16;
     while (__any_sync(0xffffffffu, p < n)) {
       const uint32_t cnt = p < n ? min(WS1, n - p) : 0u;
       auto group = [&](uint32_t q, auto full, uint32_t c4n) {
         uint64_t hv[4];
         roll4(hv, full, c4n);
+        if (STR) {
+          st_shared_v2_u64(rbf + (2 * q) * 16, fw4[0], fw4[1]);
+          st_shared_v2_u64(rbf + (2 * q + 1) * 16, fw4[2], fw4[3]);
+          st_shared_v2_u64(rbr + (2 * q) * 16, rv4[0], rv4[1]);
+          st_shared_v2_u64(rbr + (2 * q + 1) * 16, rv4[2], rv4[3]);
+        }
         if (H == 1) {
           st_shared_v2_u64(rb + (2 * q) * 16, hv[0], hv[1]);
           st_shared_v2_u64(rb + (2 * q + 1) * 16, hv[2], hv[3]);
@@ -647,24 +669,32 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
         }
       }
       st_shared_v2_u64(desc0 + lane * 16, (uint64_t)(uintptr_t)(P.out + (my_out + p) * HH), (uint64_t)(cnt * HH * 8));
+      if (STR) {
+        st_shared_v2_u64(desc0 + (32 + lane) * 16, (uint64_t)(uintptr_t)(P.out_fwd + my_out + p), (uint64_t)(cnt * 8));
+        st_shared_v2_u64(desc0 + (64 + lane) * 16, (uint64_t)(uintptr_t)(P.out_rev + my_out + p), (uint64_t)(cnt * 8));
+      }
       __syncwarp();
       // all loads of a batch of rows first (they do not depend on each other), then the stores
 #pragma unroll
-      for (uint32_t r0 = 0; r0 < 16; r0 += 8) {
-        uint4 d[8], v[8];
+      for (uint32_t arr = 0; arr < NARR; ++arr) {
+        const uint32_t descA = desc0 + arr * 32 * 16, rowsA = rows0 + arr * 32 * ROW1_BYTES;
 #pragma unroll
-        for (uint32_t rr = 0; rr < 8; ++rr) {
-          const uint32_t row = 2 * (r0 + rr) + hw;
-          d[rr] = lds_v4(desc0 + row * 16); // {address lo, address hi, bytes, 0}
-          v[rr] = lds_v4(rows0 + row * ROW1_BYTES + c16);
-        }
+        for (uint32_t r0 = 0; r0 < 16; r0 += 8) {
+          uint4 d[8], v[8];
 #pragma unroll
-        for (uint32_t rr = 0; rr < 8; ++rr) {
-          uint8_t* ga = reinterpret_cast<uint8_t*>(((uint64_t)d[rr].y << 32) | d[rr].x) + c16;
-          if (c16 + 16 <= d[rr].z)
-            asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(ga), "r"(v[rr].x), "r"(v[rr].y), "r"(v[rr].z), "r"(v[rr].w) : "memory");
-          else if (c16 + 8 == d[rr].z) // odd last u64 of an item (odd number of hashes only)
-            asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(ga), "r"(v[rr].x), "r"(v[rr].y) : "memory");
+          for (uint32_t rr = 0; rr < 8; ++rr) {
+            const uint32_t row = 2 * (r0 + rr) + hw;
+            d[rr] = lds_v4(descA + row * 16); // {address lo, address hi, bytes, 0}
+            v[rr] = lds_v4(rowsA + row * ROW1_BYTES + c16);
+          }
+#pragma unroll
+          for (uint32_t rr = 0; rr < 8; ++rr) {
+            uint8_t* ga = reinterpret_cast<uint8_t*>(((uint64_t)d[rr].y << 32) | d[rr].x) + c16;
+            if (c16 + 16 <= d[rr].z)
+              asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(ga), "r"(v[rr].x), "r"(v[rr].y), "r"(v[rr].z), "r"(v[rr].w) : "memory");
+            else if (c16 + 8 == d[rr].z) // odd last u64 of an item
+              asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(ga), "r"(v[rr].x), "r"(v[rr].y) : "memory");
+          }
         }
       }
       __syncwarp(); // rows are rewritten next; also orders these stores before the scrub's zeros
@@ -756,9 +786,9 @@ cudaError_t make_out_map(const KmerParams& P, uint32_t blocks, CUtensorMap* map)
 template<int H, int CONS, int WS, int NBUF, bool BOX>
 cudaError_t launch_fast_t(const KmerParams& P, uint32_t nt, cudaStream_t st)
 {
-  constexpr bool REDUCE = CONS != 0;
+  constexpr bool REDUCE = CONS != 0 && CONS != 4; // consumers allocate no output buffers
   auto fn = kmer_fast_kernel<H, CONS, WS, NBUF, BOX>;
-  const uint32_t buf = BOX ? (nt / 32) * NBUF * (uint32_t)(WS * H / 8) * 2048u : nt * (ROW1_BYTES + 16);
+  const uint32_t buf = BOX ? (nt / 32) * NBUF * (uint32_t)(WS * H / 8) * 2048u : nt * (CONS == 4 ? 3u : 1u) * (ROW1_BYTES + 16);
   uint32_t smem_bytes = fast_smem_bytes(P.tile_cap, REDUCE ? 0u : buf);
   if (const char* e = getenv("NTHASH_B200_SMEM_PAD")) smem_bytes += (uint32_t)atoi(e); // experiments: lower the occupancy
   if (smem_bytes > 227u * 1024u) return cudaErrorInvalidConfiguration;
@@ -799,6 +829,7 @@ template<int H>
 cudaError_t launch_fast_h(const KmerParams& P, const FastCfg& c, cudaStream_t st)
 {
   if (P.reduce_out) return launch_fast_t<H, 1, fast_ws<H>(0), 1, false>(P, c.nt, st);
+  if (P.out_fwd) return launch_fast_t<H, 4, fast_ws<H>(0), 1, false>(P, c.nt, st); // hashes + strand hashes
   if (!c.box) return launch_fast_t<H, 0, fast_ws<H>(0), 1, false>(P, c.nt, st); // WS / NBUF are unused there
   switch (c.ws) {
     case 0: return launch_fast_nbuf<H, fast_ws<H>(0)>(P, c, st);
@@ -818,7 +849,8 @@ uint32_t env_u32(const char* name, uint32_t dflt)
 bool kmer_fast_ok(const KmerParams& P)
 {
   const KmerGeom& g = P.g;
-  return !P.out_fwd && ((P.h >= 1 && P.h <= 4) || (P.h <= 8 && !P.reduce_out) || P.bloom_mode) && g.n_items > 0 &&
+  if (P.out_fwd && (P.reduce_out || P.bloom_mode || (((uintptr_t)P.out_fwd | (uintptr_t)P.out_rev) & 31))) return false;
+  return ((P.h >= 1 && P.h <= 4) || (P.h <= 8 && !P.reduce_out) || P.bloom_mode) && g.n_items > 0 &&
          (P.reduce_out || ((uintptr_t)P.out & 31) == 0) && (g.item_byte || (g.seg && g.segs));
 }
 
@@ -840,7 +872,7 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
       g.seg = g.nk;
       g.segs = 1;
       // tensor stores need rows that are whole 64-byte blocks (then every row is 64-byte aligned too)
-      c.box = !P.reduce_out && P.h <= 4 && ((uint64_t)g.nk * P.h) % 8 == 0 && !getenv("NTHASH_B200_FAST_NO_BOX");
+      c.box = !P.reduce_out && !P.out_fwd && P.h <= 4 && ((uint64_t)g.nk * P.h) % 8 == 0 && !getenv("NTHASH_B200_FAST_NO_BOX");
     } else {
       // balanced items, the last one shorter.  seg = 4 (mod 8): an odd number of 32-bit words between the rows of
       // neighbouring lanes keeps their LDS.32 on distinct banks (seg = 256 ran 1.7x slower than 244), and a
@@ -860,7 +892,7 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
   // long ones that cost occupancy), then CTA size (fewer prologues): the largest CTA that leaves >= 16 warps resident
   const uint32_t buf_per_warp = P.reduce_out ? 0u
                                 : c.box    ? c.nbuf * (uint32_t)(fast_ws_rt(P.h, c.ws) * P.h / 8) * 2048u
-                                           : 32u * (ROW1_BYTES + 16);
+                                           : 32u * (P.out_fwd ? 3u : 1u) * (ROW1_BYTES + 16);
   c.nt = 32;
   for (uint32_t nt : { 256u, 192u, 128u, 96u, 64u, 32u }) { // the small ones only matter for huge k
     const uint64_t cap = tile_cap_for(nt);
@@ -895,7 +927,8 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
     case 2: return launch_fast_h<2>(P, c, st);
     case 3: return launch_fast_h<3>(P, c, st);
     case 4: return launch_fast_h<4>(P, c, st);
-    default: return launch_fast_t<0, 0, 8, 1, false>(P, c.nt, st); // 5..8 hashes: runtime count, general output path
+    default: // 5..8 hashes: runtime count, general output path
+      return P.out_fwd ? launch_fast_t<0, 4, 8, 1, false>(P, c.nt, st) : launch_fast_t<0, 0, 8, 1, false>(P, c.nt, st);
   }
 }
 
