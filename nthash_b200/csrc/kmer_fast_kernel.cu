@@ -1,21 +1,22 @@
-// kmer_fast_kernel.cu — NtHash batch kernel for uniform batches (fixed read length, every item full,
-// rows that are 16-byte multiples): the BASELINE configs' shape.  Same arithmetic and the same
-// reference lines as kmer_kernel.cu (NtHash::roll src/kmer.cpp:246-264, extend_hashes
-// src/internal.hpp:104-118); what differs is how bytes get in and hashes get out.
+// kmer_fast_kernel.cu — the NtHash batch kernel: uniform and ragged batches, 1..8 hashes per k-mer, optional strand
+// hashes, and the fused consumers (count/sum/xor, Bloom filter).  Same arithmetic and the same reference lines as
+// kmer_kernel.cu (NtHash::roll src/kmer.cpp:246-264, extend_hashes src/internal.hpp:104-118); what differs is how
+// bytes get in and hashes get out.
 //
-// What the first profile (profiles/r01_ncu_kmer_c2_v1.txt) and the microbenchmarks
-// (profiles/r01_microbench_*.txt) showed, and what this kernel does about it:
-//  * L1TEX data pipe 99.5 % busy: two 16-byte byte-indexed table lookups (4 wavefronts each) and two
-//    bank-conflicting LDS.U8 per window.  Here each lane streams its row as 32-bit words (one LDS.32
-//    per four windows per stream, realigned with PRMT) and ONE 16-byte lookup per window fetches the
-//    combined in/out contribution from a 16-entry pair table indexed by the 2-bit codes
-//    (byte >> 1) & 3 of the incoming and outgoing base.  Codes of non-ACGTU bytes are garbage but
-//    self-consistent (the same byte enters and leaves with the same code), so windows free of such
-//    bytes stay exact; a 256-byte validity LUT flags rows that need the exact scrub pass.
-//  * lane-strided 32-byte stores cap at 4.6 TB/s (every sector its own L2 request).  Here each warp
-//    collects a [32 items] x [16 u64] tile in shared memory (128-byte rows, SWIZZLE_128B so the
-//    per-lane STS.128 are conflict-free) and one elected lane issues cp.async.bulk.tensor.2d
-//    (UTMASTG): the output leaves the SM as full 128-byte row segments (7.2 TB/s pattern).
+// What the profiles (profiles/r01_ncu_kmer_c2_v*.txt) and the microbenchmarks (profiles/r01_microbench_*.txt)
+// showed, and what this kernel does about it:
+//  * L1TEX data pipe 99.5 % busy in the first kernel: two 16-byte byte-indexed table lookups (4 wavefronts each)
+//    and two bank-conflicting LDS.U8 per window.  Here each lane streams its row as 32-bit words (one LDS.32 per
+//    four windows per stream, requested one group ahead, realigned with PRMT) and ONE lookup per window and strand
+//    fetches the combined in/out contribution from a 16-entry pair table indexed by the 2-bit codes
+//    (byte >> 1) & 3 of the incoming and outgoing base.  Codes of non-ACGTU bytes are garbage but self-consistent
+//    (the same byte enters and leaves with the same code), so windows free of such bytes stay exact; a SWAR test on
+//    the incoming words flags rows that need the exact scrub pass.
+//  * the HBM write path wants long contiguous pieces (128-byte pieces of 960-byte rows: 5.1-5.4 TB/s, 192-byte 5.6,
+//    320-byte 6.3-7.0, lane-strided 32-byte sector stores 4.6).  Uniform batches of whole-read items: a warp tile
+//    [blocks][32 rows][8 u64] under the 64-byte TMA swizzle leaves through ONE 3-D tensor store (UTMASTG) of
+//    192-256 bytes per row.  Everything else (ragged, cut-up reads, odd rows, 5..8 hashes, strand outputs): per-lane
+//    256-byte rows in shared memory, copied out with coalesced 16-byte stores, a half-warp per row.
 #include "kmer_common.cuh"
 
 #include <algorithm>

@@ -16,8 +16,8 @@
 // per-base decode, exact for any byte value); hashes leave as full 32-byte sectors
 // (st.global.v4.u64 -> STG.E.ENL2.256), four consecutive windows of one item per store.
 //
-// This is the GENERAL kernel (ragged batches, any row pitch, optional strand outputs).  Uniform
-// batches whose rows are 16-byte multiples take kmer_fast_kernel.cu instead (TMA tile stores).
+// This is the FALLBACK kernel: what kmer_fast_kernel.cu does not take (more than 8 hashes per k-mer, unaligned output
+// pointers, NTHASH_B200_DISABLE_TMA_STORE=1 for A/B runs).  Its per-lane stores reach ~0.1-0.6 of the HBM peak.
 #include "engine.hpp"
 #include "kmer_common.cuh"
 
