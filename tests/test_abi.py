@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_fn_name_and_version():
     import nthash_b200
     assert nthash_b200.FN_NAME == "ntHash_v2"  # reference include/nthash/nthash.hpp:18
-    assert nthash_b200.LIB.nthash_b200_abi_version() >= 1
+    assert nthash_b200.LIB.nthash_b200_abi_version() >= 2
 
 
 def test_window_rows_helper():
@@ -54,6 +54,36 @@ def test_invalid_arguments_are_reported_not_fatal():
     assert rc == -1 and b"num_hashes" in L.nthash_last_error()
     rc = L.nthash_kmer_batch(None, None, 1, 31, 1, None, None, None, None, 0)
     assert rc == -1
+
+
+def test_new_entry_points_validate_before_touching_a_device():
+    # every entry point added for the rows around the path (consumers, packed input, FASTQ staging, compaction, multi-GPU,
+    # BlindSeed) rejects bad arguments with a code and a message - no exit(), no crash, no GPU needed to find out
+    import nthash_b200
+    L = nthash_b200.LIB
+    cnt = np.zeros(3, np.uint64)
+    n64 = C.c_uint64(0)
+    cases = [
+        (L.nthash_kmer_batch_uniform, (None, 1, 150, 2, 1, None, None, None, None, 0), b"k=2"),
+        (L.nthash_kmer_batch_multi, (None, None, 1, 31, 1, None, None, None, None, None, 0), b"device"),
+        (L.nthash_kmer_batch_packed2bit, (None, None, None, 1, 0, 31, 1, cnt.ctypes.data, None, 0), b"packed"),
+        (L.nthash_kmer_reduce_packed2bit, (cnt.ctypes.data, None, None, 1, 0, 31, 1, cnt.ctypes.data, 0), b"uniform_read_len"),
+        (L.nthash_kmer_reduce_packed2bit, (cnt.ctypes.data, None, None, 1, 150, 31, 1, None, 0), b"result"),
+        (L.nthash_kmer_bloom_uniform_dev, (None, 0, 1, 150, 31, 3, None, 0, 0, cnt.ctypes.data, None), b"filter"),
+        (L.nthash_kmer_bloom_uniform_dev, (None, 0, 1, 150, 31, 0, cnt.ctypes.data, 64, 0, cnt.ctypes.data, None), b"num_hashes"),
+        (L.nthash_compact_rows_dev, (None, None, 10, 1, None, None, None, None), b"d_count"),
+        (L.nthash_fastq_extract_dev, (None, 10, None, 0, None, 0, C.byref(n64), C.byref(n64), None), b"d_read_off"),
+        (L.nthash_seed_reduce_uniform_dev, (None, None, 0, 1, 150, cnt.ctypes.data, None), b"plan"),
+        (L.nthash_blind_seed_roll_batch_dev, (None, None, 0, None, 1, None, None, None, None), b"plan"),
+        (L.nthash_unpack2bit_dev, (None, None, 0, 16, None, None), b"d_packed"),
+    ]
+    for fn, args, needle in cases:
+        rc = fn(*args)
+        assert rc < 0, (fn.__name__, rc)
+        assert needle in L.nthash_last_error(), (fn.__name__, L.nthash_last_error())
+    # zero-sized requests are fine and touch nothing
+    assert L.nthash_kmer_batch_uniform(None, 0, 150, 31, 1, cnt.ctypes.data, None, None, None, 0) == 0
+    assert L.nthash_kmer_reduce_packed2bit(None, None, None, 0, 150, 31, 1, cnt.ctypes.data, 0) == 0
 
 
 def test_specialised_seed_kernel_compiles_without_a_gpu():
