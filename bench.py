@@ -269,14 +269,18 @@ def main():
         # ---- dominant kernel alone (roofline): same launch without the bitmap memset ----
         step(False)
         torch.cuda.synchronize()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
         k0.record()
-        for _ in range(args.steps):
+        marks[0].record()
+        for i in range(args.steps):
             step(False)
+            marks[i + 1].record()
         k1.record()
         clk.sample_now()
         torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / args.steps
     kernel_ms = k0.elapsed_time(k1) / args.steps
+    each = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))  # per-launch times (best and median)
     ms, kernel_ms = nd.max_over_ranks([ms, kernel_ms])
 
     # ---- end to end through the host-buffer C ABI call ----------------------------------------
@@ -467,7 +471,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (load_traffic(args.config) or {}).get("dram_bytes_per_launch") if not args.reads else None,
                      "traffic_source": (load_traffic(args.config) or {}).get("source"), "peak_source": peak_src, "kernel": ("seed_jit_kernel (NVRTC-specialised)" if seeds else "kmer_fast_kernel<H=%d>" % h), "kernel_ms": kernel_ms,
-                     "algorithmic_bytes_per_launch": abytes},
+                     "kernel_ms_best": each[0], "kernel_ms_median": statistics.median(each), "algorithmic_bytes_per_launch": abytes},
         "cpu_baseline": cpu, "fused_consumer": consumer,
     }
     if consumer and cpu and sample_reads == n_reads:
