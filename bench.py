@@ -5,13 +5,19 @@
     torchrun ... bench.py --gpus N ...                             # N ranks, weak scaling (one shard per GPU)
     python bench.py --impl reference ...                           # the reference's own CPU roll() loop
 
-A "step" is one pass of the hot path (NtHash roll over every read) over one batch of synthetic
-reads: BASELINE.json configs[1], 10 M x 150 bp, k=31, h=1 per GPU.  `value` is device-resident
-throughput (inputs in HBM, CUDA events on the launching stream, max over ranks); `e2e` is the same
-metric through the host-buffer C ABI call (pinned host buffers, H2D + kernel + D2H inside the timed
-region); `roofline` compares the kernel's algorithmic bytes/s with the measured HBM copy peak;
-`cpu_baseline` is the compiled reference (oracle/_ref) timed on this box's host cores.
-The oracle/ directory is executed here only for cpu_baseline / --impl reference and a checksum check.
+A "step" is one pass of the hot path (NtHash / SeedNtHash roll over every read) over one batch of synthetic reads.
+The headline line is BASELINE.json configs[1] (C2: 10 M x 150 bp, k=31, h=1 per GPU); `value` is device-resident
+throughput (inputs in HBM, CUDA events on the launching stream, max over ranks); `e2e` is the same metric through the
+host-buffer C ABI call (pinned host buffers, H2D + kernel + D2H inside the timed region); `roofline` compares the
+kernel's algorithmic bytes/s with the measured HBM copy peak; `cpu_baseline` is the compiled reference (oracle/_ref)
+timed on this box's host cores.  The other BASELINE configs ride along as compact sub-records under `configs`:
+c3 (h=4), c4 (SeedNtHash, two seeds x 3) and c5 (50 kb reads, k=63: 100 k reads over 8 GPUs = 12.5 k per rank, so a
+`--gpus 8` run IS configs[4] as stated), each with its device-resident time, roofline fraction and a checksum against
+the compiled reference on a stated prefix of the same reads.
+
+Reads are the generator SURVEY.md §8(d) pins, in BOTH arms: one splitmix64 stream (seed 42; 44 for c5), 32 bases per
+draw; rank r hashes reads [r*n, (r+1)*n) of that stream, the reference arm a prefix of it.
+The oracle/ directory is executed here only for cpu_baseline / --impl reference and the checksum checks.
 """
 import argparse
 import json
@@ -26,16 +32,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+SEED_A = "1010101010101010101010101010101"
+SEED_B = "1101101101101101011011011011011"
 CONFIGS = {
-    # name: (reads per GPU, read length, k, hashes)
-    "c2": dict(n_reads=10_000_000, read_len=150, k=31, h=1, desc="10M x 150bp reads, k=31, h=1 canonical (BASELINE.json configs[1])"),
-    "c3": dict(n_reads=10_000_000, read_len=150, k=31, h=4, desc="10M x 150bp reads, k=31, h=4 (configs[2])"),
-    "c4": dict(n_reads=10_000_000, read_len=150, k=31, h=3, seeds=["1010101010101010101010101010101", "1101101101101101011011011011011"],
+    # reads per GPU, read length, k, hashes (per seed), splitmix seed, reads of the CPU sample
+    "c2": dict(n_reads=10_000_000, read_len=150, k=31, h=1, seed=42, cpu_reads=2_000_000,
+               desc="10M x 150bp reads, k=31, h=1 canonical (BASELINE.json configs[1])"),
+    "c3": dict(n_reads=10_000_000, read_len=150, k=31, h=4, seed=42, cpu_reads=1_000_000,
+               desc="10M x 150bp reads, k=31, h=4 (configs[2])"),
+    "c4": dict(n_reads=10_000_000, read_len=150, k=31, h=3, seed=42, cpu_reads=300_000, seeds=[SEED_A, SEED_B],
                desc="SeedNtHash: 10M x 150bp reads, two spaced seeds, k=31, h=3 per seed (configs[3])"),
-    "c5": dict(n_reads=12_500, read_len=50_000, k=63, h=1, desc="12.5k x 50kb reads per GPU, k=63, h=1 (configs[4] shard)"),
+    "c5": dict(n_reads=12_500, read_len=50_000, k=63, h=1, seed=44, cpu_reads=4_000,
+               desc="50kb reads, k=63, h=1: 100k reads sharded over 8 GPUs = 12.5k reads per GPU (configs[4])"),
 }
 METRIC = "kmers_hashed_per_sec"
 UNIT = "kmers/s"
+M64 = (1 << 64) - 1
 
 
 def algorithmic_bytes(n_reads, read_len, k, H):
@@ -58,6 +70,53 @@ def load_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---- the synthetic reads of SURVEY.md §8(d) / Appendix C: one splitmix64 stream, 32 bases per draw -------------------
+def _s64(v):
+    v &= M64
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def splitmix_bases_torch(torch, n_bases, seed, first_base=0, device="cuda", slack=64):
+    """Bases [first_base, first_base + n_bases) of the stream, as a uint8 tensor with `slack` readable bytes after
+    them.  int64 arithmetic wraps like uint64; logical shifts are emulated with a mask."""
+    assert first_base % 32 == 0
+    buf = torch.zeros(n_bases + slack, dtype=torch.uint8, device=device)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    shifts = torch.arange(0, 64, 2, dtype=torch.int64, device=device)
+    d0, n_draws = first_base // 32, (n_bases + 31) // 32
+    step = 1 << 22
+    for o in range(0, n_draws, step):
+        m = min(step, n_draws - o)
+        i = torch.arange(d0 + o + 1, d0 + o + 1 + m, dtype=torch.int64, device=device)
+        z = i * _s64(0x9E3779B97F4A7C15) + _s64(seed)
+        z = (z ^ ((z >> 30) & ((1 << 34) - 1))) * _s64(0xBF58476D1CE4E5B9)
+        z = (z ^ ((z >> 27) & ((1 << 37) - 1))) * _s64(0x94D049BB133111EB)
+        z = z ^ ((z >> 31) & ((1 << 33) - 1))
+        b = lut[((z.unsqueeze(1) >> shifts) & 3)].reshape(-1)
+        lo, hi = o * 32, min(n_bases, (o + m) * 32)
+        buf[lo:hi] = b[: hi - lo]
+    return buf
+
+
+def splitmix_bases_numpy(n_bases, seed, first_base=0):
+    import numpy as np
+    assert first_base % 32 == 0
+    d0, n_draws = first_base // 32, (n_bases + 31) // 32
+    out = np.empty(n_draws * 32, np.uint8)
+    lut = np.frombuffer(b"ACGT", np.uint8)
+    shifts = np.arange(0, 64, 2, dtype=np.uint64)
+    step = 1 << 20
+    with np.errstate(over="ignore"):
+        for o in range(0, n_draws, step):
+            m = min(step, n_draws - o)
+            z = np.arange(d0 + o + 1, d0 + o + 1 + m, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+            out[o * 32:(o + m) * 32] = lut[((z[:, None] >> shifts) & np.uint64(3)).astype(np.intp)].reshape(-1)
+    return out[:n_bases]
 
 
 class ClockSampler:
@@ -137,20 +196,9 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
-def synth_reads_device(torch, n_bases, seed):
-    g = torch.Generator(device="cuda")
-    g.manual_seed(seed)
-    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device="cuda")
-    buf = torch.zeros(n_bases + 64, dtype=torch.uint8, device="cuda")  # readable slack past the last base
-    step = 1 << 28
-    for o in range(0, n_bases, step):
-        m = min(step, n_bases - o)
-        buf[o:o + m] = lut[torch.randint(0, 4, (m,), dtype=torch.uint8, device="cuda", generator=g).long()]
-    return buf
-
-
+# ---- the reference's own loop on the host cores (oracle/_ref = the unmodified reference compiled here) -----------------
 def cpu_reference_pass(lib, bases_np, n_reads, read_len, k, h, threads, seeds=None):
-    """One pass of the reference's own loop over `n_reads` reads -> (windows/s, emitted, sum)."""
+    """One pass of the reference's own loop over `n_reads` reads -> (windows/s, emitted, sum, seconds)."""
     import numpy as np
     off = np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(read_len)
     t0 = time.perf_counter()
@@ -162,35 +210,160 @@ def cpu_reference_pass(lib, bases_np, n_reads, read_len, k, h, threads, seeds=No
     return r["n_emit"] / dt, r["n_emit"], r["sum"], dt
 
 
+def cpu_reference_measure(cfg, sample_reads, passes, warm=1):
+    """The policy BOTH CPU numbers (`--impl reference` and the in-arm `cpu_baseline`) follow: the first `sample_reads`
+    reads of the config's splitmix stream, all host threads, `warm` untimed passes, then `passes` timed ones."""
+    from oracle_lib import ORACLE, REF
+    lib = REF if REF is not None else ORACLE
+    threads = os.cpu_count() or 1
+    L, k, h, seeds = cfg["read_len"], cfg["k"], cfg["h"], cfg.get("seeds")
+    bases = splitmix_bases_numpy(sample_reads * L, cfg["seed"])
+    for _ in range(warm):
+        cpu_reference_pass(lib, bases, sample_reads, L, k, h, threads, seeds)
+    emitted, ssum, each = 0, 0, []
+    t0 = time.perf_counter()
+    for _ in range(passes):
+        _, ne, s, dt1 = cpu_reference_pass(lib, bases, sample_reads, L, k, h, threads, seeds)
+        emitted += ne
+        ssum = s
+        each.append(dt1)
+    dt = time.perf_counter() - t0
+    return dict(value=emitted / dt, emitted_per_pass=emitted // max(passes, 1), sum=ssum, seconds=dt, threads=threads, kind=lib.kind,
+                sample_reads=sample_reads, passes=passes, best_pass_s=min(each) if each else None)
+
+
+def cpu_sample_label(cfg, m):
+    H = cfg["h"] * (len(cfg["seeds"]) if cfg.get("seeds") else 1)
+    return (f"first {m['sample_reads']} reads x {cfg['read_len']} bp of the splitmix64(seed={cfg['seed']}) stream "
+            f"(a bounded sample of the {cfg['n_reads']}-read batch), {m['passes']} timed passes after 1 warm-up, "
+            f"{m['seconds']:.2f} s wall on {m['threads']} threads, {H} hash value(s) per window")
+
+
 def run_reference(args, cfg):
     """--impl reference: the reference's CPU implementation of the path on this box's host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
-    from oracle_lib import ORACLE, REF
-    lib = REF if REF is not None else ORACLE
-    threads = os.cpu_count() or 1
-    sample_reads = min(cfg["n_reads"], args.ref_sample_reads)
-    bases = ORACLE.gen_bases(sample_reads * cfg["read_len"], 42)
-    for _ in range(args.warmup):
-        cpu_reference_pass(lib, bases, sample_reads, cfg["read_len"], cfg["k"], cfg["h"], threads, cfg.get("seeds"))
-    t0 = time.perf_counter()
-    emitted = 0
-    for _ in range(args.steps):
-        _, ne, _, _ = cpu_reference_pass(lib, bases, sample_reads, cfg["read_len"], cfg["k"], cfg["h"], threads, cfg.get("seeds"))
-        emitted += ne
-    dt = time.perf_counter() - t0
-    value = emitted / dt
-    sample = f"{sample_reads} reads x {cfg['read_len']} bp per step (a bounded sample of the {cfg['n_reads']}-read batch)"
+    sample_reads = min(cfg["n_reads"], args.ref_sample_reads or cfg["cpu_reads"])
+    m = cpu_reference_measure(cfg, sample_reads, args.steps, warm=max(1, min(args.warmup, 2)))
+    value = m["value"]
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": m["seconds"] / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": cfg["desc"], "reads_per_step": sample_reads, "read_len": cfg["read_len"], "k": cfg["k"], "h": cfg["h"]},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": lib.kind, "sample": sample},
+        "config": workload_config(cfg, cfg["n_reads"]),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": m["threads"], "kind": m["kind"], "sample": cpu_sample_label(cfg, m)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def workload_config(cfg, n_reads):
+    """The `config` object both arms print (identical: the driver compares them)."""
+    abytes = algorithmic_bytes(n_reads, cfg["read_len"], cfg["k"], cfg["h"] * (len(cfg["seeds"]) if cfg.get("seeds") else 1))
+    return {"workload": cfg["desc"], "reads_per_gpu": n_reads, "read_len": cfg["read_len"], "k": cfg["k"], "h": cfg["h"],
+            "seeds": cfg.get("seeds"), "generator": "splitmix64 seed %d, 32 bases per draw (SURVEY.md 8d)" % cfg["seed"],
+            "l2_policy": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2; no explicit flush" % (abytes / 1e9),
+            "sharding": "independent read shards per GPU, no collective"}
+
+
+class Workload:
+    """One BASELINE config resident on this rank's GPU: bases, output rows, validity bitmap, and its step()."""
+
+    def __init__(self, torch, nthash_b200, LIB, cfg, rank):
+        self.torch, self.nb, self.cfg = torch, nthash_b200, cfg
+        self.n, self.L, self.k, self.h = cfg["n_reads"], cfg["read_len"], cfg["k"], cfg["h"]
+        self.seeds = cfg.get("seeds")
+        self.H = self.h * (len(self.seeds) if self.seeds else 1)
+        self.plan = nthash_b200.SeedPlan(self.seeds, self.h) if self.seeds else None
+        self.nk = self.L - self.k + 1
+        self.rows = self.n * self.nk
+        self.n_bases = self.n * self.L
+        self.buf = splitmix_bases_torch(torch, self.n_bases, cfg["seed"], first_base=rank * self.n_bases)
+        self.bases = self.buf[: self.n_bases]
+        self.out = torch.empty((self.rows, self.H), dtype=torch.int64, device="cuda")
+        self.valid = torch.empty(int(LIB.nthash_valid_words(self.rows)), dtype=torch.int32, device="cuda")
+
+    def step(self, with_valid=True):
+        if self.plan is not None:
+            self.nb.seed_hashes_uniform(self.plan, self.bases, self.n, self.L, want_valid=with_valid, out=self.out,
+                                        valid_bits=self.valid if with_valid else None)
+        else:
+            self.nb.kmer_hashes_uniform(self.bases, self.n, self.L, self.k, self.h, want_valid=with_valid, out=self.out,
+                                        valid_bits=self.valid if with_valid else None)
+
+    def time_steps(self, steps, with_valid, warm):
+        """CUDA events on the launching stream around `steps` back-to-back calls -> (mean ms, sorted per-launch ms)."""
+        torch = self.torch
+        for _ in range(warm):
+            self.step(with_valid)
+        torch.cuda.synchronize()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        marks[0].record()
+        for i in range(steps):
+            self.step(with_valid)
+            marks[i + 1].record()
+        torch.cuda.synchronize()
+        return marks[0].elapsed_time(marks[steps]) / steps, sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(steps))
+
+    def checksum_prefix(self, reads):
+        """(windows, 64-bit sum of every hash value) of the first `reads` reads' rows, from the device-resident output."""
+        v = self.out[: reads * self.nk]
+        return reads * self.nk, int(v.sum()) & M64
+
+    def kernel_name(self):
+        return "seed_jit_kernel (NVRTC-specialised)" if self.seeds else "kmer_fast_kernel<H=%d>" % self.h
+
+
+def sub_record(torch, nthash_b200, LIB, nd, name, args, rank, world, peak, want_cpu):
+    """Compact record of one of the other BASELINE configs: device-resident time, roofline fraction, checksum vs the
+    compiled reference on a stated prefix (rank 0).  Everything is freed before the next config is built."""
+    cfg = dict(CONFIGS[name])
+    w = Workload(torch, nthash_b200, LIB, cfg, rank)
+    steps = max(3, min(args.steps, args.sub_steps))
+    ms_valid, _ = w.time_steps(steps, True, 2)
+    nd.barrier()
+    ms, each = w.time_steps(steps, False, 1)
+    ms_valid, ms = nd.max_over_ranks([ms_valid, ms])
+    abytes = algorithmic_bytes(w.n, w.L, w.k, w.H)
+    achieved = abytes / (ms * 1e-3) / 1e9
+    rec = {"workload": cfg["desc"], "reads_per_gpu": w.n, "n_gpus": world, "value": world * w.rows / (ms_valid * 1e-3), "unit": UNIT,
+           "ms_per_step": ms_valid, "steps": steps,
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "kernel": w.kernel_name(), "kernel_ms": ms, "kernel_ms_best": each[0], "kernel_ms_median": statistics.median(each),
+                        "algorithmic_bytes_per_launch": abytes,
+                        "traffic": (load_traffic(name) or {}).get("dram_bytes_per_launch")}}
+    if name == "c5":
+        # end to end through the host-buffer C ABI for the long-read shard too (this is configs[4]'s per-GPU share)
+        h_bases = torch.empty(w.n_bases, dtype=torch.uint8).pin_memory()
+        h_bases.copy_(w.bases)
+        h_out = torch.empty((w.rows, w.H), dtype=torch.int64).pin_memory()
+        h_valid = torch.empty(int(LIB.nthash_valid_words(w.rows)), dtype=torch.int32).pin_memory()
+        from nthash_b200._lib import check
+        local = torch.cuda.current_device()
+
+        def e2e_step():
+            check(LIB.nthash_kmer_batch_uniform(h_bases.data_ptr(), w.n, w.L, w.k, w.h, h_out.data_ptr(), h_valid.data_ptr(), None, None, local))
+
+        e2e_step()
+        nd.barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            e2e_step()
+        e_dt = nd.max_over_ranks([(time.perf_counter() - t0) / 3])[0]
+        rec["e2e"] = {"value": world * w.rows / e_dt, "unit": UNIT, "ms_per_step": e_dt * 1e3, "h2d_bytes_per_step": int(h_bases.numel()),
+                      "d2h_bytes_per_step": int(h_out.numel() * 8 + h_valid.numel() * 4),
+                      "matches_device_path": bool((h_out[: 100 * w.nk].cuda() == w.out[: 100 * w.nk]).all())}
+        del h_bases, h_out, h_valid
+    # whole-job checksum of checksums (every rank's full output) — the size-independent property the multi-GPU run reports
+    rec["sum_all_ranks"] = nd.sum_over_ranks(int(w.out.sum()) & M64)
+    if rank == 0 and want_cpu:
+        m = cpu_reference_measure(cfg, min(cfg["cpu_reads"], w.n), 1, warm=0)
+        windows, gsum = w.checksum_prefix(m["sample_reads"])
+        rec["cpu_reference"] = {"value": m["value"], "unit": UNIT, "cores": m["threads"], "kind": m["kind"], "sample": cpu_sample_label(cfg, m)}
+        rec["checksum_matches_reference"] = bool(gsum == m["sum"] and windows == m["emitted_per_pass"])
+    del w
+    torch.cuda.empty_cache()
+    return rec
 
 
 def main():
@@ -201,17 +374,21 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--reads", type=int, default=0, help="override reads per GPU (debugging only; invalidates the number)")
-    ap.add_argument("--ref-sample-reads", type=int, default=2_000_000)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--ref-sample-reads", type=int, default=0, help="reads of the CPU sample (default: the config's cpu_reads)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--sub-steps", type=int, default=5, help="timed launches per sub-record config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub-records", action="store_true", help="only the headline config (skip configs.c3/c4/c5)")
+    ap.add_argument("--no-consumers", action="store_true")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.reads:
         cfg["n_reads"] = args.reads
+        cfg["cpu_reads"] = min(cfg["cpu_reads"], args.reads)
     if args.impl == "reference":
         return run_reference(args, cfg)
 
-    import numpy as np
+    import numpy as np  # noqa: F401
     import torch
 
     import nthash_b200
@@ -230,26 +407,12 @@ def main():
         pass
     nd.init("nccl", torch.device("cuda", local))
     barrier = nd.barrier
+    peak, peak_src = load_peak()
 
-    n_reads, L, k, h = cfg["n_reads"], cfg["read_len"], cfg["k"], cfg["h"]
-    seeds = cfg.get("seeds")
-    H = h * (len(seeds) if seeds else 1)  # u64 values per window
-    plan = nthash_b200.SeedPlan(seeds, h) if seeds else None
-    nk = L - k + 1
-    rows = n_reads * nk
-    n_bases = n_reads * L
-    bases_buf = synth_reads_device(torch, n_bases, 1234 + rank)
-    bases = bases_buf[:n_bases]
-    out = torch.empty((rows, H), dtype=torch.int64, device="cuda")
-    valid = torch.empty(int(LIB.nthash_valid_words(rows)), dtype=torch.int32, device="cuda")
-
-    def step(with_valid=True):
-        if plan is not None:
-            nthash_b200.seed_hashes_uniform(plan, bases, n_reads, L, want_valid=with_valid, out=out,
-                                            valid_bits=valid if with_valid else None)
-        else:
-            nthash_b200.kmer_hashes_uniform(bases, n_reads, L, k, h, want_valid=with_valid, out=out,
-                                            valid_bits=valid if with_valid else None)
+    w = Workload(torch, nthash_b200, LIB, cfg, rank)
+    n_reads, L, k, h, seeds, H, nk, rows, n_bases, plan = w.n, w.L, w.k, w.h, w.seeds, w.H, w.nk, w.rows, w.n_bases, w.plan
+    bases, out = w.bases, w.out
+    step = w.step
 
     # ---- device-resident throughput (value) -------------------------------------------------
     for _ in range(max(args.warmup, 3)):
@@ -282,6 +445,9 @@ def main():
     kernel_ms = k0.elapsed_time(k1) / args.steps
     each = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))  # per-launch times (best and median)
     ms, kernel_ms = nd.max_over_ranks([ms, kernel_ms])
+    step()  # leave the full result (with its bitmap) in `out` for the checks below
+    torch.cuda.synchronize()
+    sum_all = nd.sum_over_ranks(int(out.sum()) & M64)
 
     # ---- end to end through the host-buffer C ABI call ----------------------------------------
     e2e = None
@@ -320,14 +486,14 @@ def main():
     e_dt = (time.perf_counter() - t0) / args.e2e_steps
     e_dt = nd.max_over_ranks([e_dt])[0]
     # parity of the e2e result with the device-resident one (same reads): checksum of checksums
-    same = bool((h_out[: 1000 * nk].cuda() == out[: 1000 * nk]).all())
+    same = bool((h_out[: 1000 * nk].cuda() == out[: 1000 * nk]).all()) and (e2e_reads != n_reads or (int(h_out.sum()) & M64) == (int(out.sum()) & M64))
     e2e = {"value": world * e_rows / e_dt, "unit": UNIT, "h2d_bytes_per_step": int(h_bases.numel()),
            "d2h_bytes_per_step": int(h_out.numel() * 8 + h_valid.numel() * 4), "reads_per_step": e2e_reads,
-           "ms_per_step": e_dt * 1e3, "matches_device_path": same}
+           "ms_per_step": e_dt * 1e3, "steps": args.e2e_steps, "matches_device_path": same}
 
     # ---- fused consumer (count/sum/xor on the device: what the reference's own benchmark loop computes) ----
     consumer = None
-    if not seeds:
+    if not seeds and not args.no_consumers:
         red = nthash_b200.kmer_reduce_uniform(bases, n_reads, L, k, h)
         torch.cuda.synchronize()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -376,7 +542,9 @@ def main():
                     "e2e_packed2bit": {"value": world * e_rows / ep_dt, "unit": UNIT, "ms_per_step": ep_dt * 1e3,
                                        "h2d_bytes_per_step": int(h_packed.numel()), "d2h_bytes_per_step": 24,
                                        "matches_ascii_path": bool((h_res2 == h_res).all())},
-                    "windows": int(red[0]), "sum": int(red[1]) & (2**64 - 1)}
+                    "windows": int(red[0]), "sum": int(red[1]) & M64,
+                    "matches_stored_hashes": bool((int(red[1]) & M64) == (int(out.sum()) & M64))}
+        del h_packed
 
         # second fused consumer: Bloom filter insert / query (the caller nthash.hpp:14-17 names), 3 hashes per
         # k-mer into a 1 GiB (2^33 bit) device-resident filter; bound by random 32-byte atomics, not by streaming
@@ -401,10 +569,10 @@ def main():
             del filt
         except Exception as e:  # the filter did not fit next to the batch
             consumer["bloom"] = {"skipped": str(e)[:80]}
+        consumer.update(extra_consumers(torch, nthash_b200, nd, w, args, world))
 
-    if seeds:
-        # SeedNtHash consumer: count / sum / xor of every visited window's hashes, two passes on the device (rows to scratch
-        # memory, then a reduction): no hash crosses PCIe
+    if seeds and not args.no_consumers:
+        # SeedNtHash consumer: count / sum / xor of every visited window's hashes; no hash crosses PCIe
         red = nthash_b200.seed_reduce_uniform(plan, bases, n_reads, L)
         torch.cuda.synchronize()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -426,58 +594,66 @@ def main():
             e2e_seed_reduce_step()
         er_dt = (time.perf_counter() - t0) / args.e2e_steps
         red_ms, er_dt = nd.max_over_ranks([red_ms, er_dt])
-        consumer = {"kind": "count/sum/xor of all SeedNtHash hashes (nthash_seed_reduce*: rows to device scratch, then a reduction; not fused)",
+        consumer = {"kind": "count/sum/xor of all SeedNtHash hashes (nthash_seed_reduce*)",
                     "value": world * rows / (red_ms * 1e-3), "unit": UNIT, "ms_per_step": red_ms,
                     "e2e": {"value": world * e_rows / er_dt, "unit": UNIT, "ms_per_step": er_dt * 1e3,
                             "h2d_bytes_per_step": int(h_bases.numel()), "d2h_bytes_per_step": 24},
-                    "windows": int(red[0]), "sum": int(red[1]) & (2**64 - 1),
+                    "windows": int(red[0]), "sum": int(red[1]) & M64,
                     "e2e_matches_device": bool(e2e_reads != n_reads or (h_res.cuda() == red).all())}
 
-    if rank != 0:
-        nd.finalize()
-        return
-
-    # ---- CPU baseline: the compiled reference on this box's host cores -------------------------
+    # ---- CPU baseline: the compiled reference on this box's host cores (rank 0; same policy as --impl reference) ----
     cpu = None
-    checksum_ok = None
-    if not args.no_cpu_baseline:
-        from oracle_lib import ORACLE, REF
-        lib = REF if REF is not None else ORACLE
-        threads = os.cpu_count() or 1
-        sample_reads = min(n_reads, args.ref_sample_reads)
-        h_sample = bases[: sample_reads * L].cpu().numpy()
-        v, ne, s, dt = cpu_reference_pass(lib, h_sample, sample_reads, L, k, h, threads, seeds)
-        # grow the sample until it is a meaningful amount of CPU work (about 10-30 core-seconds)
-        if dt * threads < 10 and sample_reads < n_reads:
-            sample_reads = min(n_reads, int(sample_reads * 20 / max(dt * threads, 0.5)))
-            h_sample = bases[: sample_reads * L].cpu().numpy()
-            v, ne, s, dt = cpu_reference_pass(lib, h_sample, sample_reads, L, k, h, threads, seeds)
-        got = int(out[: sample_reads * nk].cpu().numpy().view(np.uint64).sum(dtype=np.uint64))
-        checksum_ok = (got == s) and ne == sample_reads * nk
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": lib.kind,
-               "sample": f"first {sample_reads} of {n_reads} reads, {dt:.2f} s wall on {threads} threads", "checksum_matches_gpu": checksum_ok}
+    if rank == 0 and not args.no_cpu_baseline:
+        m = cpu_reference_measure(cfg, min(n_reads, args.ref_sample_reads or cfg["cpu_reads"]), 3)
+        windows, gsum = w.checksum_prefix(m["sample_reads"])
+        cpu = {"value": m["value"], "unit": UNIT, "cores": m["threads"], "kind": m["kind"], "sample": cpu_sample_label(cfg, m),
+               "checksum_matches_gpu": bool(gsum == m["sum"] and windows == m["emitted_per_pass"])}
 
-    peak, peak_src = load_peak()
     abytes = algorithmic_bytes(n_reads, L, k, H)
     achieved = abytes / (kernel_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": world * rows / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": cfg["desc"], "reads_per_gpu": n_reads, "read_len": L, "k": k, "h": h, "seeds": seeds,
-                   "l2_policy": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2; no explicit flush" % (abytes / 1e9),
-                   "sharding": "independent read shards per GPU, no collective"},
+        "config": workload_config(cfg, n_reads),
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (load_traffic(args.config) or {}).get("dram_bytes_per_launch") if not args.reads else None,
-                     "traffic_source": (load_traffic(args.config) or {}).get("source"), "peak_source": peak_src, "kernel": ("seed_jit_kernel (NVRTC-specialised)" if seeds else "kmer_fast_kernel<H=%d>" % h), "kernel_ms": kernel_ms,
+                     "traffic_source": (load_traffic(args.config) or {}).get("source"), "peak_source": peak_src, "kernel": w.kernel_name(), "kernel_ms": kernel_ms,
                      "kernel_ms_best": each[0], "kernel_ms_median": statistics.median(each), "algorithmic_bytes_per_launch": abytes},
-        "cpu_baseline": cpu, "fused_consumer": consumer,
+        "cpu_baseline": cpu, "fused_consumer": consumer, "sum_all_ranks": sum_all,
     }
-    if consumer and cpu and sample_reads == n_reads:
-        consumer["matches_cpu_reference"] = consumer["sum"] == s and consumer["windows"] == ne
-    print(json.dumps(line))
+    # ---- the other BASELINE configs as sub-records (every rank takes part; rank 0 checks against the reference) ----
+    del h_bases, h_out, h_valid, w, bases, out, step
+    torch.cuda.empty_cache()
+    if not args.no_sub_records and not args.reads:
+        subs = {}
+        for name in ("c3", "c4", "c5"):
+            if name == args.config:
+                continue
+            try:
+                subs[name] = sub_record(torch, nthash_b200, LIB, nd, name, args, rank, world, peak, not args.no_cpu_baseline)
+            except Exception as e:  # a sub-record must never take the headline line down with it
+                subs[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                torch.cuda.empty_cache()
+        line["configs"] = subs
+    if rank == 0:
+        print(json.dumps(line))
     nd.finalize()
+
+
+def extra_consumers(torch, nthash_b200, nd, w, args, world):
+    """Consumers added in round 2 (minimizers, cardinality sketch) when the library exports them."""
+    rec = {}
+    for name, fn in (("minimizer", getattr(nthash_b200, "bench_minimizer_record", None)),
+                     ("cardinality_sketch", getattr(nthash_b200, "bench_sketch_record", None))):
+        if fn is None:
+            continue
+        try:
+            rec[name] = fn(torch, nd, w, args, world)
+        except Exception as e:
+            rec[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    return rec
 
 
 if __name__ == "__main__":

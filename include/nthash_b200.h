@@ -35,6 +35,14 @@
  *    and D2H themselves on `device`.
  *  - Supported domain: 3 <= k <= 65535 (the reference segfaults for k < 3, kmer.cpp:47),
  *    1 <= num_hashes <= 255 (uint8_t in the reference), any read lengths.
+ *  - Byte semantics: every byte value is handled as the reference handles it (SEED_TAB,
+ *    src/internal.hpp:132-165: ACGTU in either case hash, anything else is an invalid base
+ *    for NtHash and a zero forward seed / `c & 7` complement seed for SeedNtHash), with ONE
+ *    documented deviation: the raw control bytes 0x01, 0x03, 0x04, 0x05, 0x07.  They are the
+ *    reference's complement slots (SEED_TAB[c & 7], internal.hpp:133) and make NtHash disagree
+ *    with itself there (init() maps them through CONVERT_TAB = 255, roll() hashes them).  This
+ *    engine — and oracle/, which restates the same choice — treats them as invalid bases in
+ *    NtHash (no window containing one is emitted).  Text input never contains them.
  *  - Thread-safe: no mutable global state besides per-thread error text.
  */
 #ifndef NTHASH_B200_H

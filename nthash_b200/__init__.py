@@ -2,7 +2,7 @@
 
 Layout: csrc/ holds the hand-written CUDA kernels and the C ABI (include/nthash_b200.h);
 _lib.py binds that ABI with ctypes; api.py is a thin device-resident front end that uses
-PyTorch only for HBM buffers and streams; host.py drives host-buffer calls and multi-GPU shards.
+PyTorch only for HBM buffers and streams; dist.py shards read batches over one process per GPU.
 """
 from ._lib import LIB, LIB_PATH, NtHashError  # noqa: F401
 from .api import (HashBatch, SeedPlan, blind_peek4, blind_roll, blind_seed_roll, kmer_hashes, kmer_hashes_uniform,  # noqa: F401

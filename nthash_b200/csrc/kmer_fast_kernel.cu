@@ -764,15 +764,13 @@ cudaError_t make_out_map(const KmerParams& P, uint32_t blocks, CUtensorMap* map)
   using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeFn encode = nullptr;
-  if (!encode) {
+  static const EncodeFn encode = []() -> EncodeFn { // initialised once, thread-safe (function-local static)
     void* fp = nullptr;
     cudaDriverEntryPointQueryResult qr;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qr);
-    if (e != cudaSuccess) return e;
-    if (!fp || qr != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
-    encode = (EncodeFn)fp;
-  }
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qr) != cudaSuccess) return nullptr;
+    return (fp && qr == cudaDriverEntryPointSuccess) ? (EncodeFn)fp : nullptr;
+  }();
+  if (!encode) return cudaErrorNotSupported;
   const uint64_t row_u64 = (uint64_t)P.g.seg * P.h;
   const cuuint64_t dims[3] = { 8, P.g.n_items, row_u64 / 8 };
   const cuuint64_t strides[2] = { row_u64 * 8, 64 };
