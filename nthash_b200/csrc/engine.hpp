@@ -21,6 +21,10 @@ struct KmerGeom
   const uint64_t* item_out = nullptr;
   uint64_t n_items = 0;
   uint32_t read_len = 0, nk = 0, seg = 0, segs = 1;
+  // flat (fast kernel, uniform long reads): item i = dense windows [i*seg, (i+1)*seg) of the whole batch, whichever
+  // read(s) they fall in; `total` = n_reads * nk.  An item that crosses a read boundary is finished by the fix-up kernel.
+  uint32_t flat = 0;
+  uint64_t total = 0;
 };
 
 struct KmerParams

@@ -169,9 +169,20 @@ NTH_D uint64_t canonical2(const State& s)
 
 // Geometry of item i (shared with kmer_kernel.cu's item_geom, restated here with the last item of a cut-up
 // read allowed to be short).
+// byte offset of dense window w of a uniform batch (flat geometry)
+NTH_D uint64_t flat_byte(const KmerGeom& g, uint64_t w)
+{
+  const uint64_t r = (w >> 32) ? w / g.nk : (uint64_t)((uint32_t)w / g.nk);
+  return r * g.read_len + (w - r * g.nk);
+}
+
 NTH_D void fast_item_geom(const KmerGeom& g, uint64_t i, uint64_t& byte, uint64_t& out, uint32_t& n)
 {
-  if (g.item_byte) { // ragged: arrays are read_off/koff themselves when every read is one item
+  if (g.flat) { // a fixed number of dense windows per item; the bytes of two reads are adjacent, so a lane that crosses a
+    out = i * g.seg; // read boundary simply keeps rolling (its rows past the boundary are redone by kmer_flat_fix_kernel)
+    byte = flat_byte(g, out);
+    n = g.seg;
+  } else if (g.item_byte) { // ragged: arrays are read_off/koff themselves when every read is one item
     byte = g.item_byte[i];
     out = g.item_out[i];
     n = (uint32_t)(g.item_out[i + 1] - out);
@@ -241,7 +252,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
 
   constexpr bool STR = CONS == 4;                  // CONS == 4: store the hashes AND the strand hashes (general output path)
   constexpr bool REDUCE = CONS != 0 && CONS != 4;  // consumers proper: nothing is stored
-  const uint32_t HH = H ? (uint32_t)H : P.h; // H == 0: runtime number of hashes (5..8, general output path only)
+  const uint32_t HH = H ? (uint32_t)H : P.h; // H == 0: runtime number of hashes (5..255, general output path only)
   const uint32_t NT = blockDim.x;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t i0 = (uint64_t)blockIdx.x * NT;
@@ -253,7 +264,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   if (i0 + tid < i1) {
     fast_item_geom(P.g, i0 + tid, my_byte, my_out, n);
     if (tid == 0) s_range[0] = my_byte;
-    if (i0 + tid == i1 - 1) s_range[1] = my_byte + (n ? n + k - 1 : 0);
+    if (i0 + tid == i1 - 1) s_range[1] = P.g.flat ? flat_byte(P.g, my_out + n - 1) + k : my_byte + (n ? n + k - 1 : 0);
   }
   if (P.g.item_byte) {
     // Ragged batch: a warp runs as long as its longest item, so hand the CTA's items out by length class
@@ -337,7 +348,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   const bool active = n != 0;
   if (BOX && !REDUCE && !active) { // warp-synchronous output path: idle lanes hash a dummy row that the TMA store clips
     my_byte = g0 + 1;
-    n = P.g.nk;
+    n = P.g.seg;
   }
   const uint32_t ps = keep(sbase + F_TILE_OFF + F_TILE_PAD + (uint32_t)(my_byte - g0)); // shared address of base 0
   const uint32_t lut = keep(sbase + F_LUT_OFF);
@@ -406,11 +417,19 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
       if (CONS == 1) {
         acc_sum += h0;
         acc_xor ^= h0;
+        if (H) {
 #pragma unroll
-        for (int q = 1; q < H; ++q) {
-          const uint64_t e = ext_hash(h0, P.mult[q]);
-          acc_sum += e;
-          acc_xor ^= e;
+          for (int q = 1; q < H; ++q) {
+            const uint64_t e = ext_hash(h0, P.mult[q]);
+            acc_sum += e;
+            acc_xor ^= e;
+          }
+        } else { // runtime number of hashes (5..255); mult[0] = k * MULTISEED
+          for (uint32_t q = 1; q < HH; ++q) {
+            const uint64_t e = ext_hash(h0, (uint64_t)q ^ P.mult[0]);
+            acc_sum += e;
+            acc_xor ^= e;
+          }
         }
       } else { // Bloom filter: P.h positions per window (extend_hashes, src/internal.hpp:104-118, with a runtime count)
         const uint64_t kmul = P.mult[0]; // k * MULTISEED
@@ -604,19 +623,98 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
       else bulk_wait_read0();          // shared memory must outlive the TMA read
     }
     __syncwarp();
-    if (dirty) scrub_lane<H>(P, lut, ps, my_out, n);
+    if (dirty) { // flat geometry: only the windows before the read boundary are this lane's to clean
+      const uint32_t n_own = P.g.flat ? (uint32_t)min((uint64_t)n, (uint64_t)P.g.nk - my_out % P.g.nk) : n;
+      scrub_lane<H>(P, lut, ps, my_out, n_own);
+    }
   } else {
     // General output path (ragged batches, cut-up reads, rows that are not 64-byte multiples): every lane collects
     // 256 bytes of its row (32/H windows) in a private shared-memory row, then the warp copies the 32 rows out
     // with coalesced 16-byte stores, two rows per instruction (a half-warp per row).  Each row's global address
     // and byte count travel through a 16-byte descriptor, so lanes may differ in length and alignment.
-    constexpr uint32_t WS1 = H == 0 ? 4 : H == 3 ? 8 : 32 / (H ? H : 1); // windows per row piece: <= 256 bytes
+    constexpr uint32_t WS1 = H == 3 ? 8 : 32 / (H ? H : 1); // windows per row piece (compile-time h): <= 256 bytes
     constexpr uint32_t NARR = STR ? 3 : 1; // output arrays: hashes (+ forward and reverse strand hashes)
     const uint32_t wbase = rb_base + (tid & ~31u) * NARR * (ROW1_BYTES + 16); // this warp: NARR x [32 descriptors], NARR x [32 rows]
     const uint32_t desc0 = wbase, rows0 = wbase + NARR * 32 * 16;
     const uint32_t rb = rows0 + lane * ROW1_BYTES;
     const uint32_t rbf = rb + 32 * ROW1_BYTES, rbr = rb + 64 * ROW1_BYTES; // STR only
     const uint32_t hw = lane >> 4, c16 = (lane & 15) * 16;
+    // the warp's 32 rows of one output array -> global memory: all loads of a batch of rows first (they do not depend
+    // on each other), then the stores; a half-warp per row, each row's address and byte count from its descriptor
+    auto copy_rows = [&](uint32_t descA, uint32_t rowsA) {
+#pragma unroll
+      for (uint32_t r0 = 0; r0 < 16; r0 += 8) {
+        uint4 d[8], v[8];
+#pragma unroll
+        for (uint32_t rr = 0; rr < 8; ++rr) {
+          const uint32_t row = 2 * (r0 + rr) + hw;
+          d[rr] = lds_v4(descA + row * 16); // {address lo, address hi, bytes, 0}
+          v[rr] = lds_v4(rowsA + row * ROW1_BYTES + c16);
+        }
+#pragma unroll
+        for (uint32_t rr = 0; rr < 8; ++rr) {
+          uint8_t* ga = reinterpret_cast<uint8_t*>(((uint64_t)d[rr].y << 32) | d[rr].x) + c16;
+          if (c16 + 16 <= d[rr].z)
+            asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(ga), "r"(v[rr].x), "r"(v[rr].y), "r"(v[rr].z), "r"(v[rr].w) : "memory");
+          else if (c16 + 8 == d[rr].z) // odd last u64 of an item
+            asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(ga), "r"(v[rr].x), "r"(v[rr].y) : "memory");
+        }
+      }
+    };
+    if constexpr (H == 0) {
+      // Runtime number of hashes (5..255): a lane's output is one contiguous stream of u64 (window after window, h values
+      // each), cut into 256-byte pieces wherever they fall.  Values are appended to the lane's row; when a running lane
+      // has 32 of them the warp copies its rows out.  `ufill` counts as a lane that is still running does (warp-uniform),
+      // `fill` what this lane really appended (lanes whose item has ended append nothing).
+      uint32_t fill = 0, ufill = 0;
+      uint64_t gaddr = (uint64_t)(uintptr_t)(P.out + (my_out + p) * HH);
+      auto flush = [&]() {
+        st_shared_v2_u64(desc0 + lane * 16, gaddr, (uint64_t)(fill * 8u));
+        __syncwarp();
+        copy_rows(desc0, rows0);
+        __syncwarp();
+        gaddr += fill * 8u;
+        fill = 0;
+        ufill = 0;
+      };
+      const uint64_t kmul = P.mult[0]; // k * MULTISEED
+      while (__any_sync(0xffffffffu, p < n)) {
+        const uint32_t cnt = p < n ? min(4u, n - p) : 0u;
+        uint64_t hv[4] = { 0, 0, 0, 0 };
+        if (cnt == 4) roll4(hv, full_t(), 4u);
+        else if (cnt) roll4(hv, part_t(), cnt);
+        if (STR) {
+          st_shared_v2_u64(rbf, fw4[0], fw4[1]);
+          st_shared_v2_u64(rbf + 16, fw4[2], fw4[3]);
+          st_shared_v2_u64(rbr, rv4[0], rv4[1]);
+          st_shared_v2_u64(rbr + 16, rv4[2], rv4[3]);
+          st_shared_v2_u64(desc0 + (32 + lane) * 16, (uint64_t)(uintptr_t)(P.out_fwd + my_out + p), (uint64_t)(cnt * 8));
+          st_shared_v2_u64(desc0 + (64 + lane) * 16, (uint64_t)(uintptr_t)(P.out_rev + my_out + p), (uint64_t)(cnt * 8));
+          __syncwarp();
+          copy_rows(desc0 + 32 * 16, rows0 + 32 * ROW1_BYTES);
+          copy_rows(desc0 + 64 * 16, rows0 + 64 * ROW1_BYTES);
+          __syncwarp();
+        }
+#pragma unroll 1
+        for (uint32_t i = 0; i < 4; ++i) {
+          const uint64_t h0 = hv[0];
+          hv[0] = hv[1]; // rotate instead of indexing: hv stays in registers
+          hv[1] = hv[2];
+          hv[2] = hv[3];
+          const bool on = i < cnt;
+#pragma unroll 1
+          for (uint32_t e = 0; e < HH; ++e) {
+            if (on) {
+              st_shared_u64(rb + fill * 8u, e ? ext_hash(h0, (uint64_t)e ^ kmul) : h0);
+              ++fill;
+            }
+            if (++ufill == 32) flush();
+          }
+        }
+        p += cnt;
+      }
+      if (ufill) flush();
+    } else {
     while (__any_sync(0xffffffffu, p < n)) {
       const uint32_t cnt = p < n ? min(WS1, n - p) : 0u;
       auto group = [&](uint32_t q, auto full, uint32_t c4n) {
@@ -644,13 +742,6 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
           }
 #pragma unroll
           for (int c = 0; c < 6; ++c) st_shared_v2_u64(rb + (6 * q + c) * 16, v[2 * c], v[2 * c + 1]);
-        } else if (H == 0) { // 5..8 hashes: one group of four windows is the whole row piece
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t a = rb + (uint32_t)i * HH * 8u;
-            st_shared_u64(a, hv[i]);
-            for (uint32_t e = 1; e < HH; ++e) st_shared_u64(a + e * 8u, ext_hash(hv[i], (uint64_t)e ^ P.mult[0]));
-          }
         } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -675,33 +766,68 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
         st_shared_v2_u64(desc0 + (64 + lane) * 16, (uint64_t)(uintptr_t)(P.out_rev + my_out + p), (uint64_t)(cnt * 8));
       }
       __syncwarp();
-      // all loads of a batch of rows first (they do not depend on each other), then the stores
 #pragma unroll
-      for (uint32_t arr = 0; arr < NARR; ++arr) {
-        const uint32_t descA = desc0 + arr * 32 * 16, rowsA = rows0 + arr * 32 * ROW1_BYTES;
-#pragma unroll
-        for (uint32_t r0 = 0; r0 < 16; r0 += 8) {
-          uint4 d[8], v[8];
-#pragma unroll
-          for (uint32_t rr = 0; rr < 8; ++rr) {
-            const uint32_t row = 2 * (r0 + rr) + hw;
-            d[rr] = lds_v4(descA + row * 16); // {address lo, address hi, bytes, 0}
-            v[rr] = lds_v4(rowsA + row * ROW1_BYTES + c16);
-          }
-#pragma unroll
-          for (uint32_t rr = 0; rr < 8; ++rr) {
-            uint8_t* ga = reinterpret_cast<uint8_t*>(((uint64_t)d[rr].y << 32) | d[rr].x) + c16;
-            if (c16 + 16 <= d[rr].z)
-              asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(ga), "r"(v[rr].x), "r"(v[rr].y), "r"(v[rr].z), "r"(v[rr].w) : "memory");
-            else if (c16 + 8 == d[rr].z) // odd last u64 of an item
-              asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(ga), "r"(v[rr].x), "r"(v[rr].y) : "memory");
-          }
-        }
-      }
+      for (uint32_t arr = 0; arr < NARR; ++arr) copy_rows(desc0 + arr * 32 * 16, rows0 + arr * 32 * ROW1_BYTES);
       __syncwarp(); // rows are rewritten next; also orders these stores before the scrub's zeros
       p += cnt;
     }
+    }
     if (bad != 0) scrub_lane<H>(P, lut, ps, my_out, n);
+  }
+}
+
+// FLAT geometry, second launch: the rows the main kernel cannot produce.  Thread f >= 1 owns the windows of read f that
+// share a flat item with the end of read f-1 (the main kernel rolled across the boundary there and stored junk);
+// thread 0 owns the partial last item of the batch, which the tensor map leaves out.  At most seg windows each, hashed
+// from scratch straight out of global memory: base hashes by Horner's rule over the k bytes (the closed form of
+// base_forward_hash / base_reverse_hash, src/kmer.cpp:43-73, :123-152), then NtHash::roll (src/kmer.cpp:246-264).
+__global__ void __launch_bounds__(128) kmer_flat_fix_kernel(const __grid_constant__ KmerParams P, uint64_t n_reads)
+{
+  const uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_reads) return;
+  const uint64_t nk = P.g.nk, seg = P.g.seg, w_tail = P.g.total / seg * seg;
+  uint64_t w0;
+  uint32_t n;
+  if (f == 0) {
+    w0 = w_tail;
+    n = (uint32_t)(P.g.total - w_tail);
+  } else {
+    w0 = f * nk;
+    const uint32_t rem = (uint32_t)(w0 % seg);
+    n = (rem && w0 < w_tail) ? (uint32_t)min(seg - rem, nk) : 0u;
+  }
+  if (!n) return;
+  const uint64_t r = w0 / nk;
+  const uint8_t* sq = P.bases + r * P.g.read_len + (w0 - r * nk);
+  const uint32_t k = P.k, h = P.h;
+  // code (byte >> 1) & 3: 0 = A, 1 = C, 2 = T/U, 3 = G; index into P.s / P.sk (A, C, G, T) = code ^ (code >> 1)
+  auto fs = [&](uint32_t c) { const uint32_t x = (c >> 1) & 3u; return P.s[x ^ (x >> 1)]; };
+  auto fk = [&](uint32_t c) { const uint32_t x = (c >> 1) & 3u; return P.sk[x ^ (x >> 1)]; };
+  auto cs = [&](uint32_t c) { const uint32_t x = ((c >> 1) & 3u) ^ 2u; return P.s[x ^ (x >> 1)]; };
+  auto ck = [&](uint32_t c) { const uint32_t x = ((c >> 1) & 3u) ^ 2u; return P.sk[x ^ (x >> 1)]; };
+  uint64_t F = 0, R = 0;
+  uint32_t run = 0;
+  for (uint32_t i = 0; i < k; ++i) {
+    const uint32_t c = sq[i];
+    run = is_acgtu(c) ? run + 1 : 0;
+    F = srol1(F) ^ fs(c);
+  }
+  for (uint32_t i = k; i-- > 0;) R = srol1(R) ^ cs(sq[i]);
+  for (uint32_t p = 0;; ++p) {
+    const uint64_t w = w0 + p, h0 = F + R;
+    uint64_t* o = P.out + w * h;
+    if (run >= k) {
+      o[0] = h0;
+      for (uint32_t q = 1; q < h; ++q) o[q] = ext_hash(h0, P.mult[q]);
+    } else { // a window the reference does not visit (kmer.cpp:232-235, :255-258)
+      for (uint32_t q = 0; q < h; ++q) o[q] = 0;
+      if (P.valid_bits) atomicAnd(&P.valid_bits[(P.valid_row0 + w) >> 5], ~(1u << ((P.valid_row0 + w) & 31)));
+    }
+    if (p + 1 == n) break;
+    const uint32_t cin = sq[p + k], cout = sq[p];
+    run = is_acgtu(cin) ? run + 1 : 0;
+    F = srol1(F) ^ fs(cin) ^ fk(cout);
+    R = sror1(R ^ ck(cin) ^ cs(cout));
   }
 }
 
@@ -772,7 +898,7 @@ cudaError_t make_out_map(const KmerParams& P, uint32_t blocks, CUtensorMap* map)
   }();
   if (!encode) return cudaErrorNotSupported;
   const uint64_t row_u64 = (uint64_t)P.g.seg * P.h;
-  const cuuint64_t dims[3] = { 8, P.g.n_items, row_u64 / 8 };
+  const cuuint64_t dims[3] = { 8, P.g.n_items, row_u64 / 8 }; // flat: n_items = the FULL items only, so nothing lands past `out`
   const cuuint64_t strides[2] = { row_u64 * 8, 64 };
   const cuuint32_t box[3] = { 8, 32, blocks };
   const cuuint32_t estr[3] = { 1, 1, 1 };
@@ -849,7 +975,7 @@ bool kmer_fast_ok(const KmerParams& P)
 {
   const KmerGeom& g = P.g;
   if (P.out_fwd && (P.reduce_out || P.bloom_mode || (((uintptr_t)P.out_fwd | (uintptr_t)P.out_rev) & 31))) return false;
-  return ((P.h >= 1 && P.h <= 4) || (P.h <= 8 && !P.reduce_out) || P.bloom_mode) && g.n_items > 0 &&
+  return (P.h >= 1 && P.h <= 255) && g.n_items > 0 &&
          (P.reduce_out || ((uintptr_t)P.out & 31) == 0) && (g.item_byte || (g.seg && g.segs));
 }
 
@@ -867,11 +993,25 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
     KmerGeom& g = P.g;
     const uint64_t n_reads = g.n_items / g.segs;
     const uint32_t whole = env_u32("NTHASH_B200_FAST_WHOLE_READ", 400), seg_t = env_u32("NTHASH_B200_FAST_SEG", 240);
+    uint32_t flat_seg = env_u32("NTHASH_B200_FLAT_SEG", 264);
+    flat_seg = std::max(24u, flat_seg / 24u * 24u);
+    const bool flat_ok = !P.reduce_out && !P.out_fwd && !P.bloom_mode && P.h <= 4 && g.nk >= 2 * flat_seg &&
+                         (n_reads * (uint64_t)g.nk) / flat_seg > 0 && !getenv("NTHASH_B200_FAST_NO_BOX") && !getenv("NTHASH_B200_NO_FLAT");
     if (g.read_len <= whole) { // one item per read
       g.seg = g.nk;
       g.segs = 1;
       // tensor stores need rows that are whole 64-byte blocks (then every row is 64-byte aligned too)
       c.box = !P.reduce_out && !P.out_fwd && P.h <= 4 && ((uint64_t)g.nk * P.h) % 8 == 0 && !getenv("NTHASH_B200_FAST_NO_BOX");
+    } else if (flat_ok) {
+      // FLAT: item i = dense windows [i*seg, (i+1)*seg) of the whole batch.  Every row of the [items][seg] view is full
+      // and seg*h*8-byte pitched, so long reads leave through the same 3-D tensor stores as short ones.  seg = 264 =
+      // 11 tiles of 24 windows (12 x h=2, 8 x h=3/4) and 66 words between neighbouring lanes' rows (2-way LDS.32
+      // conflicts; 64 words would be 32-way).  Rows past a read boundary are junk and are redone by the fix-up kernel.
+      g.flat = 1;
+      g.total = n_reads * g.nk;
+      g.seg = flat_seg;
+      g.segs = 1;
+      c.box = true;
     } else {
       // balanced items, the last one shorter.  seg = 4 (mod 8): an odd number of 32-bit words between the rows of
       // neighbouring lanes keeps their LDS.32 on distinct banks (seg = 256 ran 1.7x slower than 244), and a
@@ -880,10 +1020,11 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
       g.seg = (x & ~7u) + ((x & 7u) <= 4 ? 4u : 12u);
       g.segs = (g.nk + g.seg - 1) / g.seg;
     }
-    g.n_items = n_reads * g.segs;
+    g.n_items = g.flat ? g.total / g.seg : n_reads * g.segs; // flat: full items only; the tail belongs to the fix-up kernel
   }
   auto tile_cap_for = [&](uint32_t nt) -> uint64_t {
     if (!uniform) return ((uint64_t)Pin.tile_cap * nt + KMER_NT - 1) / KMER_NT + 2 * (uint64_t)P.k + 64; // sized for KMER_NT items
+    if (P.g.flat) return (uint64_t)nt * P.g.seg + ((uint64_t)nt * P.g.seg / P.g.nk + 2) * (P.k - 1) + 64;
     if (P.g.segs == 1) return (uint64_t)nt * P.g.read_len + 64;
     return (uint64_t)nt * P.g.seg + ((uint64_t)nt / P.g.segs + 2) * (P.k - 1) + 64;
   };
@@ -922,13 +1063,21 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
                              : launch_fast_t<1, 3, fast_ws<1>(0), 1, false>(P, c.nt, st);
   }
   switch (P.h) {
-    case 1: return launch_fast_h<1>(P, c, st);
-    case 2: return launch_fast_h<2>(P, c, st);
-    case 3: return launch_fast_h<3>(P, c, st);
-    case 4: return launch_fast_h<4>(P, c, st);
-    default: // 5..8 hashes: runtime count, general output path
-      return P.out_fwd ? launch_fast_t<0, 4, 8, 1, false>(P, c.nt, st) : launch_fast_t<0, 0, 8, 1, false>(P, c.nt, st);
+    case 1: e = launch_fast_h<1>(P, c, st); break;
+    case 2: e = launch_fast_h<2>(P, c, st); break;
+    case 3: e = launch_fast_h<3>(P, c, st); break;
+    case 4: e = launch_fast_h<4>(P, c, st); break;
+    default: // 5..255 hashes: runtime count, general output path (a stream of 256-byte pieces per lane)
+      return P.reduce_out ? launch_fast_t<0, 1, 8, 1, false>(P, c.nt, st)
+             : P.out_fwd  ? launch_fast_t<0, 4, 8, 1, false>(P, c.nt, st)
+                          : launch_fast_t<0, 0, 8, 1, false>(P, c.nt, st);
   }
+  if (e == cudaSuccess && P.g.flat) { // rows behind every read boundary + the partial last item, after the junk has landed
+    const uint64_t n_reads = P.g.total / P.g.nk;
+    kmer_flat_fix_kernel<<<(unsigned)((n_reads + 127) / 128), 128, 0, st>>>(P, n_reads);
+    e = cudaGetLastError();
+  }
+  return e;
 }
 
 } // namespace nthb

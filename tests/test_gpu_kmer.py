@@ -125,6 +125,31 @@ def test_fast_kernel_output_paths(n, read_len, k, h, no_box, monkeypatch):
         assert torch.equal(res2.out, res.out) and torch.equal(res2.valid_bits, res.valid_bits)
 
 
+@pytest.mark.parametrize("n,read_len,k,h", [(37, 5000, 63, 1), (100, 1200, 31, 2), (50, 3000, 21, 4), (64, 2113, 31, 3), (3, 700, 31, 1),
+                                            (1, 100000, 63, 1), (1000, 600, 33, 1), (700, 1057, 5, 1)])
+@pytest.mark.parametrize("flat_seg", [264, 96])
+def test_flat_items_long_uniform_reads(n, read_len, k, h, flat_seg, monkeypatch):
+    """Uniform long reads run as FLAT items (fixed runs of dense windows that ignore read boundaries, 3-D tensor stores)
+    plus a fix-up launch for the rows behind every read boundary and the partial last item.  Dirty bytes are planted on
+    both sides of read boundaries, where the two kernels' responsibilities meet."""
+    monkeypatch.setenv("NTHASH_B200_FLAT_SEG", str(flat_seg))
+    rng = np.random.default_rng(n * 17 + read_len + k + h)
+    bases = synth(rng, n * read_len, p_bad=0.0003, lower=0.05)
+    for r in range(1, n, max(1, n // 7)):
+        b = r * read_len
+        for d in (-1, 0, k - 1, -k, k + 5)[: 2 + (r % 4)]:
+            bases[b + d] = ord("N")
+    d_b, _keep = to_dev(bases)
+    res = nthash_b200.kmer_hashes_uniform(d_b, n, read_len, k, h)
+    torch.cuda.synchronize()
+    off = np.arange(n + 1, dtype=np.uint64) * read_len
+    assert_batch_equal(res, ORACLE.kmer_batch(bases, off, k, h, threads=8), h)
+    monkeypatch.setenv("NTHASH_B200_NO_FLAT", "1")
+    res2 = nthash_b200.kmer_hashes_uniform(d_b, n, read_len, k, h)
+    torch.cuda.synchronize()
+    assert torch.equal(res2.out, res.out) and torch.equal(res2.valid_bits, res.valid_bits)
+
+
 @pytest.mark.parametrize("n,read_len,k,h", [(40, 6000, 2000, 1), (6, 70000, 65535, 2), (300, 1300, 1023, 4)])
 def test_huge_k_uniform(n, read_len, k, h):
     # k up to uint16 max (the reference's k is a uint16_t, nthash.hpp:74); the general kernel's CTA tile no longer
