@@ -30,7 +30,9 @@
  *    `valid_bits`, `out_fwd`, `out_rev` may be NULL (both of fwd/rev or neither).
  *  - `*_dev` entry points take DEVICE pointers on the current CUDA device and only enqueue
  *    work on `stream` (a cudaStream_t, NULL = default stream); nothing is copied and the
- *    host is not synchronised unless stated.  `bases` must be 16-byte aligned (cudaMalloc
+ *    host is not synchronised unless stated (nthash_kmer_plan_dev, nthash_ragged_plan_create and
+ *    nthash_fastq_extract_dev return counts to the host and therefore do synchronise; the hashing
+ *    entries never do: scratch comes from the stream-ordered pool, totals stay on the device).  `bases` must be 16-byte aligned (cudaMalloc
  *    memory is).  The un-suffixed entry points take HOST pointers and do H2D, the kernel
  *    and D2H themselves on `device`.
  *  - Supported domain: 3 <= k <= 65535 (the reference segfaults for k < 3, kmer.cpp:47),
@@ -95,6 +97,28 @@ int nthash_kmer_batch_dev(const uint8_t* d_bases, uint64_t n_bases_readable, con
                           const uint64_t* d_koff, uint64_t n_reads, uint64_t max_read_len, uint32_t k,
                           uint32_t num_hashes, uint64_t* d_out, uint32_t* d_valid_bits, uint64_t* d_out_fwd,
                           uint64_t* d_out_rev, void* stream);
+
+/* Ragged reads, planned once.  nthash_ragged_plan_create() computes the layout of a batch — koff, the row total, the
+ * longest read, and the item tables the kernels use when reads are too long to be one work item — and synchronises the
+ * host ONCE; the plan then serves any number of calls on batches with the same read_off (the bases may change: same
+ * layout, new sequence).  The *_planned_dev entries only enqueue kernels: no allocation that blocks, no read-back, no
+ * host synchronisation, so they can be captured into a CUDA graph.  d_read_off is borrowed (keep it alive and
+ * unchanged while the plan lives); the plan owns koff (nthash_ragged_plan_koff, device pointer, n_reads + 1 entries).
+ * The reference has no counterpart: its get_pos() (nthash.hpp:170) is this arithmetic done one k-mer at a time.   */
+typedef struct nthash_ragged_plan nthash_ragged_plan;
+int nthash_ragged_plan_create(const uint64_t* d_read_off, uint64_t n_reads, uint32_t k, void* stream,
+                              nthash_ragged_plan** plan_out);
+void nthash_ragged_plan_destroy(nthash_ragged_plan* plan);
+uint64_t nthash_ragged_plan_rows(const nthash_ragged_plan* plan);
+uint64_t nthash_ragged_plan_max_read_len(const nthash_ragged_plan* plan);
+const uint64_t* nthash_ragged_plan_koff(const nthash_ragged_plan* plan);
+/* NtHash over the planned batch: same outputs and optional arguments as nthash_kmer_batch_dev. */
+int nthash_kmer_batch_planned_dev(const nthash_ragged_plan* plan, const uint8_t* d_bases, uint64_t n_bases_readable,
+                                  uint32_t num_hashes, uint64_t* d_out, uint32_t* d_valid_bits, uint64_t* d_out_fwd,
+                                  uint64_t* d_out_rev, void* stream);
+/* The fused count / sum / xor consumer over the planned batch (see nthash_kmer_reduce_dev). */
+int nthash_kmer_reduce_planned_dev(const nthash_ragged_plan* plan, const uint8_t* d_bases, uint64_t n_bases_readable,
+                                   uint32_t num_hashes, uint64_t* d_result, void* stream);
 
 /* Host buffers in, host buffers out (H2D + kernel + D2H on `device`). */
 int nthash_kmer_batch(const char* bases, const uint64_t* read_off, uint64_t n_reads, uint32_t k,
@@ -214,6 +238,10 @@ int nthash_seed_batch_uniform_dev(const nthash_seed_plan* plan, const uint8_t* d
                                   uint64_t n_bases_readable, uint64_t n_reads, uint32_t read_len,
                                   uint64_t* d_out, uint32_t* d_valid_bits, uint64_t* d_out_fwd,
                                   uint64_t* d_out_rev, void* stream);
+/* SeedNtHash over a planned ragged batch (plan made with k = the seed length); enqueue only, like the k-mer form. */
+int nthash_seed_batch_planned_dev(const nthash_seed_plan* seeds, const nthash_ragged_plan* plan, const uint8_t* d_bases,
+                                  uint64_t n_bases_readable, uint64_t* d_out, uint32_t* d_valid_bits,
+                                  uint64_t* d_out_fwd, uint64_t* d_out_rev, void* stream);
 /* Ragged reads: d_koff / max_read_len from nthash_kmer_plan_dev(..., k = seed length, ...). */
 int nthash_seed_batch_dev(const nthash_seed_plan* plan, const uint8_t* d_bases, uint64_t n_bases_readable,
                           const uint64_t* d_read_off, const uint64_t* d_koff, uint64_t n_reads,

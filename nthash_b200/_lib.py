@@ -20,6 +20,14 @@ _SIGS = {
     "nthash_kmer_batch_uniform_dev": (C.c_int, [u8p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u64p, u32p, u64p, u64p, C.c_void_p]),
     "nthash_kmer_plan_dev": (C.c_int, [u64p, C.c_uint64, C.c_uint32, u64p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]),
     "nthash_kmer_batch_dev": (C.c_int, [u8p, C.c_uint64, u64p, u64p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, u64p, u32p, u64p, u64p, C.c_void_p]),
+    "nthash_ragged_plan_create": (C.c_int, [u64p, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "nthash_ragged_plan_destroy": (None, [C.c_void_p]),
+    "nthash_ragged_plan_rows": (C.c_uint64, [C.c_void_p]),
+    "nthash_ragged_plan_max_read_len": (C.c_uint64, [C.c_void_p]),
+    "nthash_ragged_plan_koff": (C.c_void_p, [C.c_void_p]),
+    "nthash_kmer_batch_planned_dev": (C.c_int, [C.c_void_p, u8p, C.c_uint64, C.c_uint32, u64p, u32p, u64p, u64p, C.c_void_p]),
+    "nthash_kmer_reduce_planned_dev": (C.c_int, [C.c_void_p, u8p, C.c_uint64, C.c_uint32, u64p, C.c_void_p]),
+    "nthash_seed_batch_planned_dev": (C.c_int, [C.c_void_p, C.c_void_p, u8p, C.c_uint64, u64p, u32p, u64p, u64p, C.c_void_p]),
     "nthash_kmer_batch": (C.c_int, [u8p, u64p, C.c_uint64, C.c_uint32, C.c_uint32, u64p, u32p, u64p, u64p, C.c_int]),
     "nthash_kmer_reduce_uniform_dev": (C.c_int, [u8p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u64p, C.c_void_p]),
     "nthash_kmer_reduce_dev": (C.c_int, [u8p, C.c_uint64, u64p, u64p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, u64p, C.c_void_p]),

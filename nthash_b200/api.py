@@ -94,6 +94,77 @@ def kmer_hashes(bases, read_off, k, num_hashes=1, want_valid=True, want_strands=
     return HashBatch(out, valid_bits, koff, rows, fwd, rev)
 
 
+class RaggedPlan:
+    """Layout of one ragged batch, planned once on the current device (C ABI: nthash_ragged_plan_create): koff, the row
+    total and the kernels' item tables.  `read_off` (int64 CUDA tensor, n_reads + 1) is kept alive by this object.
+    Calls made with a plan only enqueue kernels (no host synchronisation; CUDA-graph capturable)."""
+
+    def __init__(self, read_off, k, stream=None):
+        if not (read_off.is_cuda and read_off.dtype == torch.int64 and read_off.is_contiguous()):
+            raise ValueError("read_off must be a contiguous int64 CUDA tensor")
+        self.read_off, self.k, self.n_reads = read_off, k, read_off.numel() - 1
+        self._h = C.c_void_p()
+        with torch.cuda.device(read_off.device):
+            check(LIB.nthash_ragged_plan_create(_ptr(read_off), self.n_reads, k, _stream_ptr(stream), C.byref(self._h)))
+        self.rows = int(LIB.nthash_ragged_plan_rows(self._h))
+        self.max_read_len = int(LIB.nthash_ragged_plan_max_read_len(self._h))
+
+    def koff(self):
+        """int64 CUDA tensor [n_reads + 1]: the dense row offset of every read (recomputed into a tensor of the caller's;
+        the plan's own copy stays inside the library: nthash_ragged_plan_koff)."""
+        out = torch.empty(self.n_reads + 1, dtype=torch.int64, device=self.read_off.device)
+        rows, max_len = C.c_uint64(0), C.c_uint64(0)
+        with torch.cuda.device(self.read_off.device):
+            check(LIB.nthash_kmer_plan_dev(_ptr(self.read_off), self.n_reads, self.k, _ptr(out), C.byref(rows), C.byref(max_len), _stream_ptr(None)))
+        return out
+
+    def close(self):
+        if self._h:
+            LIB.nthash_ragged_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def kmer_hashes_planned(plan, bases, num_hashes=1, want_valid=True, want_strands=False, out=None, valid_bits=None, stream=None) -> HashBatch:
+    """NtHash over a planned ragged batch (nthash_kmer_batch_planned_dev): enqueue only."""
+    _check_bases(bases)
+    dev = bases.device
+    rows = plan.rows
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((rows, num_hashes), dtype=torch.int64, device=dev)
+        if want_valid and valid_bits is None:
+            valid_bits = torch.empty(int(LIB.nthash_valid_words(rows)), dtype=torch.int32, device=dev)
+        fwd = torch.empty(rows, dtype=torch.int64, device=dev) if want_strands else None
+        rev = torch.empty(rows, dtype=torch.int64, device=dev) if want_strands else None
+        check(LIB.nthash_kmer_batch_planned_dev(plan._h, _ptr(bases), bases.numel(), num_hashes, _ptr(out), _ptr(valid_bits if want_valid else None),
+                                                _ptr(fwd), _ptr(rev), _stream_ptr(stream)))
+    return HashBatch(out, valid_bits if want_valid else None, None, rows, fwd, rev)
+
+
+def seed_hashes_planned(seed_plan, plan, bases, want_valid=True, want_strands=False, out=None, valid_bits=None, stream=None) -> HashBatch:
+    """SeedNtHash over a planned ragged batch (nthash_seed_batch_planned_dev): enqueue only."""
+    _check_bases(bases)
+    m, H = len(seed_plan.seeds), len(seed_plan.seeds) * seed_plan.h
+    dev = bases.device
+    rows = plan.rows
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((rows, H), dtype=torch.int64, device=dev)
+        if want_valid and valid_bits is None:
+            valid_bits = torch.empty(int(LIB.nthash_valid_words(rows)), dtype=torch.int32, device=dev)
+        fwd = torch.empty((rows, m), dtype=torch.int64, device=dev) if want_strands else None
+        rev = torch.empty((rows, m), dtype=torch.int64, device=dev) if want_strands else None
+        check(LIB.nthash_seed_batch_planned_dev(seed_plan._h, plan._h, _ptr(bases), bases.numel(), _ptr(out), _ptr(valid_bits if want_valid else None),
+                                                _ptr(fwd), _ptr(rev), _stream_ptr(stream)))
+    return HashBatch(out, valid_bits if want_valid else None, None, rows, fwd, rev)
+
+
 class SeedPlan:
     """Compiled spaced-seed set on the current device (C ABI: nthash_seed_plan_create / _destroy).
 

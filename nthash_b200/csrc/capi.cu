@@ -122,10 +122,19 @@ static int check_device_ready()
   return NTHASH_OK;
 }
 
-static int run_kmer(KmerParams& P, uint64_t rows, cudaStream_t st)
+// Pre-sets the validity bitmap: `rows` known on the host, or (ragged *_dev entries, which must not read anything back)
+// taken from device memory at *d_rows with `rows_bound` only sizing the grid.
+static cudaError_t preset_valid(uint32_t* d_valid, uint64_t rows, const uint64_t* d_rows, uint64_t rows_bound, cudaStream_t st)
+{
+  if (!d_valid) return cudaSuccess;
+  if (d_rows) return launch_fill_valid(d_valid, d_rows, rows_bound, st);
+  return rows ? cudaMemsetAsync(d_valid, 0xFF, ((rows + 31) / 32) * 4, st) : cudaSuccess;
+}
+
+static int run_kmer(KmerParams& P, uint64_t rows, const uint64_t* d_rows, uint64_t rows_bound, cudaStream_t st)
 {
   if (getenv("NTHASH_B200_DISABLE_TMA_STORE")) P.use_tma = false; // A/B switch for tests and profiling
-  if (P.valid_bits && rows) NTH_CUDA(cudaMemsetAsync(P.valid_bits, 0xFF, ((rows + 31) / 32) * 4, st));
+  NTH_CUDA(preset_valid(P.valid_bits, rows, d_rows, rows_bound, st));
   if (P.g.n_items == 0) return NTHASH_OK;
   const cudaError_t e = launch_kmer(P, st);
   if (e == cudaErrorInvalidConfiguration || e == cudaErrorNotSupported) {
@@ -148,8 +157,10 @@ struct RaggedItems
   const uint64_t* item_read = nullptr; // NULL when items are reads
 };
 
+// Nothing is read back: the item tables are sized by a host-side bound of the item count (every read contributes at
+// most ceil(windows / SEG_LONG) <= bases / SEG_LONG + 1 items) and the surplus is padded with empty items.
 static int plan_ragged(const uint64_t* d_read_off, const uint64_t* d_koff, uint64_t n_reads, uint64_t max_read_len,
-                       uint32_t k, uint32_t tile_budget, cudaStream_t st, RaggedItems& R)
+                       uint64_t n_bases, uint32_t k, uint32_t tile_budget, cudaStream_t st, RaggedItems& R)
 {
   if ((uint64_t)KMER_NT * max_read_len + 64 <= tile_budget) { // every read is one item
     R.g.item_byte = d_read_off;
@@ -159,27 +170,19 @@ static int plan_ragged(const uint64_t* d_read_off, const uint64_t* d_koff, uint6
     return NTHASH_OK;
   }
   R.tile_cap = span_bound(SEG_LONG, 1, k);
-  uint64_t* d_tmp = nullptr;
-  NTH_CUDA(cudaMallocAsync(&d_tmp, (n_reads + 3) * sizeof(uint64_t), st));
-  cudaError_t e = launch_koff_scan(d_read_off, n_reads, k, SEG_LONG, d_tmp, d_tmp + n_reads + 1, st);
-  uint64_t n_items = 0;
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&n_items, d_tmp + n_reads + 1, sizeof n_items, cudaMemcpyDeviceToHost, st);
-  cudaFreeAsync(d_tmp, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  NTH_CUDA(e);
-  R.g.n_items = n_items;
-  if (n_items == 0) return NTHASH_OK;
-  NTH_CUDA(cudaMallocAsync(&R.d_items, 3 * (n_items + 1) * sizeof(uint64_t), st));
-  e = launch_item_fill(d_read_off, d_koff, n_reads, k, SEG_LONG, R.d_items, R.d_items + n_items + 1,
-                       R.d_items + 2 * (n_items + 1), n_items, st);
+  const uint64_t cap = n_reads + n_bases / SEG_LONG + 1;
+  R.g.n_items = cap;
+  NTH_CUDA(cudaMallocAsync(&R.d_items, 3 * (cap + 1) * sizeof(uint64_t), st));
+  const cudaError_t e = launch_item_fill(d_read_off, d_koff, n_reads, k, SEG_LONG, R.d_items, R.d_items + cap + 1,
+                                         R.d_items + 2 * (cap + 1), cap, st);
   if (e != cudaSuccess) {
     cudaFreeAsync(R.d_items, st);
     R.d_items = nullptr;
     NTH_CUDA(e);
   }
   R.g.item_byte = R.d_items;
-  R.g.item_out = R.d_items + n_items + 1;
-  R.item_read = R.d_items + 2 * (n_items + 1);
+  R.g.item_out = R.d_items + cap + 1;
+  R.item_read = R.d_items + 2 * (cap + 1);
   return NTHASH_OK;
 }
 
@@ -193,6 +196,18 @@ struct nthash_seed_plan
   int device = 0;
   nthb::SeedJit* jit = nullptr; // specialised kernel, or NULL (then jit_note says why)
   std::string jit_note;
+};
+
+// Opaque handle of include/nthash_b200.h: the layout of one ragged batch (dense row offsets, totals, item tables),
+// computed once so that steady-state calls neither re-plan nor synchronise.
+struct nthash_ragged_plan
+{
+  int device = 0;
+  uint32_t k = 0;
+  uint64_t n_reads = 0, rows = 0, max_len = 0, n_bases = 0;
+  const uint64_t* d_read_off = nullptr; // borrowed: the caller keeps it alive and unchanged
+  uint64_t* d_koff = nullptr;           // owned, n_reads + 1
+  nthb::RaggedItems items;              // for the k-mer kernels' tile budget (item table owned when reads are cut up)
 };
 
 namespace nthb {
@@ -213,9 +228,10 @@ static void fill_seed_params(const nthash_seed_plan* plan, SeedParams& P)
   P.any_ignore = h.any_ignore ? 1u : 0u;
 }
 
-static int run_seed(const nthash_seed_plan* plan, SeedParams& P, uint64_t n_reads, uint64_t rows, cudaStream_t st)
+static int run_seed(const nthash_seed_plan* plan, SeedParams& P, uint64_t n_reads, uint64_t rows, const uint64_t* d_rows,
+                    uint64_t rows_bound, cudaStream_t st)
 {
-  if (P.valid_bits && rows) NTH_CUDA(cudaMemsetAsync(P.valid_bits, 0xFF, ((rows + 31) / 32) * 4, st));
+  NTH_CUDA(preset_valid(P.valid_bits, rows, d_rows, rows_bound, st));
   if (P.g.n_items == 0) return NTHASH_OK;
   if (seed_smem_bytes(P.plan_smem_bytes, P.tile_cap) > SMEM_MAX)
     return fail(NTHASH_ERR_UNSUPPORTED, "seed tables (%u B) plus a %u-byte base tile exceed shared memory",
@@ -250,6 +266,9 @@ struct DevBatch
   uint32_t* d_valid = nullptr;
   uint64_t valid_row0 = 0; // row 0 of this batch is bit valid_row0 of d_valid
   uint64_t memset_rows = 0; // > 0: pre-set that many validity bits first
+  const uint64_t* d_rows = nullptr; // ragged *_dev entries: the row count lives on the device (koff[n_reads]) ...
+  uint64_t rows_bound = 0;          // ... and only this bound of it is known here
+  const RaggedItems* items = nullptr; // ragged layout planned earlier (nthash_ragged_plan)
   uint64_t *d_fwd = nullptr, *d_rev = nullptr;
   uint64_t* d_reduce = nullptr; // fused consumer output {windows, sum, xor}; then d_out etc. are NULL
   uint64_t rows = 0;            // dense rows of this batch (set by the host pipeline)
@@ -279,12 +298,14 @@ static int kmer_dev_run(const DevBatch& B, uint32_t k, uint32_t h, cudaStream_t 
     // the fast kernel plans its own (smaller) CTAs, so a tile too large for the general kernel is not fatal yet
     P.general_fits = plan_uniform(B.n_reads, B.uniform_len, k, P.g, P.tile_cap);
   } else {
-    if (int rc = plan_ragged(B.d_read_off, B.d_koff, B.n_reads, B.max_len, k, TILE_BUDGET, st, R)) return rc;
-    P.g = R.g;
-    P.tile_cap = R.tile_cap;
+    if (!B.items)
+      if (int rc = plan_ragged(B.d_read_off, B.d_koff, B.n_reads, B.max_len, B.n_bases, k, TILE_BUDGET, st, R)) return rc;
+    const RaggedItems& I = B.items ? *B.items : R;
+    P.g = I.g;
+    P.tile_cap = I.tile_cap;
     P.general_fits = kmer_smem_bytes(P.tile_cap) <= SMEM_MAX;
   }
-  int rc = run_kmer(P, B.memset_rows, st);
+  int rc = run_kmer(P, B.memset_rows, B.d_rows, B.rows_bound, st);
   if (R.d_items) cudaFreeAsync(R.d_items, st);
   return rc;
 }
@@ -308,12 +329,17 @@ static int seed_dev_run(const nthash_seed_plan* plan, const DevBatch& B, cudaStr
     P.read_off = B.d_read_off;
     P.koff = B.d_koff;
     const uint32_t budget = TILE_BUDGET > P.plan_smem_bytes / 2 ? TILE_BUDGET - P.plan_smem_bytes / 2 : 0;
-    if (int rc = plan_ragged(B.d_read_off, B.d_koff, B.n_reads, B.max_len, P.k, budget, st, R)) return rc;
-    P.g = R.g;
-    P.tile_cap = R.tile_cap;
-    P.item_read = R.item_read;
+    // a layout planned for the k-mer kernels' budget can be taken over when it is the one-item-per-read form and that
+    // still fits this (smaller) budget, or when it is already the cut-up form
+    const bool reuse = B.items && (B.items->d_items || (uint64_t)KMER_NT * B.max_len + 64 <= budget);
+    if (!reuse)
+      if (int rc = plan_ragged(B.d_read_off, B.d_koff, B.n_reads, B.max_len, B.n_bases, P.k, budget, st, R)) return rc;
+    const RaggedItems& I = reuse ? *B.items : R;
+    P.g = I.g;
+    P.tile_cap = I.tile_cap;
+    P.item_read = I.item_read;
   }
-  int rc = run_seed(plan, P, B.n_reads, B.memset_rows, st);
+  int rc = run_seed(plan, P, B.n_reads, B.memset_rows, B.d_rows, B.rows_bound, st);
   if (R.d_items) cudaFreeAsync(R.d_items, st);
   return rc;
 }
@@ -620,10 +646,8 @@ int nthash_kmer_batch_dev(const uint8_t* d_bases, uint64_t n_bases_readable, con
   if (int rc = check_device_ready()) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   DevBatch B;
-  if (d_valid_bits) { // the row total is needed to pre-set the validity bitmap
-    NTH_CUDA(cudaMemcpyAsync(&B.memset_rows, d_koff + n_reads, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    NTH_CUDA(cudaStreamSynchronize(st));
-  }
+  B.d_rows = d_koff + n_reads; // the row total stays on the device: the bitmap is pre-set by a kernel that reads it there
+  B.rows_bound = n_bases_readable;
   B.d_bases = d_bases;
   B.n_bases = n_bases_readable;
   B.d_read_off = d_read_off;
@@ -635,6 +659,128 @@ int nthash_kmer_batch_dev(const uint8_t* d_bases, uint64_t n_bases_readable, con
   B.d_fwd = d_out_fwd;
   B.d_rev = d_out_rev;
   return kmer_dev_run(B, k, num_hashes, st);
+}
+
+// ---- ragged layout planned once (nthash_ragged_plan): steady-state calls neither re-plan nor synchronise ----------
+
+int nthash_ragged_plan_create(const uint64_t* d_read_off, uint64_t n_reads, uint32_t k, void* stream, nthash_ragged_plan** plan_out)
+{
+  if (!plan_out) return fail(NTHASH_ERR_INVALID_ARG, "plan_out must not be NULL");
+  *plan_out = nullptr;
+  if (int rc = check_kh(k, 1)) return rc;
+  if (!d_read_off) return fail(NTHASH_ERR_INVALID_ARG, "d_read_off must not be NULL");
+  if (int rc = check_device_ready()) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  nthash_ragged_plan* pl = new nthash_ragged_plan();
+  cudaGetDevice(&pl->device);
+  pl->k = k;
+  pl->n_reads = n_reads;
+  pl->d_read_off = d_read_off;
+  uint64_t* d_stats = nullptr;
+  uint64_t h_stats[2] = { 0, 0 }, ends[2] = { 0, 0 };
+  cudaError_t e = cudaMalloc(&pl->d_koff, (n_reads + 1) * sizeof(uint64_t));
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_stats, 2 * sizeof(uint64_t), st);
+  if (e == cudaSuccess) e = launch_koff_scan(d_read_off, n_reads, k, 0, pl->d_koff, d_stats, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_stats, d_stats, sizeof h_stats, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&ends[0], d_read_off, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&ends[1], d_read_off + n_reads, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+  if (d_stats) cudaFreeAsync(d_stats, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st); // the one synchronisation of a plan's life
+  int rc = NTHASH_OK;
+  if (e == cudaSuccess) {
+    pl->rows = h_stats[0];
+    pl->max_len = h_stats[1];
+    pl->n_bases = ends[1];
+    if (pl->rows) {
+      rc = plan_ragged(d_read_off, pl->d_koff, n_reads, pl->max_len, ends[1] - ends[0], k, TILE_BUDGET, st, pl->items);
+      const uint4* t4 = nullptr; // the 4 KB warm-up table of this k is created on first use: do it now, not inside a graph capture
+      if (rc == NTHASH_OK) e = get_t4_table(k, &t4);
+      if (rc == NTHASH_OK && e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+  }
+  if (e != cudaSuccess && rc == NTHASH_OK) rc = fail(NTHASH_ERR_CUDA, "ragged plan: %s", cudaGetErrorString(e));
+  if (rc != NTHASH_OK) {
+    nthash_ragged_plan_destroy(pl);
+    return rc;
+  }
+  *plan_out = pl;
+  return NTHASH_OK;
+}
+
+void nthash_ragged_plan_destroy(nthash_ragged_plan* plan)
+{
+  if (!plan) return;
+  if (plan->items.d_items) cudaFree(plan->items.d_items);
+  cudaFree(plan->d_koff);
+  delete plan;
+}
+
+uint64_t nthash_ragged_plan_rows(const nthash_ragged_plan* plan) { return plan ? plan->rows : 0; }
+uint64_t nthash_ragged_plan_max_read_len(const nthash_ragged_plan* plan) { return plan ? plan->max_len : 0; }
+const uint64_t* nthash_ragged_plan_koff(const nthash_ragged_plan* plan) { return plan ? plan->d_koff : nullptr; }
+
+static int planned_batch(const nthash_ragged_plan* plan, const uint8_t* d_bases, uint64_t n_bases_readable, DevBatch& B)
+{
+  if (!plan) return fail(NTHASH_ERR_INVALID_ARG, "plan must not be NULL");
+  if (!d_bases || ((uintptr_t)d_bases & 15)) return fail(NTHASH_ERR_INVALID_ARG, "d_bases must be 16-byte aligned");
+  if (n_bases_readable < plan->n_bases) return fail(NTHASH_ERR_INVALID_ARG, "n_bases_readable smaller than the plan's last read end");
+  B.d_bases = d_bases;
+  B.n_bases = n_bases_readable;
+  B.d_read_off = plan->d_read_off;
+  B.d_koff = plan->d_koff;
+  B.n_reads = plan->n_reads;
+  B.max_len = plan->max_len;
+  B.memset_rows = plan->rows;
+  B.items = &plan->items;
+  return NTHASH_OK;
+}
+
+int nthash_kmer_batch_planned_dev(const nthash_ragged_plan* plan, const uint8_t* d_bases, uint64_t n_bases_readable, uint32_t num_hashes,
+                                  uint64_t* d_out, uint32_t* d_valid_bits, uint64_t* d_out_fwd, uint64_t* d_out_rev, void* stream)
+{
+  if (!plan) return fail(NTHASH_ERR_INVALID_ARG, "plan must not be NULL");
+  if (int rc = check_kh(plan->k, num_hashes)) return rc;
+  if (plan->rows == 0) return NTHASH_OK;
+  if (int rc = check_outputs(d_out, d_out_fwd, d_out_rev)) return rc;
+  DevBatch B;
+  if (int rc = planned_batch(plan, d_bases, n_bases_readable, B)) return rc;
+  B.d_out = d_out;
+  B.d_valid = d_valid_bits;
+  B.d_fwd = d_out_fwd;
+  B.d_rev = d_out_rev;
+  return kmer_dev_run(B, plan->k, num_hashes, (cudaStream_t)stream);
+}
+
+int nthash_kmer_reduce_planned_dev(const nthash_ragged_plan* plan, const uint8_t* d_bases, uint64_t n_bases_readable, uint32_t num_hashes,
+                                   uint64_t* d_result, void* stream)
+{
+  if (!plan) return fail(NTHASH_ERR_INVALID_ARG, "plan must not be NULL");
+  if (int rc = check_kh(plan->k, num_hashes)) return rc;
+  if (!d_result) return fail(NTHASH_ERR_INVALID_ARG, "d_result must not be NULL");
+  NTH_CUDA(cudaMemsetAsync(d_result, 0, 3 * sizeof(uint64_t), (cudaStream_t)stream));
+  if (plan->rows == 0) return NTHASH_OK;
+  DevBatch B;
+  if (int rc = planned_batch(plan, d_bases, n_bases_readable, B)) return rc;
+  B.memset_rows = 0;
+  B.d_reduce = d_result;
+  return kmer_dev_run(B, plan->k, num_hashes, (cudaStream_t)stream);
+}
+
+int nthash_seed_batch_planned_dev(const nthash_seed_plan* seeds, const nthash_ragged_plan* plan, const uint8_t* d_bases,
+                                  uint64_t n_bases_readable, uint64_t* d_out, uint32_t* d_valid_bits, uint64_t* d_out_fwd,
+                                  uint64_t* d_out_rev, void* stream)
+{
+  if (!seeds || !plan) return fail(NTHASH_ERR_INVALID_ARG, "the seed plan and the ragged plan must not be NULL");
+  if (seeds->host.k != plan->k) return fail(NTHASH_ERR_INVALID_ARG, "the ragged plan was made for k=%u, the seeds have length %u", plan->k, seeds->host.k);
+  if (plan->rows == 0) return NTHASH_OK;
+  if (int rc = check_outputs(d_out, d_out_fwd, d_out_rev)) return rc;
+  DevBatch B;
+  if (int rc = planned_batch(plan, d_bases, n_bases_readable, B)) return rc;
+  B.d_out = d_out;
+  B.d_valid = d_valid_bits;
+  B.d_fwd = d_out_fwd;
+  B.d_rev = d_out_rev;
+  return seed_dev_run(seeds, B, (cudaStream_t)stream);
 }
 
 int nthash_kmer_batch(const char* bases, const uint64_t* read_off, uint64_t n_reads, uint32_t k,
@@ -1031,10 +1177,8 @@ int nthash_seed_batch_dev(const nthash_seed_plan* plan, const uint8_t* d_bases, 
   if (int rc = check_device_ready()) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   DevBatch B;
-  if (d_valid_bits) {
-    NTH_CUDA(cudaMemcpyAsync(&B.memset_rows, d_koff + n_reads, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    NTH_CUDA(cudaStreamSynchronize(st));
-  }
+  B.d_rows = d_koff + n_reads;
+  B.rows_bound = n_bases_readable;
   B.d_bases = d_bases;
   B.n_bases = n_bases_readable;
   B.d_read_off = d_read_off;

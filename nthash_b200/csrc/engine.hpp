@@ -56,6 +56,8 @@ uint32_t kmer_smem_bytes(uint32_t tile_cap);
 bool kmer_fast_ok(const KmerParams& P);
 cudaError_t launch_kmer_fast(const KmerParams& P, cudaStream_t st);
 cudaError_t launch_kmer(KmerParams P, cudaStream_t st);
+// the per-(device, k) tetramer warm-up table of the fast kernel (created on first use, kept for the life of the process)
+cudaError_t get_t4_table(uint32_t k, const uint4** out);
 
 // ---- SeedNtHash (seed_kernel.cu) -------------------------------------------------------------
 struct SeedParams
@@ -124,9 +126,12 @@ cudaError_t launch_compact_rows(const uint64_t* d_out, const uint32_t* d_valid, 
 // stream go to d_out[0 .. n_bases) (16-byte aligned, padded to a 16-byte multiple).
 cudaError_t launch_unpack2bit(const uint8_t* d_packed, const uint32_t* d_invalid, uint64_t first_base, uint64_t n_bases, uint8_t* d_out,
                               cudaStream_t st);
-// Expands reads into items (only needed when some read exceeds the whole-read tile budget).
+// Expands reads into items (only needed when some read exceeds the whole-read tile budget).  The tables hold `cap` + 1
+// entries, `cap` >= the true item count (a host-side bound); the surplus is padded with empty items.
 cudaError_t launch_item_fill(const uint64_t* read_off, const uint64_t* koff, uint64_t n_reads, uint32_t k,
                              uint32_t seg, uint64_t* item_byte, uint64_t* item_out, uint64_t* item_read,
-                             uint64_t n_items, cudaStream_t st);
+                             uint64_t cap, cudaStream_t st);
+// valid_bits <- ones for *d_rows rows (<= rows_bound, which only sizes the grid); nothing is read back.
+cudaError_t launch_fill_valid(uint32_t* d_valid, const uint64_t* d_rows, uint64_t rows_bound, cudaStream_t st);
 
 } // namespace nthb

@@ -250,6 +250,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   uint64_t* s_range = reinterpret_cast<uint64_t*>(smem + F_RANGE_OFF);
   uint8_t* tile = smem + F_TILE_OFF;
 
+  constexpr bool DIRECT = !BOX && NBUF == 2;       // general output path without the shared-memory rows: 32-byte stores from registers
   constexpr bool STR = CONS == 4;                  // CONS == 4: store the hashes AND the strand hashes (general output path)
   constexpr bool REDUCE = CONS != 0 && CONS != 4;  // consumers proper: nothing is stored
   const uint32_t HH = H ? (uint32_t)H : P.h; // H == 0: runtime number of hashes (5..255, general output path only)
@@ -266,6 +267,33 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     if (tid == 0) s_range[0] = my_byte;
     if (i0 + tid == i1 - 1) s_range[1] = P.g.flat ? flat_byte(P.g, my_out + n - 1) + k : my_byte + (n ? n + k - 1 : 0);
   }
+  // ---- stage the CTA's byte range (TMA bulk copy) and build the tables -------------------------
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (tid < F_TILE_PAD) tile[tid] = 'A';
+  __syncthreads();
+  const uint64_t lo_byte = s_range[0], g1 = max(s_range[1], lo_byte);
+  const uint64_t g0 = (lo_byte ? lo_byte - 1 : 0) & ~15ull;
+  if (g1 - g0 > P.tile_cap) __trap();
+  const uint64_t bulk_end = min((g1 + 15) & ~15ull, P.n_bases & ~15ull);
+  const uint32_t bulk_bytes = bulk_end > g0 ? (uint32_t)(bulk_end - g0) : 0u;
+  // row buffers follow the staged bases; the 4 KB tetramer table is parked in them for the warm-up phase
+  const uint32_t rb_base = (sbase + F_TILE_OFF + F_TILE_PAD + P.tile_cap + 16 + 1023u) & ~1023u;
+  if (tid == 0) {
+    mbar_expect_tx(bar, bulk_bytes + T4_BYTES);
+    if (bulk_bytes) bulk_g2s(tile + F_TILE_PAD, P.bases + g0, bulk_bytes, bar);
+    bulk_g2s(smem + (rb_base - sbase), P.t4, T4_BYTES, bar);
+    // pull the bases of the CTA that will take this SM slot next into L2 (same extent, one residency wave ahead),
+    // so that its start-up wait is an L2 hit instead of a DRAM read queued behind the output stream
+    if (P.prefetch_ctas) {
+      const uint64_t nxt = g0 + (uint64_t)P.prefetch_ctas * ((g1 - g0) & ~15ull);
+      const uint64_t len = (g1 - g0 + 15) & ~15ull;
+      if (len && nxt + len <= (P.n_bases & ~15ull)) bulk_prefetch_l2(P.bases + nxt, (uint32_t)len);
+    }
+  }
+  // (the loads are in flight from here on; the bookkeeping below hides behind them)
   if (P.g.item_byte) {
     // Ragged batch: a warp runs as long as its longest item, so hand the CTA's items out by length class
     // (32 classes, longest first; counting sort through shared memory that the tables overwrite later).
@@ -299,32 +327,6 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     __syncthreads(); // the scratch is reused for the tables below
   }
 
-  // ---- stage the CTA's byte range (TMA bulk copy) and build the tables -------------------------
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    fence_mbar_init();
-  }
-  if (tid < F_TILE_PAD) tile[tid] = 'A';
-  __syncthreads();
-  const uint64_t lo_byte = s_range[0], g1 = max(s_range[1], lo_byte);
-  const uint64_t g0 = (lo_byte ? lo_byte - 1 : 0) & ~15ull;
-  if (g1 - g0 > P.tile_cap) __trap();
-  const uint64_t bulk_end = min((g1 + 15) & ~15ull, P.n_bases & ~15ull);
-  const uint32_t bulk_bytes = bulk_end > g0 ? (uint32_t)(bulk_end - g0) : 0u;
-  // row buffers follow the staged bases; the 4 KB tetramer table is parked in them for the warm-up phase
-  const uint32_t rb_base = (sbase + F_TILE_OFF + F_TILE_PAD + P.tile_cap + 16 + 1023u) & ~1023u;
-  if (tid == 0) {
-    mbar_expect_tx(bar, bulk_bytes + T4_BYTES);
-    if (bulk_bytes) bulk_g2s(tile + F_TILE_PAD, P.bases + g0, bulk_bytes, bar);
-    bulk_g2s(smem + (rb_base - sbase), P.t4, T4_BYTES, bar);
-    // pull the bases of the CTA that will take this SM slot next into L2 (same extent, one residency wave ahead),
-    // so that its start-up wait is an L2 hit instead of a DRAM read queued behind the output stream
-    if (P.prefetch_ctas) {
-      const uint64_t nxt = g0 + (uint64_t)P.prefetch_ctas * ((g1 - g0) & ~15ull);
-      const uint64_t len = (g1 - g0 + 15) & ~15ull;
-      if (len && nxt + len <= (P.n_bases & ~15ull)) bulk_prefetch_l2(P.bases + nxt, (uint32_t)len);
-    }
-  }
   {
     // code (byte >> 1) & 3 : 0 = A, 1 = C, 2 = T/U, 3 = G ; complement = code ^ 2
     auto code2base = [](int c) { return c ^ (c >> 1); }; // code -> index into P.s / P.sk (A, C, G, T order)
@@ -632,6 +634,61 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     // 256 bytes of its row (32/H windows) in a private shared-memory row, then the warp copies the 32 rows out
     // with coalesced 16-byte stores, two rows per instruction (a half-warp per row).  Each row's global address
     // and byte count travel through a 16-byte descriptor, so lanes may differ in length and alignment.
+    if constexpr (DIRECT && H != 0) {
+      // DIRECT: no staging at all.  After the peel every group of four windows starts on a 32-byte boundary of each
+      // output array, so it leaves as full-sector 32-byte stores straight from the registers (STG.E.ENL2.256; a 16-byte
+      // store is a partial sector and ran 5x slower in profiles/r01_microbench_store_patterns.txt).  Lanes are
+      // independent here: no warp-level hand-off, no row buffers, no descriptors.
+      for (; p + 4 <= n; p += 4) {
+        uint64_t hv[4];
+        roll4(hv, full_t(), 4u);
+        uint64_t* o = P.out + (my_out + p) * H;
+        if (H == 1) {
+          st_global_v4_u64(o, hv[0], hv[1], hv[2], hv[3]);
+        } else if (H == 2) {
+          st_global_v4_u64(o, hv[0], ext_hash(hv[0], P.mult[1]), hv[1], ext_hash(hv[1], P.mult[1]));
+          st_global_v4_u64(o + 4, hv[2], ext_hash(hv[2], P.mult[1]), hv[3], ext_hash(hv[3], P.mult[1]));
+        } else if (H == 3) {
+          uint64_t v[12];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[3 * i] = hv[i];
+            v[3 * i + 1] = ext_hash(hv[i], P.mult[1]);
+            v[3 * i + 2] = ext_hash(hv[i], P.mult[2]);
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) st_global_v4_u64(o + 4 * c, v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            st_global_v4_u64(o + 4 * i, hv[i], ext_hash(hv[i], P.mult[1]), ext_hash(hv[i], P.mult[2]), ext_hash(hv[i], P.mult[3]));
+        }
+        if (STR) {
+          st_global_v4_u64(P.out_fwd + my_out + p, fw4[0], fw4[1], fw4[2], fw4[3]);
+          st_global_v4_u64(P.out_rev + my_out + p, rv4[0], rv4[1], rv4[2], rv4[3]);
+        }
+      }
+      if (p < n) { // the last one to three windows of the item
+        uint64_t hv[4];
+        const uint32_t cnt = n - p;
+        roll4(hv, part_t(), cnt);
+        for (uint32_t i = 0; i < cnt; ++i) {
+          const uint64_t h0 = i == 0 ? hv[0] : i == 1 ? hv[1] : hv[2];
+          uint64_t* o = P.out + (my_out + p + i) * H;
+          o[0] = h0;
+#pragma unroll
+          for (int q = 1; q < H; ++q) o[q] = ext_hash(h0, P.mult[q]);
+          if (STR) {
+            P.out_fwd[my_out + p + i] = i == 0 ? fw4[0] : i == 1 ? fw4[1] : fw4[2];
+            P.out_rev[my_out + p + i] = i == 0 ? rv4[0] : i == 1 ? rv4[1] : rv4[2];
+          }
+        }
+        p = n;
+      }
+      __syncwarp();
+      if (bad != 0) scrub_lane<H>(P, lut, ps, my_out, n);
+      return;
+    }
     constexpr uint32_t WS1 = H == 3 ? 8 : 32 / (H ? H : 1); // windows per row piece (compile-time h): <= 256 bytes
     constexpr uint32_t NARR = STR ? 3 : 1; // output arrays: hashes (+ forward and reverse strand hashes)
     const uint32_t wbase = rb_base + (tid & ~31u) * NARR * (ROW1_BYTES + 16); // this warp: NARR x [32 descriptors], NARR x [32 rows]
@@ -776,14 +833,17 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   }
 }
 
-// FLAT geometry, second launch: the rows the main kernel cannot produce.  Thread f >= 1 owns the windows of read f that
+// FLAT geometry, second launch: the rows the main kernel cannot produce.  Item f >= 1 = the windows of read f that
 // share a flat item with the end of read f-1 (the main kernel rolled across the boundary there and stored junk);
-// thread 0 owns the partial last item of the batch, which the tensor map leaves out.  At most seg windows each, hashed
-// from scratch straight out of global memory: base hashes by Horner's rule over the k bytes (the closed form of
-// base_forward_hash / base_reverse_hash, src/kmer.cpp:43-73, :123-152), then NtHash::roll (src/kmer.cpp:246-264).
+// item 0 = the partial last item of the batch, which the tensor map leaves out.  At most seg windows each, FIX_LANES
+// lanes per item: every lane hashes its own run of windows from scratch straight out of global memory, the way the main
+// kernel does it — k in-only steps (four bases at a time through the tetramer table; base_forward_hash /
+// base_reverse_hash, src/kmer.cpp:43-73, :123-152) starting one base early, then NtHash::roll (src/kmer.cpp:246-264).
+constexpr uint32_t FIX_LANES = 8;
 __global__ void __launch_bounds__(128) kmer_flat_fix_kernel(const __grid_constant__ KmerParams P, uint64_t n_reads)
 {
-  const uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t f = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / FIX_LANES;
+  const uint32_t sub = threadIdx.x % FIX_LANES;
   if (f >= n_reads) return;
   const uint64_t nk = P.g.nk, seg = P.g.seg, w_tail = P.g.total / seg * seg;
   uint64_t w0;
@@ -796,25 +856,36 @@ __global__ void __launch_bounds__(128) kmer_flat_fix_kernel(const __grid_constan
     const uint32_t rem = (uint32_t)(w0 % seg);
     n = (rem && w0 < w_tail) ? (uint32_t)min(seg - rem, nk) : 0u;
   }
-  if (!n) return;
+  const uint32_t per = (n + FIX_LANES - 1) / FIX_LANES, p_lo = min(n, sub * per), p_hi = min(n, p_lo + per);
+  if (p_lo >= p_hi) return;
   const uint64_t r = w0 / nk;
-  const uint8_t* sq = P.bases + r * P.g.read_len + (w0 - r * nk);
+  const uint8_t* sq = P.bases + r * P.g.read_len + (w0 - r * nk) + p_lo; // first base of this lane's first window; sq[-1] exists
+  w0 += p_lo;
+  n = p_hi - p_lo;
   const uint32_t k = P.k, h = P.h;
-  // code (byte >> 1) & 3: 0 = A, 1 = C, 2 = T/U, 3 = G; index into P.s / P.sk (A, C, G, T) = code ^ (code >> 1)
-  auto fs = [&](uint32_t c) { const uint32_t x = (c >> 1) & 3u; return P.s[x ^ (x >> 1)]; };
-  auto fk = [&](uint32_t c) { const uint32_t x = (c >> 1) & 3u; return P.sk[x ^ (x >> 1)]; };
-  auto cs = [&](uint32_t c) { const uint32_t x = ((c >> 1) & 3u) ^ 2u; return P.s[x ^ (x >> 1)]; };
-  auto ck = [&](uint32_t c) { const uint32_t x = ((c >> 1) & 3u) ^ 2u; return P.sk[x ^ (x >> 1)]; };
-  uint64_t F = 0, R = 0;
+  // 2-bit code (byte >> 1) & 3: 0 = A, 1 = C, 2 = T/U, 3 = G; index into P.s / P.sk (A, C, G, T) = code ^ (code >> 1)
+  auto sidx = [](uint32_t c) { const uint32_t x = (c >> 1) & 3u; return x ^ (x >> 1); };
+  State st = { 0u, 0u, 0u, 0u };
   uint32_t run = 0;
-  for (uint32_t i = 0; i < k; ++i) {
-    const uint32_t c = sq[i];
-    run = is_acgtu(c) ? run + 1 : 0;
-    F = srol1(F) ^ fs(c);
+  const uint32_t nq = k >> 2;
+  for (uint32_t q = 0; q < nq; ++q) { // bases 4q-1 .. 4q+2
+    const uint32_t c0 = sq[(int)(4 * q) - 1], c1 = sq[4 * q], c2 = sq[4 * q + 1], c3 = sq[4 * q + 2];
+    const uint32_t idx = ((c0 & 6u) << 5) | ((c1 & 6u) << 3) | ((c2 & 6u) << 1) | ((c3 & 6u) >> 1);
+    roll4_in(st, __ldg(P.t4 + idx));
   }
-  for (uint32_t i = k; i-- > 0;) R = srol1(R) ^ cs(sq[i]);
-  for (uint32_t p = 0;; ++p) {
-    const uint64_t w = w0 + p, h0 = F + R;
+  for (uint32_t j = 4 * nq; j < k; ++j) { // bases j-1
+    const uint32_t c = sq[j - 1];
+    const uint64_t fi = P.s[sidx(c)], ri = P.sk[sidx(c ^ 4u)]; // c ^ 4 flips code bit 1: the complement
+    roll_step(st, make_uint4((uint32_t)fi, (uint32_t)(fi >> 32), (uint32_t)ri, (uint32_t)(ri >> 32)));
+  }
+  // hashable bases in a row, ending at base k-2
+  for (uint32_t j = 0; j + 1 < k; ++j) run = is_acgtu(sq[j]) ? run + 1 : 0;
+  for (uint32_t p = 0; p < n; ++p) {
+    const uint32_t cin = sq[p + k - 1], cout = sq[(int)p - 1];
+    run = is_acgtu(cin) ? run + 1 : 0;
+    const uint64_t fe = P.s[sidx(cin)] ^ P.sk[sidx(cout)], re = P.sk[sidx(cin ^ 4u)] ^ P.s[sidx(cout ^ 4u)];
+    roll_step(st, make_uint4((uint32_t)fe, (uint32_t)(fe >> 32), (uint32_t)re, (uint32_t)(re >> 32)));
+    const uint64_t w = w0 + p, h0 = canonical2(st);
     uint64_t* o = P.out + w * h;
     if (run >= k) {
       o[0] = h0;
@@ -823,11 +894,6 @@ __global__ void __launch_bounds__(128) kmer_flat_fix_kernel(const __grid_constan
       for (uint32_t q = 0; q < h; ++q) o[q] = 0;
       if (P.valid_bits) atomicAnd(&P.valid_bits[(P.valid_row0 + w) >> 5], ~(1u << ((P.valid_row0 + w) & 31)));
     }
-    if (p + 1 == n) break;
-    const uint32_t cin = sq[p + k], cout = sq[p];
-    run = is_acgtu(cin) ? run + 1 : 0;
-    F = srol1(F) ^ fs(cin) ^ fk(cout);
-    R = sror1(R ^ ck(cin) ^ cs(cout));
   }
 }
 
@@ -840,7 +906,7 @@ uint32_t fast_smem_bytes(uint32_t tile_cap, uint32_t buf_bytes)
 //   TF = srol^3 S[c0] ^ srol^2 S[c1] ^ srol S[c2] ^ S[c3]
 //   TR = Skc[c0] ^ srol Skc[c1] ^ srol^2 Skc[c2] ^ srol^3 Skc[c3],  Skc[c] = srol^k S[complement c]
 // One small device buffer per (device, k), created on first use and kept for the life of the process.
-cudaError_t get_t4_table(uint32_t k, const uint4** out)
+cudaError_t get_t4_table_impl(uint32_t k, const uint4** out)
 {
   static std::mutex mu;
   static std::map<std::pair<int, uint32_t>, uint4*> cache;
@@ -880,7 +946,7 @@ cudaError_t get_t4_table(uint32_t k, const uint4** out)
 struct FastCfg
 {
   uint32_t nt, ws, nbuf;
-  bool box;
+  bool box, direct;
 };
 
 // Tensor map of the output seen as [rows*H/8 blocks][n_items rows][8 u64] (blocks outermost), boxes of
@@ -913,7 +979,9 @@ cudaError_t launch_fast_t(const KmerParams& P, uint32_t nt, cudaStream_t st)
 {
   constexpr bool REDUCE = CONS != 0 && CONS != 4; // consumers allocate no output buffers
   auto fn = kmer_fast_kernel<H, CONS, WS, NBUF, BOX>;
-  const uint32_t buf = BOX ? (nt / 32) * NBUF * (uint32_t)(WS * H / 8) * 2048u : nt * (CONS == 4 ? 3u : 1u) * (ROW1_BYTES + 16);
+  const uint32_t buf = BOX ? (nt / 32) * NBUF * (uint32_t)(WS * H / 8) * 2048u
+                       : (NBUF == 2 && H != 0) ? 0u // DIRECT: no row buffers
+                                               : nt * (CONS == 4 ? 3u : 1u) * (ROW1_BYTES + 16);
   uint32_t smem_bytes = fast_smem_bytes(P.tile_cap, REDUCE ? 0u : buf);
   if (const char* e = getenv("NTHASH_B200_SMEM_PAD")) smem_bytes += (uint32_t)atoi(e); // experiments: lower the occupancy
   if (smem_bytes > 227u * 1024u) return cudaErrorInvalidConfiguration;
@@ -954,8 +1022,10 @@ template<int H>
 cudaError_t launch_fast_h(const KmerParams& P, const FastCfg& c, cudaStream_t st)
 {
   if (P.reduce_out) return launch_fast_t<H, 1, fast_ws<H>(0), 1, false>(P, c.nt, st);
-  if (P.out_fwd) return launch_fast_t<H, 4, fast_ws<H>(0), 1, false>(P, c.nt, st); // hashes + strand hashes
-  if (!c.box) return launch_fast_t<H, 0, fast_ws<H>(0), 1, false>(P, c.nt, st); // WS / NBUF are unused there
+  if (P.out_fwd) // hashes + strand hashes
+    return c.direct ? launch_fast_t<H, 4, fast_ws<H>(0), 2, false>(P, c.nt, st) : launch_fast_t<H, 4, fast_ws<H>(0), 1, false>(P, c.nt, st);
+  if (!c.box) // general output path: WS is unused there, NBUF == 2 selects the DIRECT form
+    return c.direct ? launch_fast_t<H, 0, fast_ws<H>(0), 2, false>(P, c.nt, st) : launch_fast_t<H, 0, fast_ws<H>(0), 1, false>(P, c.nt, st);
   switch (c.ws) {
     case 0: return launch_fast_nbuf<H, fast_ws<H>(0)>(P, c, st);
     case 1: return launch_fast_nbuf<H, fast_ws<H>(1)>(P, c, st);
@@ -970,6 +1040,8 @@ uint32_t env_u32(const char* name, uint32_t dflt)
 }
 
 } // namespace
+
+cudaError_t get_t4_table(uint32_t k, const uint4** out) { return get_t4_table_impl(k, out); }
 
 bool kmer_fast_ok(const KmerParams& P)
 {
@@ -986,6 +1058,7 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
   KmerParams P = Pin;
   FastCfg c;
   c.box = false;
+  c.direct = env_u32("NTHASH_B200_FAST_DIRECT", 0) != 0 && P.h <= 4 && !P.reduce_out && !P.bloom_mode;
   c.nbuf = env_u32("NTHASH_B200_FAST_NBUF", 1);
   c.ws = env_u32("NTHASH_B200_FAST_WS", 0);
   const bool uniform = !P.g.item_byte;
@@ -1032,6 +1105,7 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
   // long ones that cost occupancy), then CTA size (fewer prologues): the largest CTA that leaves >= 16 warps resident
   const uint32_t buf_per_warp = P.reduce_out ? 0u
                                 : c.box    ? c.nbuf * (uint32_t)(fast_ws_rt(P.h, c.ws) * P.h / 8) * 2048u
+                                : c.direct ? 0u
                                            : 32u * (P.out_fwd ? 3u : 1u) * (ROW1_BYTES + 16);
   c.nt = 32;
   for (uint32_t nt : { 256u, 192u, 128u, 96u, 64u, 32u }) { // the small ones only matter for huge k
@@ -1045,7 +1119,7 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
   if (c.nt < 32 || c.nt > 256 || c.nt % 32) return cudaErrorInvalidValue;
   if (tile_cap_for(c.nt) > 227u * 1024u) return cudaErrorInvalidConfiguration;
   P.tile_cap = (uint32_t)tile_cap_for(c.nt);
-  cudaError_t e = get_t4_table(P.k, &P.t4);
+  cudaError_t e = get_t4_table_impl(P.k, &P.t4);
   if (e != cudaSuccess) return e;
   {
     int dev = 0, sms = 148;
@@ -1074,7 +1148,7 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
   }
   if (e == cudaSuccess && P.g.flat) { // rows behind every read boundary + the partial last item, after the junk has landed
     const uint64_t n_reads = P.g.total / P.g.nk;
-    kmer_flat_fix_kernel<<<(unsigned)((n_reads + 127) / 128), 128, 0, st>>>(P, n_reads);
+    kmer_flat_fix_kernel<<<(unsigned)((n_reads * FIX_LANES + 127) / 128), 128, 0, st>>>(P, n_reads);
     e = cudaGetLastError();
   }
   return e;

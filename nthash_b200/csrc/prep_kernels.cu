@@ -17,7 +17,9 @@ __device__ __forceinline__ uint64_t read_value(const uint64_t* read_off, uint64_
 {
   len = read_off[r + 1] - read_off[r];
   const uint64_t nk = len >= k ? len - k + 1 : 0;
-  return seg ? (nk + seg - 1) / seg : nk;
+  // item mode: a read without windows still gets one (empty) item, so that its bytes are counted when a CTA's staged
+  // span is bounded by items x (seg + k - 1) bytes (many reads shorter than k next to a long one used to overflow it)
+  return seg ? (nk ? (nk + seg - 1) / seg : 1) : nk;
 }
 
 __device__ __forceinline__ uint64_t block_reduce_sum_max(uint64_t v, uint64_t& mx)
@@ -132,15 +134,17 @@ scan_write(const uint64_t* read_off, uint64_t n, uint32_t k, uint32_t seg, const
   }
 }
 
+// `cap` = entries the table was sized for (a host-side upper bound of the item count, so that nothing has to be read
+// back): entries [ioff[n], cap] are padded with empty items at the end of the batch.
 __global__ void item_fill(const uint64_t* read_off, const uint64_t* koff, const uint64_t* ioff, uint64_t n,
                           uint32_t k, uint32_t seg, uint64_t* item_byte, uint64_t* item_out, uint64_t* item_read,
-                          uint64_t n_items)
+                          uint64_t cap)
 {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r == 0) {
-    item_byte[n_items] = read_off[n];
-    item_out[n_items] = koff[n];
-    item_read[n_items] = n;
+  for (uint64_t i = ioff[n] + r; i <= cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    item_byte[i] = read_off[n];
+    item_out[i] = koff[n];
+    item_read[i] = n ? n - 1 : 0;
   }
   if (r >= n) return;
   const uint64_t i0 = ioff[r], i1 = ioff[r + 1];
@@ -331,6 +335,21 @@ cudaError_t launch_unpack2bit(const uint8_t* d_packed, const uint32_t* d_invalid
   return cudaGetLastError();
 }
 
+// valid_bits words [0, ceil(*d_rows / 32)) <- all ones, the row count taken from device memory (no read-back)
+__global__ void fill_valid_kernel(uint32_t* valid, const uint64_t* d_rows)
+{
+  const uint64_t words = (*d_rows + 31) / 32;
+  for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (uint64_t)gridDim.x * blockDim.x) valid[w] = 0xFFFFFFFFu;
+}
+
+cudaError_t launch_fill_valid(uint32_t* d_valid, const uint64_t* d_rows, uint64_t rows_bound, cudaStream_t st)
+{
+  const uint64_t words = (rows_bound + 31) / 32;
+  if (words == 0) return cudaSuccess;
+  fill_valid_kernel<<<(unsigned)std::min<uint64_t>((words + 1023) / 1024, 148 * 8), 256, 0, st>>>(d_valid, d_rows);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_koff_scan(const uint64_t* read_off, uint64_t n_reads, uint32_t k, uint32_t seg, uint64_t* excl,
                              uint64_t* stats, cudaStream_t st)
 {
@@ -353,7 +372,7 @@ cudaError_t launch_koff_scan(const uint64_t* read_off, uint64_t n_reads, uint32_
 
 cudaError_t launch_item_fill(const uint64_t* read_off, const uint64_t* koff, uint64_t n_reads, uint32_t k,
                              uint32_t seg, uint64_t* item_byte, uint64_t* item_out, uint64_t* item_read,
-                             uint64_t n_items, cudaStream_t st)
+                             uint64_t cap, cudaStream_t st)
 {
   // item offsets per read = exclusive scan of ceil(nk / seg)
   uint64_t* ioff = nullptr;
@@ -363,7 +382,7 @@ cudaError_t launch_item_fill(const uint64_t* read_off, const uint64_t* koff, uin
   if (e == cudaSuccess) {
     const unsigned bs = 256;
     item_fill<<<(unsigned)((n_reads + bs - 1) / bs), bs, 0, st>>>(read_off, koff, ioff, n_reads, k, seg,
-                                                                 item_byte, item_out, item_read, n_items);
+                                                                 item_byte, item_out, item_read, cap);
     e = cudaGetLastError();
   }
   cudaFreeAsync(ioff, st);

@@ -15,7 +15,7 @@ from nthash_b200._lib import LIB, check
 
 n, L, k, h = 10_000_000, 150, 31, 1
 rows = n * (L - k + 1)
-d = bench.synth_reads_device(torch, n * L, 7)[: n * L]
+d = bench.splitmix_bases_torch(torch, n * L, 42)[: n * L]
 hb = torch.empty(n * L, dtype=torch.uint8).pin_memory(); hb.copy_(d)
 ho = torch.empty((rows, h), dtype=torch.int64).pin_memory()
 hv = torch.empty(int(LIB.nthash_valid_words(rows)), dtype=torch.int32).pin_memory()

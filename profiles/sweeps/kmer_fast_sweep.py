@@ -18,12 +18,12 @@ grid = [(nt, ws, nb) for nt in (96, 128, 160, 192, 256) for ws in (0, 1, 2) for 
 for name in sys.argv[1:] or ["c2"]:
     cfg = bench.CONFIGS[name]
     n, L, k, h = cfg["n_reads"], cfg["read_len"], cfg["k"], cfg["h"]
-    bases = bench.synth_reads_device(torch, n * L, 1234)[: n * L]
+    bases = bench.splitmix_bases_torch(torch, n * L, cfg["seed"])[: n * L]
     rows = n * (L - k + 1)
     out = torch.empty((rows, h), dtype=torch.int64, device="cuda")
     ab = bench.algorithmic_bytes(n, L, k, h)
     ref = None
-    for nt, ws, nb in (grid if L <= 400 else [(nt, 0, 1) for nt in (64, 96, 128, 160, 192, 256)]):
+    for nt, ws, nb in (grid if L <= 400 else [(nt, ws, nb) for nt in (64, 96, 128, 192, 256) for ws in (0, 1) for nb in (1, 2)]):
         os.environ["NTHASH_B200_FAST_NT"] = str(nt)
         os.environ["NTHASH_B200_FAST_WS"] = str(ws)
         os.environ["NTHASH_B200_FAST_NBUF"] = str(nb)

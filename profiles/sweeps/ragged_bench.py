@@ -18,7 +18,7 @@ for n, lo, hi, k, h in ((10_000_000, 100, 150, 31, 1), (10_000_000, 36, 150, 31,
     lens = torch.randint(lo, hi + 1, (n,), device="cuda", generator=g, dtype=torch.int64)
     off = torch.zeros(n + 1, dtype=torch.int64, device="cuda"); off[1:] = torch.cumsum(lens, 0)
     nb = int(off[-1])
-    bases = bench.synth_reads_device(torch, nb, 99)[:nb]
+    bases = bench.splitmix_bases_torch(torch, (nb + 31) // 32 * 32, 99)[:nb]
     rows = int(torch.clamp(lens - k + 1, min=0).sum())
     ab = nb + rows * h * 8
     res = nthash_b200.kmer_hashes(bases, off, k, h, want_valid=False)
@@ -43,7 +43,7 @@ for n, lo, hi in ((5_000_000, 100, 150),):
     lens = torch.randint(lo, hi + 1, (n,), device="cuda", generator=g, dtype=torch.int64)
     off = torch.zeros(n + 1, dtype=torch.int64, device="cuda"); off[1:] = torch.cumsum(lens, 0)
     nb = int(off[-1])
-    bases = bench.synth_reads_device(torch, nb, 98)[:nb]
+    bases = bench.splitmix_bases_torch(torch, (nb + 31) // 32 * 32, 98)[:nb]
     rows = int(torch.clamp(lens - 31 + 1, min=0).sum())
     ab = nb + rows * 6 * 8
     for label, env in (("specialised (ragged variant)", None), ("generic interpreter", "1")):

@@ -18,7 +18,7 @@ cfg = bench.CONFIGS["c4"]
 n = int(sys.argv[1]) if len(sys.argv) > 1 else cfg["n_reads"]
 L, k, h, seeds = cfg["read_len"], cfg["k"], cfg["h"], cfg["seeds"]
 H = h * len(seeds)
-bases = bench.synth_reads_device(torch, n * L, 1234)[: n * L]
+bases = bench.splitmix_bases_torch(torch, n * L, 42)[: n * L]
 out = torch.empty((n * (L - k + 1), H), dtype=torch.int64, device="cuda")
 ab = bench.algorithmic_bytes(n, L, k, H)
 ref = None
