@@ -252,6 +252,9 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
 
   constexpr bool DIRECT = !BOX && NBUF == 2;       // general output path without the shared-memory rows: 32-byte stores from registers
   constexpr bool STR = CONS == 4;                  // CONS == 4: store the hashes AND the strand hashes (general output path)
+  // DIRECT with whole-sector stores at row boundaries too: the u64s between a row's start and the next 32-byte boundary
+  // travel through shared memory to the lane that owns the END of the previous row, which stores the shared sector whole
+  constexpr bool MERGE = DIRECT && (H == 1 || (H == 2 && !STR));
   constexpr bool REDUCE = CONS != 0 && CONS != 4;  // consumers proper: nothing is stored
   const uint32_t HH = H ? (uint32_t)H : P.h; // H == 0: runtime number of hashes (5..255, general output path only)
   const uint32_t NT = blockDim.x;
@@ -262,6 +265,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
 
   uint64_t my_byte = 0, my_out = 0;
   uint32_t n = 0;
+  uint32_t slot = tid; // position of this thread's item among the CTA's items (the ragged re-deal below permutes them)
   if (i0 + tid < i1) {
     fast_item_geom(P.g, i0 + tid, my_byte, my_out, n);
     if (tid == 0) s_range[0] = my_byte;
@@ -321,6 +325,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     perm[cnt[cls] + pos] = (uint8_t)tid;
     __syncthreads();
     const uint32_t src = perm[tid];
+    slot = src;
     my_byte = my_out = 0;
     n = 0;
     if (i0 + src < i1) fast_item_geom(P.g, i0 + src, my_byte, my_out, n);
@@ -396,7 +401,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
       roll_step(s, lds_v4(sbase + F_IN_OFF + ((c & 6u) << 3)));
     }
   }
-  __syncthreads(); // the tetramer table is dead from here on: its bytes become row buffers
+  if (!MERGE) __syncthreads(); // the tetramer table is dead from here on: its bytes become row buffers
 
   // one window through single-byte loads (alignment peel)
   auto roll1 = [&](uint32_t p) -> uint64_t {
@@ -407,10 +412,6 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     const uint32_t ea = pair + (((ci & 6u) << 4) | ((co & 6u) << 2));
     const uint2 ef = lds_v2(ea), er = lds_v2(ea + (F_PAIR_R_OFF - F_PAIR_OFF));
     roll_step(s, make_uint4(ef.x, ef.y, er.x, er.y));
-    if (STR) { // get_forward_hash() / get_reverse_hash() of this window (nthash.hpp:183-194)
-      P.out_fwd[my_out + p] = ((uint64_t)s.fhi << 32) | s.flo;
-      P.out_rev[my_out + p] = ((uint64_t)s.rhi << 32) | s.rlo;
-    }
     return canonical2(s);
   };
   auto consume = [&](uint64_t h0) { // one window the reference visits
@@ -456,14 +457,27 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     }
   };
 
-  // ---- alignment peel: plain stores until the lane's next output u64 sits on a 32-byte boundary ----
+  // ---- alignment peel: the windows before the lane's next output u64 sits on a 32-byte boundary ----
+  // MERGE: shared memory behind the (still live) tetramer table: [ok flag per item][32 B per item and output array]
+  const uint32_t hd_ok = rb_base + T4_BYTES, hd_val = hd_ok + 256;
+  bool okme = false;
   uint32_t p = 0;
   if (!REDUCE) {
     // windows per 32-byte boundary of the row: 4 / gcd(h, 4)
     const uint32_t ALIGN_W = STR ? 4 : (HH & 3) == 0 ? 1 : (HH & 1) == 0 ? 2 : 4; // strand rows are 8 bytes per window
-    const uint32_t peel = min(n, (uint32_t)((0 - my_out) & (uint64_t)(ALIGN_W - 1)));
+    const uint32_t pw = (uint32_t)((0 - my_out) & (uint64_t)(ALIGN_W - 1));
+    const uint32_t peel = min(n, pw);
     for (; p < peel; ++p) {
       const uint64_t h0 = roll1(p);
+      if (MERGE) { // parked; who stores them is decided after the barrier below
+        st_shared_u64(hd_val + slot * 32u + p * (uint32_t)H * 8u, h0);
+        if (H == 2) st_shared_u64(hd_val + slot * 32u + 8u, ext_hash(h0, P.mult[1]));
+        if (STR) {
+          st_shared_u64(hd_val + (NT + slot) * 32u + p * 8u, ((uint64_t)s.fhi << 32) | s.flo);
+          st_shared_u64(hd_val + (2u * NT + slot) * 32u + p * 8u, ((uint64_t)s.rhi << 32) | s.rlo);
+        }
+        continue;
+      }
       uint64_t* o = P.out + (my_out + p) * HH;
       o[0] = h0;
       if (H) {
@@ -471,6 +485,36 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
         for (int q = 1; q < H; ++q) o[q] = ext_hash(h0, P.mult[q]);
       } else {
         for (uint32_t q = 1; q < HH; ++q) o[q] = ext_hash(h0, (uint64_t)q ^ P.mult[0]);
+      }
+      if (STR) { // get_forward_hash() / get_reverse_hash() of this window (nthash.hpp:183-194)
+        P.out_fwd[my_out + p] = ((uint64_t)s.fhi << 32) | s.flo;
+        P.out_rev[my_out + p] = ((uint64_t)s.rhi << 32) | s.rlo;
+      }
+    }
+    if (MERGE) {
+      // mergeable: the row reaches its first sector boundary, and no byte seen so far (bases -1 .. peel+k-2) was flagged,
+      // i.e. the parked values are final: the owner's scrub pass, which is not ordered against the neighbour's store of
+      // them, will never have to zero them
+      okme = n >= pw && n != 0 && bad == 0;
+      asm volatile("st.shared.u8 [%0], %1;" ::"r"(hd_ok + slot), "r"(okme ? 1u : 0u) : "memory");
+      __syncthreads();
+      // the previous item's lane takes these u64s along with its own last ones iff both rows reach the shared sector's
+      // boundaries and both items sit in this CTA; otherwise they go out from here as plain (partial-sector) stores
+      const bool prev_takes = okme && slot > 0 && lds_u8(hd_ok + slot - 1) != 0;
+      if (peel && !prev_takes) {
+        for (uint32_t j = 0; j < peel * (uint32_t)H; ++j) {
+          uint64_t v;
+          asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(hd_val + slot * 32u + j * 8u));
+          P.out[my_out * H + j] = v;
+        }
+        if (STR)
+          for (uint32_t j = 0; j < peel; ++j) {
+            uint64_t a, b;
+            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(a) : "r"(hd_val + (NT + slot) * 32u + j * 8u));
+            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(b) : "r"(hd_val + (2u * NT + slot) * 32u + j * 8u));
+            P.out_fwd[my_out + j] = a;
+            P.out_rev[my_out + j] = b;
+          }
       }
     }
   }
@@ -672,7 +716,39 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
         uint64_t hv[4];
         const uint32_t cnt = n - p;
         roll4(hv, part_t(), cnt);
-        for (uint32_t i = 0; i < cnt; ++i) {
+        bool done = false;
+        if constexpr (MERGE) {
+          // the sector this row ends in also holds the first u64s of the next row: if that row's lane parked them
+          // (same CTA, both rows reach their boundaries), store the sector whole
+          if (okme && slot + 1 < (uint32_t)(i1 - i0) && lds_u8(hd_ok + slot + 1) != 0) {
+            auto nh = [&](uint32_t arr, uint32_t j) {
+              uint64_t v;
+              asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(hd_val + (arr * NT + slot + 1) * 32u + j * 8u));
+              return v;
+            };
+            auto put4 = [&](uint64_t* o, uint32_t arr, const uint64_t (&x)[4]) { // x[0..cnt) then the neighbour's first 4 - cnt
+              if (cnt == 1) st_global_v4_u64(o, x[0], nh(arr, 0), nh(arr, 1), nh(arr, 2));
+              else if (cnt == 2) st_global_v4_u64(o, x[0], x[1], nh(arr, 0), nh(arr, 1));
+              else st_global_v4_u64(o, x[0], x[1], x[2], nh(arr, 0));
+            };
+            if (H == 1) {
+              put4(P.out + my_out + p, 0, hv);
+              if (STR) {
+                put4(P.out_fwd + my_out + p, 1, fw4);
+                put4(P.out_rev + my_out + p, 2, rv4);
+              }
+            } else { // H == 2: whole sectors for window pairs, the odd last window shares its sector with the next row
+              uint64_t* o = P.out + (my_out + p) * 2;
+              if (cnt >= 2) st_global_v4_u64(o, hv[0], ext_hash(hv[0], P.mult[1]), hv[1], ext_hash(hv[1], P.mult[1]));
+              if (cnt & 1) {
+                const uint64_t hl = cnt == 1 ? hv[0] : hv[2];
+                st_global_v4_u64(o + 2 * (cnt - 1), hl, ext_hash(hl, P.mult[1]), nh(0, 0), nh(0, 1));
+              }
+            }
+            done = true;
+          }
+        }
+        for (uint32_t i = 0; i < cnt && !done; ++i) {
           const uint64_t h0 = i == 0 ? hv[0] : i == 1 ? hv[1] : hv[2];
           uint64_t* o = P.out + (my_out + p + i) * H;
           o[0] = h0;
@@ -980,7 +1056,7 @@ cudaError_t launch_fast_t(const KmerParams& P, uint32_t nt, cudaStream_t st)
   constexpr bool REDUCE = CONS != 0 && CONS != 4; // consumers allocate no output buffers
   auto fn = kmer_fast_kernel<H, CONS, WS, NBUF, BOX>;
   const uint32_t buf = BOX ? (nt / 32) * NBUF * (uint32_t)(WS * H / 8) * 2048u
-                       : (NBUF == 2 && H != 0) ? 0u // DIRECT: no row buffers
+                       : (NBUF == 2 && H != 0) ? (uint32_t)T4_BYTES + 256u + nt * 32u * (CONS == 4 ? 3u : 1u) // DIRECT: table + parked row heads
                                                : nt * (CONS == 4 ? 3u : 1u) * (ROW1_BYTES + 16);
   uint32_t smem_bytes = fast_smem_bytes(P.tile_cap, REDUCE ? 0u : buf);
   if (const char* e = getenv("NTHASH_B200_SMEM_PAD")) smem_bytes += (uint32_t)atoi(e); // experiments: lower the occupancy
@@ -1058,7 +1134,7 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
   KmerParams P = Pin;
   FastCfg c;
   c.box = false;
-  c.direct = env_u32("NTHASH_B200_FAST_DIRECT", 0) != 0 && P.h <= 4 && !P.reduce_out && !P.bloom_mode;
+  c.direct = false;
   c.nbuf = env_u32("NTHASH_B200_FAST_NBUF", 1);
   c.ws = env_u32("NTHASH_B200_FAST_WS", 0);
   const bool uniform = !P.g.item_byte;
@@ -1095,6 +1171,11 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
     }
     g.n_items = g.flat ? g.total / g.seg : n_reads * g.segs; // flat: full items only; the tail belongs to the fix-up kernel
   }
+  // General output path, two forms (profiles/r02_ragged_*.txt): DIRECT (32-byte stores from registers, row-boundary sectors
+  // merged through shared memory; 32-48 registers, almost no shared memory) wins wherever items are short or ragged —
+  // ragged 100-150 bp reads 0.57 -> 0.72 of the HBM peak, 36-150 bp 0.45 -> 0.64, ragged long reads 0.65 -> 0.80 — while
+  // uniform reads cut into long items keep the shared-memory rows (0.76 vs 0.67).
+  c.direct = env_u32("NTHASH_B200_FAST_DIRECT", (!uniform || P.g.segs == 1) ? 1u : 0u) != 0 && !c.box && P.h <= 4 && !P.reduce_out && !P.bloom_mode;
   auto tile_cap_for = [&](uint32_t nt) -> uint64_t {
     if (!uniform) return ((uint64_t)Pin.tile_cap * nt + KMER_NT - 1) / KMER_NT + 2 * (uint64_t)P.k + 64; // sized for KMER_NT items
     if (P.g.flat) return (uint64_t)nt * P.g.seg + ((uint64_t)nt * P.g.seg / P.g.nk + 2) * (P.k - 1) + 64;
@@ -1105,13 +1186,13 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
   // long ones that cost occupancy), then CTA size (fewer prologues): the largest CTA that leaves >= 16 warps resident
   const uint32_t buf_per_warp = P.reduce_out ? 0u
                                 : c.box    ? c.nbuf * (uint32_t)(fast_ws_rt(P.h, c.ws) * P.h / 8) * 2048u
-                                : c.direct ? 0u
+                                : c.direct ? 32u * 32u * (P.out_fwd ? 3u : 1u) // DIRECT: parked row heads only
                                            : 32u * (P.out_fwd ? 3u : 1u) * (ROW1_BYTES + 16);
   c.nt = 32;
   for (uint32_t nt : { 256u, 192u, 128u, 96u, 64u, 32u }) { // the small ones only matter for huge k
     const uint64_t cap = tile_cap_for(nt);
     if (cap > 227u * 1024u) continue;
-    const uint32_t smem = fast_smem_bytes((uint32_t)cap, (nt / 32) * buf_per_warp) + 1024;
+    const uint32_t smem = fast_smem_bytes((uint32_t)cap, (nt / 32) * buf_per_warp + (c.direct ? (uint32_t)T4_BYTES + 256u : 0u)) + 1024;
     c.nt = nt;
     if (smem <= 227u * 1024u && ((227u * 1024u / smem) * (nt / 32) >= 16 || nt <= 96)) break;
   }
@@ -1125,7 +1206,7 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const uint32_t smem = fast_smem_bytes(P.tile_cap, (c.nt / 32) * buf_per_warp) + 1024;
+    const uint32_t smem = fast_smem_bytes(P.tile_cap, (c.nt / 32) * buf_per_warp + (c.direct ? (uint32_t)T4_BYTES + 256u : 0u)) + 1024;
     const uint32_t resident = std::max(1u, 227u * 1024u / smem) * (uint32_t)sms;
     // measured (profiles/r01_prefetch_sweep.txt): the prefetch costs 1-10 % on every config, so it stays off
     P.prefetch_ctas = env_u32("NTHASH_B200_PREFETCH_CTAS", 0);

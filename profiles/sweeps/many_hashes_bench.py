@@ -15,7 +15,7 @@ import nthash_b200  # noqa: E402
 
 L, K = 150, 31
 peak, _ = bench.load_peak()
-hs = [int(x) for x in sys.argv[1:]] or [5, 8, 9, 16, 32, 64, 255]
+hs = [int(x) for x in sys.argv[1:]] or [1, 4, 5, 8, 9, 16, 32, 64, 255]
 buf = bench.splitmix_bases_torch(torch, 10_000_000 * L, 42)
 for h in hs:
     for strands in (False, True):
