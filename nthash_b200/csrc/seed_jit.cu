@@ -46,6 +46,9 @@ struct JitParams
   const uint64_t* item_byte; // ragged batches (RAGGED variant): item i starts at byte item_byte[i], its windows are
   const uint64_t* item_out;  // dense rows [item_out[i], item_out[i+1]); item_read[i] = its read (NULL: items are reads)
   const uint64_t* item_read;
+  uint64_t* out_fwd;         // STRANDS variant: get_forward_hash() / get_reverse_hash() per window and seed, [rows][M]
+  uint64_t* out_rev;
+  uint32_t str_aligned;      // both are 32-byte aligned (then whole-sector stores apply wherever a row group is)
 };
 
 const char* const JIT_PRELUDE = R"JIT(
@@ -68,6 +71,9 @@ struct JitParams
   const uint64_t* item_byte; // ragged batches (RAGGED variant): item i starts at byte item_byte[i], its windows are
   const uint64_t* item_out;  // dense rows [item_out[i], item_out[i+1]); item_read[i] = its read (NULL: items are reads)
   const uint64_t* item_read;
+  uint64_t* out_fwd;         // STRANDS variant: get_forward_hash() / get_reverse_hash() per window and seed, [rows][M]
+  uint64_t* out_rev;
+  uint32_t str_aligned;      // both are 32-byte aligned (then whole-sector stores apply wherever a row group is)
 };
 #define DI __device__ __forceinline__
 DI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -102,6 +108,11 @@ DI uint2 lds_v2(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [
 DI uint4 lds_v4(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
 DI uint2 lds_u2x(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 DI void stg_v4(void* p, uint4 v) { asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+#if HAVE_ST256 // one whole 32-byte sector (STG.E.ENL2.256); needs the PTX of CUDA 12.9
+DI void stg_v4q(uint64_t* p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) { asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory"); }
+#else
+DI void stg_v4q(uint64_t* p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) { asm volatile("st.global.v2.u64 [%0], {%1,%2};\n\tst.global.v2.u64 [%0+16], {%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory"); }
+#endif
 DI void stg_v2(void* p, uint2 v) { asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory"); }
 DI void sts_v2(uint32_t a, uint64_t x, uint64_t y) { asm volatile("st.shared.v2.u64 [%0], {%1,%2};" ::"r"(a), "l"(x), "l"(y) : "memory"); }
 DI void sts_u64(uint32_t a, uint64_t x) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(x) : "memory"); }
@@ -109,15 +120,25 @@ DI void sts_u8(uint32_t a, uint32_t x) { asm volatile("st.shared.u8 [%0], %1;" :
 DI uint32_t rotr(uint32_t x, uint32_t r) { return __funnelshift_r(x, x, r); }
 DI uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 struct State { uint32_t flo, fhi, rlo, rhi; };
-// F <- srol(F) ^ e.xy ; R <- sror(R ^ e.zw)   (src/internal.hpp:41-47, :83-88)
+template<int LUT> DI uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT)); return d; }
+// F <- srol(F) ^ e.xy ; R <- sror(R ^ e.zw)   (src/internal.hpp:41-47, :83-88); the k-mer kernel's form: 12 ALU-pipe ops,
+// the plain shifts as IMAD.HI on the FMA pipe (the ALU pipe is the busy one: profiles/r01_ncu_c4_v7.txt)
 DI void roll_step(State& s, const uint4 e)
 {
-  const uint32_t lo = s.flo, hi = s.fhi;
-  s.flo = ((lo << 1) | (hi & 1u)) ^ e.x;
-  s.fhi = ((__funnelshift_l(lo, hi, 1) & ~2u) | ((hi >> 30) & 2u)) ^ e.y;
-  const uint32_t rl = s.rlo ^ e.z, rh = s.rhi ^ e.w;
-  s.rlo = __funnelshift_r(rl, rh, 1);
-  s.rhi = (__funnelshift_r(rh, rh >> 1, 1) & ~1u) | (rl & 1u);
+  {
+    const uint32_t lo = s.flo, hi = s.fhi;
+    const uint32_t hi1 = __funnelshift_l(lo, hi, 1);
+    const uint32_t nhi = lop3<0x50 | 0x88>(hi1, __umulhi(hi, 4u), 2u);   // (a & ~c) | (b & c): bit 33 <- old bit 63
+    const uint32_t nlo = lop3<0xF0 | 0x88>(lo + lo, hi, 1u);             // a | (b & c): bit 0 <- old bit 32
+    s.flo = nlo ^ e.x;
+    s.fhi = nhi ^ e.y;
+  }
+  {
+    const uint32_t lo = s.rlo ^ e.z, hi = s.rhi ^ e.w;
+    s.rlo = __funnelshift_r(lo, hi, 1);
+    const uint32_t y = __funnelshift_r(hi, __umulhi(hi, 0x80000000u), 1);
+    s.rhi = lop3<0x50 | 0x88>(y, lo, 1u);
+  }
 }
 // Strided care block, stride D: F <- srol^D(F) ^ ef ; R <- sror^D(R ^ er).  srol^D (D <= 31) is a 64-bit rotate
 // followed by a swap of the D bits that crossed the 33|31 split (src/internal.hpp:56-66); sror^D is its inverse.
@@ -134,7 +155,16 @@ DI void blk_step(State& a, const uint2 ef, const uint2 er)
   a.rlo = __funnelshift_r(zlo, zhi, D);
   a.rhi = __funnelshift_r(zhi, zlo, D);
 }
-DI uint64_t ext_hash(uint64_t h0, uint64_t mult) { const uint64_t t = h0 * mult; return t ^ (t >> 27); }
+// extend_hashes (src/internal.hpp:104-118): t = h0 * mult; t ^ (t >> 27).  The shifts run as IMAD / IMAD.HI on the FMA pipe,
+// the two xors (one fused with the or) on the ALU pipe.
+DI uint64_t ext_hash(uint64_t h0, uint64_t mult)
+{
+  const uint64_t t = h0 * mult;
+  const uint32_t lo = (uint32_t)t, hi = (uint32_t)(t >> 32);
+  const uint32_t nlo = lop3<0x1E>(lo, __umulhi(lo, 32u), hi * 32u); // lo ^ ((lo >> 27) | (hi << 5))
+  const uint32_t nhi = hi ^ __umulhi(hi, 32u);
+  return ((uint64_t)nhi << 32) | nlo;
+}
 DI uint64_t srol_n(uint64_t x, unsigned d)
 {
   const uint64_t m33 = (1ULL << 33) - 1, m31 = (1ULL << 31) - 1;
@@ -301,6 +331,7 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
   // where they cancel); roll the full-window hash over bases -1 .. k-2 (in-only)
   DECL_W
   DECL_BLOCKS
+  DECL_STR
   State full = { 0u, 0u, 0u, 0u };
   uint32_t bad = 0;
   for (int j = -(int)OLDER; j < (int)K - 1; ++j) {
@@ -324,6 +355,7 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
     MAIN_TILES
   }
 
+  STR_TAIL
   const bool dirty = active && bad != 0;
   const bool any_dirty = __any_sync(0xffffffffu, dirty);
   if (lane == 0) {
@@ -353,6 +385,10 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
           const uint64_t h0 = f + r;
           P.out[row * HT + s * HPS] = h0;
           for (uint32_t q = 1; q < HPS; ++q) P.out[row * HT + s * HPS + q] = ext_hash(h0, MULT[q]);
+#if STRANDS
+          P.out_fwd[row * M + s] = f;
+          P.out_rev[row * M + s] = r;
+#endif
         }
       }
     }
@@ -376,6 +412,7 @@ struct Nvrtc
   nvrtcResult (*log_size)(nvrtcProgram, size_t*) = nullptr;
   nvrtcResult (*log)(nvrtcProgram, char*) = nullptr;
   nvrtcResult (*destroy)(nvrtcProgram*) = nullptr;
+  int version = 0; // major * 100 + minor
 };
 
 const Nvrtc& nvrtc()
@@ -383,7 +420,9 @@ const Nvrtc& nvrtc()
   static Nvrtc n = [] {
     Nvrtc x;
     void* h = nullptr;
-    for (const char* name : { "libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12" }) {
+    // the toolkit's own NVRTC first: a process that has imported torch already holds torch's bundled (older) libnvrtc.so.12,
+    // whose ptxas rejects the 256-bit st.global.v4.u64 the strand stores use
+    for (const char* name : { "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so.12", "libnvrtc.so" }) {
       h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
       if (h) break;
     }
@@ -396,6 +435,10 @@ const Nvrtc& nvrtc()
     x.log = (decltype(x.log))dlsym(h, "nvrtcGetProgramLog");
     x.destroy = (decltype(x.destroy))dlsym(h, "nvrtcDestroyProgram");
     x.ok = x.create && x.compile && x.cubin_size && x.cubin && x.log_size && x.log && x.destroy;
+    if (auto ver = (nvrtcResult (*)(int*, int*))dlsym(h, "nvrtcVersion")) {
+      int a = 0, b = 0;
+      if (ver(&a, &b) == NVRTC_SUCCESS) x.version = a * 100 + b;
+    }
     return x;
   }();
   return n;
@@ -422,6 +465,9 @@ struct SeedJit
   const SeedPlanHost* plan = nullptr;
   mutable SeedJit* alt = nullptr;  // the 2-D tile variant for other row lengths, compiled on first use
   mutable SeedJit* alt_ragged = nullptr; // the ragged variant, compiled on first use
+  mutable SeedJit* alt_str = nullptr;    // uniform batches with strand outputs (3-D box stores for the hashes), compiled on first use
+  mutable SeedJit* alt_str2d = nullptr;  // the same over the 2-D tile variant
+  bool strands = false;
   mutable std::mutex mu;
   std::string source; // kept for inspection (nthash_seed_plan_jit_source)
 };
@@ -431,6 +477,8 @@ void seed_jit_destroy(SeedJit* j)
   if (!j) return;
   seed_jit_destroy(j->alt);
   seed_jit_destroy(j->alt_ragged);
+  seed_jit_destroy(j->alt_str);
+  seed_jit_destroy(j->alt_str2d);
   if (j->lib) cudaLibraryUnload(j->lib);
   cudaFree(j->d_tables);
   delete j;
@@ -442,18 +490,19 @@ const char* seed_jit_source(const SeedJit* j) { return j ? j->source.c_str() : "
 // specialised path does not apply; the caller then uses the generic kernel.
 // mode 0: dense 2-D tiles (TMA 2-D tensor stores), 1: [blocks][rows][8 u64] tiles (TMA 3-D tensor stores; the default
 // for uniform batches), 2: ragged batches (per-lane rows, coalesced stores, item arrays)
-static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& why, bool load, int mode);
+static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& why, bool load, int mode, bool strands = false);
 
 SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
 {
   return seed_jit_build_variant(plan, why, load, getenv("NTHASH_B200_SEED_JIT_NO_BOX") ? 0 : 1);
 }
 
-static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& why, bool load, int mode)
+static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& why, bool load, int mode, bool strands)
 {
   const bool box3 = mode == 1, ragged = mode == 2;
   const uint32_t k = plan.k, m = plan.n_seeds, hps = plan.h, ht = m * hps;
-  if (k > 128) { why = "k > 128"; return nullptr; }
+  if (k > 256) { why = "k > 256"; return nullptr; }
+  if (strands && (ragged || m > 8)) { why = "strand outputs: uniform batches of at most 8 seeds"; return nullptr; }
   if (ht > 64) { why = "more than 64 hashes per window"; return nullptr; }
   // ---- decomposition of every seed's lookup positions: strided blocks (arithmetic progressions of >= 6
   //      positions, stride 1..4, rolled like the whole window) + pairs for the rest ----
@@ -598,6 +647,11 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
     while (b2) { const uint32_t t = a % b2; a = b2; b2 = t; }
     unroll = unroll / a * lcm_d;
   }
+  if (strands) { // strand hashes leave in groups of four windows (whole 32-byte sectors): the loop body must hold whole groups
+    uint32_t a = unroll, b2 = 4;
+    while (b2) { const uint32_t t = a % b2; a = b2; b2 = t; }
+    unroll = unroll / a * 4;
+  }
   if (unroll > 24) { why = "strided blocks with incompatible strides"; return nullptr; }
   // CTA size / output buffering: defaults found on C4 (profiles/r01_seed_jit_sweeps.txt), overridable for experiments
   // (box3 on C4: 128 threads with three 6 KB tiles per warp 0.89 of the HBM peak, two 0.85, one 0.76; 2-D tiles 0.63)
@@ -634,6 +688,8 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
              << gi << ".x, er" << gi + 1 << ".x); rhi = xor3(rhi, er" << gi << ".y, er" << gi + 1 << ".y); \\\n";
       if (gi < pv.size())
         body << "          flo ^= ef" << gi << ".x; fhi ^= ef" << gi << ".y; rlo ^= er" << gi << ".x; rhi ^= er" << gi << ".y; \\\n";
+      if (strands)
+        body << "          sf[" << (u % 4) * m + s << "] = ((uint64_t)fhi << 32) | flo; sr[" << (u % 4) * m + s << "] = ((uint64_t)rhi << 32) | rlo; \\\n";
       body << "          const uint64_t h0 = (((uint64_t)fhi << 32) | flo) + (((uint64_t)rhi << 32) | rlo); \\\n";
       body << "          hv[" << s * hps << "] = h0; \\\n";
       for (uint32_t q = 1; q < hps; ++q) body << "          hv[" << s * hps + q << "] = ext_hash(h0, " << hex64(ext_mult(q, k)) << "); \\\n";
@@ -643,6 +699,7 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
   };
 
   std::ostringstream src;
+  src << "#define HAVE_ST256 " << (nvrtc().version >= 1209 ? 1 : 0) << "\n";
   src << JIT_PRELUDE;
   src << "#define NT " << nt << "u\n#define NBUF " << nbuf << "u\n#define BULK_WAIT_READ asm volatile(\"cp.async.bulk.wait_group.read "
       << nbuf - 1 << ";\" ::: \"memory\");\n";
@@ -655,6 +712,28 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
     // else 8-byte chunks, one row per instruction; rows padded to an odd number of 16-byte chunks (conflict-free STS.128)
     const uint32_t chunk = ht % 2 ? 8 : 16, pitch = (row_bytes + 15) / 16 * 16 + ((((row_bytes + 15) / 16) % 2) ? 0 : 16);
     src << "#define RAGGED " << (ragged ? 1 : 0) << "\n#define CHUNK " << chunk << "u\n#define LANES_PER_ROW " << 256 / chunk << "u\n#define ROW_PITCH " << pitch << "u\n";
+  }
+  src << "#define STRANDS " << (strands ? 1 : 0) << "\n";
+  if (strands) {
+    // STR_FLUSH(w0): the strand hashes of windows w0 .. w0+3 (4*M u64 per array, contiguous in both arrays) as M whole
+    // 32-byte sectors when the group starts on one, else value by value; STR_TAIL: the last n % 4 windows of the row
+    src << "#define DECL_STR uint64_t sf[" << 4 * m << "], sr[" << 4 * m << "]; const bool str_al = P.str_aligned && (((my_out * M) & 3ull) == 0);\n";
+    src << "#define STR_FLUSH(w0) if (active) { uint64_t* pf = P.out_fwd + (my_out + (w0)) * M; uint64_t* pr = P.out_rev + (my_out + (w0)) * M; if (str_al) {";
+    for (uint32_t c = 0; c < m; ++c)
+      src << " stg_v4q(pf + " << 4 * c << ", sf[" << 4 * c << "], sf[" << 4 * c + 1 << "], sf[" << 4 * c + 2 << "], sf[" << 4 * c + 3 << "]);"
+          << " stg_v4q(pr + " << 4 * c << ", sr[" << 4 * c << "], sr[" << 4 * c + 1 << "], sr[" << 4 * c + 2 << "], sr[" << 4 * c + 3 << "]);";
+    src << " } else {";
+    for (uint32_t j = 0; j < 4 * m; ++j) src << " pf[" << j << "] = sf[" << j << "]; pr[" << j << "] = sr[" << j << "];";
+    src << " } }\n";
+    src << "#define STR_TAIL { const uint32_t rem = n & 3u; if (active && rem) { uint64_t* pf = P.out_fwd + (my_out + (n - rem)) * M; uint64_t* pr = P.out_rev + (my_out + (n - rem)) * M;";
+    for (uint32_t w = 0; w < 3; ++w) {
+      src << " if (rem > " << w << "u) {";
+      for (uint32_t q = 0; q < m; ++q) src << " pf[" << w * m + q << "] = sf[" << w * m + q << "]; pr[" << w * m + q << "] = sr[" << w * m + q << "];";
+      src << " }";
+    }
+    src << " } }\n";
+  } else {
+    src << "#define DECL_STR\n#define STR_FLUSH(w0)\n#define STR_TAIL\n";
   }
   src << "__device__ const uint64_t MULT[" << (hps > 1 ? hps : 1) << "] = { 0";
   for (uint32_t q = 1; q < hps; ++q) src << ", " << hex64(ext_mult(q, k));
@@ -701,7 +780,9 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
         << window_body(u);
       if (i == 0) // this buffer's previous tile must have left shared memory; waiting only now hides the TMA read behind one window
         o << "        if (p0 + " << t * tw << "u >= NBUF * TW) { if (lane == 0) BULK_WAIT_READ __syncwarp(); } \\\n";
-      o << "        STORE_WINDOW_" << i << "(rowaddr) \\\n      } \\\n";
+      o << "        STORE_WINDOW_" << i << "(rowaddr) \\\n";
+      if (strands && u % 4 == 3) o << "        STR_FLUSH(p0 + " << u - 3 << "u) \\\n";
+      o << "      } \\\n";
     }
     o << "      fence_proxy_async_smem(); __syncwarp(); \\\n      if (lane == 0) { ";
     if (box3) o << "tma_store_3d(&omap, ot, 0, row0, (int)((p0 + " << t * tw << "u) * HT / 8u));";
@@ -746,6 +827,7 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
   j->nbuf = nbuf;
   j->box3 = box3;
   j->ragged = ragged;
+  j->strands = strands;
   j->row_pitch = (row_bytes + 15) / 16 * 16 + ((((row_bytes + 15) / 16) % 2) ? 0 : 16);
   j->plan = &plan;
   nvrtcProgram prog = nullptr;
@@ -772,8 +854,9 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
   rt.cubin(prog, cubin.data());
   rt.destroy(&prog);
   if (const char* dump = getenv("NTHASH_B200_SEED_JIT_DUMP")) { // inspection: <prefix>.cu and <prefix>.cubin
-    if (FILE* f = fopen((std::string(dump) + ".cu").c_str(), "w")) { fputs(j->source.c_str(), f); fclose(f); }
-    if (FILE* f = fopen((std::string(dump) + ".cubin").c_str(), "wb")) { fwrite(cubin.data(), 1, cubin.size(), f); fclose(f); }
+    const std::string pre = std::string(dump) + "_mode" + std::to_string(mode);
+    if (FILE* f = fopen((pre + ".cu").c_str(), "w")) { fputs(j->source.c_str(), f); fclose(f); }
+    if (FILE* f = fopen((pre + ".cubin").c_str(), "wb")) { fwrite(cubin.data(), 1, cubin.size(), f); fclose(f); }
   }
   if (!load) return j; // build check on a machine without a GPU
   cudaError_t e = cudaLibraryLoadData(&j->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
@@ -809,10 +892,11 @@ static uint32_t seed_jit_tile_cap(const SeedJit* j, const SeedParams& P)
 // Build check without a GPU: compiles every variant (3-D box, 2-D tiles, ragged) for sm_100a.
 bool seed_jit_compile_all(const SeedPlanHost& plan, std::string& why)
 {
-  for (int mode : { 1, 0, 2 }) {
+  for (int mode : { 1, 0, 2, 11, 10 }) { // 1x: with strand outputs
     if (mode == 2 && plan.n_seeds * plan.h > 32) continue;
+    if (mode >= 10 && plan.n_seeds > 8) continue;
     std::string w;
-    SeedJit* j = seed_jit_build_variant(plan, w, false, mode);
+    SeedJit* j = seed_jit_build_variant(plan, w, false, mode % 10, mode >= 10);
     if (!j && (mode == 1 || w.rfind("NVRTC compilation failed", 0) == 0)) { // "does not apply" is fine for the side variants
       why = "variant " + std::to_string(mode) + ": " + w;
       return false;
@@ -825,11 +909,11 @@ bool seed_jit_compile_all(const SeedPlanHost& plan, std::string& why)
 // The variant of the compiled kernel that fits the geometry: ragged batches take the ragged variant; uniform ones the
 // 3-D box stores when rows are whole 64-byte blocks, else the 2-D tile variant.  Variants other than the one built with
 // the plan are compiled on first use.
-static const SeedJit* seed_jit_variant(const SeedJit* j, const KmerGeom& g)
+static const SeedJit* seed_jit_variant(const SeedJit* j, const KmerGeom& g, bool strands)
 {
   if (!j) return j;
   if (g.item_byte) {
-    if (j->ht > 32 || getenv("NTHASH_B200_SEED_JIT_NO_RAGGED")) return nullptr; // a window must fit a 256-byte row piece
+    if (strands || j->ht > 32 || getenv("NTHASH_B200_SEED_JIT_NO_RAGGED")) return nullptr; // a window must fit a 256-byte row piece
     std::lock_guard<std::mutex> lock(j->mu);
     if (!j->alt_ragged) {
       std::string why;
@@ -837,28 +921,31 @@ static const SeedJit* seed_jit_variant(const SeedJit* j, const KmerGeom& g)
     }
     return j->alt_ragged;
   }
-  if (!j->box3 || ((uint64_t)g.seg * j->ht) % 8 == 0) return j;
+  const bool box = j->box3 && ((uint64_t)g.seg * j->ht) % 8 == 0;
+  if (!strands && (box || !j->box3)) return j;
   std::lock_guard<std::mutex> lock(j->mu);
-  if (!j->alt) {
+  SeedJit*& slot = strands ? (box ? j->alt_str : j->alt_str2d) : j->alt;
+  if (!slot) {
     std::string why;
-    j->alt = seed_jit_build_variant(*j->plan, why, true, 0);
+    slot = seed_jit_build_variant(*j->plan, why, true, box ? 1 : 0, strands);
   }
-  return j->alt;
+  return slot;
 }
 
 // Uniform batches whose items are all full and whose rows are 16-byte multiples; ragged batches without strand outputs.
 bool seed_jit_applies(const SeedJit* j0, const SeedParams& P)
 {
   const KmerGeom& g = P.g;
-  if (!j0 || P.out_fwd || !g.n_items || g.n_items >= 0x7fffffffull || ((uintptr_t)P.out & 15)) return false;
+  if (!j0 || !g.n_items || g.n_items >= 0x7fffffffull || ((uintptr_t)P.out & 15)) return false;
+  if (P.out_fwd && (g.item_byte || getenv("NTHASH_B200_SEED_JIT_NO_STRANDS"))) return false;
   if (!g.item_byte && (!g.seg || g.nk % g.seg || ((uint64_t)g.seg * j0->ht) % 2)) return false;
-  const SeedJit* j = seed_jit_variant(j0, g);
+  const SeedJit* j = seed_jit_variant(j0, g, P.out_fwd != nullptr);
   return j && seed_jit_smem_bytes(j, seed_jit_tile_cap(j, P)) <= 227u * 1024u;
 }
 
 cudaError_t launch_seed_jit(const SeedJit* j0, const SeedParams& P, cudaStream_t st)
 {
-  const SeedJit* j = seed_jit_variant(j0, P.g);
+  const SeedJit* j = seed_jit_variant(j0, P.g, P.out_fwd != nullptr);
   if (!j) return cudaErrorNotSupported;
   using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -912,6 +999,9 @@ cudaError_t launch_seed_jit(const SeedJit* j0, const SeedParams& P, cudaStream_t
   jp.item_byte = P.g.item_byte;
   jp.item_out = P.g.item_out;
   jp.item_read = P.item_read;
+  jp.out_fwd = P.out_fwd;
+  jp.out_rev = P.out_rev;
+  jp.str_aligned = (((uintptr_t)P.out_fwd | (uintptr_t)P.out_rev) & 31) == 0 ? 1u : 0u;
   const uint32_t smem = seed_jit_smem_bytes(j, jp.tile_cap);
   cudaError_t e = cudaFuncSetAttribute((const void*)j->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

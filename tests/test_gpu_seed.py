@@ -124,6 +124,41 @@ def test_ragged_specialised_kernel(seeds, h, capfd, monkeypatch):
     capfd.readouterr()
 
 
+def _long_seed(k, rng):
+    half = "".join(rng.choice(list("0111"), k // 2))
+    s = half + ("1" if k % 2 else "") + half[::-1]
+    return "1" + s[1:-1] + "1"
+
+
+@pytest.mark.parametrize("case", list(range(len(SEED_SETS))) + ["k200", "k255x2"])
+def test_uniform_strand_outputs_specialised_kernel(case, monkeypatch):
+    """get_forward_hash() / get_reverse_hash() arrays (nthash.hpp:489-500) from the NVRTC-specialised kernel (what the C++
+    SeedNtHash shim asks for on every call), and seeds up to k = 256 there: equal to the oracle and to the interpreter,
+    on rows that are and are not 32-byte multiples, with dirty bytes and NULs."""
+    rng = np.random.default_rng(1000 + len(str(case)))
+    if case == "k200":
+        seeds, h = [_long_seed(200, rng)], 2
+    elif case == "k255x2":
+        seeds, h = [_long_seed(255, rng), "1" * 255], 1
+    else:
+        seeds, h = SEED_SETS[case]
+    k, m = len(seeds[0]), len(seeds)
+    plan = nthash_b200.SeedPlan(seeds, h)
+    for n, L in ((600, k + 119), (301, k + 120), (23, 3 * k + 1501)):
+        bases = synth(rng, n * L, p_bad=0.002, lower=0.1)
+        bases[rng.integers(0, len(bases), 3)] = 0
+        d_b, _keep = to_dev(bases)
+        res = nthash_b200.seed_hashes_uniform(plan, d_b, n, L, want_strands=True)
+        torch.cuda.synchronize()
+        ora = ORACLE.seed_batch(bases, np.arange(n + 1, dtype=np.uint64) * L, seeds, h, threads=8)
+        assert_batch_equal(res, ora, m * h, check_strands=True)
+        monkeypatch.setenv("NTHASH_B200_SEED_JIT_NO_STRANDS", "1")
+        slow = nthash_b200.seed_hashes_uniform(plan, d_b, n, L, want_strands=True)
+        monkeypatch.delenv("NTHASH_B200_SEED_JIT_NO_STRANDS")
+        torch.cuda.synchronize()
+        assert torch.equal(res.out, slow.out) and torch.equal(res.fwd, slow.fwd) and torch.equal(res.rev, slow.rev) and torch.equal(res.valid_bits, slow.valid_bits)
+
+
 def test_generic_and_specialised_kernels_agree(monkeypatch):
     # uniform batches take the NVRTC-specialised kernel; the generic interpreter must give the same rows
     rng = np.random.default_rng(12)
