@@ -655,7 +655,9 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
   if (unroll > 24) { why = "strided blocks with incompatible strides"; return nullptr; }
   // CTA size / output buffering: defaults found on C4 (profiles/r01_seed_jit_sweeps.txt), overridable for experiments
   // (box3 on C4: 128 threads with three 6 KB tiles per warp 0.89 of the HBM peak, two 0.85, one 0.76; 2-D tiles 0.63)
-  uint32_t nt = box3 || ragged ? 128 : 256, nbuf = box3 ? 3 : 1;
+  // round 2 (profiles/r02_seed_jit_sweep.txt, after the ALU diet of roll_step / ext_hash): 160 threads with two tiles per
+  // warp 10.43 ms, 96 x 3 10.45, 128 x 2 10.59, 128 x 3 (the round-1 default) 11.00: resident warps beat a third tile now
+  uint32_t nt = box3 ? 160 : ragged ? 128 : 256, nbuf = box3 ? 2 : 1;
   if (const char* e = getenv("NTHASH_B200_SEED_JIT_NT")) nt = (uint32_t)atoi(e);
   if (const char* e = getenv("NTHASH_B200_SEED_JIT_NBUF")) nbuf = (uint32_t)atoi(e);
   if (nt < 32 || nt > 1024 || nt % 32 || nbuf < 1 || nbuf > 4) { why = "bad NT/NBUF override"; return nullptr; }
