@@ -208,6 +208,39 @@ int nthash_kmer_bloom_dev(const uint8_t* d_bases, uint64_t n_bases_readable, con
                           uint32_t num_hashes, uint32_t* d_filter_words, uint64_t filter_bits, int query,
                           uint64_t* d_result, void* stream);
 
+/* ---- consumer: minimizer selection ---------------------------------------------------------------------
+ * The sketch most k-mer pipelines keep instead of all hashes.  A window is `window` consecutive k-mers of one read
+ * (dense rows j .. j+window-1, 1 <= window <= 64); its minimizer is the k-mer with the smallest canonical hash
+ * hashes()[0] among those the reference's loop visits, the leftmost one on ties; a window without a visited k-mer has
+ * none; reads with fewer than `window` k-mers have no windows.  Bit (w & 31) of word (w >> 5) of min_bits is set iff
+ * k-mer row w is the minimizer of at least one window ((rows + 31) / 32 words, zeroed here).  min_hash / min_row
+ * (nullable, `capacity` entries each) receive the selected rows' hashes and dense row numbers in increasing row order;
+ * *count = number of selected rows (entries past `capacity` are counted, not written).  About 2 / (window + 1) of the
+ * rows are selected on random sequence, so that fraction of 8 bytes per k-mer is all that has to leave the device.  */
+int nthash_kmer_minimizer_uniform_dev(const uint8_t* d_bases, uint64_t n_bases_readable, uint64_t n_reads,
+                                      uint32_t read_len, uint32_t k, uint32_t window, uint32_t* d_min_bits,
+                                      uint64_t* d_min_hash, uint64_t* d_min_row, uint64_t capacity, uint64_t* d_count,
+                                      void* stream);
+/* Host buffers; fixed-length reads when read_off == NULL (then uniform_read_len > 0), ragged otherwise. */
+int nthash_kmer_minimizers(const char* bases, const uint64_t* read_off, uint64_t n_reads, uint32_t uniform_read_len,
+                           uint32_t k, uint32_t window, uint32_t* min_bits, uint64_t* min_hash, uint64_t* min_row,
+                           uint64_t capacity, uint64_t* count, int device);
+
+/* ---- fused consumer: cardinality sketch in the style of ntCard (the k-mer counting tool built on ntHash that
+ * nthash.hpp:56-57 points at).  Every window the reference's loop visits contributes its canonical hash h
+ * (hashes()[0]): if the top `sample_bits` bits of h are zero (a 2^-sample_bits sample of the distinct k-mers), the
+ * counter indexed by the next `index_bits` bits, d_counters[(h >> (64 - sample_bits - index_bits)) & (2^index_bits - 1)],
+ * is incremented (uint32, atomically; NOT zeroed here so that batches accumulate).  The multiplicity histogram of that
+ * table is what ntCard's estimator consumes (F0, f1, f2, ...).  d_result = {windows visited, windows sampled, 0}.
+ * Nothing but the counters leaves the SM: the kernel runs at the speed of the reduce consumer.                     */
+int nthash_kmer_sketch_uniform_dev(const uint8_t* d_bases, uint64_t n_bases_readable, uint64_t n_reads,
+                                   uint32_t read_len, uint32_t k, uint32_t sample_bits, uint32_t index_bits,
+                                   uint32_t* d_counters, uint64_t* d_result, void* stream);
+int nthash_kmer_sketch_dev(const uint8_t* d_bases, uint64_t n_bases_readable, const uint64_t* d_read_off,
+                           const uint64_t* d_koff, uint64_t n_reads, uint64_t max_read_len, uint32_t k,
+                           uint32_t sample_bits, uint32_t index_bits, uint32_t* d_counters, uint64_t* d_result,
+                           void* stream);
+
 /* ---- SeedNtHash: spaced seeds ----------------------------------------------------------------
  * Replaces `nthash::SeedNtHash it(seq, len, seeds, h, k); while (it.roll()) use(it.hashes())`
  * (nthash.hpp:313-521; SeedNtHash::init/roll src/seed.cpp:493-544; ntmsm64 :130-270).

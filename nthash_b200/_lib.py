@@ -46,6 +46,10 @@ _SIGS = {
                                                 C.c_int, u64p, C.c_void_p]),
     "nthash_kmer_bloom_dev": (C.c_int, [u8p, C.c_uint64, u64p, u64p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p,
                                         C.c_uint64, C.c_int, u64p, C.c_void_p]),
+    "nthash_kmer_minimizer_uniform_dev": (C.c_int, [u8p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u32p, u64p, u64p, C.c_uint64, u64p, C.c_void_p]),
+    "nthash_kmer_minimizers": (C.c_int, [u8p, u64p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u32p, u64p, u64p, C.c_uint64, u64p, C.c_int]),
+    "nthash_kmer_sketch_uniform_dev": (C.c_int, [u8p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, u64p, C.c_void_p]),
+    "nthash_kmer_sketch_dev": (C.c_int, [u8p, C.c_uint64, u64p, u64p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, u64p, C.c_void_p]),
     "nthash_seed_plan_create": (C.c_int, [C.POINTER(C.c_char_p), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
     "nthash_seed_plan_destroy": (None, [C.c_void_p]),
     "nthash_seed_plan_symmetric": (C.c_int, [C.c_void_p]),

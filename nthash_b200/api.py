@@ -365,3 +365,53 @@ def kmer_bloom(bases, read_off, k, num_hashes, filt, bits, query=False, stream=N
         check(LIB.nthash_kmer_bloom_dev(_ptr(bases), bases.numel(), _ptr(read_off), _ptr(koff), n_reads, max_len.value, k, num_hashes,
                                         _ptr(filt), int(bits), 1 if query else 0, _ptr(res), _stream_ptr(stream)))
     return res
+
+
+def kmer_sketch_uniform(bases, n_reads, read_len, k, sample_bits=11, index_bits=20, counters=None, stream=None):
+    """ntCard-style cardinality sketch (nthash_kmer_sketch_uniform_dev): returns (counters int32 [2^index_bits] on the GPU,
+    int64 [windows visited, windows sampled, 0]).  Pass `counters` to accumulate over batches."""
+    _check_bases(bases)
+    dev = bases.device
+    with torch.cuda.device(dev):
+        if counters is None:
+            counters = torch.zeros(1 << index_bits, dtype=torch.int32, device=dev)
+        res = torch.empty(3, dtype=torch.int64, device=dev)
+        check(LIB.nthash_kmer_sketch_uniform_dev(_ptr(bases), bases.numel(), n_reads, read_len, k, sample_bits, index_bits, _ptr(counters), _ptr(res),
+                                                 _stream_ptr(stream)))
+    return counters, res
+
+
+def kmer_sketch(bases, read_off, k, sample_bits=11, index_bits=20, counters=None, stream=None):
+    """The same over ragged reads (nthash_kmer_plan_dev + nthash_kmer_sketch_dev)."""
+    _check_bases(bases)
+    n_reads = read_off.numel() - 1
+    dev = bases.device
+    with torch.cuda.device(dev):
+        if counters is None:
+            counters = torch.zeros(1 << index_bits, dtype=torch.int32, device=dev)
+        res = torch.empty(3, dtype=torch.int64, device=dev)
+        koff = torch.empty(n_reads + 1, dtype=torch.int64, device=dev)
+        rows, max_len = C.c_uint64(0), C.c_uint64(0)
+        check(LIB.nthash_kmer_plan_dev(_ptr(read_off), n_reads, k, _ptr(koff), C.byref(rows), C.byref(max_len), _stream_ptr(stream)))
+        check(LIB.nthash_kmer_sketch_dev(_ptr(bases), bases.numel(), _ptr(read_off), _ptr(koff), n_reads, max_len.value, k, sample_bits, index_bits,
+                                         _ptr(counters), _ptr(res), _stream_ptr(stream)))
+    return counters, res
+
+
+def kmer_minimizers_uniform(bases, n_reads, read_len, k, window, want_lists=True, capacity=None, stream=None):
+    """Minimizer selection (nthash_kmer_minimizer_uniform_dev): returns (min_bits int32 words, hashes int64 [n] or None,
+    rows int64 [n] or None, count).  Synchronises to learn the count."""
+    _check_bases(bases)
+    dev = bases.device
+    rows = n_reads * max(read_len - k + 1, 0)
+    with torch.cuda.device(dev):
+        bits = torch.empty(int(LIB.nthash_valid_words(rows)), dtype=torch.int32, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        if capacity is None:
+            capacity = rows
+        mh = torch.empty(capacity, dtype=torch.int64, device=dev) if want_lists else None
+        mr = torch.empty(capacity, dtype=torch.int64, device=dev) if want_lists else None
+        check(LIB.nthash_kmer_minimizer_uniform_dev(_ptr(bases), bases.numel(), n_reads, read_len, k, window, _ptr(bits), _ptr(mh), _ptr(mr),
+                                                    capacity if want_lists else 0, _ptr(cnt), _stream_ptr(stream)))
+        n = int(cnt.item())
+    return bits, (mh[: min(n, capacity)] if want_lists else None), (mr[: min(n, capacity)] if want_lists else None), n

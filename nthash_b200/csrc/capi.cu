@@ -1073,6 +1073,254 @@ int nthash_kmer_bloom_dev(const uint8_t* d_bases, uint64_t n_bases_readable, con
   return kmer_dev_run(B, k, num_hashes, st);
 }
 
+// ---- consumer: minimizer selection ----------------------------------------------------------------------------
+// Chunks of reads whose hash rows stay L2-resident between the hash kernel and the selection kernel; the rows themselves
+// never leave the device (and, for the host entry, never cross PCIe): out come a bitmap over the dense rows and, on
+// request, the selected hashes and their row numbers in row order.
+struct MinimizerOut
+{
+  uint32_t* d_bits;
+  uint64_t *d_hash, *d_row, capacity, *d_count;
+};
+
+static int minimizer_chunk(const DevBatch& geom, uint32_t k, uint32_t w, uint64_t rows, uint64_t row0, const uint64_t* d_koff_local,
+                           uint64_t* d_rows, uint32_t* d_valid, uint32_t* d_end, const MinimizerOut& O, cudaStream_t st)
+{
+  DevBatch B = geom;
+  B.d_out = d_rows;
+  B.d_valid = d_valid;
+  B.memset_rows = rows;
+  if (int rc = kmer_dev_run(B, k, 1, st)) return rc;
+  NTH_CUDA(launch_mark_read_ends(d_end, rows, d_koff_local, geom.n_reads, geom.uniform_len ? geom.uniform_len - k + 1 : 0, st));
+  NTH_CUDA(launch_minimizer_select(d_rows, d_valid, d_end, rows, w, O.d_bits, row0, st));
+  if (O.d_hash || O.d_row)
+    NTH_CUDA(launch_compact_rows_at(d_rows, O.d_bits + row0 / 32, rows, 1, O.d_hash, O.d_row, O.d_count, true, row0, O.capacity, st));
+  return NTHASH_OK;
+}
+
+static int minimizer_args(uint32_t k, uint32_t w, const void* bits, const void* count)
+{
+  if (int rc = check_kh(k, 1)) return rc;
+  if (w < 1 || w > 64) return fail(NTHASH_ERR_INVALID_ARG, "window=%u k-mers outside [1, 64]", w);
+  if (!bits || !count) return fail(NTHASH_ERR_INVALID_ARG, "the minimizer bitmap and the count must not be NULL");
+  return NTHASH_OK;
+}
+
+int nthash_kmer_minimizer_uniform_dev(const uint8_t* d_bases, uint64_t n_bases_readable, uint64_t n_reads, uint32_t read_len, uint32_t k,
+                                      uint32_t window, uint32_t* d_min_bits, uint64_t* d_min_hash, uint64_t* d_min_row, uint64_t capacity,
+                                      uint64_t* d_count, void* stream)
+{
+  if (int rc = minimizer_args(k, window, d_min_bits, d_count)) return rc;
+  if (int rc = check_device_ready()) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  NTH_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
+  if (n_reads == 0 || read_len < k) return NTHASH_OK;
+  if (!d_bases || ((uintptr_t)d_bases & 15)) return fail(NTHASH_ERR_INVALID_ARG, "d_bases must be 16-byte aligned");
+  if (n_bases_readable < n_reads * (uint64_t)read_len) return fail(NTHASH_ERR_INVALID_ARG, "n_bases_readable smaller than n_reads*read_len");
+  const uint64_t nk = read_len - k + 1, total = n_reads * nk;
+  NTH_CUDA(cudaMemsetAsync(d_min_bits, 0, ((total + 31) / 32) * 4, st));
+  // reads per chunk: a multiple of 32 (chunk rows start on a word of the bitmap, chunk bases on a 16-byte boundary),
+  // about 8 M rows = 64 MB of hashes, which the 126 MB L2 keeps for the selection pass
+  uint64_t per = std::max<uint64_t>(32, ((8ull << 20) / nk) & ~31ull);
+  if (const char* e = getenv("NTHASH_B200_MINIMIZER_CHUNK_READS")) per = std::max<uint64_t>(32, strtoull(e, nullptr, 10) & ~31ull);
+  per = std::min<uint64_t>(per, (n_reads + 31) & ~31ull);
+  uint64_t* d_rows = nullptr;
+  uint32_t *d_valid = nullptr, *d_end = nullptr;
+  const uint64_t words = (per * nk + 31) / 32 + 4;
+  NTH_CUDA(cudaMallocAsync(&d_rows, (per * nk + 64) * sizeof(uint64_t), st));
+  cudaError_t e = cudaMallocAsync(&d_valid, 2 * words * 4, st);
+  int rc = e == cudaSuccess ? NTHASH_OK : fail(NTHASH_ERR_CUDA, "cudaMallocAsync: %s", cudaGetErrorString(e));
+  d_end = d_valid + words;
+  const MinimizerOut O = { d_min_bits, d_min_hash, d_min_row, capacity, d_count };
+  for (uint64_t r0 = 0; r0 < n_reads && rc == NTHASH_OK; r0 += per) {
+    DevBatch G;
+    G.d_bases = d_bases + r0 * read_len;
+    G.n_bases = n_bases_readable - r0 * read_len;
+    G.n_reads = std::min(per, n_reads - r0);
+    G.uniform_len = read_len;
+    rc = minimizer_chunk(G, k, window, G.n_reads * nk, r0 * nk, nullptr, d_rows, d_valid, d_end, O, st);
+  }
+  if (rc == NTHASH_OK && !(d_min_hash || d_min_row)) {
+    e = launch_popcount(d_min_bits, total, d_count, st);
+    if (e != cudaSuccess) rc = fail(NTHASH_ERR_CUDA, "launch_popcount: %s", cudaGetErrorString(e));
+  }
+  if (d_valid) cudaFreeAsync(d_valid, st);
+  cudaFreeAsync(d_rows, st);
+  return rc;
+}
+
+// Host buffers: the bases go up (ASCII), the bitmap and the selected (hash, row) pairs come back; fixed-length reads when
+// read_off is NULL.  One stream, chunk after chunk (the selection needs each chunk's rows while they are cache-resident).
+int nthash_kmer_minimizers(const char* bases, const uint64_t* read_off, uint64_t n_reads, uint32_t uniform_read_len, uint32_t k,
+                           uint32_t window, uint32_t* min_bits, uint64_t* min_hash, uint64_t* min_row, uint64_t capacity, uint64_t* count,
+                           int device)
+{
+  if (int rc = minimizer_args(k, window, min_bits, count)) return rc;
+  *count = 0;
+  if (n_reads == 0) return NTHASH_OK;
+  if (!bases) return fail(NTHASH_ERR_INVALID_ARG, "bases must not be NULL");
+  if (!read_off && !uniform_read_len) return fail(NTHASH_ERR_INVALID_ARG, "give read_off or a uniform_read_len > 0");
+  if ((min_hash || min_row) && !capacity) return fail(NTHASH_ERR_INVALID_ARG, "capacity must be > 0 when the lists are requested");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(NTHASH_ERR_NO_DEVICE, "cannot select CUDA device %d", device);
+  if (int rc = check_device_ready()) return rc;
+  std::vector<uint64_t> koff;
+  uint64_t total, n_bases, base0 = 0;
+  if (read_off) {
+    koff.resize(n_reads + 1);
+    total = nthash_window_rows(read_off, n_reads, k, koff.data());
+    base0 = read_off[0];
+    n_bases = read_off[n_reads] - base0;
+  } else {
+    total = uniform_read_len >= k ? n_reads * (uint64_t)(uniform_read_len - k + 1) : 0;
+    n_bases = n_reads * (uint64_t)uniform_read_len;
+  }
+  std::fill(min_bits, min_bits + (total + 31) / 32, 0u);
+  if (total == 0) return NTHASH_OK;
+  cudaStream_t st = nullptr;
+  uint8_t* d_bases = nullptr;
+  uint32_t* d_bits = nullptr;
+  uint64_t *d_hash = nullptr, *d_row = nullptr, *d_count = nullptr, *d_off = nullptr, *d_rows = nullptr;
+  uint32_t* d_valid = nullptr;
+  std::vector<uint64_t> h_off;
+  int rc = NTHASH_OK;
+  auto cu = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess && rc == NTHASH_OK) rc = fail(NTHASH_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return e == cudaSuccess;
+  };
+  const uint64_t bwords = (total + 31) / 32;
+  const uint64_t cap = (min_hash || min_row) ? capacity : 0;
+  if (cu(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate") &&
+      cu(cudaMallocAsync(&d_bases, n_bases + 96, st), "cudaMallocAsync") && cu(cudaMallocAsync(&d_bits, bwords * 4 + 16, st), "cudaMallocAsync") &&
+      cu(cudaMallocAsync(&d_count, 8, st), "cudaMallocAsync") && (!min_hash || cu(cudaMallocAsync(&d_hash, cap * 8, st), "cudaMallocAsync")) &&
+      (!min_row || cu(cudaMallocAsync(&d_row, cap * 8, st), "cudaMallocAsync"))) {
+    cu(cudaMemcpyAsync(d_bases + 16, bases + base0, n_bases, cudaMemcpyHostToDevice, st), "H2D bases");
+    cu(cudaMemsetAsync(d_bits, 0, bwords * 4 + 16, st), "memset");
+    cu(cudaMemsetAsync(d_count, 0, 8, st), "memset");
+    const MinimizerOut O = { d_bits, d_hash, d_row, cap, d_count };
+    if (!read_off) {
+      // the device entry does its own chunking; its bitmap / count arguments are ours (it zeroes them again: harmless)
+      if (rc == NTHASH_OK)
+        rc = nthash_kmer_minimizer_uniform_dev(d_bases + 16, n_bases + 64, n_reads, uniform_read_len, k, window, d_bits, d_hash, d_row, cap, d_count, st);
+    } else {
+      // ragged: chunk boundaries where the dense row number is a multiple of 32 (whole bitmap words per chunk)
+      const uint64_t CH_ROWS = 8ull << 20;
+      uint64_t max_reads = 0, max_rows = 0;
+      std::vector<uint64_t> cut(1, 0);
+      for (uint64_t r = 0; r < n_reads;) {
+        uint64_t e = r + 1;
+        while (e < n_reads && (koff[e] - koff[r] < CH_ROWS || (koff[e] & 31))) ++e;
+        if (e < n_reads && (koff[e] & 31)) e = n_reads;
+        cut.push_back(e);
+        max_reads = std::max(max_reads, e - r);
+        max_rows = std::max(max_rows, koff[e] - koff[r]);
+        r = e;
+      }
+      const uint64_t words = (max_rows + 31) / 32 + 4;
+      if (cu(cudaMallocAsync(&d_off, 2 * (max_reads + 1) * 8, st), "cudaMallocAsync") && cu(cudaMallocAsync(&d_rows, (max_rows + 64) * 8, st), "cudaMallocAsync") &&
+          cu(cudaMallocAsync(&d_valid, 2 * words * 4, st), "cudaMallocAsync")) {
+        for (size_t c = 0; c + 1 < cut.size() && rc == NTHASH_OK; ++c) {
+          const uint64_t r0 = cut[c], r1 = cut[c + 1], nr = r1 - r0, rows = koff[r1] - koff[r0];
+          if (rows == 0) continue;
+          cu(cudaStreamSynchronize(st), "sync"); // h_off is reused
+          h_off.resize(2 * (nr + 1));
+          uint64_t mx = 0;
+          const uint64_t b0 = read_off[r0] & ~15ull; // chunk bases start on a 16-byte boundary of the device copy (base0 sits at +16)
+          const uint64_t shift = (read_off[r0] - base0) - ((read_off[r0] - base0) & ~15ull);
+          (void)b0;
+          for (uint64_t i = 0; i <= nr; ++i) {
+            h_off[i] = read_off[r0 + i] - read_off[r0] + shift;
+            h_off[nr + 1 + i] = koff[r0 + i] - koff[r0];
+            if (i < nr) mx = std::max(mx, read_off[r0 + i + 1] - read_off[r0 + i]);
+          }
+          cu(cudaMemcpyAsync(d_off, h_off.data(), 2 * (nr + 1) * 8, cudaMemcpyHostToDevice, st), "H2D offsets");
+          DevBatch G;
+          G.d_bases = d_bases + 16 + ((read_off[r0] - base0) & ~15ull);
+          G.n_bases = n_bases + 64 - ((read_off[r0] - base0) & ~15ull);
+          G.d_read_off = d_off;
+          G.d_koff = d_off + nr + 1;
+          G.n_reads = nr;
+          G.max_len = mx;
+          if (rc == NTHASH_OK) rc = minimizer_chunk(G, k, window, rows, koff[r0], d_off + nr + 1, d_rows, d_valid, d_valid + words, O, st);
+        }
+      }
+    }
+    if (rc == NTHASH_OK && !cap) cu(launch_popcount(d_bits, total, d_count, st), "launch_popcount");
+    cu(cudaMemcpyAsync(min_bits, d_bits, bwords * 4, cudaMemcpyDeviceToHost, st), "D2H bitmap");
+    cu(cudaMemcpyAsync(count, d_count, 8, cudaMemcpyDeviceToHost, st), "D2H count");
+    cu(cudaStreamSynchronize(st), "sync");
+    if (rc == NTHASH_OK && cap) {
+      const uint64_t n = std::min<uint64_t>(*count, cap);
+      if (min_hash) cu(cudaMemcpyAsync(min_hash, d_hash, n * 8, cudaMemcpyDeviceToHost, st), "D2H hashes");
+      if (min_row) cu(cudaMemcpyAsync(min_row, d_row, n * 8, cudaMemcpyDeviceToHost, st), "D2H rows");
+      cu(cudaStreamSynchronize(st), "sync");
+    }
+  }
+  for (void* q : { (void*)d_bases, (void*)d_bits, (void*)d_hash, (void*)d_row, (void*)d_count, (void*)d_off, (void*)d_rows, (void*)d_valid })
+    if (q) cudaFreeAsync(q, st);
+  if (st) {
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+  }
+  return rc;
+}
+
+// ---- fused consumer: ntCard-style cardinality sketch ---------------------------------------------------
+
+static int sketch_args(uint32_t k, uint32_t sample_bits, uint32_t index_bits, const uint32_t* d_counters, const uint64_t* d_result)
+{
+  if (int rc = check_kh(k, 1)) return rc;
+  if (sample_bits < 1 || index_bits < 1 || index_bits > 31 || sample_bits + index_bits > 63)
+    return fail(NTHASH_ERR_INVALID_ARG, "sample_bits=%u, index_bits=%u: need 1 <= sample_bits, 1 <= index_bits <= 31, sum <= 63", sample_bits, index_bits);
+  if (!d_counters || ((uintptr_t)d_counters & 3)) return fail(NTHASH_ERR_INVALID_ARG, "d_counters must not be NULL (4-byte aligned)");
+  if (!d_result) return fail(NTHASH_ERR_INVALID_ARG, "d_result must not be NULL");
+  return check_device_ready();
+}
+
+int nthash_kmer_sketch_uniform_dev(const uint8_t* d_bases, uint64_t n_bases_readable, uint64_t n_reads, uint32_t read_len, uint32_t k,
+                                   uint32_t sample_bits, uint32_t index_bits, uint32_t* d_counters, uint64_t* d_result, void* stream)
+{
+  if (int rc = sketch_args(k, sample_bits, index_bits, d_counters, d_result)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  NTH_CUDA(cudaMemsetAsync(d_result, 0, 3 * sizeof(uint64_t), st));
+  if (n_reads == 0 || read_len < k) return NTHASH_OK;
+  if (!d_bases || ((uintptr_t)d_bases & 15)) return fail(NTHASH_ERR_INVALID_ARG, "d_bases must be 16-byte aligned");
+  if (n_bases_readable < n_reads * (uint64_t)read_len) return fail(NTHASH_ERR_INVALID_ARG, "n_bases_readable smaller than n_reads*read_len");
+  DevBatch B;
+  B.d_bases = d_bases;
+  B.n_bases = n_bases_readable;
+  B.n_reads = n_reads;
+  B.uniform_len = read_len;
+  B.d_reduce = d_result;
+  B.d_bloom = d_counters;
+  B.bloom_bits = ((uint64_t)sample_bits << 8) | index_bits;
+  B.bloom_mode = 3;
+  return kmer_dev_run(B, k, 1, st);
+}
+
+int nthash_kmer_sketch_dev(const uint8_t* d_bases, uint64_t n_bases_readable, const uint64_t* d_read_off, const uint64_t* d_koff,
+                           uint64_t n_reads, uint64_t max_read_len, uint32_t k, uint32_t sample_bits, uint32_t index_bits,
+                           uint32_t* d_counters, uint64_t* d_result, void* stream)
+{
+  if (int rc = sketch_args(k, sample_bits, index_bits, d_counters, d_result)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  NTH_CUDA(cudaMemsetAsync(d_result, 0, 3 * sizeof(uint64_t), st));
+  if (n_reads == 0 || max_read_len < k) return NTHASH_OK;
+  if (!d_bases || ((uintptr_t)d_bases & 15)) return fail(NTHASH_ERR_INVALID_ARG, "d_bases must be 16-byte aligned");
+  if (!d_read_off || !d_koff) return fail(NTHASH_ERR_INVALID_ARG, "d_read_off and d_koff must not be NULL");
+  DevBatch B;
+  B.d_bases = d_bases;
+  B.n_bases = n_bases_readable;
+  B.d_read_off = d_read_off;
+  B.d_koff = d_koff;
+  B.n_reads = n_reads;
+  B.max_len = max_read_len;
+  B.d_reduce = d_result;
+  B.d_bloom = d_counters;
+  B.bloom_bits = ((uint64_t)sample_bits << 8) | index_bits;
+  B.bloom_mode = 3;
+  return kmer_dev_run(B, k, 1, st);
+}
+
 // ---- SeedNtHash -------------------------------------------------------------------------------
 
 int nthash_seed_plan_create(const char* const* seeds, uint32_t n_seeds, uint32_t k, uint32_t num_hashes_per_seed,

@@ -42,7 +42,7 @@ struct KmerParams
   // fused Bloom-filter consumer (reduce_out = {windows visited, windows whose bits were all set already, 0}):
   uint32_t* bloom_words = nullptr; // bit b of the filter = bit (b & 31) of word b >> 5
   uint64_t bloom_bits = 0;         // filter size in bits; bit index = hash % bloom_bits
-  uint32_t bloom_mode = 0;         // 0: none, 1: insert (atomicOr), 2: query
+  uint32_t bloom_mode = 0;         // 0: none, 1: insert (atomicOr), 2: query, 3: cardinality sketch (bloom_words = counters, bloom_bits = s << 8 | r)
   uint32_t tile_cap = 0; // bytes of base tile a CTA may stage
   bool use_tma = true;   // allow the fast kernel (kmer_fast_kernel.cu) when the request permits
   bool general_fits = true; // false: the general kernel's CTA tile would not fit shared memory (huge k) - fast kernel or nothing
@@ -122,10 +122,21 @@ cudaError_t launch_reduce_rows(const uint64_t* d_out, const uint32_t* d_valid, u
 // Dense rows -> only the rows whose validity bit is set, in order (what the reference's `while (roll())` loop yields).
 cudaError_t launch_compact_rows(const uint64_t* d_out, const uint32_t* d_valid, uint64_t rows, uint32_t H, uint64_t* d_compact,
                                 uint64_t* d_row_index, uint64_t* d_count, cudaStream_t st);
+cudaError_t launch_compact_rows_at(const uint64_t* d_out, const uint32_t* d_valid, uint64_t rows, uint32_t H, uint64_t* d_compact,
+                                   uint64_t* d_row_index, uint64_t* d_count, bool append, uint64_t row_offset, uint64_t capacity,
+                                   cudaStream_t st);
 // 2-bit packed bases (+ optional invalid-base bitmap) -> ASCII; bases [first_base, first_base + n_bases) of the packed
 // stream go to d_out[0 .. n_bases) (16-byte aligned, padded to a 16-byte multiple).
 cudaError_t launch_unpack2bit(const uint8_t* d_packed, const uint32_t* d_invalid, uint64_t first_base, uint64_t n_bases, uint8_t* d_out,
                               cudaStream_t st);
+// ---- minimizer selection (minimizer.cu): chunk-local hash rows + validity bitmap -> bits of the caller's bitmap ----
+// d_end_bits: one bit per chunk row, set on the last row of every read (memset + marked here; (rows+31)/32 + 3 words).
+cudaError_t launch_mark_read_ends(uint32_t* d_end_bits, uint64_t rows, const uint64_t* d_koff, uint64_t n_reads, uint32_t uniform_nk,
+                                  cudaStream_t st);
+// one thread per window of w consecutive k-mers; d_valid / d_end_bits need two readable words past their last one
+cudaError_t launch_minimizer_select(const uint64_t* d_rows, const uint32_t* d_valid, const uint32_t* d_end_bits, uint64_t n_rows, uint32_t w,
+                                    uint32_t* d_min_bits, uint64_t row0, cudaStream_t st);
+cudaError_t launch_popcount(const uint32_t* d_bits, uint64_t n_bits, uint64_t* d_count, cudaStream_t st);
 // Expands reads into items (only needed when some read exceeds the whole-read tile budget).  The tables hold `cap` + 1
 // entries, `cap` >= the true item count (a host-side bound); the surplus is padded with empty items.
 cudaError_t launch_item_fill(const uint64_t* read_off, const uint64_t* koff, uint64_t n_reads, uint32_t k,

@@ -238,7 +238,7 @@ constexpr uint32_t ROW1_BYTES = 272;
 // and ONE elected lane issues a 3-D tensor store (cp.async.bulk.tensor.3d -> UTMASTG) of box 8 x 32 x blocks:
 // the same WS*H*8 contiguous bytes per row, without the 32-iteration issue loop a per-lane bulk copy costs.
 //
-// CONS: 0 = store the hashes; 1 = REDUCE (count / sum / xor); 2 / 3 = Bloom-filter insert / query (runtime number
+// CONS: 0 = store the hashes; 1 = REDUCE (count / sum / xor); 5 = cardinality sketch; 2 / 3 = Bloom-filter insert / query (runtime number
 // of hashes P.h; position = hash % P.bloom_bits; counts the windows whose positions were all set already).
 template<int H, int CONS, int WS, int NBUF, bool BOX>
 __global__ void __launch_bounds__(256)
@@ -433,6 +433,14 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
             acc_sum += e;
             acc_xor ^= e;
           }
+        }
+      } else if (CONS == 5) {
+        // ntCard-style cardinality sketch: of the k-mers whose canonical hash has its top s bits clear (a 2^-s sample),
+        // count the multiplicity of the next r bits in a table of 2^r counters (bloom_bits = s << 8 | r)
+        const uint32_t sb = (uint32_t)(P.bloom_bits >> 8), rb = (uint32_t)(P.bloom_bits & 0xFF);
+        if ((h0 >> (64 - sb)) == 0) {
+          atomicAdd(P.bloom_words + (uint32_t)((h0 >> (64 - sb - rb)) & ((1ull << rb) - 1)), 1u);
+          acc_sum += 1; // k-mers sampled
         }
       } else { // Bloom filter: P.h positions per window (extend_hashes, src/internal.hpp:104-118, with a runtime count)
         const uint64_t kmul = P.mult[0]; // k * MULTISEED
@@ -1214,8 +1222,9 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
   }
   if (P.bloom_mode) { // runtime number of hashes; mult[0] carries k * MULTISEED
     P.mult[0] = (uint64_t)P.k * MULTISEED;
-    return P.bloom_mode == 1 ? launch_fast_t<1, 2, fast_ws<1>(0), 1, false>(P, c.nt, st)
-                             : launch_fast_t<1, 3, fast_ws<1>(0), 1, false>(P, c.nt, st);
+    return P.bloom_mode == 1   ? launch_fast_t<1, 2, fast_ws<1>(0), 1, false>(P, c.nt, st)
+           : P.bloom_mode == 2 ? launch_fast_t<1, 3, fast_ws<1>(0), 1, false>(P, c.nt, st)
+                               : launch_fast_t<1, 5, fast_ws<1>(0), 1, false>(P, c.nt, st); // 3: cardinality sketch
   }
   switch (P.h) {
     case 1: e = launch_fast_h<1>(P, c, st); break;

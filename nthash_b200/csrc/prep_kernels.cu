@@ -200,11 +200,12 @@ __global__ void compact_count(const uint32_t* valid, uint64_t rows, uint64_t* bl
 }
 
 // one block: exclusive scan of the block sums in place, total to *count
-__global__ void compact_scan(uint64_t* block_sums, uint64_t nb, uint64_t* count)
+// `append`: *count holds the number of entries already written by earlier chunks: offsets start there and it is advanced
+__global__ void compact_scan(uint64_t* block_sums, uint64_t nb, uint64_t* count, bool append)
 {
   __shared__ uint64_t carry;
   __shared__ uint64_t ws[32];
-  if (threadIdx.x == 0) carry = 0;
+  if (threadIdx.x == 0) carry = append ? *count : 0;
   __syncthreads();
   for (uint64_t base = 0; base < nb; base += blockDim.x) {
     const uint64_t i = base + threadIdx.x;
@@ -229,7 +230,7 @@ __global__ void compact_scan(uint64_t* block_sums, uint64_t nb, uint64_t* count)
 // every warp walks its 32 bitmap words; for one word the 32 lanes are 32 consecutive rows (coalesced reads), the kept
 // ones land at consecutive compact rows
 __global__ void compact_write(const uint64_t* out, const uint32_t* valid, uint64_t rows, uint32_t H, const uint64_t* block_off,
-                              uint64_t* compact, uint64_t* row_index)
+                              uint64_t* compact, uint64_t* row_index, uint64_t row_offset, uint64_t capacity)
 {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t w0 = (uint64_t)blockIdx.x * CMP_T + warp * 32, nw = (rows + 31) / 32;
@@ -254,8 +255,10 @@ __global__ void compact_write(const uint64_t* out, const uint32_t* valid, uint64
     const uint64_t dst0 = base + __shfl_sync(0xffffffffu, excl, j);
     if (word >> lane & 1u) {
       const uint64_t r = (w0 + j) * 32 + lane, d = dst0 + __popc(word & ((1u << lane) - 1u));
-      for (uint32_t q = 0; q < H; ++q) compact[d * H + q] = out[r * H + q];
-      if (row_index) row_index[d] = r;
+      if (d >= capacity) continue;
+      if (compact)
+        for (uint32_t q = 0; q < H; ++q) compact[d * H + q] = out[r * H + q];
+      if (row_index) row_index[d] = row_offset + r;
     }
   }
 }
@@ -312,14 +315,23 @@ cudaError_t launch_reduce_rows(const uint64_t* d_out, const uint32_t* d_valid, u
 cudaError_t launch_compact_rows(const uint64_t* d_out, const uint32_t* d_valid, uint64_t rows, uint32_t H, uint64_t* d_compact,
                                 uint64_t* d_row_index, uint64_t* d_count, cudaStream_t st)
 {
-  if (rows == 0) return cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st);
+  return launch_compact_rows_at(d_out, d_valid, rows, H, d_compact, d_row_index, d_count, false, 0, ~0ull, st);
+}
+
+// append = true: entries go behind the *d_count already there (chunked producers on one stream), row numbers are shifted
+// by row_offset, and nothing is written past `capacity` entries (the count keeps counting).
+cudaError_t launch_compact_rows_at(const uint64_t* d_out, const uint32_t* d_valid, uint64_t rows, uint32_t H, uint64_t* d_compact,
+                                   uint64_t* d_row_index, uint64_t* d_count, bool append, uint64_t row_offset, uint64_t capacity,
+                                   cudaStream_t st)
+{
+  if (rows == 0) return append ? cudaSuccess : cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st);
   const uint64_t nb = (rows + CMP_ROWS - 1) / CMP_ROWS;
   uint64_t* sums = nullptr;
   cudaError_t e = cudaMallocAsync(&sums, nb * sizeof(uint64_t), st);
   if (e != cudaSuccess) return e;
   compact_count<<<(unsigned)nb, CMP_T, 0, st>>>(d_valid, rows, sums);
-  compact_scan<<<1, 1024, 0, st>>>(sums, nb, d_count);
-  compact_write<<<(unsigned)nb, CMP_T, 0, st>>>(d_out, d_valid, rows, H, sums, d_compact, d_row_index);
+  compact_scan<<<1, 1024, 0, st>>>(sums, nb, d_count, append);
+  compact_write<<<(unsigned)nb, CMP_T, 0, st>>>(d_out, d_valid, rows, H, sums, d_compact, d_row_index, row_offset, capacity);
   e = cudaGetLastError();
   cudaFreeAsync(sums, st);
   return e;

@@ -148,3 +148,35 @@ def _load():
 
 
 ORACLE, REF = _load()
+
+
+# ---- consumers restated on top of the oracle's hash rows (numpy; what the fused GPU consumers must reproduce) -------------
+def minimizer_bits(out0, valid, koff, w):
+    """Boolean [rows]: row j is the leftmost minimum of hashes()[0] over the visited k-mers of at least one window of w
+    consecutive k-mers of its read (include/nthash_b200.h: nthash_kmer_minimizer_*).  out0: uint64 [rows], valid: bool
+    [rows], koff: dense row offsets of the reads."""
+    from numpy.lib.stride_tricks import sliding_window_view
+    out0 = np.asarray(out0, np.uint64)
+    valid = np.asarray(valid).astype(bool)
+    sel = np.zeros(len(out0), bool)
+    big = np.uint64(0xFFFFFFFFFFFFFFFF)
+    for r in range(len(koff) - 1):
+        a, b = int(koff[r]), int(koff[r + 1])
+        if b - a < w:
+            continue
+        key = np.where(valid[a:b], out0[a:b], big)      # an unvisited k-mer never wins (a visited one equal to 2^64-1: 2^-64)
+        kw = sliding_window_view(key, w)
+        m = kw.argmin(axis=1)                           # first occurrence = leftmost
+        anyv = sliding_window_view(valid[a:b], w).any(axis=1)
+        pos = (np.arange(len(m)) + m)[anyv]
+        sel[a + pos] = True
+    return sel
+
+
+def sketch_counts(out0, valid, sample_bits, index_bits):
+    """ntCard-style table: multiplicity of the index_bits below the top sample_bits of every visited k-mer's canonical hash
+    whose top sample_bits are zero -> (counters uint32 [2^index_bits], number sampled)."""
+    h = np.asarray(out0, np.uint64)[np.asarray(valid).astype(bool)]
+    s = h[(h >> np.uint64(64 - sample_bits)) == 0]
+    idx = ((s >> np.uint64(64 - sample_bits - index_bits)) & np.uint64((1 << index_bits) - 1)).astype(np.int64)
+    return np.bincount(idx, minlength=1 << index_bits).astype(np.uint32), len(s)
