@@ -637,9 +637,44 @@ def main():
                 subs[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
                 torch.cuda.empty_cache()
         line["configs"] = subs
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["class_api"] = class_api_record()
     if rank == 0:
         print(json.dumps(line))
     nd.finalize()
+
+
+def class_api_record():
+    """The reference's C++ class loop (`NtHash h(read, ...); while (h.roll()) ...`, examples/benchmark.cpp:31-39) timed
+    through this repo's drop-in header against the unmodified reference, both compiled from tests/cpp/class_bench.cpp
+    (oracle/Makefile).  Short reads are rolled on the host by the header (no GPU round trip per object); one long sequence
+    goes through the CUDA engine in bounded chunks.  Single host thread in both builds."""
+    rec = {}
+    cases = {"short_reads": ["kmer", "300000", "100", "64", "3"],       # the shape of the reference's own benchmark
+             "long_sequence": ["kmer", "1", "100000000", "31", "1"],    # one 100 Mbp sequence
+             "seed_long_sequence": ["seed", "1", "20000000", "3"]}
+    for name, argv in cases.items():
+        r = {}
+        for which in ("ref", "shim"):
+            exe = os.path.join(ROOT, "oracle", "_ref", "class_bench_" + which)
+            if not os.path.exists(exe):
+                r[which] = {"unavailable": "oracle/_ref/class_bench_%s not built" % which}
+                continue
+            try:
+                env = dict(os.environ, NTHASH_BENCH_PASSES="2", NTHASH_BENCH_NO_STRANDS="1")
+                out = subprocess.run([exe] + argv, capture_output=True, text=True, timeout=300, env=env)
+                j = json.loads(out.stdout.strip().splitlines()[-1])
+                # first pass (pays the CUDA context once per process) and the better of two passes
+                r[which] = {"windows_per_sec": j["windows_per_sec_best"], "windows_per_sec_first_pass": j["windows_per_sec"],
+                            "seconds": j["seconds_best"], "max_rss_mb": j["max_rss_mb"], "sum": j["sum"], "windows": j["windows"]}
+            except Exception as e:
+                r[which] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        if "sum" in r.get("ref", {}) and "sum" in r.get("shim", {}):
+            r["bit_exact"] = r["ref"]["sum"] == r["shim"]["sum"] and r["ref"]["windows"] == r["shim"]["windows"]
+            r["shim_over_ref"] = r["shim"]["windows_per_sec"] / r["ref"]["windows_per_sec"]
+        r["workload"] = " ".join(argv)
+        rec[name] = r
+    return rec
 
 
 def extra_consumers(torch, nthash_b200, nd, w, args, world):
