@@ -320,14 +320,15 @@ def sub_record(torch, nthash_b200, LIB, nd, name, args, rank, world, peak, want_
     cfg = dict(CONFIGS[name])
     w = Workload(torch, nthash_b200, LIB, cfg, rank)
     steps = max(3, min(args.steps, args.sub_steps))
-    ms_valid, _ = w.time_steps(steps, True, 2)
-    nd.barrier()
-    ms, each = w.time_steps(steps, False, 1)
+    with ClockSampler(torch.cuda.current_device()) as clk:  # these launches run for 50-100 ms back to back: note what the clocks did
+        ms_valid, _ = w.time_steps(steps, True, 2)
+        nd.barrier()
+        ms, each = w.time_steps(steps, False, 1)
     ms_valid, ms = nd.max_over_ranks([ms_valid, ms])
     abytes = algorithmic_bytes(w.n, w.L, w.k, w.H)
     achieved = abytes / (ms * 1e-3) / 1e9
     rec = {"workload": cfg["desc"], "reads_per_gpu": w.n, "n_gpus": world, "value": world * w.rows / (ms_valid * 1e-3), "unit": UNIT,
-           "ms_per_step": ms_valid, "steps": steps,
+           "ms_per_step": ms_valid, "steps": steps, "clocks": clk.summary(),
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "kernel": w.kernel_name(), "kernel_ms": ms, "kernel_ms_best": each[0], "kernel_ms_median": statistics.median(each),
                         "algorithmic_bytes_per_launch": abytes,

@@ -30,7 +30,9 @@ def build(force=False, verbose=False):
     """Compile every .cu under csrc/ into one shared library.  nvcc cross-compiles without a GPU."""
     if not force and not stale():
         return LIB
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    # NTHASH_B200_NVCC_FLAGS / NTHASH_B200_LIB_OUT: experiments (e.g. an A/B build with -DNTH_ROLL_V1 next to the product library)
+    extra = os.environ.get("NTHASH_B200_NVCC_FLAGS", "").split()
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", os.environ.get("NTHASH_B200_LIB_OUT", LIB)] + sources()
     subprocess.run(cmd, check=True)
     return LIB
 

@@ -1477,8 +1477,35 @@ int nthash_seed_batch(const char* bases, const uint64_t* read_off, uint64_t n_re
   return host_pipeline(hb, [&](const DevBatch& B, cudaStream_t st) { return seed_dev_run(plan, B, st); });
 }
 
-// SeedNtHash consumer (two passes on the device: the seed kernels write a chunk of rows, a reduction reads them back; no
-// hash crosses PCIe).  result = {windows visited, sum, xor} over all n_seeds * num_hashes_per_seed values.
+// Fused SeedNtHash consumer for a uniform device-resident batch: the specialised kernel accumulates count / sum / xor of
+// every item without a byte for the exact path (no hash is stored), a second small launch redoes the flagged items window
+// by window.  Adds into d_result (not cleared here).  Returns 1 when the fused form does not apply to this plan / geometry.
+static int seed_reduce_fused(const nthash_seed_plan* plan, const uint8_t* d_bases, uint64_t n_bases, uint64_t n_reads, uint32_t read_len,
+                             uint64_t* d_result, cudaStream_t st)
+{
+  if (getenv("NTHASH_B200_DISABLE_SEED_JIT")) return 1;
+  SeedParams P;
+  fill_seed_params(plan, P);
+  P.bases = d_bases;
+  P.n_bases = n_bases;
+  P.reduce_out = d_result;
+  if (!plan_uniform(n_reads, read_len, P.k, P.g, P.tile_cap)) return 1;
+  if (!seed_jit_reduce_applies(plan->jit, P)) return 1;
+  uint8_t* d_dirty = nullptr;
+  NTH_CUDA(cudaMallocAsync(&d_dirty, n_reads + P.g.n_items, st));
+  cudaError_t e = cudaMemsetAsync(d_dirty, 0, n_reads + P.g.n_items, st);
+  P.read_dirty = d_dirty;
+  P.item_dirty = d_dirty + n_reads;
+  if (e == cudaSuccess) e = launch_seed_jit(plan->jit, P, st);
+  if (e == cudaSuccess) e = launch_seed_reduce_dirty(P, n_reads, st);
+  cudaFreeAsync(d_dirty, st);
+  NTH_CUDA(e);
+  return NTHASH_OK;
+}
+
+// SeedNtHash consumer: fused into the specialised kernel for fixed-length reads (seed_reduce_fused); otherwise two passes on
+// the device (the seed kernels write a chunk of rows, a reduction reads them back).  No hash crosses PCIe either way.
+// result = {windows visited, sum, xor} over all n_seeds * num_hashes_per_seed values.
 int nthash_seed_reduce(const char* bases, const uint64_t* read_off, uint64_t n_reads, const char* const* seeds, uint32_t n_seeds,
                        uint32_t k, uint32_t num_hashes_per_seed, uint64_t* result, int device)
 {
@@ -1495,6 +1522,10 @@ int nthash_seed_reduce(const char* bases, const uint64_t* read_off, uint64_t n_r
   hb.reduce_result = result;
   hb.scratch_rows = true;
   const int rc = host_pipeline(hb, [&](const DevBatch& B, cudaStream_t st) {
+    if (B.uniform_len) {
+      const int f = seed_reduce_fused(plan, B.d_bases, B.n_bases, B.n_reads, B.uniform_len, B.d_reduce, st);
+      if (f != 1) return f;
+    }
     if (int r = seed_dev_run(plan, B, st)) return r;
     NTH_CUDA(launch_reduce_rows(B.d_out, B.d_valid, B.valid_row0, B.rows, H, B.d_reduce, st));
     return (int)NTHASH_OK;
@@ -1515,7 +1546,11 @@ int nthash_seed_reduce_uniform_dev(const nthash_seed_plan* plan, const uint8_t* 
   if (!d_bases || ((uintptr_t)d_bases & 15)) return fail(NTHASH_ERR_INVALID_ARG, "d_bases must be 16-byte aligned");
   if (n_bases_readable < n_reads * (uint64_t)read_len)
     return fail(NTHASH_ERR_INVALID_ARG, "n_bases_readable smaller than n_reads*read_len");
-  // chunks of reads whose rows fit a fixed scratch buffer (~512 MB of hashes); chunk starts stay 16-byte aligned
+  {
+    const int f = seed_reduce_fused(plan, d_bases, n_bases_readable, n_reads, read_len, d_result, st);
+    if (f != 1) return f;
+  }
+  // two passes: chunks of reads whose rows fit a fixed scratch buffer (~512 MB of hashes); chunk starts stay 16-byte aligned
   const uint64_t nk = read_len - k + 1;
   uint64_t per = std::max<uint64_t>(16, ((64ull << 20) / (nk * H)) & ~15ull);
   per = std::min<uint64_t>(per, (n_reads + 15) & ~(uint64_t)15);

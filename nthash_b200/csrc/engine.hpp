@@ -49,6 +49,7 @@ struct KmerParams
   uint64_t s[4], sk[4], mult[4]; // filled by launch_kmer
   uint32_t prefetch_ctas = 0;    // fast kernel: L2-prefetch the base tile this many CTAs ahead (0 = off)
   const uint4* t4 = nullptr;     // tetramer warm-up table (fast kernel only), filled by launch_kmer_fast
+  uint32_t two = 2;              // the constant 2 as a kernel parameter (roll_step: keeps a multiply on the FMA pipe)
 };
 
 uint32_t kmer_smem_bytes(uint32_t tile_cap);
@@ -75,6 +76,8 @@ struct SeedParams
   uint64_t* out_fwd = nullptr;
   uint64_t* out_rev = nullptr;
   uint8_t* read_dirty = nullptr; // one byte per read, zeroed by the caller
+  uint64_t* reduce_out = nullptr; // fused consumer (uniform batches, specialised kernel): {windows visited, sum, xor}; no outputs then
+  uint8_t* item_dirty = nullptr;  // fused consumer: one byte per item, zeroed by the caller
   uint32_t tile_cap = 0;
   const uint8_t* plan_blob = nullptr; // device copy of SeedPlanHost::blob
   uint32_t plan_smem_bytes = 0, groups_off = 0, tables_off = 0, care_off = 0, refblk_off = 0, care_words = 0;
@@ -84,6 +87,7 @@ struct SeedParams
 uint32_t seed_smem_bytes(uint32_t plan_smem, uint32_t tile_cap);
 cudaError_t launch_seed(SeedParams P, uint64_t n_reads, cudaStream_t st);      // generic hash kernel + emission replay
 cudaError_t launch_seed_emit(const SeedParams& P, uint64_t n_reads, cudaStream_t st); // emission replay only
+cudaError_t launch_seed_reduce_dirty(const SeedParams& P, uint64_t n_reads, cudaStream_t st); // fused consumer: the flagged items, exactly
 
 // Seed kernel specialised per seed set at run time (seed_jit.cu).
 struct SeedJit;
@@ -93,6 +97,7 @@ void seed_jit_destroy(SeedJit* j);
 bool seed_jit_compile_all(const SeedPlanHost& plan, std::string& why); // every variant, compile only (no GPU needed)
 const char* seed_jit_source(const SeedJit* j);
 bool seed_jit_applies(const SeedJit* j, const SeedParams& P);
+bool seed_jit_reduce_applies(const SeedJit* j, const SeedParams& P); // fused consumer variant (P.reduce_out)
 cudaError_t launch_seed_jit(const SeedJit* j, const SeedParams& P, cudaStream_t st);
 
 // BlindNtHash::roll / peek over n independent (fwd, rev) states (blind_kernel.cu).

@@ -119,22 +119,55 @@ constexpr int LUT_OR_AND = 0xF0 | (0xCC & 0xAA);                 // a | (b & c)
 constexpr int LUT_XOR_AND = (0xF0 ^ 0xCC) & 0xAA;                // (a ^ b) & c
 constexpr int LUT_XOR3 = 0xF0 ^ 0xCC ^ 0xAA;                     // a ^ b ^ c
 
-// F <- srol(F) ^ e.xy ; R <- sror(R ^ e.zw) with one combined table entry (12 ALU-pipe ops + 1 IMAD)
-NTH_D void roll_step(State& s, const uint4 e)
+// F <- srol(F) ^ e.xy ; R <- sror(R ^ e.zw) with one combined table entry: 10 ALU-pipe ops + 3 on the FMA pipe
+// (IMAD.SHL / IMAD.HI stand in for the plain shifts).
+// NTH_ROLL_V2 (round-2 experiment, off): 8 ALU + 7 FMA-pipe ops — "x + (x << 31)" as one IMAD, the bit that crosses from the
+// low into the high word as the addend of an IMAD.HI whose multiplier 2 comes from the constant bank (`two`; a literal 2
+// is strength-reduced back into an ALU-pipe LEA.HI).  ALU-pipe instructions per window fell 12.5 -> 10.9, the total rose
+// 21 -> 22.5, and on the same box the store kernels got 1-1.5 % SLOWER (C2 1.809 -> 1.836 ms, C5 1.007 -> 1.019, C4 10.29 ->
+// 10.38; only the store-free reduce consumer gained, 1.657 -> 1.595-1.648): issue slots and latency, not the ALU pipe, are
+// what these kernels run out of (profiles/r02_ab_roll_step.txt).
+NTH_D uint32_t mad_hi(uint32_t a, uint32_t b, uint32_t c)
 {
+  uint32_t d;
+  asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+NTH_D void roll_step(State& s, const uint4 e, const uint32_t two)
+{
+#ifndef NTH_ROLL_V2
   {
     const uint32_t lo = s.flo, hi = s.fhi;
-    const uint32_t hi1 = __funnelshift_l(lo, hi, 1);              // (hi:lo << 1) high word
-    const uint32_t nhi = lop3<LUT_SEL_C>(hi1, __umulhi(hi, 4u), 2u); // bit 33 <- old bit 63 (hi >> 30 as IMAD.HI: FMA pipe)
-    const uint32_t nlo = lop3<LUT_OR_AND>(lo + lo, hi, 1u);       // bit 0  <- old bit 32
+    const uint32_t hi1 = __funnelshift_l(lo, hi, 1);
+    const uint32_t nhi = lop3<LUT_SEL_C>(hi1, __umulhi(hi, 4u), 2u);
+    const uint32_t nlo = lop3<LUT_OR_AND>(lo + lo, hi, 1u);
+    s.flo = nlo ^ e.x;
+    s.fhi = nhi ^ e.y;
+  }
+  {
+    const uint32_t lo = s.rlo ^ e.z, hi = s.rhi ^ e.w;
+    s.rlo = __funnelshift_r(lo, hi, 1);
+    const uint32_t y = __funnelshift_r(hi, __umulhi(hi, 0x80000000u), 1);
+    s.rhi = lop3<LUT_SEL_C>(y, lo, 1u);
+  }
+  (void)two;
+  return;
+#endif
+  {
+    const uint32_t lo = s.flo, hi = s.fhi;
+    // 31-bit field (bits 31:1 of hi) rotated left by one, bit 0 clear: bits 31:2 <- hi << 1, bit 1 <- old bit 31
+    const uint32_t ch = lop3<LUT_SEL_C>(hi * 2u, __umulhi(hi, 4u), 2u);
+    const uint32_t nhi = mad_hi(lo, two, ch);                     // bit 0 (word bit 32) <- old bit 31 of lo
+    const uint32_t nlo = lop3<LUT_OR_AND>(lo * 2u, hi, 1u);       // bit 0 <- old bit 32
     s.flo = nlo ^ e.x;
     s.fhi = nhi ^ e.y;
   }
   {
     const uint32_t lo = s.rlo ^ e.z, hi = s.rhi ^ e.w;
     s.rlo = __funnelshift_r(lo, hi, 1);                           // bit 31 <- old bit 32
-    const uint32_t y = __funnelshift_r(hi, __umulhi(hi, 0x80000000u), 1); // bit 31 <- old bit 33 (hi bit 1); hi >> 1 as IMAD.HI
-    s.rhi = lop3<LUT_SEL_C>(y, lo, 1u);                           // bit 32 <- old bit 0
+    const uint32_t a = __umulhi(hi, 0x80000000u);                 // hi >> 1: bits 30:1 in place, bit 0 = old bit 33
+    const uint32_t y = a * 0x80000001u;                           // a + (a << 31): bit 31 (word bit 63) <- old bit 33
+    s.rhi = lop3<LUT_SEL_C>(y, lo, 1u);                           // bit 0 (word bit 32) <- old bit 0
   }
 }
 
@@ -398,7 +431,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
       const uint32_t v = lds_u8(lut + c);
       bad |= v;
       if (REDUCE) run = v ? 0 : run + 1;
-      roll_step(s, lds_v4(sbase + F_IN_OFF + ((c & 6u) << 3)));
+      roll_step(s, lds_v4(sbase + F_IN_OFF + ((c & 6u) << 3)), P.two);
     }
   }
   if (!MERGE) __syncthreads(); // the tetramer table is dead from here on: its bytes become row buffers
@@ -411,7 +444,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     if (REDUCE) run = v ? 0 : run + 1;
     const uint32_t ea = pair + (((ci & 6u) << 4) | ((co & 6u) << 2));
     const uint2 ef = lds_v2(ea), er = lds_v2(ea + (F_PAIR_R_OFF - F_PAIR_OFF));
-    roll_step(s, make_uint4(ef.x, ef.y, er.x, er.y));
+    roll_step(s, make_uint4(ef.x, ef.y, er.x, er.y), P.two);
     return canonical2(s);
   };
   auto consume = [&](uint64_t h0) { // one window the reference visits
@@ -559,7 +592,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
       for (int i = 0; i < 4; ++i) {
         const uint32_t ea = __byte_perm(c4, pair, 0x7650u | i);
         const uint2 ef = lds_v2(ea), er = lds_v2(ea + (F_PAIR_R_OFF - F_PAIR_OFF));
-        roll_step(s, make_uint4(ef.x, ef.y, er.x, er.y));
+        roll_step(s, make_uint4(ef.x, ef.y, er.x, er.y), P.two);
         consume(canonical2(s));
       }
       run += 4;
@@ -576,7 +609,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
       }
       const uint32_t ea = __byte_perm(c4, pair, 0x7650u | i); // (pair & ~0xFF) | byte i of c4
       const uint2 ef = lds_v2(ea), er = lds_v2(ea + (F_PAIR_R_OFF - F_PAIR_OFF));
-      roll_step(s, make_uint4(ef.x, ef.y, er.x, er.y));
+      roll_step(s, make_uint4(ef.x, ef.y, er.x, er.y), P.two);
       hv[i] = canonical2(s);
       if (STR) {
         fw4[i] = ((uint64_t)s.fhi << 32) | s.flo;
@@ -923,12 +956,13 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
 // lanes per item: every lane hashes its own run of windows from scratch straight out of global memory, the way the main
 // kernel does it — k in-only steps (four bases at a time through the tetramer table; base_forward_hash /
 // base_reverse_hash, src/kmer.cpp:43-73, :123-152) starting one base early, then NtHash::roll (src/kmer.cpp:246-264).
-constexpr uint32_t FIX_LANES = 8;
-__global__ void __launch_bounds__(128) kmer_flat_fix_kernel(const __grid_constant__ KmerParams P, uint64_t n_reads)
+constexpr uint32_t FIX_LANES = 32; // a warp per item: its bytes are staged once (coalesced), every lane hashes n / 32 windows
+__global__ void __launch_bounds__(128) kmer_flat_fix_kernel(const __grid_constant__ KmerParams P, uint64_t n_reads, uint32_t warp_bytes)
 {
-  const uint64_t f = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / FIX_LANES;
-  const uint32_t sub = threadIdx.x % FIX_LANES;
-  if (f >= n_reads) return;
+  extern __shared__ __align__(16) uint8_t fix_smem[];
+  const uint32_t wpb = blockDim.x / FIX_LANES, warp = threadIdx.x / FIX_LANES, sub = threadIdx.x % FIX_LANES;
+  const uint64_t f = (uint64_t)blockIdx.x * wpb + warp;
+  if (f >= n_reads) return; // whole warps leave together
   const uint64_t nk = P.g.nk, seg = P.g.seg, w_tail = P.g.total / seg * seg;
   uint64_t w0;
   uint32_t n;
@@ -940,13 +974,20 @@ __global__ void __launch_bounds__(128) kmer_flat_fix_kernel(const __grid_constan
     const uint32_t rem = (uint32_t)(w0 % seg);
     n = (rem && w0 < w_tail) ? (uint32_t)min(seg - rem, nk) : 0u;
   }
+  if (n == 0) return;
+  const uint32_t k = P.k, h = P.h;
+  // the item's bytes -1 .. n+k-2 (byte -1 exists: f >= 1 items start a read that is not the first, and the batch's tail
+  // item never starts at base 0 of the batch because flat batches hold at least two full items)
+  const uint64_t r = w0 / nk;
+  const uint8_t* g0 = P.bases + r * P.g.read_len + (w0 - r * nk) - 1;
+  uint8_t* sb = fix_smem + (size_t)warp * warp_bytes;
+  for (uint32_t j = sub; j < n + k; j += FIX_LANES) sb[j] = g0[j];
+  __syncwarp();
   const uint32_t per = (n + FIX_LANES - 1) / FIX_LANES, p_lo = min(n, sub * per), p_hi = min(n, p_lo + per);
   if (p_lo >= p_hi) return;
-  const uint64_t r = w0 / nk;
-  const uint8_t* sq = P.bases + r * P.g.read_len + (w0 - r * nk) + p_lo; // first base of this lane's first window; sq[-1] exists
+  const uint8_t* sq = sb + 1 + p_lo; // first base of this lane's first window; sq[-1] is staged
   w0 += p_lo;
   n = p_hi - p_lo;
-  const uint32_t k = P.k, h = P.h;
   // 2-bit code (byte >> 1) & 3: 0 = A, 1 = C, 2 = T/U, 3 = G; index into P.s / P.sk (A, C, G, T) = code ^ (code >> 1)
   auto sidx = [](uint32_t c) { const uint32_t x = (c >> 1) & 3u; return x ^ (x >> 1); };
   State st = { 0u, 0u, 0u, 0u };
@@ -960,7 +1001,7 @@ __global__ void __launch_bounds__(128) kmer_flat_fix_kernel(const __grid_constan
   for (uint32_t j = 4 * nq; j < k; ++j) { // bases j-1
     const uint32_t c = sq[j - 1];
     const uint64_t fi = P.s[sidx(c)], ri = P.sk[sidx(c ^ 4u)]; // c ^ 4 flips code bit 1: the complement
-    roll_step(st, make_uint4((uint32_t)fi, (uint32_t)(fi >> 32), (uint32_t)ri, (uint32_t)(ri >> 32)));
+    roll_step(st, make_uint4((uint32_t)fi, (uint32_t)(fi >> 32), (uint32_t)ri, (uint32_t)(ri >> 32)), P.two);
   }
   // hashable bases in a row, ending at base k-2
   for (uint32_t j = 0; j + 1 < k; ++j) run = is_acgtu(sq[j]) ? run + 1 : 0;
@@ -968,7 +1009,7 @@ __global__ void __launch_bounds__(128) kmer_flat_fix_kernel(const __grid_constan
     const uint32_t cin = sq[p + k - 1], cout = sq[(int)p - 1];
     run = is_acgtu(cin) ? run + 1 : 0;
     const uint64_t fe = P.s[sidx(cin)] ^ P.sk[sidx(cout)], re = P.sk[sidx(cin ^ 4u)] ^ P.s[sidx(cout ^ 4u)];
-    roll_step(st, make_uint4((uint32_t)fe, (uint32_t)(fe >> 32), (uint32_t)re, (uint32_t)(re >> 32)));
+    roll_step(st, make_uint4((uint32_t)fe, (uint32_t)(fe >> 32), (uint32_t)re, (uint32_t)(re >> 32)), P.two);
     const uint64_t w = w0 + p, h0 = canonical2(st);
     uint64_t* o = P.out + w * h;
     if (run >= k) {
@@ -1238,7 +1279,14 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
   }
   if (e == cudaSuccess && P.g.flat) { // rows behind every read boundary + the partial last item, after the junk has landed
     const uint64_t n_reads = P.g.total / P.g.nk;
-    kmer_flat_fix_kernel<<<(unsigned)((n_reads * FIX_LANES + 127) / 128), 128, 0, st>>>(P, n_reads);
+    const uint32_t warp_bytes = (P.g.seg + P.k + 16 + 15) & ~15u; // bytes -1 .. n+k-2 of one item, n <= seg
+    const uint32_t wpb = std::max(1u, std::min(4u, (200u * 1024u) / warp_bytes));
+    if (warp_bytes > 200u * 1024u) return cudaErrorInvalidConfiguration;
+    if (wpb * warp_bytes > 48u * 1024u) {
+      e = cudaFuncSetAttribute(kmer_flat_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wpb * warp_bytes));
+      if (e != cudaSuccess) return e;
+    }
+    kmer_flat_fix_kernel<<<(unsigned)((n_reads + wpb - 1) / wpb), wpb * FIX_LANES, wpb * warp_bytes, st>>>(P, n_reads, warp_bytes);
     e = cudaGetLastError();
   }
   return e;

@@ -276,7 +276,7 @@ reduce_rows_kernel(const uint64_t* out, const uint32_t* valid, uint64_t valid_ro
   for (uint64_t r0 = w * 32; r0 < rows; r0 += warps * 32) {
     const uint64_t nvals = min((uint64_t)span, (rows - r0) * H);
     for (uint32_t i = lane; i < nvals; i += 32) {
-      const uint32_t q = __umulhi(i, magic); // i / H, exact for i < 2^16
+      const uint32_t q = H == 1 ? i : __umulhi(i, magic); // i / H, exact for i < 2^16 (H = 1: the reciprocal 2^32 does not fit 32 bits)
       const uint64_t row = r0 + q, bit = valid_row0 + row;
       if (valid[bit >> 5] >> (bit & 31) & 1u) {
         const uint64_t v = out[r0 * H + i];

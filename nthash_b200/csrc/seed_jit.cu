@@ -49,6 +49,9 @@ struct JitParams
   uint64_t* out_fwd;         // STRANDS variant: get_forward_hash() / get_reverse_hash() per window and seed, [rows][M]
   uint64_t* out_rev;
   uint32_t str_aligned;      // both are 32-byte aligned (then whole-sector stores apply wherever a row group is)
+  uint32_t two;              // the constant 2 from the constant bank (roll_step: keeps one multiply-add on the FMA pipe)
+  uint64_t* reduce_out;      // REDUCE variant (fused consumer): {windows visited, sum, xor} of the clean items; nothing is stored
+  uint8_t* item_dirty;       // REDUCE variant: items holding a byte that needs the exact path (left to seed_reduce_dirty_kernel)
 };
 
 const char* const JIT_PRELUDE = R"JIT(
@@ -74,6 +77,9 @@ struct JitParams
   uint64_t* out_fwd;         // STRANDS variant: get_forward_hash() / get_reverse_hash() per window and seed, [rows][M]
   uint64_t* out_rev;
   uint32_t str_aligned;      // both are 32-byte aligned (then whole-sector stores apply wherever a row group is)
+  uint32_t two;              // the constant 2 from the constant bank (roll_step: keeps one multiply-add on the FMA pipe)
+  uint64_t* reduce_out;      // REDUCE variant (fused consumer): {windows visited, sum, xor} of the clean items; nothing is stored
+  uint8_t* item_dirty;       // REDUCE variant: items holding a byte that needs the exact path (left to seed_reduce_dirty_kernel)
 };
 #define DI __device__ __forceinline__
 DI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,15 +127,18 @@ DI uint32_t rotr(uint32_t x, uint32_t r) { return __funnelshift_r(x, x, r); }
 DI uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 struct State { uint32_t flo, fhi, rlo, rhi; };
 template<int LUT> DI uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT)); return d; }
-// F <- srol(F) ^ e.xy ; R <- sror(R ^ e.zw)   (src/internal.hpp:41-47, :83-88); the k-mer kernel's form: 12 ALU-pipe ops,
-// the plain shifts as IMAD.HI on the FMA pipe (the ALU pipe is the busy one: profiles/r01_ncu_c4_v7.txt)
-DI void roll_step(State& s, const uint4 e)
+// F <- srol(F) ^ e.xy ; R <- sror(R ^ e.zw)   (src/internal.hpp:41-47, :83-88); the k-mer kernel's form: 10 ALU-pipe ops,
+// the plain shifts as IMAD.HI on the FMA pipe.  ROLL_V2 (NTHASH_B200_ROLL_V2=1, off by default): 8 ALU + 7 FMA-pipe ops; measured
+// 1 % slower on C4 (profiles/r02_ab_roll_step.txt) — see kmer_fast_kernel.cu.
+DI uint32_t mad_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+DI void roll_step(State& s, const uint4 e, const uint32_t two)
 {
+#if !ROLL_V2
   {
     const uint32_t lo = s.flo, hi = s.fhi;
     const uint32_t hi1 = __funnelshift_l(lo, hi, 1);
-    const uint32_t nhi = lop3<0x50 | 0x88>(hi1, __umulhi(hi, 4u), 2u);   // (a & ~c) | (b & c): bit 33 <- old bit 63
-    const uint32_t nlo = lop3<0xF0 | 0x88>(lo + lo, hi, 1u);             // a | (b & c): bit 0 <- old bit 32
+    const uint32_t nhi = lop3<0x50 | 0x88>(hi1, __umulhi(hi, 4u), 2u);
+    const uint32_t nlo = lop3<0xF0 | 0x88>(lo + lo, hi, 1u);
     s.flo = nlo ^ e.x;
     s.fhi = nhi ^ e.y;
   }
@@ -137,6 +146,23 @@ DI void roll_step(State& s, const uint4 e)
     const uint32_t lo = s.rlo ^ e.z, hi = s.rhi ^ e.w;
     s.rlo = __funnelshift_r(lo, hi, 1);
     const uint32_t y = __funnelshift_r(hi, __umulhi(hi, 0x80000000u), 1);
+    s.rhi = lop3<0x50 | 0x88>(y, lo, 1u);
+  }
+  return;
+#endif
+  {
+    const uint32_t lo = s.flo, hi = s.fhi;
+    const uint32_t ch = lop3<0x50 | 0x88>(hi * 2u, __umulhi(hi, 4u), 2u); // (a & ~c) | (b & c): bit 33 <- old bit 63; bit 32 clear
+    const uint32_t nhi = mad_hi(lo, two, ch);                            // bit 32 <- old bit 31
+    const uint32_t nlo = lop3<0xF0 | 0x88>(lo * 2u, hi, 1u);             // a | (b & c): bit 0 <- old bit 32
+    s.flo = nlo ^ e.x;
+    s.fhi = nhi ^ e.y;
+  }
+  {
+    const uint32_t lo = s.rlo ^ e.z, hi = s.rhi ^ e.w;
+    s.rlo = __funnelshift_r(lo, hi, 1);
+    const uint32_t a = __umulhi(hi, 0x80000000u); // hi >> 1
+    const uint32_t y = a * 0x80000001u;           // a + (a << 31): bit 63 <- old bit 33
     s.rhi = lop3<0x50 | 0x88>(y, lo, 1u);
   }
 }
@@ -279,7 +305,8 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
     if (bulk_bytes) bulk_g2s(tile + 16, P.bases + g0, bulk_bytes, bar);
     bulk_g2s(sbase, P.tables, TABLE_BYTES, bar);
   }
-  for (uint32_t c = tid; c < 256; c += NT) sts_u8(lut + c, seed_of_byte(c) != 0 ? 0u : 1u);
+  // 1: byte-exact path for the windows holding the byte (no seed, or a raw byte 1/3/4/5/7 whose 2-bit code is not its seed's base)
+  for (uint32_t c = tid; c < 256; c += NT) sts_u8(lut + c, (seed_of_byte(c) != 0 && c > 7) ? 0u : 1u);
   for (uint64_t g = (bulk_end > g0 ? bulk_end : g0) + tid; g < g1; g += NT) sts_u8(tile + 16 + (uint32_t)(g - g0), P.bases[g]);
   mbar_wait(bar, 0);
   __syncthreads();
@@ -332,6 +359,9 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
   DECL_W
   DECL_BLOCKS
   DECL_STR
+#if REDUCE
+  uint64_t acc_sum = 0ull, acc_xor = 0ull;
+#endif
   State full = { 0u, 0u, 0u, 0u };
   uint32_t bad = 0;
   for (int j = -(int)OLDER; j < (int)K - 1; ++j) {
@@ -339,7 +369,7 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
     if (j >= 0) bad |= lds_u8(lut + c);
     SHIFT_IN(c >> 1)
 #if ANY_IGNORE
-    if (j >= -1) roll_step(full, lds_v4(sbase + INTAB_OFF + ((c & 6u) << 3)));
+    if (j >= -1) roll_step(full, lds_v4(sbase + INTAB_OFF + ((c & 6u) << 3)), P.two);
 #endif
   }
   WARMUP_BLOCKS
@@ -355,6 +385,31 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
     MAIN_TILES
   }
 
+#if REDUCE
+  {
+    // Fused consumer: an item without a byte for the exact path has every window visited by the reference's loop (the
+    // windows init / roll skip all hold such a byte: seed.cpp:151, :524-530), so its count / sum / xor are final; an item
+    // with one contributes nothing here and is redone, window by window, by seed_reduce_dirty_kernel.
+    const bool dirty = active && bad != 0;
+    uint64_t cnt = (active && !dirty) ? (uint64_t)n : 0ull;
+    if (!active || dirty) acc_sum = acc_xor = 0ull;
+    for (int o = 16; o; o >>= 1) {
+      cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+      acc_sum += __shfl_down_sync(0xffffffffu, acc_sum, o);
+      acc_xor ^= __shfl_down_sync(0xffffffffu, acc_xor, o);
+    }
+    if (lane == 0) {
+      atomicAdd((unsigned long long*)P.reduce_out, (unsigned long long)cnt);
+      atomicAdd((unsigned long long*)P.reduce_out + 1, (unsigned long long)acc_sum);
+      atomicXor((unsigned long long*)P.reduce_out + 2, (unsigned long long)acc_xor);
+    }
+    if (dirty) {
+      P.item_dirty[item] = 1;
+      P.read_dirty[P.segs > 1 ? item / P.segs : item] = 1;
+    }
+    return;
+  }
+#endif
   STR_TAIL
   const bool dirty = active && bad != 0;
   const bool any_dirty = __any_sync(0xffffffffu, dirty);
@@ -467,6 +522,8 @@ struct SeedJit
   mutable SeedJit* alt_ragged = nullptr; // the ragged variant, compiled on first use
   mutable SeedJit* alt_str = nullptr;    // uniform batches with strand outputs (3-D box stores for the hashes), compiled on first use
   mutable SeedJit* alt_str2d = nullptr;  // the same over the 2-D tile variant
+  mutable SeedJit* alt_reduce = nullptr; // fused consumer (count / sum / xor, nothing stored), compiled on first use
+  bool reduce = false;
   bool strands = false;
   mutable std::mutex mu;
   std::string source; // kept for inspection (nthash_seed_plan_jit_source)
@@ -479,6 +536,7 @@ void seed_jit_destroy(SeedJit* j)
   seed_jit_destroy(j->alt_ragged);
   seed_jit_destroy(j->alt_str);
   seed_jit_destroy(j->alt_str2d);
+  seed_jit_destroy(j->alt_reduce);
   if (j->lib) cudaLibraryUnload(j->lib);
   cudaFree(j->d_tables);
   delete j;
@@ -489,7 +547,8 @@ const char* seed_jit_source(const SeedJit* j) { return j ? j->source.c_str() : "
 // Generates, compiles and loads the kernel for one seed set.  Returns nullptr (with a reason) when the
 // specialised path does not apply; the caller then uses the generic kernel.
 // mode 0: dense 2-D tiles (TMA 2-D tensor stores), 1: [blocks][rows][8 u64] tiles (TMA 3-D tensor stores; the default
-// for uniform batches), 2: ragged batches (per-lane rows, coalesced stores, item arrays)
+// for uniform batches), 2: ragged batches (per-lane rows, coalesced stores, item arrays), 3: fused consumer for uniform
+// batches (count / sum / xor accumulated in registers, no output tiles)
 static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& why, bool load, int mode, bool strands = false);
 
 SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
@@ -499,7 +558,7 @@ SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
 
 static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& why, bool load, int mode, bool strands)
 {
-  const bool box3 = mode == 1, ragged = mode == 2;
+  const bool box3 = mode == 1, ragged = mode == 2, reduce = mode == 3;
   const uint32_t k = plan.k, m = plan.n_seeds, hps = plan.h, ht = m * hps;
   if (k > 256) { why = "k > 256"; return nullptr; }
   if (strands && (ragged || m > 8)) { why = "strand outputs: uniform batches of at most 8 seeds"; return nullptr; }
@@ -618,8 +677,8 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
   //  box3: rows of whole 64-byte blocks ([blocks][32 rows][8 u64] under the TMA 64-byte swizzle), 192-256 bytes preferred
   //        (the k-mer kernel's finding: longer pieces cost more occupancy than they gain on the write path);
   //  else: one dense [32 rows][TW*HT u64] tile, an odd number of 16-byte chunks per row preferred (conflict-free STS.128)
-  uint32_t tw = 0, best = 0;
-  for (uint32_t t = 1; t <= 32; ++t) {
+  uint32_t tw = reduce ? 4 : 0, best = 0;
+  for (uint32_t t = 1; t <= 32 && !reduce; ++t) {
     const uint32_t rb = t * ht * 8;
     if (rb > 512 || t * ht > 256) continue;
     uint32_t score;
@@ -637,10 +696,10 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
   }
   if (const char* e = getenv("NTHASH_B200_SEED_JIT_TW")) { // experiments
     const uint32_t t = (uint32_t)atoi(e);
-    if (!ragged && t >= 1 && (t * ht * 8) % (box3 ? 64 : 16) == 0 && t * ht <= 256) tw = t;
+    if (!ragged && !reduce && t >= 1 && (t * ht * 8) % (box3 ? 64 : 16) == 0 && t * ht <= 256) tw = t;
   }
   if (!tw) { why = "no tile row shape for this number of hashes"; return nullptr; }
-  const uint32_t row_bytes = tw * ht * 8, ot_bytes = box3 ? (row_bytes / 64) * 2048u : (32 * row_bytes + 127) & ~127u;
+  const uint32_t row_bytes = tw * ht * 8, ot_bytes = reduce ? 0u : box3 ? (row_bytes / 64) * 2048u : (32 * row_bytes + 127) & ~127u;
   uint32_t unroll = tw; // windows per generated loop body: a multiple of the tile and of every block stride
   {
     uint32_t a = unroll, b2 = lcm_d;
@@ -658,6 +717,7 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
   // round 2 (profiles/r02_seed_jit_sweep.txt, after the ALU diet of roll_step / ext_hash): 160 threads with two tiles per
   // warp 10.43 ms, 96 x 3 10.45, 128 x 2 10.59, 128 x 3 (the round-1 default) 11.00: resident warps beat a third tile now
   uint32_t nt = box3 ? 160 : ragged ? 128 : 256, nbuf = box3 ? 2 : 1;
+  if (reduce) nt = 192; // no output tiles: shared memory holds the bases only, registers decide the occupancy
   if (const char* e = getenv("NTHASH_B200_SEED_JIT_NT")) nt = (uint32_t)atoi(e);
   if (const char* e = getenv("NTHASH_B200_SEED_JIT_NBUF")) nbuf = (uint32_t)atoi(e);
   if (nt < 32 || nt > 1024 || nt % 32 || nbuf < 1 || nbuf > 4) { why = "bad NT/NBUF override"; return nullptr; }
@@ -701,7 +761,7 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
   };
 
   std::ostringstream src;
-  src << "#define HAVE_ST256 " << (nvrtc().version >= 1209 ? 1 : 0) << "\n";
+  src << "#define HAVE_ST256 " << (nvrtc().version >= 1209 ? 1 : 0) << "\n#define ROLL_V2 " << (getenv("NTHASH_B200_ROLL_V2") ? 1 : 0) << "\n";
   src << JIT_PRELUDE;
   src << "#define NT " << nt << "u\n#define NBUF " << nbuf << "u\n#define BULK_WAIT_READ asm volatile(\"cp.async.bulk.wait_group.read "
       << nbuf - 1 << ";\" ::: \"memory\");\n";
@@ -715,7 +775,7 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
     const uint32_t chunk = ht % 2 ? 8 : 16, pitch = (row_bytes + 15) / 16 * 16 + ((((row_bytes + 15) / 16) % 2) ? 0 : 16);
     src << "#define RAGGED " << (ragged ? 1 : 0) << "\n#define CHUNK " << chunk << "u\n#define LANES_PER_ROW " << 256 / chunk << "u\n#define ROW_PITCH " << pitch << "u\n";
   }
-  src << "#define STRANDS " << (strands ? 1 : 0) << "\n";
+  src << "#define STRANDS " << (strands ? 1 : 0) << "\n#define REDUCE " << (reduce ? 1 : 0) << "\n";
   if (strands) {
     // STR_FLUSH(w0): the strand hashes of windows w0 .. w0+3 (4*M u64 per array, contiguous in both arrays) as M whole
     // 32-byte sectors when the group starts on one, else value by value; STR_TAIL: the last n % 4 windows of the row
@@ -751,7 +811,7 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
   if (plan.any_ignore)
     src << " { const uint32_t po = ((c << 4) & 0x60u) | (rotr(W" << off / 16 << ", " << ((2 * (off % 16) + 32 - 3) % 32)
         << "u) & 0x18u); const uint2 ef = lds_v2(sbase + PAIRF_OFF + po), er = lds_v2(sbase + PAIRR_OFF + po);"
-           " roll_step(full, make_uint4(ef.x, ef.y, er.x, er.y)); }";
+           " roll_step(full, make_uint4(ef.x, ef.y, er.x, er.y), P.two); }";
   src << "\n#define WIN_PRE(P) const uint32_t c = lds_u8(ps + (K - 1) + (P)); bad |= lds_u8(lut + c); FULL_ROLL SHIFT_IN(c >> 1)\n";
   // STORE_WINDOW_i(base): window i of the tile row -> shared memory
   for (uint32_t i = 0; i < tw; ++i) {
@@ -775,6 +835,16 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
   // per-window bound checks, a partial one (end of a row) keeps them
   auto tile_text = [&](uint32_t t, bool full) {
     std::ostringstream o;
+    if (reduce) { // fused consumer: the window's values go straight into the accumulators
+      for (uint32_t i = 0; i < tw; ++i) {
+        const uint32_t u = t * tw + i;
+        o << "      " << (full ? "{" : "if (p0 + " + std::to_string(u) + "u < n) {") << " \\\n        WIN_PRE(p0 + " << u << "u) \\\n        uint64_t hv[HT]; \\\n"
+          << window_body(u) << "       ";
+        for (uint32_t q = 0; q < ht; ++q) o << " acc_sum += hv[" << q << "]; acc_xor ^= hv[" << q << "];";
+        o << " \\\n      } \\\n";
+      }
+      return o.str();
+    }
     o << "      const uint32_t ot = ot0 + buf * OT_BYTES, rowaddr = ot + " << (box3 ? "lterm" : "lane * ROW_BYTES") << "; \\\n";
     for (uint32_t i = 0; i < tw; ++i) {
       const uint32_t u = t * tw + i;
@@ -830,6 +900,7 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
   j->box3 = box3;
   j->ragged = ragged;
   j->strands = strands;
+  j->reduce = reduce;
   j->row_pitch = (row_bytes + 15) / 16 * 16 + ((((row_bytes + 15) / 16) % 2) ? 0 : 16);
   j->plan = &plan;
   nvrtcProgram prog = nullptr;
@@ -876,7 +947,7 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
 
 uint32_t seed_jit_smem_bytes(const SeedJit* j, uint32_t tile_cap)
 {
-  const uint32_t out_bytes = j->ragged ? (j->nt / 32) * 32u * (j->row_pitch + 16u) + 256u : (j->nt / 32) * j->nbuf * j->ot_bytes;
+  const uint32_t out_bytes = j->reduce ? 0u : j->ragged ? (j->nt / 32) * 32u * (j->row_pitch + 16u) + 256u : (j->nt / 32) * j->nbuf * j->ot_bytes;
   return j->table_bytes + 256 + 16 + 16 + tile_cap + 16 + 1024 + out_bytes;
 }
 
@@ -894,7 +965,7 @@ static uint32_t seed_jit_tile_cap(const SeedJit* j, const SeedParams& P)
 // Build check without a GPU: compiles every variant (3-D box, 2-D tiles, ragged) for sm_100a.
 bool seed_jit_compile_all(const SeedPlanHost& plan, std::string& why)
 {
-  for (int mode : { 1, 0, 2, 11, 10 }) { // 1x: with strand outputs
+  for (int mode : { 1, 0, 2, 3, 11, 10 }) { // 1x: with strand outputs
     if (mode == 2 && plan.n_seeds * plan.h > 32) continue;
     if (mode >= 10 && plan.n_seeds > 8) continue;
     std::string w;
@@ -911,9 +982,18 @@ bool seed_jit_compile_all(const SeedPlanHost& plan, std::string& why)
 // The variant of the compiled kernel that fits the geometry: ragged batches take the ragged variant; uniform ones the
 // 3-D box stores when rows are whole 64-byte blocks, else the 2-D tile variant.  Variants other than the one built with
 // the plan are compiled on first use.
-static const SeedJit* seed_jit_variant(const SeedJit* j, const KmerGeom& g, bool strands)
+static const SeedJit* seed_jit_variant(const SeedJit* j, const KmerGeom& g, bool strands, bool reduce = false)
 {
   if (!j) return j;
+  if (reduce) { // fused consumer: uniform batches only
+    if (g.item_byte) return nullptr;
+    std::lock_guard<std::mutex> lock(j->mu);
+    if (!j->alt_reduce) {
+      std::string why;
+      j->alt_reduce = seed_jit_build_variant(*j->plan, why, true, 3);
+    }
+    return j->alt_reduce;
+  }
   if (g.item_byte) {
     if (strands || j->ht > 32 || getenv("NTHASH_B200_SEED_JIT_NO_RAGGED")) return nullptr; // a window must fit a 256-byte row piece
     std::lock_guard<std::mutex> lock(j->mu);
@@ -945,9 +1025,20 @@ bool seed_jit_applies(const SeedJit* j0, const SeedParams& P)
   return j && seed_jit_smem_bytes(j, seed_jit_tile_cap(j, P)) <= 227u * 1024u;
 }
 
+// Fused consumer (P.reduce_out, P.item_dirty set; no outputs): uniform batches whose items are all full.
+bool seed_jit_reduce_applies(const SeedJit* j0, const SeedParams& P)
+{
+  const KmerGeom& g = P.g;
+  if (!j0 || !g.n_items || g.n_items >= 0x7fffffffull || g.item_byte || !g.seg || g.nk % g.seg) return false;
+  if (getenv("NTHASH_B200_SEED_REDUCE_TWO_PASS")) return false;
+  const SeedJit* j = seed_jit_variant(j0, g, false, true);
+  return j && seed_jit_smem_bytes(j, seed_jit_tile_cap(j, P)) <= 227u * 1024u;
+}
+
 cudaError_t launch_seed_jit(const SeedJit* j0, const SeedParams& P, cudaStream_t st)
 {
-  const SeedJit* j = seed_jit_variant(j0, P.g, P.out_fwd != nullptr);
+  const bool reduce = P.reduce_out != nullptr;
+  const SeedJit* j = seed_jit_variant(j0, P.g, P.out_fwd != nullptr, reduce);
   if (!j) return cudaErrorNotSupported;
   using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -965,8 +1056,8 @@ cudaError_t launch_seed_jit(const SeedJit* j0, const SeedParams& P, cudaStream_t
   memset(&map, 0, sizeof map);
   const uint64_t row_u64 = (uint64_t)P.g.seg * j->ht;
   CUresult cr = CUDA_SUCCESS;
-  if (j->ragged) {
-    // no tensor map: rows leave through plain coalesced stores
+  if (j->ragged || j->reduce) {
+    // no tensor map: rows leave through plain coalesced stores / nothing is stored
   } else if (j->box3) { // [row blocks][items][8 u64], boxes of (row_bytes / 64) x 32 x 8 under the 64-byte swizzle
     const cuuint64_t dims[3] = { 8, P.g.n_items, row_u64 / 8 };
     const cuuint64_t strides[2] = { row_u64 * 8, 64 };
@@ -998,6 +1089,9 @@ cudaError_t launch_seed_jit(const SeedJit* j0, const SeedParams& P, cudaStream_t
   jp.care = reinterpret_cast<const uint32_t*>(P.plan_blob + P.care_off);
   jp.tile_cap = seed_jit_tile_cap(j, P);
   jp.care_words = P.care_words;
+  jp.two = 2;
+  jp.reduce_out = P.reduce_out;
+  jp.item_dirty = P.item_dirty;
   jp.item_byte = P.g.item_byte;
   jp.item_out = P.g.item_out;
   jp.item_read = P.item_read;

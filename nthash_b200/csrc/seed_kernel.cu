@@ -97,7 +97,10 @@ __global__ void __launch_bounds__(KMER_NT) seed_kernel(const __grid_constant__ S
     if (bulk_bytes) bulk_g2s(tile + TILE_PAD, P.bases + g0, bulk_bytes, bar);
     bulk_g2s(smem, P.plan_blob, plan_bytes, bar);
   }
-  lut[tid] = seed_of_byte(tid) != 0 ? 0 : 1; // SeedNtHash::roll's test: SEED_TAB[c] == SEED_N (seed.cpp:527)
+  // 1: the byte's windows need the byte-exact path (and the read the emission replay, which applies SeedNtHash::roll's own
+  // test SEED_TAB[c] == SEED_N, seed.cpp:527).  That is every byte without a seed, and the raw bytes 1, 3, 4, 5, 7: they do
+  // have seeds (SEED_TAB's complement slots) but their 2-bit code (c >> 1) & 3 is not the base that seed belongs to.
+  lut[tid] = (seed_of_byte(tid) != 0 && tid > 7) ? 0 : 1;
   if (tid < 16) {
     auto seed_code = [&](int c) { return c ^ (c >> 1); }; // code -> index into P.s/P.sk (A,C,G,T order)
     const int ci = tid >> 2, co = tid & 3;
@@ -269,7 +272,82 @@ __global__ void __launch_bounds__(128) seed_emit_kernel(const __grid_constant__ 
   clear_rows(next_unvisited, nk);
 }
 
+// Fused consumer, second launch (uniform batches): the items the specialised kernel left out because they hold a byte
+// that needs the exact path.  One thread per flagged read replays SeedNtHash's visiting order (init: seed.cpp:493-516,
+// roll: :518-544) and adds the byte-exact hashes (seed.cpp:149-171) of every visited window that lies in a flagged item;
+// the read's other items were complete and are already in the result.
+__global__ void __launch_bounds__(128) seed_reduce_dirty_kernel(const __grid_constant__ SeedParams P, uint64_t n_reads)
+{
+  const uint64_t rd = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (rd >= n_reads || !P.read_dirty[rd]) return;
+  const uint32_t k = P.k, m = P.n_seeds, h = P.h;
+  const uint64_t len = P.g.read_len, nk = P.g.nk, seg = P.g.seg, segs = P.g.segs ? P.g.segs : 1;
+  if (len < k) return;
+  const uint8_t* s = P.bases + rd * len;
+  const SeedDesc* descs = reinterpret_cast<const SeedDesc*>(P.plan_blob);
+  const uint32_t* refblk = reinterpret_cast<const uint32_t*>(P.plan_blob + P.refblk_off);
+  const uint32_t* care = reinterpret_cast<const uint32_t*>(P.plan_blob + P.care_off);
+  uint64_t cnt = 0, sum = 0, x = 0;
+  auto visit = [&](uint64_t p) {
+    if (!P.item_dirty[rd * segs + p / seg]) return;
+    ++cnt;
+    for (uint32_t sd = 0; sd < m; ++sd) {
+      uint64_t f, r;
+      exact_window(s + p, care + (size_t)sd * P.care_words, k, f, r);
+      const uint64_t h0 = f + r;
+      sum += h0;
+      x ^= h0;
+      for (uint32_t q = 1; q < h; ++q) {
+        const uint64_t e = ext_hash(h0, ext_mult(q, k));
+        sum += e;
+        x ^= e;
+      }
+    }
+  };
+  auto first_nul = [&](uint64_t pos, uint32_t& loc) { // ntmsm64 (base) fails only on a NUL byte at a block position
+    for (uint32_t sd = 0; sd < m; ++sd)
+      for (uint32_t b = descs[sd].rb0; b < descs[sd].rb1; ++b)
+        for (uint32_t q = refblk[2 * b]; q < refblk[2 * b + 1]; ++q)
+          if (s[pos + q] == 0) {
+            loc = q;
+            return true;
+          }
+    return false;
+  };
+  uint64_t pos = 0;
+  bool done = false;
+  while (!done) {
+    uint32_t loc = 0;
+    while (pos < nk && first_nul(pos, loc)) pos += loc + 1; // init()
+    if (pos > len - k) break;
+    visit(pos);
+    for (;;) { // roll() until the next jump
+      if (pos >= len - k) {
+        done = true;
+        break;
+      }
+      if (seed_of_byte(s[pos + k]) == 0) {
+        pos += k;
+        break; // -> init()
+      }
+      ++pos;
+      visit(pos);
+    }
+  }
+  if (cnt) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(P.reduce_out), (unsigned long long)cnt);
+    atomicAdd(reinterpret_cast<unsigned long long*>(P.reduce_out) + 1, (unsigned long long)sum);
+    atomicXor(reinterpret_cast<unsigned long long*>(P.reduce_out) + 2, (unsigned long long)x);
+  }
+}
+
 } // namespace
+
+cudaError_t launch_seed_reduce_dirty(const SeedParams& P, uint64_t n_reads, cudaStream_t st)
+{
+  seed_reduce_dirty_kernel<<<(unsigned)((n_reads + 127) / 128), 128, 0, st>>>(P, n_reads);
+  return cudaGetLastError();
+}
 
 uint32_t seed_smem_bytes(uint32_t plan_smem, uint32_t tile_cap)
 {

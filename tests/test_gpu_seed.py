@@ -90,6 +90,33 @@ def test_ragged_dirty_reads_all_seed_sets(seeds, h, capfd):
     capfd.readouterr()
 
 
+@pytest.mark.parametrize("jit", [True, False])
+def test_raw_control_bytes_hash_like_the_reference(jit, monkeypatch):
+    """Raw bytes 1, 3, 4, 5, 7 are SEED_TAB's complement slots (src/internal.hpp:133): SeedNtHash hashes them with those
+    seeds and never jumps on them.  Uniform (specialised kernel, with and without strands) and ragged batches."""
+    if not jit:
+        monkeypatch.setenv("NTHASH_B200_DISABLE_SEED_JIT", "1")
+    rng = np.random.default_rng(99)
+    seeds = [SEED_A31, SEED_B31]
+    plan = nthash_b200.SeedPlan(seeds, 2)
+    n, L = 600, 160
+    bases = synth(rng, n * L, p_bad=0.001)
+    at = rng.integers(0, n * L, 400)
+    bases[at] = rng.choice(np.array([1, 3, 4, 5, 7, 2, 6], np.uint8), 400)
+    d_b, _keep = to_dev(bases)
+    off = np.arange(n + 1, dtype=np.uint64) * L
+    ora = ORACLE.seed_batch(bases, off, seeds, 2, threads=4)
+    for strands in (True, False):
+        res = nthash_b200.seed_hashes_uniform(plan, d_b, n, L, want_strands=strands)
+        torch.cuda.synchronize()
+        assert_batch_equal(res, ora, 4, check_strands=strands)
+    lens = rng.integers(20, 300, 500)
+    roff = ragged_offsets(lens)
+    rb = bases[: int(roff[-1])]
+    res = run_ragged(plan, rb, roff, strands=False)
+    assert_batch_equal(res, ORACLE.seed_batch(rb, roff.astype(np.uint64), seeds, 2, threads=4), 4)
+
+
 @pytest.mark.parametrize("read_len,n,p_bad", [(150, 3000, 0.0), (150, 3000, 0.002), (151, 500, 0.001), (40, 1000, 0.0), (3000, 60, 0.0005)])
 def test_uniform_config4_shape(read_len, n, p_bad):
     rng = np.random.default_rng(read_len + n)
@@ -300,8 +327,30 @@ def test_blind_seed_roll_batch():
         assert (u64(out) == ora["out"]).all() and (u64(fwd) == ora["fwd"]).all() and (u64(rev) == ora["rev"]).all()
 
 
+@pytest.mark.parametrize("seeds,h,n,L,p_bad", [([SEED_A31, SEED_B31], 3, 4000, 150, 0.002), ([SEED_A31, SEED_B31], 1, 40, 5000, 0.0008),
+                                               (["110011", "101101"], 2, 3000, 64, 0.01), (["11100111"], 3, 1000, 151, 0.0),
+                                               (["1" * 40 + "0" * 23 + "1" * 40], 1, 500, 300, 0.003)])
+def test_seed_reduce_fused_in_the_specialised_kernel(seeds, h, n, L, p_bad, monkeypatch):
+    """Uniform batches: count / sum / xor accumulated inside the generated kernel (nothing stored); items holding a byte for
+    the exact path are redone by seed_reduce_dirty_kernel with the reference's visiting rule (jump on an invalid incoming
+    base, NUL rule).  Same result as the oracle and as the two-pass form, short reads and reads cut into several items."""
+    rng = np.random.default_rng(n + L)
+    bases = synth(rng, n * L, p_bad=p_bad, lower=0.05)
+    if p_bad:
+        bases[rng.integers(0, n * L, 5)] = 0
+        bases[rng.integers(0, n * L, 20)] = rng.choice(np.array([1, 3, 4, 5, 7], np.uint8), 20)
+    d_b, _keep = to_dev(bases)
+    plan = nthash_b200.SeedPlan(seeds, h)
+    ora = ORACLE.seed_batch(bases, np.arange(n + 1, dtype=np.uint64) * L, seeds, h, want=(), threads=8)
+    got = u64(nthash_b200.seed_reduce_uniform(plan, d_b, n, L))
+    assert (int(got[0]), int(got[1]), int(got[2])) == (ora["n_emit"], ora["sum"], ora["xor"])
+    monkeypatch.setenv("NTHASH_B200_SEED_REDUCE_TWO_PASS", "1")
+    two = u64(nthash_b200.seed_reduce_uniform(plan, d_b, n, L))
+    assert (got == two).all()
+
+
 def test_seed_reduce_consumer(monkeypatch):
-    # count / sum / xor of every visited window's hashes for SeedNtHash, computed on the device (two passes); dirty reads
+    # count / sum / xor of every visited window's hashes for SeedNtHash, computed on the device; dirty reads
     # follow the reference's own visiting rule
     rng = np.random.default_rng(15)
     seeds, h = ["1010101010101010101010101010101", "1101101101101101011011011011011"], 3
@@ -322,3 +371,8 @@ def test_seed_reduce_consumer(monkeypatch):
     arr = (C.c_char_p * 2)(*[s.encode() for s in seeds])
     assert nthash_b200.LIB.nthash_seed_reduce(rb.ctypes.data, off.ctypes.data, len(lens), arr, 2, 31, h, res.ctypes.data, 0) == 0, nthash_b200.LIB.nthash_last_error()
     assert (int(res[0]), int(res[1]), int(res[2])) == (ora2["n_emit"], ora2["sum"], ora2["xor"])
+    # one seed, one hash per window (rows of a single value) through the two-pass form
+    ora3 = ORACLE.seed_batch(rb, off, ["11100111"], 1, want=())
+    arr1 = (C.c_char_p * 1)(b"11100111")
+    assert nthash_b200.LIB.nthash_seed_reduce(rb.ctypes.data, off.ctypes.data, len(lens), arr1, 1, 8, 1, res.ctypes.data, 0) == 0, nthash_b200.LIB.nthash_last_error()
+    assert (int(res[0]), int(res[1]), int(res[2])) == (ora3["n_emit"], ora3["sum"], ora3["xor"])
