@@ -950,6 +950,277 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// kmer_pack_kernel — the BOX path (uniform batches, 1..4 hashes, tensor stores) with WARP-PRIVATE, NIBBLE-PACKED bases.
+//
+// What the profile of kmer_fast_kernel says at HEAD of round 2 (profiles/r02_ncu_c2_head.txt): 17.8 % of the stall samples
+// sit on the CTA's wait for its base tile, sm__warps_active is 23.8 % (2 CTAs x 8 warps: 150 bytes of staged ASCII per
+// thread next to the 192-byte output rows), and neither the ALU pipe (66 %) nor DRAM (74 %) is saturated: the kernel
+// runs out of warps to hide latency with.  Here
+//   * every warp stages the bytes of ITS 32 items itself: coalesced 16-byte global loads, converted in registers to one
+//     nibble per base (2-bit code (byte >> 1) & 3 in the low bits) and stored to a warp-private strip — 1/2 byte of shared
+//     memory per base instead of 1, no CTA-wide barrier after the tables, no TMA round trip: a warp that waits for its
+//     bytes only stalls itself, and ~1.5x as many warps fit an SM;
+//   * validity is decided once per 16-byte chunk during the conversion (SWAR test, one ballot per 32 chunks); a lane
+//     whose row touches a flagged chunk takes the exact scrub pass over the ASCII bytes in global memory afterwards;
+//   * the main loop reads one aligned word per 8 windows per stream (funnel shift by the lane's nibble offset), merges
+//     the in- and out-stream into one word of 4-bit table indices with a single IMAD, and forms each pair-table address
+//     with one rotate and one LOP3: ~2.4 ALU-pipe ops per window for the lookups against 5.25 in kmer_fast_kernel;
+//   * hashes leave exactly as there: warp tile [blocks][32 rows][8 u64] under the 64-byte swizzle, one 3-D tensor store.
+// Same arithmetic, same reference lines (NtHash::roll src/kmer.cpp:246-264, extend_hashes src/internal.hpp:104-118).
+//
+// MEASURED (profiles/r02_ab_pack.txt, profiles/r02_ncu_c2_pack.txt, same box as kmer_fast_kernel): sm__warps_active 23.8 -> 35.9 %,
+// issue slots 57.6 -> 65 %, the tile wait is gone — but the conversion costs more than the leaner loop saves: 38 instructions
+// per window overall against 31.8 (1.43 G vs 1.19 G warp instructions on C2; the SWAR validity test alone is 9 ALU ops per
+// four staged bases, and 1.26 bases are staged per window of a 150 bp read), the ALU pipe goes from 66 to 75 % busy, and the
+// kernel is SLOWER: C2 1.896 ms vs 1.809 (0.89 vs 0.94 of the HBM peak), C5 1.030 vs 0.986, C3 6.46 vs 6.24.  (With one
+// chunk load in flight per lane instead of four it was 2.22 ms: the warp-private staging is latency-bound.)  It therefore
+// stays OFF by default (NTHASH_B200_PACK=1 selects it; tests/test_gpu_kmer.py runs both).  What it would take to win: input
+// that needs no validity scan and no byte -> code step, i.e. 2-bit packed bases handed in by the caller.
+// shared memory: [output tiles: one per warp, 1024-byte aligned][tables at PK_TAB][strips: one per warp]
+constexpr int PK_PAIR_OFF = 0;     // (from PK_TAB) 16 x 8 B forward pair table, 16 x 8 B reverse pair table (256-byte aligned)
+constexpr int PK_IN_OFF = 256;     // 4 x 16 B in-only entries (warm-up tail)
+constexpr int PK_T4_OFF = 512;     // 256 x 16 B tetramer table, re-indexed by c0 | c1 << 2 | c2 << 4 | c3 << 6
+constexpr int PK_TAB_BYTES = 512 + T4_BYTES;
+constexpr uint32_t PK_LEAD = 16;   // nibbles of zero padding in front of a strip (base -1 of the batch's first read lives there)
+constexpr uint32_t PK_MAX_CHUNKS = 512; // 16-byte chunks of ASCII a warp may stage (16 bad-chunk words)
+
+template<int H, int WS>
+__global__ void __launch_bounds__(256)
+kmer_pack_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ CUtensorMap omap, const uint32_t strip_bytes)
+{
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr uint32_t TILE = (uint32_t)(WS * H / 8) * 2048u; // blocks x 32 rows x 64 bytes
+  const uint32_t NT = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t tab_off = (NT / 32) * TILE;
+  const uint32_t sbase = smem_u32(smem) + tab_off; // the tables' base: PK_* offsets count from here
+  uint8_t* const tabs = smem + tab_off;
+  const uint32_t k = P.k;
+  // ---- CTA-wide tables (the only barrier of the kernel) ----
+  {
+    auto code2base = [](int c) { return c ^ (c >> 1); }; // code 0 = A, 1 = C, 2 = T/U, 3 = G -> index into P.s / P.sk (A, C, G, T)
+    if (tid < 16) {
+      const int ci = tid >> 2, co = tid & 3;
+      reinterpret_cast<uint64_t*>(tabs + PK_PAIR_OFF)[tid] = P.s[code2base(ci)] ^ P.sk[code2base(co)];
+      reinterpret_cast<uint64_t*>(tabs + PK_PAIR_OFF + 128)[tid] = P.sk[code2base(ci ^ 2)] ^ P.s[code2base(co ^ 2)];
+    } else if (tid < 20) {
+      const int ci = tid - 16;
+      const uint64_t f = P.s[code2base(ci)], r = P.sk[code2base(ci ^ 2)];
+      reinterpret_cast<uint4*>(tabs + PK_IN_OFF)[ci] = make_uint4((uint32_t)f, (uint32_t)(f >> 32), (uint32_t)r, (uint32_t)(r >> 32));
+    }
+    for (uint32_t j = tid; j < 256; j += NT) { // j = c0 | c1 << 2 | c2 << 4 | c3 << 6  ->  P.t4's c0 << 6 | c1 << 4 | c2 << 2 | c3
+      const uint32_t src = ((j & 3u) << 6) | ((j & 12u) << 2) | ((j & 48u) >> 2) | (j >> 6);
+      reinterpret_cast<uint4*>(tabs + PK_T4_OFF)[j] = __ldg(P.t4 + src);
+    }
+  }
+  __syncthreads();
+
+  // ---- this warp's 32 items ----
+  const uint64_t it0 = (uint64_t)blockIdx.x * NT + warp * 32;
+  if (it0 >= P.g.n_items) return;
+  const uint32_t n = P.g.seg; // windows per item: the same for every item of a BOX batch
+  auto item_byte = [&](uint64_t i) -> uint64_t { return P.g.flat ? flat_byte(P.g, i * n) : i * (uint64_t)P.g.read_len; };
+  const uint64_t it_last = min(it0 + 31, P.g.n_items - 1);
+  const uint64_t b_first = item_byte(it0);
+  const uint64_t b_end = (P.g.flat ? flat_byte(P.g, it_last * n + n - 1) : it_last * (uint64_t)P.g.read_len + n - 1) + k; // one past the last byte
+  const uint64_t a0 = (b_first ? b_first - 1 : 0) & ~15ull; // 16-byte aligned start of the staged range
+  const uint32_t n_chunks = (uint32_t)((b_end - a0 + 15) >> 4);
+  const uint32_t strip = sbase + PK_TAB_BYTES + warp * (strip_bytes + 64u); // [nibble strip][16 bad-chunk words]
+  const uint32_t badw = strip + strip_bytes;
+  const uint32_t tb0 = smem_u32(smem) + warp * TILE;
+  if (n_chunks * 8u + 48u > strip_bytes || n_chunks > PK_MAX_CHUNKS) __trap(); // the launcher sized the strip for this geometry
+
+  // ---- stage + convert: chunk c = bytes a0 + 16c .. +15 -> two words of nibbles at strip + 8 + 8c ----
+  if (lane < 2) asm volatile("st.shared.u32 [%0], %1;" ::"r"(strip + lane * 4), "r"(0u) : "memory"); // the lead-in: code 0 ('A'), cancels out
+  // four chunks per lane in flight (the loads do not depend on each other: one round trip to DRAM per 2 KB of the strip)
+  auto load_chunk = [&](uint32_t c) {
+    uint4 x = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u); // 'A': hashable, never stored past n_chunks
+    const uint64_t gb = a0 + 16ull * c;
+    if (c < n_chunks) {
+      if (gb + 16 <= P.n_bases) {
+        x = __ldg(reinterpret_cast<const uint4*>(P.bases + gb));
+      } else { // the last bytes of the buffer
+        uint32_t w[4] = { 0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u };
+        for (uint32_t j = 0; j < 16 && gb + j < P.n_bases; ++j) w[j >> 2] = (w[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | ((uint32_t)P.bases[gb + j] << (8 * (j & 3)));
+        x = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    return x;
+  };
+  auto convert_chunk = [&](uint32_t c0, const uint4 x) {
+    const uint32_t c = c0 + lane;
+    const uint32_t anybad = swar_bad(x.x) | swar_bad(x.y) | swar_bad(x.z) | swar_bad(x.w);
+    const uint32_t m = __ballot_sync(0xffffffffu, anybad != 0);
+    if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(badw + (c0 >> 5) * 4), "r"(m) : "memory");
+    // per word: codes (x >> 1) & 3 per byte, then byte pairs folded into nibbles: z = y | y >> 4 has c0 | c1 << 4 in byte 0 and
+    // c2 | c3 << 4 in byte 2; PRMT gathers bytes 0, 2 of two words
+    auto nib = [](uint32_t v) {
+      const uint32_t y = (v >> 1) & 0x03030303u;
+      return y | (y >> 4);
+    };
+    const uint32_t lo = __byte_perm(nib(x.x), nib(x.y), 0x6420u), hi = __byte_perm(nib(x.z), nib(x.w), 0x6420u);
+    if (c < n_chunks) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(strip + 8u + 8u * c), "r"(lo), "r"(hi) : "memory");
+  };
+  for (uint32_t c0 = 0; c0 < n_chunks; c0 += 128) {
+    uint4 x[4];
+#pragma unroll
+    for (uint32_t u = 0; u < 4; ++u) x[u] = load_chunk(c0 + 32 * u + lane);
+#pragma unroll
+    for (uint32_t u = 0; u < 4; ++u)
+      if (c0 + 32 * u < n_chunks) convert_chunk(c0 + 32 * u, x[u]);
+  }
+  __syncwarp();
+
+  // ---- this lane's item ----
+  const uint64_t item = it0 + lane;
+  const bool active = item < P.g.n_items;
+  const uint64_t my_byte = active ? item_byte(item) : b_first; // idle lanes hash the first item again; the tensor store clips their rows
+  const uint64_t my_out = item * (uint64_t)n;
+  const uint32_t q0 = PK_LEAD + (uint32_t)(my_byte - a0); // nibble index of the item's base 0
+  // any flagged chunk among the row's bytes -1 .. n+k-2?
+  bool bad = false;
+  {
+    const uint32_t c_lo = (q0 - 1 - PK_LEAD) >> 4, c_hi = (q0 + n + k - 2 - PK_LEAD) >> 4; // q0 - 1 - LEAD may wrap for the batch's first base
+    for (uint32_t c = (q0 > PK_LEAD ? c_lo : 0u); c <= c_hi; ++c) bad |= (lds_u32(badw + (c >> 5) * 4) >> (c & 31)) & 1u;
+  }
+  const uint32_t pair = keep(sbase + PK_PAIR_OFF);
+  const uint32_t t4a = keep(sbase + PK_T4_OFF);
+
+  // nibble stream reader: aligned word j of the stream that starts at nibble position `pos`
+  auto stream_word = [&](uint32_t pos, uint32_t j) {
+    const uint32_t wa = strip + ((pos >> 3) + j) * 4;
+    return __funnelshift_r(lds_u32(wa), lds_u32(wa + 4), (pos & 7u) * 4u);
+  };
+
+  // ---- warm-up: k in-only steps over bases -1 .. k-2, four per step through the tetramer table ----
+  State s = { 0u, 0u, 0u, 0u };
+  {
+    const uint32_t nq = k >> 2;
+    uint32_t wv = 0;
+    for (uint32_t q = 0; q < nq; ++q) {
+      if ((q & 1u) == 0) wv = stream_word(q0 - 1, q >> 1);
+      const uint32_t v = (q & 1u) ? (wv >> 16) : (wv & 0xFFFFu);      // c0 | c1 << 4 | c2 << 8 | c3 << 12
+      const uint32_t t = (v | (v >> 2)) & 0x0F0Fu;
+      const uint32_t j = (t | (t >> 4)) & 0xFFu;                       // c0 | c1 << 2 | c2 << 4 | c3 << 6
+      roll4_in(s, lds_v4(t4a + j * 16u));
+    }
+    for (uint32_t j = 4 * nq; j < k; ++j) {
+      const uint32_t pos = q0 - 1 + j;
+      const uint32_t c = (lds_u32(strip + (pos >> 3) * 4) >> ((pos & 7u) * 4u)) & 3u;
+      roll_step(s, lds_v4(sbase + PK_IN_OFF + c * 16u), P.two);
+    }
+  }
+
+  // ---- main loop ----
+  const uint32_t lterm = keep(lane * 64 + (((lane >> 1) & 3) << 4));
+  const uint32_t tb = tb0 + lterm;
+  const int row0 = (int)it0;
+  auto chunk_addr = [&](uint32_t cc) { return (tb ^ ((cc & 3u) << 4)) + (cc >> 2) * 2048u; };
+  const uint32_t pos_in = q0 + k - 1, pos_out = q0 - 1;
+  const uint32_t sh_in = (pos_in & 7u) * 4u, sh_out = (pos_out & 7u) * 4u;
+  uint32_t wa_in = strip + (pos_in >> 3) * 4, wa_out = strip + (pos_out >> 3) * 4;
+  uint32_t in0 = lds_u32(wa_in), out0 = lds_u32(wa_out);
+  // eight windows: one aligned word of each stream -> nibble i = code_in << 2 | code_out = pair-table index of window i
+  auto next8 = [&]() {
+    wa_in += 4;
+    wa_out += 4;
+    const uint32_t in1 = lds_u32(wa_in), out1 = lds_u32(wa_out);
+    const uint32_t wi = __funnelshift_r(in0, in1, sh_in), wo = __funnelshift_r(out0, out1, sh_out);
+    in0 = in1;
+    out0 = out1;
+    return wi * 4u + wo;
+  };
+  auto window = [&](uint32_t cw, int i) -> uint64_t { // window i (0..7) of the index word
+    const uint32_t ea = lop3<LUT_OR_AND>(pair, __funnelshift_r(cw, cw, (4 * i + 29) & 31), 0x78u); // pair | (idx << 3)
+    const uint2 ef = lds_v2(ea), er = lds_v2(ea + 128u);
+    roll_step(s, make_uint4(ef.x, ef.y, er.x, er.y), P.two);
+    return canonical2(s);
+  };
+  auto store4 = [&](uint32_t g, const uint64_t (&hv)[4]) { // group g of four windows of the tile -> shared memory
+    if (H == 1) {
+      st_shared_v2_u64(chunk_addr(2 * g), hv[0], hv[1]);
+      st_shared_v2_u64(chunk_addr(2 * g + 1), hv[2], hv[3]);
+    } else if (H == 2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) st_shared_v2_u64(chunk_addr(4 * g + i), hv[i], ext_hash(hv[i], P.mult[1]));
+    } else if (H == 3) {
+      uint64_t v[12];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[3 * i] = hv[i];
+        v[3 * i + 1] = ext_hash(hv[i], P.mult[1]);
+        v[3 * i + 2] = ext_hash(hv[i], P.mult[2]);
+      }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) st_shared_v2_u64(chunk_addr(6 * g + c), v[2 * c], v[2 * c + 1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        st_shared_v2_u64(chunk_addr(8 * g + 2 * i), hv[i], ext_hash(hv[i], P.mult[1]));
+        st_shared_v2_u64(chunk_addr(8 * g + 2 * i + 1), ext_hash(hv[i], P.mult[2]), ext_hash(hv[i], P.mult[3]));
+      }
+    }
+  };
+  static_assert(WS % 8 == 0, "tiles are whole index words");
+  for (uint32_t p = 0; p < n; p += WS) {
+    if (p) { // the previous tile must have left shared memory
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+    }
+    if (p + WS <= n) {
+#pragma unroll
+      for (uint32_t w8 = 0; w8 < (uint32_t)WS / 8; ++w8) {
+        const uint32_t cw = next8();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint64_t hv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hv[i] = window(cw, 4 * half + i);
+          store4(2 * w8 + half, hv);
+        }
+      }
+    } else { // the last, shorter tile of a row (kept rolled up); windows past the row's end land in the tile but are clipped
+#pragma unroll 1
+      for (uint32_t w8 = 0; 8 * w8 < n - p; ++w8) {
+        const uint32_t cw = next8();
+#pragma unroll 1
+        for (uint32_t half = 0; half < 2; ++half) {
+          uint64_t hv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hv[i] = window(half ? cw >> 16 : cw, i);
+          store4(2 * w8 + half, hv);
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(&omap, tb0, 0, row0, (int)(p * H / 8));
+      bulk_commit();
+    }
+  }
+  const bool dirty = active && bad;
+  const bool any_dirty = __any_sync(0xffffffffu, dirty);
+  if (lane == 0) {
+    if (any_dirty) bulk_wait_all0(); // zeros must land after the tile they overwrite
+    else bulk_wait_read0();          // shared memory must outlive the TMA read
+  }
+  __syncwarp();
+  if (dirty) { // exact clean-up from the ASCII bytes: windows touching a non-ACGTU byte are not emitted (kmer.cpp:232-235, :255-258)
+    const uint32_t n_own = P.g.flat ? (uint32_t)min((uint64_t)n, (uint64_t)P.g.nk - my_out % P.g.nk) : n;
+    const uint8_t* sq = P.bases + my_byte;
+    uint32_t run = 0;
+    for (uint32_t j = 0; j < n_own + k - 1; ++j) {
+      run = is_acgtu(sq[j]) ? run + 1 : 0;
+      if (j >= k - 1 && run < k) {
+        const uint64_t w = my_out + (j - (k - 1));
+        for (uint32_t q = 0; q < (uint32_t)H; ++q) P.out[w * H + q] = 0;
+        if (P.valid_bits) atomicAnd(&P.valid_bits[(P.valid_row0 + w) >> 5], ~(1u << ((P.valid_row0 + w) & 31)));
+      }
+    }
+  }
+}
+
 // FLAT geometry, second launch: the rows the main kernel cannot produce.  Item f >= 1 = the windows of read f that
 // share a flat item with the end of read f-1 (the main kernel rolled across the boundary there and stored junk);
 // item 0 = the partial last item of the batch, which the tensor map leaves out.  At most seg windows each, FIX_LANES
@@ -1158,10 +1429,74 @@ cudaError_t launch_fast_h(const KmerParams& P, const FastCfg& c, cudaStream_t st
   }
 }
 
+// ---- kmer_pack_kernel launch: strip size from the geometry, CTA size by resident warps ----
+template<int H>
+constexpr int pack_ws()
+{
+  return H == 1 ? 24 : H == 2 ? 16 : 8; // windows per tensor store: 192 / 256 / 192 / 256 bytes per row, whole index words
+}
+
+// 16-byte chunks of ASCII one warp (32 consecutive items) stages at most
+uint64_t pack_max_chunks(const KmerGeom& g, uint32_t k)
+{
+  const uint64_t span = g.flat ? 32ull * g.seg + (32ull * g.seg / g.nk + 2) * (k - 1) : 31ull * g.read_len + g.seg + k - 1;
+  return (span + 1 + 15 + 15) / 16 + 1; // base -1, the aligned start, the rounded-up end
+}
+
+template<int H>
+cudaError_t launch_pack_t(const KmerParams& P, uint32_t nt_env, cudaStream_t st)
+{
+  constexpr int WS = pack_ws<H>();
+  constexpr uint32_t TILE = (uint32_t)(WS * H / 8) * 2048u;
+  const uint32_t strip_bytes = (uint32_t)pack_max_chunks(P.g, P.k) * 8u + 48u;
+  auto smem_for = [&](uint32_t nt) { return (nt / 32) * (TILE + strip_bytes + 64u) + (uint32_t)PK_TAB_BYTES; };
+  // the CTA size that leaves the most warps resident (shared memory: 227 KB per SM, 1 KB reserved per CTA; registers: <= 32
+  // warps at the kernel's ~64 registers per thread); larger CTAs share the tables among more warps and win ties
+  uint32_t nt = 0, best = 0;
+  for (uint32_t cand : { 256u, 192u, 160u, 128u, 96u, 64u }) {
+    const uint32_t sm = smem_for(cand) + 1024u;
+    if (sm > 227u * 1024u) continue;
+    const uint32_t warps = std::min(32u / (cand / 32) * (cand / 32), (227u * 1024u / sm) * (cand / 32));
+    if (warps > best) {
+      best = warps;
+      nt = cand;
+    }
+  }
+  if (nt_env) nt = nt_env;
+  if (!nt || nt % 32 || nt > 256 || smem_for(nt) > 227u * 1024u) return cudaErrorInvalidConfiguration;
+  CUtensorMap map;
+  memset(&map, 0, sizeof map);
+  cudaError_t e = make_out_map(P, (uint32_t)(WS * H / 8), &map);
+  if (e != cudaSuccess) return e;
+  auto fn = kmer_pack_kernel<H, WS>;
+  const uint32_t smem_bytes = smem_for(nt);
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (e != cudaSuccess) return e;
+  const uint64_t ctas = (P.g.n_items + nt - 1) / nt;
+  if (ctas > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+  fn<<<(unsigned)ctas, nt, smem_bytes, st>>>(P, map, strip_bytes);
+  return cudaGetLastError();
+}
+
 uint32_t env_u32(const char* name, uint32_t dflt)
 {
   const char* e = getenv(name);
   return e ? (uint32_t)atoi(e) : dflt;
+}
+
+// FLAT geometry: rows behind every read boundary + the partial last item, after the main kernel's junk has landed
+cudaError_t launch_flat_fix(const KmerParams& P, cudaStream_t st)
+{
+  const uint64_t n_reads = P.g.total / P.g.nk;
+  const uint32_t warp_bytes = (P.g.seg + P.k + 16 + 15) & ~15u; // bytes -1 .. n+k-2 of one item, n <= seg
+  const uint32_t wpb = std::max(1u, std::min(4u, (200u * 1024u) / warp_bytes));
+  if (warp_bytes > 200u * 1024u) return cudaErrorInvalidConfiguration;
+  if (wpb * warp_bytes > 48u * 1024u) {
+    const cudaError_t e = cudaFuncSetAttribute(kmer_flat_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wpb * warp_bytes));
+    if (e != cudaSuccess) return e;
+  }
+  kmer_flat_fix_kernel<<<(unsigned)((n_reads + wpb - 1) / wpb), wpb * FIX_LANES, wpb * warp_bytes, st>>>(P, n_reads, warp_bytes);
+  return cudaGetLastError();
 }
 
 } // namespace
@@ -1191,8 +1526,12 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
     KmerGeom& g = P.g;
     const uint64_t n_reads = g.n_items / g.segs;
     const uint32_t whole = env_u32("NTHASH_B200_FAST_WHOLE_READ", 400), seg_t = env_u32("NTHASH_B200_FAST_SEG", 240);
-    uint32_t flat_seg = env_u32("NTHASH_B200_FLAT_SEG", 264);
-    flat_seg = std::max(24u, flat_seg / 24u * 24u);
+    // windows per flat item: a multiple of 8 (rows of whole 64-byte blocks for every h), 168 by default — the round-2 sweep
+    // (profiles/r02_c5_flatseg_sweep.txt: 120 0.816, 144 0.851, 168 0.864, 216 0.837, 264 0.840, 360 0.812 of the HBM peak on
+    // C5; 192 = 48 words between lanes, 16-way LDS conflicts: 0.636): shorter items leave shared memory for more resident
+    // warps, longer ones amortise the k-base warm-up
+    uint32_t flat_seg = env_u32("NTHASH_B200_FLAT_SEG", 168);
+    flat_seg = std::max(24u, flat_seg / 8u * 8u);
     const bool flat_ok = !P.reduce_out && !P.out_fwd && !P.bloom_mode && P.h <= 4 && g.nk >= 2 * flat_seg &&
                          (n_reads * (uint64_t)g.nk) / flat_seg > 0 && !getenv("NTHASH_B200_FAST_NO_BOX") && !getenv("NTHASH_B200_NO_FLAT");
     if (g.read_len <= whole) { // one item per read
@@ -1202,9 +1541,9 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
       c.box = !P.reduce_out && !P.out_fwd && P.h <= 4 && ((uint64_t)g.nk * P.h) % 8 == 0 && !getenv("NTHASH_B200_FAST_NO_BOX");
     } else if (flat_ok) {
       // FLAT: item i = dense windows [i*seg, (i+1)*seg) of the whole batch.  Every row of the [items][seg] view is full
-      // and seg*h*8-byte pitched, so long reads leave through the same 3-D tensor stores as short ones.  seg = 264 =
-      // 11 tiles of 24 windows (12 x h=2, 8 x h=3/4) and 66 words between neighbouring lanes' rows (2-way LDS.32
-      // conflicts; 64 words would be 32-way).  Rows past a read boundary are junk and are redone by the fix-up kernel.
+      // and seg*h*8-byte pitched, so long reads leave through the same 3-D tensor stores as short ones.  seg = 168 =
+      // 7 tiles of 24 windows (12 x h=2, 8 x h=3/4) and 42 words between neighbouring lanes' rows (2-way LDS.32
+      // conflicts; 48 or 64 words would be 16- or 32-way).  Rows past a read boundary are junk and are redone by the fix-up kernel.
       g.flat = 1;
       g.total = n_reads * g.nk;
       g.seg = flat_seg;
@@ -1261,6 +1600,20 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
     P.prefetch_ctas = env_u32("NTHASH_B200_PREFETCH_CTAS", 0);
     if (P.prefetch_ctas == 1) P.prefetch_ctas = resident;
   }
+  // BOX batches (whole-read items with 64-byte-multiple rows, or flat items), opt-in (NTHASH_B200_PACK=1; measured slower, see
+  // kmer_pack_kernel): the warp-private nibble-strip kernel, when a warp's bytes fit its strip (reads up to ~250 bases, any
+  // flat item); kmer_fast_kernel keeps everything else
+  if (c.box && !P.reduce_out && !P.out_fwd && !P.bloom_mode && P.h <= 4 && pack_max_chunks(P.g, P.k) <= PK_MAX_CHUNKS &&
+      env_u32("NTHASH_B200_PACK", 0) != 0) {
+    const uint32_t nt_env = env_u32("NTHASH_B200_PACK_NT", 0);
+    e = P.h == 1 ? launch_pack_t<1>(P, nt_env, st) : P.h == 2 ? launch_pack_t<2>(P, nt_env, st) : P.h == 3 ? launch_pack_t<3>(P, nt_env, st)
+                                                                                                          : launch_pack_t<4>(P, nt_env, st);
+    if (e != cudaErrorInvalidConfiguration) {
+      if (e == cudaSuccess && P.g.flat) e = launch_flat_fix(P, st);
+      return e;
+    }
+    cudaGetLastError();
+  }
   if (P.bloom_mode) { // runtime number of hashes; mult[0] carries k * MULTISEED
     P.mult[0] = (uint64_t)P.k * MULTISEED;
     return P.bloom_mode == 1   ? launch_fast_t<1, 2, fast_ws<1>(0), 1, false>(P, c.nt, st)
@@ -1277,18 +1630,7 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
              : P.out_fwd  ? launch_fast_t<0, 4, 8, 1, false>(P, c.nt, st)
                           : launch_fast_t<0, 0, 8, 1, false>(P, c.nt, st);
   }
-  if (e == cudaSuccess && P.g.flat) { // rows behind every read boundary + the partial last item, after the junk has landed
-    const uint64_t n_reads = P.g.total / P.g.nk;
-    const uint32_t warp_bytes = (P.g.seg + P.k + 16 + 15) & ~15u; // bytes -1 .. n+k-2 of one item, n <= seg
-    const uint32_t wpb = std::max(1u, std::min(4u, (200u * 1024u) / warp_bytes));
-    if (warp_bytes > 200u * 1024u) return cudaErrorInvalidConfiguration;
-    if (wpb * warp_bytes > 48u * 1024u) {
-      e = cudaFuncSetAttribute(kmer_flat_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wpb * warp_bytes));
-      if (e != cudaSuccess) return e;
-    }
-    kmer_flat_fix_kernel<<<(unsigned)((n_reads + wpb - 1) / wpb), wpb * FIX_LANES, wpb * warp_bytes, st>>>(P, n_reads, warp_bytes);
-    e = cudaGetLastError();
-  }
+  if (e == cudaSuccess && P.g.flat) e = launch_flat_fix(P, st);
   return e;
 }
 

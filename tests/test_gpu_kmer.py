@@ -127,7 +127,7 @@ def test_fast_kernel_output_paths(n, read_len, k, h, no_box, monkeypatch):
 
 @pytest.mark.parametrize("n,read_len,k,h", [(37, 5000, 63, 1), (100, 1200, 31, 2), (50, 3000, 21, 4), (64, 2113, 31, 3), (3, 700, 31, 1),
                                             (1, 100000, 63, 1), (1000, 600, 33, 1), (700, 1057, 5, 1)])
-@pytest.mark.parametrize("flat_seg", [264, 96])
+@pytest.mark.parametrize("flat_seg", [168, 264, 96])
 def test_flat_items_long_uniform_reads(n, read_len, k, h, flat_seg, monkeypatch):
     """Uniform long reads run as FLAT items (fixed runs of dense windows that ignore read boundaries, 3-D tensor stores)
     plus a fix-up launch for the rows behind every read boundary and the partial last item.  Dirty bytes are planted on
@@ -148,6 +148,31 @@ def test_flat_items_long_uniform_reads(n, read_len, k, h, flat_seg, monkeypatch)
     res2 = nthash_b200.kmer_hashes_uniform(d_b, n, read_len, k, h)
     torch.cuda.synchronize()
     assert torch.equal(res2.out, res.out) and torch.equal(res2.valid_bits, res.valid_bits)
+
+
+@pytest.mark.parametrize("n,read_len,k,h", [(3000, 150, 31, 1), (1000, 150, 31, 2), (1500, 150, 31, 3), (1000, 150, 31, 4), (33, 150, 31, 1),
+                                            (1, 150, 31, 1), (257, 102, 31, 1), (900, 250, 63, 4), (37, 5000, 63, 1), (100, 1200, 31, 2),
+                                            (1, 100000, 63, 1), (64, 2113, 31, 3), (700, 1057, 5, 1)])
+def test_nibble_strip_kernel(n, read_len, k, h, monkeypatch):
+    """kmer_pack_kernel (opt-in, NTHASH_B200_PACK=1): warp-private strips of nibble-packed bases, validity per 16-byte chunk,
+    exact scrub from global memory.  Whole-read items and flat items, dirty bytes at read boundaries, every CTA size."""
+    monkeypatch.setenv("NTHASH_B200_PACK", "1")
+    rng = np.random.default_rng(n * 31 + read_len + k + h)
+    bases = synth(rng, n * read_len, p_bad=0.0004, lower=0.05)
+    bases[-1] = ord("N")
+    bases[0] = ord("n") if n > 40 else bases[0]
+    for r in range(1, n, max(1, n // 5)):
+        bases[r * read_len - 1] = ord("N")
+        bases[r * read_len + k - 1] = ord("R")
+    d_b, _keep = to_dev(bases)
+    off = np.arange(n + 1, dtype=np.uint64) * read_len
+    ora = ORACLE.kmer_batch(bases, off, k, h, threads=8)
+    for nt in (0, 64, 160):
+        if nt:
+            monkeypatch.setenv("NTHASH_B200_PACK_NT", str(nt))
+        res = nthash_b200.kmer_hashes_uniform(d_b, n, read_len, k, h)
+        torch.cuda.synchronize()
+        assert_batch_equal(res, ora, h)
 
 
 @pytest.mark.parametrize("n,read_len,k,h", [(40, 6000, 2000, 1), (6, 70000, 65535, 2), (300, 1300, 1023, 4)])
