@@ -679,16 +679,45 @@ def class_api_record():
 
 
 def extra_consumers(torch, nthash_b200, nd, w, args, world):
-    """Consumers added in round 2 (minimizers, cardinality sketch) when the library exports them."""
+    """Consumers added in round 2 on the headline batch: window minimizers (w = 10) and the ntCard-style cardinality sketch.
+    Device-resident time (CUDA events, max over ranks) + what leaves the device per k-mer."""
     rec = {}
-    for name, fn in (("minimizer", getattr(nthash_b200, "bench_minimizer_record", None)),
-                     ("cardinality_sketch", getattr(nthash_b200, "bench_sketch_record", None))):
-        if fn is None:
-            continue
-        try:
-            rec[name] = fn(torch, nd, w, args, world)
-        except Exception as e:
-            rec[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    steps = max(3, min(args.steps, 5))
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return nd.max_over_ranks([e0.elapsed_time(e1) / steps])[0], out
+
+    try:
+        window = 10
+        cap = w.rows // 4  # ~2/(w+1) of the rows are selected on random sequence
+        ms, (bits, mh, mr, n_sel) = timed(lambda: nthash_b200.kmer_minimizers_uniform(w.bases, w.n, w.L, w.k, window, capacity=cap))
+        # size-independent properties: every selected row carries the hash the row path stored; selection density ~ 2/(w+1)
+        sample = mr[:100000].long()
+        same = bool((w.out.view(-1)[sample * w.H] == mh[:100000]).all())
+        rec["minimizer"] = {"window": window, "value": world * w.rows / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "selected": int(n_sel),
+                            "selected_fraction": n_sel / w.rows, "expected_fraction_random_sequence": 2 / (window + 1),
+                            "bytes_out_per_kmer": (16 * n_sel + w.rows / 8) / w.rows, "selected_hashes_match_row_path": same}
+        del bits, mh, mr
+    except Exception as e:
+        rec["minimizer"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    try:
+        ms, (counters, res) = timed(lambda: nthash_b200.kmer_sketch_uniform(w.bases, w.n, w.L, w.k, sample_bits=7, index_bits=20))
+        total = int(counters.sum())
+        rec["cardinality_sketch"] = {"sample_bits": 7, "index_bits": 20, "value": world * w.rows / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                                     "windows": int(res[0]), "sampled_per_step": int(res[1]),
+                                     "counters_sum_equals_sampled": total == int(res[1]),
+                                     "bytes_out_per_step": int(counters.numel() * 4)}
+    except Exception as e:
+        rec["cardinality_sketch"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    torch.cuda.empty_cache()
     return rec
 
 

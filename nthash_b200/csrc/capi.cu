@@ -273,6 +273,9 @@ struct DevBatch
   uint64_t* d_reduce = nullptr; // fused consumer output {windows, sum, xor}; then d_out etc. are NULL
   uint64_t rows = 0;            // dense rows of this batch (set by the host pipeline)
   uint32_t* d_bloom = nullptr;  // Bloom-filter consumer: filter words, size in bits, 1 = insert / 2 = query
+  const uint8_t* d_packed = nullptr; // 2-bit packed input hashed directly (uniform batches the nibble-strip kernel takes); then d_bases is unused
+  const uint32_t* d_inv = nullptr;
+  uint32_t packed_first = 0;
   uint64_t bloom_bits = 0;
   uint32_t bloom_mode = 0;
 };
@@ -293,6 +296,9 @@ static int kmer_dev_run(const DevBatch& B, uint32_t k, uint32_t h, cudaStream_t 
   P.bloom_words = B.d_bloom;
   P.bloom_bits = B.bloom_bits;
   P.bloom_mode = B.bloom_mode;
+  P.packed = B.d_packed;
+  P.inv_bits = B.d_inv;
+  P.packed_first = B.packed_first;
   RaggedItems R;
   if (B.uniform_len) {
     // the fast kernel plans its own (smaller) CTAs, so a tile too large for the general kernel is not fatal yet
@@ -462,8 +468,8 @@ static int host_pipeline(const HostBatch& hb, Launch&& launch)
   for (int i = 0; i < ns; ++i) {
     NTH_TRY(cudaStreamCreateWithFlags(&slot[i].st, cudaStreamNonBlocking));
     NTH_TRY(cudaMallocAsync(&slot[i].d_bases, max_bases + 96, slot[i].st));
-    if (hb.packed) NTH_TRY(cudaMallocAsync(&slot[i].d_packed, max_bases / 4 + 16, slot[i].st));
-    if (hb.packed && hb.invalid_bits) NTH_TRY(cudaMallocAsync(&slot[i].d_inv, (max_bases / 32 + 4) * 4, slot[i].st));
+    if (hb.packed) NTH_TRY(cudaMallocAsync(&slot[i].d_packed, max_bases / 4 + 128, slot[i].st)); // slack: whole 16-byte chunks are read
+    if (hb.packed && hb.invalid_bits) NTH_TRY(cudaMallocAsync(&slot[i].d_inv, (max_bases / 32 + 16) * 4, slot[i].st));
     if (!uniform) NTH_TRY(cudaMallocAsync(&slot[i].d_off, 2 * (max_reads + 1) * sizeof(uint64_t), slot[i].st));
     if (hb.out || hb.scratch_rows) NTH_TRY(cudaMallocAsync(&slot[i].d_out, max_rows * hb.H * sizeof(uint64_t), slot[i].st));
     if (hb.strand_cols) {
@@ -491,14 +497,20 @@ static int host_pipeline(const HostBatch& hb, Launch&& launch)
     const uint64_t b0 = uniform ? base0 + r0 * len0 : hb.read_off[r0], nbytes = uniform ? (r1 - r0) * len0 : hb.read_off[r1] - b0;
     const uint64_t row0 = koff(r0), nrows = koff(r1) - row0;
     if (nrows == 0) continue;
+    bool packed_direct = false;
+    uint32_t packed_first = 0;
     // chunk bytes sit 16 bytes into the slot so that "the base before the first one" is addressable
     if (hb.packed) { // a quarter of the bytes cross PCIe; a small kernel expands them to the ASCII the hash kernels read
       // both slices start at the bitmap word holding base b0 (base 32*v0), so one offset addresses them
       const uint64_t v0 = b0 / 32, v1 = (b0 + nbytes + 31) / 32, p0 = 8 * v0, p1 = (b0 + nbytes + 3) / 4;
       NTH_TRY(cudaMemcpyAsync(s.d_packed, hb.packed + p0, p1 - p0, cudaMemcpyHostToDevice, s.st));
       if (hb.invalid_bits) NTH_TRY(cudaMemcpyAsync(s.d_inv, hb.invalid_bits + v0, (v1 - v0) * 4, cudaMemcpyHostToDevice, s.st));
-      // the kernel indexes the staged slices with bases counted from their first byte / word
-      NTH_TRY(launch_unpack2bit(s.d_packed, hb.invalid_bits ? s.d_inv : nullptr, b0 - 32 * v0, nbytes, s.d_bases + 16, s.st));
+      // the kernels index the staged slices with bases counted from their first byte / word.  Fixed-length reads the
+      // nibble-strip kernel takes are hashed straight from the packed bytes; everything else is expanded to ASCII first
+      packed_direct = uniform && !hb.reduce_result && !hb.out_fwd && kmer_packed_direct_ok(nr, (uint32_t)len0, hb.k, (uint32_t)hb.H);
+      if (!packed_direct)
+        NTH_TRY(launch_unpack2bit(s.d_packed, hb.invalid_bits ? s.d_inv : nullptr, b0 - 32 * v0, nbytes, s.d_bases + 16, s.st));
+      packed_first = (uint32_t)(b0 - 32 * v0);
     } else {
       NTH_TRY(cudaMemcpyAsync(s.d_bases + 16, hb.bases + b0, nbytes, cudaMemcpyHostToDevice, s.st));
     }
@@ -515,6 +527,11 @@ static int host_pipeline(const HostBatch& hb, Launch&& launch)
       B.d_bases = s.d_bases + 16;
       B.n_bases = nbytes + 64;
       B.uniform_len = (uint32_t)len0;
+      if (packed_direct) {
+        B.d_packed = s.d_packed;
+        B.d_inv = hb.invalid_bits ? s.d_inv : nullptr;
+        B.packed_first = packed_first;
+      }
     } else {
       s.h_off.resize(2 * (nr + 1));
       uint64_t mx = 0;

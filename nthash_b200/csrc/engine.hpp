@@ -50,12 +50,19 @@ struct KmerParams
   uint32_t prefetch_ctas = 0;    // fast kernel: L2-prefetch the base tile this many CTAs ahead (0 = off)
   const uint4* t4 = nullptr;     // tetramer warm-up table (fast kernel only), filled by launch_kmer_fast
   uint32_t two = 2;              // the constant 2 as a kernel parameter (roll_step: keeps a multiply on the FMA pipe)
+  // 2-bit packed input read directly by kmer_pack_kernel (then `bases` is not used): 4 bases per byte, A C G T = 0 1 2 3; bit j of
+  // inv_bits (nullable) marks base j of the slice as invalid; the batch's base 0 is base `packed_first` of the slice
+  const uint8_t* packed = nullptr;
+  const uint32_t* inv_bits = nullptr;
+  uint32_t packed_first = 0;
 };
 
 uint32_t kmer_smem_bytes(uint32_t tile_cap);
 // Fast path (kmer_fast_kernel.cu): uniform batch, all items full, rows 16-byte multiples, h in {1,2,4}.
 bool kmer_fast_ok(const KmerParams& P);
 cudaError_t launch_kmer_fast(const KmerParams& P, cudaStream_t st);
+// can a fixed-length batch of 2-bit packed reads be hashed straight from the packed bytes (no ASCII expansion)?
+bool kmer_packed_direct_ok(uint64_t n_reads, uint32_t read_len, uint32_t k, uint32_t h);
 cudaError_t launch_kmer(KmerParams P, cudaStream_t st);
 // the per-(device, k) tetramer warm-up table of the fast kernel (created on first use, kept for the life of the process)
 cudaError_t get_t4_table(uint32_t k, const uint4** out);

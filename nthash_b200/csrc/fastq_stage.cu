@@ -1,42 +1,140 @@
 // fastq_stage.cu — the step before the hash path: FASTQ text that already sits in device
-// memory -> the concatenated `bases` + `read_off` layout every batch entry point takes.  No host-side parsing: the
-// newline positions come from a device-wide select, the sequence lines (every 4th line, starting at the 2nd) are
-// copied out by one warp per read.  Library scans (CUB DeviceSelect / DeviceScan) do the prefix work: this is staging,
-// not the hot path.  Records are the plain four-line form (`@id`, sequence, `+`, qualities), LF or CRLF line ends.
+// memory -> the concatenated `bases` + `read_off` layout every batch entry point takes.  No host-side parsing and no
+// library calls: the newline positions come from a three-launch select (per-tile counts, one-block scan of the tile
+// sums, ordered write), read_off from the same scan over the sequence-line lengths, and the sequence lines (every 4th
+// line, starting at the 2nd) are copied out by one warp per read.  This is staging, not the hot path.  Records are the
+// plain four-line form (`@id`, sequence, `+`, qualities), LF or CRLF line ends.
 #include "engine.hpp"
-
-#include <cub/cub.cuh>
-#include <thrust/iterator/counting_iterator.h>
 
 namespace nthb {
 
 namespace {
 
-struct IsNewline
-{
-  const uint8_t* text;
-  __device__ bool operator()(uint64_t i) const { return text[i] == '\n'; }
-};
+constexpr uint32_t FQ_T = 256;                  // threads per block
+constexpr uint32_t FQ_TILE_BYTES = FQ_T * 16;   // select: 16 bytes of text per thread
+constexpr uint32_t FQ_VALS = 8;                 // scan: values per thread
 
-__global__ void count_newlines(const uint8_t* text, uint64_t n_bytes, unsigned long long* count)
+// bytes of w equal to '\n', one flag bit per byte (bit 7 of the byte)
+__device__ __forceinline__ uint32_t nl_flags(uint32_t w)
 {
+  const uint32_t x = w ^ 0x0A0A0A0Au;
+  return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+}
+
+// 16 bytes of text starting at byte i (any alignment, bounds-checked) as four little-endian words; bytes past the end read as 0
+__device__ __forceinline__ uint4 text16(const uint8_t* text, uint64_t n_bytes, uint64_t i)
+{
+  if (i + 16 <= n_bytes && ((uintptr_t)(text + i) & 15) == 0) return *reinterpret_cast<const uint4*>(text + i);
+  uint32_t w[4] = { 0, 0, 0, 0 };
+  for (uint32_t j = 0; j < 16 && i + j < n_bytes; ++j) w[j >> 2] |= (uint32_t)text[i + j] << (8 * (j & 3));
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// exclusive scan of one value per thread across the block; returns this thread's offset, *total = the block's sum
+__device__ __forceinline__ uint64_t block_excl_scan(uint64_t v, uint64_t* total)
+{
+  __shared__ uint64_t wsum[FQ_T / 32];
+  __shared__ uint64_t btotal;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t x = v;
+  for (uint32_t o = 1; o < 32; o <<= 1) {
+    const uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) wsum[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    uint64_t s = lane < FQ_T / 32 ? wsum[lane] : 0, t = s;
+    for (uint32_t o = 1; o < 32; o <<= 1) {
+      const uint64_t y = __shfl_up_sync(0xffffffffu, t, o);
+      if (lane >= o) t += y;
+    }
+    if (lane < FQ_T / 32) wsum[lane] = t - s;
+    if (lane == 31) btotal = t;
+  }
+  __syncthreads();
+  const uint64_t r = wsum[warp] + x - v;
+  if (total) *total = btotal;
+  __syncthreads(); // wsum / btotal may be reused by the caller's next scan
+  return r;
+}
+
+// ---- select: positions of the newlines, in order ----
+__global__ void __launch_bounds__(FQ_T) nl_tile_counts(const uint8_t* text, uint64_t n_bytes, uint64_t* tile_count)
+{
+  const uint64_t i = ((uint64_t)blockIdx.x * FQ_T + threadIdx.x) * 16;
   uint32_t c = 0;
-  const uint64_t head = min(n_bytes, (uint64_t)((16 - ((uintptr_t)text & 15)) & 15)), n16 = (n_bytes - head) / 16;
-  const uint4* t16 = reinterpret_cast<const uint4*>(text + head);
-  auto nls = [](uint32_t w) { // bytes of w equal to '\n'
-    const uint32_t x = w ^ 0x0A0A0A0Au;
-    return __popc(~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u);
-  };
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint4 v = t16[i];
-    c += nls(v.x) + nls(v.y) + nls(v.z) + nls(v.w);
+  if (i < n_bytes) {
+    const uint4 v = text16(text, n_bytes, i);
+    c = __popc(nl_flags(v.x)) + __popc(nl_flags(v.y)) + __popc(nl_flags(v.z)) + __popc(nl_flags(v.w));
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    for (uint64_t i = 0; i < head; ++i) c += text[i] == '\n';
-    for (uint64_t i = head + n16 * 16; i < n_bytes; ++i) c += text[i] == '\n';
+  uint64_t total;
+  block_excl_scan(c, &total);
+  if (threadIdx.x == 0) tile_count[blockIdx.x] = total;
+}
+
+// one block: sums[0..n) -> exclusive offsets in place, the grand total to *total
+__global__ void __launch_bounds__(FQ_T) scan_tile_sums(uint64_t* sums, uint64_t n, uint64_t* total)
+{
+  uint64_t carry = 0;
+  for (uint64_t base = 0; base < n; base += (uint64_t)FQ_T * FQ_VALS) {
+    uint64_t v[FQ_VALS], mine = 0;
+    for (uint32_t j = 0; j < FQ_VALS; ++j) {
+      const uint64_t idx = base + (uint64_t)threadIdx.x * FQ_VALS + j;
+      v[j] = idx < n ? sums[idx] : 0;
+      mine += v[j];
+    }
+    uint64_t chunk_total;
+    uint64_t off = carry + block_excl_scan(mine, &chunk_total);
+    for (uint32_t j = 0; j < FQ_VALS; ++j) {
+      const uint64_t idx = base + (uint64_t)threadIdx.x * FQ_VALS + j;
+      if (idx < n) sums[idx] = off;
+      off += v[j];
+    }
+    carry += chunk_total;
   }
-  for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, (unsigned long long)c);
+  if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(FQ_T) nl_write(const uint8_t* text, uint64_t n_bytes, const uint64_t* tile_off, uint64_t* nl)
+{
+  const uint64_t i = ((uint64_t)blockIdx.x * FQ_T + threadIdx.x) * 16;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (i < n_bytes) v = text16(text, n_bytes, i);
+  const uint32_t f[4] = { nl_flags(v.x), nl_flags(v.y), nl_flags(v.z), nl_flags(v.w) };
+  const uint32_t c = __popc(f[0]) + __popc(f[1]) + __popc(f[2]) + __popc(f[3]);
+  uint64_t o = tile_off[blockIdx.x] + block_excl_scan(c, nullptr);
+  for (uint32_t w = 0; w < 4; ++w)
+    for (uint32_t m = f[w]; m; m &= m - 1) nl[o++] = i + 4 * w + ((__ffs(m) - 1) >> 3);
+}
+
+// ---- exclusive sum of per-read lengths: out[0..n] (out[n] = total) ----
+__global__ void __launch_bounds__(FQ_T) len_tile_sums(const uint64_t* len, uint64_t n, uint64_t* tile_sum)
+{
+  uint64_t mine = 0;
+  for (uint32_t j = 0; j < FQ_VALS; ++j) {
+    const uint64_t idx = ((uint64_t)blockIdx.x * FQ_T + threadIdx.x) * FQ_VALS + j;
+    if (idx < n) mine += len[idx];
+  }
+  uint64_t total;
+  block_excl_scan(mine, &total);
+  if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(FQ_T) len_scan_write(const uint64_t* len, uint64_t n, const uint64_t* tile_off, const uint64_t* total, uint64_t* out)
+{
+  uint64_t v[FQ_VALS], mine = 0;
+  const uint64_t first = ((uint64_t)blockIdx.x * FQ_T + threadIdx.x) * FQ_VALS;
+  for (uint32_t j = 0; j < FQ_VALS; ++j) {
+    v[j] = first + j < n ? len[first + j] : 0;
+    mine += v[j];
+  }
+  uint64_t off = tile_off[blockIdx.x] + block_excl_scan(mine, nullptr);
+  for (uint32_t j = 0; j < FQ_VALS; ++j) {
+    if (first + j < n) out[first + j] = off;
+    off += v[j];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *total;
 }
 
 // len[r] = length of the sequence line of record r (CR stripped); start[r] = its first byte
@@ -71,32 +169,31 @@ cudaError_t fastq_extract(const uint8_t* d_text, uint64_t n_bytes, uint8_t* d_ba
   *n_bases_out = 0;
   if (n_bytes == 0) return cudaMemsetAsync(d_read_off, 0, sizeof(uint64_t), st);
   uint64_t *d_nl = nullptr, *d_cnt = nullptr, *d_start = nullptr, *d_len = nullptr;
-  void* d_tmp = nullptr;
+  void* d_tmp = nullptr; // the tile sums of whichever scan is in flight
   auto done = [&](cudaError_t e) {
     for (void* p : { (void*)d_nl, (void*)d_cnt, (void*)d_start, (void*)d_len, d_tmp })
       if (p) cudaFreeAsync(p, st);
     return e;
   };
-  // 1. count the newlines, then list their positions
+  // 1. newline positions: per-tile counts, scan of the tile sums (one block), ordered write
+  const uint64_t n_tiles = (n_bytes + FQ_TILE_BYTES - 1) / FQ_TILE_BYTES;
+  if (n_tiles > 0x7fffffffull) return cudaErrorInvalidValue;
+  uint64_t* d_tile = nullptr;
   cudaError_t e = cudaMallocAsync(&d_cnt, sizeof(uint64_t), st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, sizeof(uint64_t), st);
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_tile, n_tiles * sizeof(uint64_t), st);
+  d_tmp = d_tile;
   if (e != cudaSuccess) return done(e);
-  count_newlines<<<1184, 256, 0, st>>>(d_text, n_bytes, reinterpret_cast<unsigned long long*>(d_cnt));
-  uint64_t max_nl = 0;
-  e = cudaMemcpyAsync(&max_nl, d_cnt, sizeof max_nl, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e == cudaSuccess) e = cudaMallocAsync(&d_nl, (max_nl + 1) * sizeof(uint64_t), st);
-  if (e != cudaSuccess) return done(e);
-  thrust::counting_iterator<uint64_t> idx(0);
-  size_t tmp_bytes = 0;
-  e = cub::DeviceSelect::If(nullptr, tmp_bytes, idx, d_nl, d_cnt, (int64_t)n_bytes, IsNewline{ d_text }, st);
-  if (e == cudaSuccess) e = cudaMallocAsync(&d_tmp, tmp_bytes, st);
-  if (e == cudaSuccess) e = cub::DeviceSelect::If(d_tmp, tmp_bytes, idx, d_nl, d_cnt, (int64_t)n_bytes, IsNewline{ d_text }, st);
+  nl_tile_counts<<<(unsigned)n_tiles, FQ_T, 0, st>>>(d_text, n_bytes, d_tile);
+  scan_tile_sums<<<1, FQ_T, 0, st>>>(d_tile, n_tiles, d_cnt);
   uint64_t n_nl = 0;
   uint8_t last = 0;
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&n_nl, d_cnt, sizeof n_nl, cudaMemcpyDeviceToHost, st);
+  e = cudaMemcpyAsync(&n_nl, d_cnt, sizeof n_nl, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(&last, d_text + n_bytes - 1, 1, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_nl, (n_nl + 1) * sizeof(uint64_t), st);
+  if (e != cudaSuccess) return done(e);
+  nl_write<<<(unsigned)n_tiles, FQ_T, 0, st>>>(d_text, n_bytes, d_tile, d_nl);
+  e = cudaGetLastError();
   if (e != cudaSuccess) return done(e);
   const uint64_t n_lines = n_nl + (last != '\n' ? 1 : 0);
   const uint64_t n_reads = n_lines / 4;
@@ -107,12 +204,18 @@ cudaError_t fastq_extract(const uint8_t* d_text, uint64_t n_bytes, uint8_t* d_ba
   if (e == cudaSuccess) e = cudaMallocAsync(&d_len, (n_reads + 1) * sizeof(uint64_t), st);
   if (e != cudaSuccess) return done(e);
   fastq_seq_lines<<<(unsigned)((n_reads + 255) / 256), 256, 0, st>>>(d_text, n_bytes, d_nl, n_nl, n_reads, d_start, d_len);
-  e = cudaMemsetAsync(d_len + n_reads, 0, sizeof(uint64_t), st);
+  // read_off = exclusive sum of the lengths (+ total): the same three launches over the lengths
   cudaFreeAsync(d_tmp, st);
   d_tmp = nullptr;
-  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len, d_read_off, (int64_t)(n_reads + 1), st);
-  if (e == cudaSuccess) e = cudaMallocAsync(&d_tmp, tmp_bytes, st);
-  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_len, d_read_off, (int64_t)(n_reads + 1), st);
+  const uint64_t n_ltiles = (n_reads + (uint64_t)FQ_T * FQ_VALS - 1) / ((uint64_t)FQ_T * FQ_VALS);
+  uint64_t* d_ltile = nullptr;
+  e = cudaMallocAsync(&d_ltile, n_ltiles * sizeof(uint64_t), st);
+  d_tmp = d_ltile;
+  if (e != cudaSuccess) return done(e);
+  len_tile_sums<<<(unsigned)n_ltiles, FQ_T, 0, st>>>(d_len, n_reads, d_ltile);
+  scan_tile_sums<<<1, FQ_T, 0, st>>>(d_ltile, n_ltiles, d_cnt);
+  len_scan_write<<<(unsigned)n_ltiles, FQ_T, 0, st>>>(d_len, n_reads, d_ltile, d_cnt, d_read_off);
+  e = cudaGetLastError();
   uint64_t n_bases = 0;
   if (e == cudaSuccess) e = cudaMemcpyAsync(&n_bases, d_read_off + n_reads, sizeof n_bases, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -982,13 +982,18 @@ constexpr int PK_PAIR_OFF = 0;     // (from PK_TAB) 16 x 8 B forward pair table,
 constexpr int PK_IN_OFF = 256;     // 4 x 16 B in-only entries (warm-up tail)
 constexpr int PK_T4_OFF = 512;     // 256 x 16 B tetramer table, re-indexed by c0 | c1 << 2 | c2 << 4 | c3 << 6
 constexpr int PK_TAB_BYTES = 512 + T4_BYTES;
-constexpr uint32_t PK_LEAD = 16;   // nibbles of zero padding in front of a strip (base -1 of the batch's first read lives there)
 constexpr uint32_t PK_MAX_CHUNKS = 512; // 16-byte chunks of ASCII a warp may stage (16 bad-chunk words)
 
-template<int H, int WS>
+// PACKED: the input is the caller's 2-bit packed sequence (4 bases per byte, A C G T = 0 1 2 3, base j of the staged slice at
+// bits 2 (j & 3) of byte j >> 2) plus an optional invalid-base bitmap (bit j set: base j is an N), P.packed / P.inv_bits, with
+// the batch's base 0 at slice position P.packed_first.  Chunks are then 64 bases (one 16-byte load); the conversion is a
+// 2-bit -> nibble spread and a code remap (no SWAR validity scan, no byte -> code step), validity is the bitmap's.
+template<int H, int WS, bool PACKED>
 __global__ void __launch_bounds__(256)
 kmer_pack_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ CUtensorMap omap, const uint32_t strip_bytes)
 {
+  constexpr uint32_t CSH = PACKED ? 6 : 4;      // log2(bases per chunk)
+  constexpr uint32_t LEAD = PACKED ? 32u : 16u; // nibbles of zero padding in front of a strip (base -1 of the first read lives there); keeps the chunk stores aligned
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr uint32_t TILE = (uint32_t)(WS * H / 8) * 2048u; // blocks x 32 rows x 64 bytes
   const uint32_t NT = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1021,45 +1026,78 @@ kmer_pack_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   const uint32_t n = P.g.seg; // windows per item: the same for every item of a BOX batch
   auto item_byte = [&](uint64_t i) -> uint64_t { return P.g.flat ? flat_byte(P.g, i * n) : i * (uint64_t)P.g.read_len; };
   const uint64_t it_last = min(it0 + 31, P.g.n_items - 1);
-  const uint64_t b_first = item_byte(it0);
-  const uint64_t b_end = (P.g.flat ? flat_byte(P.g, it_last * n + n - 1) : it_last * (uint64_t)P.g.read_len + n - 1) + k; // one past the last byte
-  const uint64_t a0 = (b_first ? b_first - 1 : 0) & ~15ull; // 16-byte aligned start of the staged range
-  const uint32_t n_chunks = (uint32_t)((b_end - a0 + 15) >> 4);
+  const uint64_t xo = PACKED ? P.packed_first : 0; // position of the batch's base 0 in the staged slice
+  const uint64_t b_first = item_byte(it0) + xo;
+  const uint64_t b_end = (P.g.flat ? flat_byte(P.g, it_last * n + n - 1) : it_last * (uint64_t)P.g.read_len + n - 1) + k + xo; // one past the last base
+  const uint64_t a0 = (b_first ? b_first - 1 : 0) & ~(uint64_t)((1u << CSH) - 1); // chunk-aligned start of the staged range
+  const uint32_t n_chunks = (uint32_t)((b_end - a0 + (1u << CSH) - 1) >> CSH);
   const uint32_t strip = sbase + PK_TAB_BYTES + warp * (strip_bytes + 64u); // [nibble strip][16 bad-chunk words]
   const uint32_t badw = strip + strip_bytes;
   const uint32_t tb0 = smem_u32(smem) + warp * TILE;
-  if (n_chunks * 8u + 48u > strip_bytes || n_chunks > PK_MAX_CHUNKS) __trap(); // the launcher sized the strip for this geometry
+  if ((n_chunks << (CSH - 1)) + LEAD / 2 + 32u > strip_bytes || n_chunks > PK_MAX_CHUNKS) __trap(); // the launcher sized the strip for this geometry
 
-  // ---- stage + convert: chunk c = bytes a0 + 16c .. +15 -> two words of nibbles at strip + 8 + 8c ----
-  if (lane < 2) asm volatile("st.shared.u32 [%0], %1;" ::"r"(strip + lane * 4), "r"(0u) : "memory"); // the lead-in: code 0 ('A'), cancels out
-  // four chunks per lane in flight (the loads do not depend on each other: one round trip to DRAM per 2 KB of the strip)
+  // ---- stage + convert: chunk c = bases a0 + (c << CSH) .. -> nibbles at strip + 8 + (c << (CSH - 1)) ----
+  if (lane < LEAD / 8) asm volatile("st.shared.u32 [%0], %1;" ::"r"(strip + lane * 4), "r"(0u) : "memory"); // the lead-in: code 0 ('A'), cancels out
+  // four chunks per lane in flight (the loads do not depend on each other: one round trip to DRAM per 2 KB of ASCII)
   auto load_chunk = [&](uint32_t c) {
-    uint4 x = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u); // 'A': hashable, never stored past n_chunks
-    const uint64_t gb = a0 + 16ull * c;
-    if (c < n_chunks) {
-      if (gb + 16 <= P.n_bases) {
-        x = __ldg(reinterpret_cast<const uint4*>(P.bases + gb));
-      } else { // the last bytes of the buffer
-        uint32_t w[4] = { 0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u };
-        for (uint32_t j = 0; j < 16 && gb + j < P.n_bases; ++j) w[j >> 2] = (w[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | ((uint32_t)P.bases[gb + j] << (8 * (j & 3)));
-        x = make_uint4(w[0], w[1], w[2], w[3]);
+    if constexpr (PACKED) {
+      uint4 x = make_uint4(0u, 0u, 0u, 0u);
+      if (c < n_chunks) x = __ldg(reinterpret_cast<const uint4*>(P.packed + (a0 >> 2)) + c); // the slice is allocated past its end
+      return x;
+    } else {
+      uint4 x = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u); // 'A': hashable, never stored past n_chunks
+      const uint64_t gb = a0 + 16ull * c;
+      if (c < n_chunks) {
+        if (gb + 16 <= P.n_bases) {
+          x = __ldg(reinterpret_cast<const uint4*>(P.bases + gb));
+        } else { // the last bytes of the buffer
+          uint32_t w[4] = { 0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u };
+          for (uint32_t j = 0; j < 16 && gb + j < P.n_bases; ++j) w[j >> 2] = (w[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | ((uint32_t)P.bases[gb + j] << (8 * (j & 3)));
+          x = make_uint4(w[0], w[1], w[2], w[3]);
+        }
       }
+      return x;
     }
-    return x;
   };
   auto convert_chunk = [&](uint32_t c0, const uint4 x) {
     const uint32_t c = c0 + lane;
-    const uint32_t anybad = swar_bad(x.x) | swar_bad(x.y) | swar_bad(x.z) | swar_bad(x.w);
-    const uint32_t m = __ballot_sync(0xffffffffu, anybad != 0);
-    if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(badw + (c0 >> 5) * 4), "r"(m) : "memory");
-    // per word: codes (x >> 1) & 3 per byte, then byte pairs folded into nibbles: z = y | y >> 4 has c0 | c1 << 4 in byte 0 and
-    // c2 | c3 << 4 in byte 2; PRMT gathers bytes 0, 2 of two words
-    auto nib = [](uint32_t v) {
-      const uint32_t y = (v >> 1) & 0x03030303u;
-      return y | (y >> 4);
-    };
-    const uint32_t lo = __byte_perm(nib(x.x), nib(x.y), 0x6420u), hi = __byte_perm(nib(x.z), nib(x.w), 0x6420u);
-    if (c < n_chunks) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(strip + 8u + 8u * c), "r"(lo), "r"(hi) : "memory");
+    if constexpr (PACKED) {
+      uint32_t anybad = 0;
+      if (P.inv_bits && c < n_chunks) {
+        const uint2 iv = __ldg(reinterpret_cast<const uint2*>(P.inv_bits + (a0 >> 5)) + c);
+        anybad = iv.x | iv.y;
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, anybad != 0);
+      if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(badw + (c0 >> 5) * 4), "r"(m) : "memory");
+      // eight 2-bit codes (16 bits) -> eight nibbles; then A C G T = 0 1 2 3 -> the kernels' (byte >> 1) & 3 order A C T G: p ^ (p >> 1)
+      auto spread = [](uint32_t h16) {
+        uint32_t v = (h16 | (h16 << 8)) & 0x00FF00FFu;
+        v = (v | (v << 4)) & 0x0F0F0F0Fu;
+        v = (v | (v << 2)) & 0x33333333u;
+        return v ^ ((v >> 1) & 0x11111111u);
+      };
+      if (c < n_chunks) {
+        const uint32_t dst = strip + LEAD / 2 + 32u * c;
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(spread(x.x & 0xFFFFu)), "r"(spread(x.x >> 16)), "r"(spread(x.y & 0xFFFFu)),
+                     "r"(spread(x.y >> 16))
+                     : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst + 16u), "r"(spread(x.z & 0xFFFFu)), "r"(spread(x.z >> 16)), "r"(spread(x.w & 0xFFFFu)),
+                     "r"(spread(x.w >> 16))
+                     : "memory");
+      }
+    } else {
+      const uint32_t anybad = swar_bad(x.x) | swar_bad(x.y) | swar_bad(x.z) | swar_bad(x.w);
+      const uint32_t m = __ballot_sync(0xffffffffu, anybad != 0);
+      if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(badw + (c0 >> 5) * 4), "r"(m) : "memory");
+      // per word: codes (x >> 1) & 3 per byte, then byte pairs folded into nibbles: z = y | y >> 4 has c0 | c1 << 4 in byte 0 and
+      // c2 | c3 << 4 in byte 2; PRMT gathers bytes 0, 2 of two words
+      auto nib = [](uint32_t v) {
+        const uint32_t y = (v >> 1) & 0x03030303u;
+        return y | (y >> 4);
+      };
+      const uint32_t lo = __byte_perm(nib(x.x), nib(x.y), 0x6420u), hi = __byte_perm(nib(x.z), nib(x.w), 0x6420u);
+      if (c < n_chunks) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(strip + LEAD / 2 + 8u * c), "r"(lo), "r"(hi) : "memory");
+    }
   };
   for (uint32_t c0 = 0; c0 < n_chunks; c0 += 128) {
     uint4 x[4];
@@ -1074,14 +1112,14 @@ kmer_pack_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   // ---- this lane's item ----
   const uint64_t item = it0 + lane;
   const bool active = item < P.g.n_items;
-  const uint64_t my_byte = active ? item_byte(item) : b_first; // idle lanes hash the first item again; the tensor store clips their rows
+  const uint64_t my_byte = active ? item_byte(item) + xo : b_first; // idle lanes hash the first item again; the tensor store clips their rows
   const uint64_t my_out = item * (uint64_t)n;
-  const uint32_t q0 = PK_LEAD + (uint32_t)(my_byte - a0); // nibble index of the item's base 0
-  // any flagged chunk among the row's bytes -1 .. n+k-2?
+  const uint32_t q0 = LEAD + (uint32_t)(my_byte - a0); // nibble index of the item's base 0
+  // any flagged chunk among the row's bases -1 .. n+k-2?
   bool bad = false;
   {
-    const uint32_t c_lo = (q0 - 1 - PK_LEAD) >> 4, c_hi = (q0 + n + k - 2 - PK_LEAD) >> 4; // q0 - 1 - LEAD may wrap for the batch's first base
-    for (uint32_t c = (q0 > PK_LEAD ? c_lo : 0u); c <= c_hi; ++c) bad |= (lds_u32(badw + (c >> 5) * 4) >> (c & 31)) & 1u;
+    const uint32_t c_lo = (q0 - 1 - LEAD) >> CSH, c_hi = (q0 + n + k - 2 - LEAD) >> CSH; // q0 - 1 - LEAD may wrap for the slice's first base
+    for (uint32_t c = (q0 > LEAD ? c_lo : 0u); c <= c_hi; ++c) bad |= (lds_u32(badw + (c >> 5) * 4) >> (c & 31)) & 1u;
   }
   const uint32_t pair = keep(sbase + PK_PAIR_OFF);
   const uint32_t t4a = keep(sbase + PK_T4_OFF);
@@ -1208,10 +1246,12 @@ kmer_pack_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   __syncwarp();
   if (dirty) { // exact clean-up from the ASCII bytes: windows touching a non-ACGTU byte are not emitted (kmer.cpp:232-235, :255-258)
     const uint32_t n_own = P.g.flat ? (uint32_t)min((uint64_t)n, (uint64_t)P.g.nk - my_out % P.g.nk) : n;
-    const uint8_t* sq = P.bases + my_byte;
     uint32_t run = 0;
     for (uint32_t j = 0; j < n_own + k - 1; ++j) {
-      run = is_acgtu(sq[j]) ? run + 1 : 0;
+      bool ok;
+      if constexpr (PACKED) ok = !((P.inv_bits[(my_byte + j) >> 5] >> ((my_byte + j) & 31)) & 1u);
+      else ok = is_acgtu(P.bases[my_byte + j]);
+      run = ok ? run + 1 : 0;
       if (j >= k - 1 && run < k) {
         const uint64_t w = my_out + (j - (k - 1));
         for (uint32_t q = 0; q < (uint32_t)H; ++q) P.out[w * H + q] = 0;
@@ -1230,7 +1270,15 @@ kmer_pack_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
 constexpr uint32_t FIX_LANES = 32; // a warp per item: its bytes are staged once (coalesced), every lane hashes n / 32 windows
 __global__ void __launch_bounds__(128) kmer_flat_fix_kernel(const __grid_constant__ KmerParams P, uint64_t n_reads, uint32_t warp_bytes)
 {
+  // [tetramer table 4 KB][seeds: S[4], srol^k S[4]][per warp: the item's bytes]; everything a step touches is in shared
+  // memory — the kernel is a few thousand short dependent chains, so its duration is the latency of one chain
   extern __shared__ __align__(16) uint8_t fix_smem[];
+  uint4* t4 = reinterpret_cast<uint4*>(fix_smem);
+  uint64_t* seeds = reinterpret_cast<uint64_t*>(fix_smem + T4_BYTES);
+  for (uint32_t j = threadIdx.x; j < 256; j += blockDim.x) t4[j] = __ldg(P.t4 + j);
+  if (threadIdx.x < 4) seeds[threadIdx.x] = P.s[threadIdx.x];
+  else if (threadIdx.x < 8) seeds[threadIdx.x] = P.sk[threadIdx.x - 4];
+  __syncthreads();
   const uint32_t wpb = blockDim.x / FIX_LANES, warp = threadIdx.x / FIX_LANES, sub = threadIdx.x % FIX_LANES;
   const uint64_t f = (uint64_t)blockIdx.x * wpb + warp;
   if (f >= n_reads) return; // whole warps leave together
@@ -1251,7 +1299,7 @@ __global__ void __launch_bounds__(128) kmer_flat_fix_kernel(const __grid_constan
   // item never starts at base 0 of the batch because flat batches hold at least two full items)
   const uint64_t r = w0 / nk;
   const uint8_t* g0 = P.bases + r * P.g.read_len + (w0 - r * nk) - 1;
-  uint8_t* sb = fix_smem + (size_t)warp * warp_bytes;
+  uint8_t* sb = fix_smem + T4_BYTES + 64 + (size_t)warp * warp_bytes;
   for (uint32_t j = sub; j < n + k; j += FIX_LANES) sb[j] = g0[j];
   __syncwarp();
   const uint32_t per = (n + FIX_LANES - 1) / FIX_LANES, p_lo = min(n, sub * per), p_hi = min(n, p_lo + per);
@@ -1259,27 +1307,33 @@ __global__ void __launch_bounds__(128) kmer_flat_fix_kernel(const __grid_constan
   const uint8_t* sq = sb + 1 + p_lo; // first base of this lane's first window; sq[-1] is staged
   w0 += p_lo;
   n = p_hi - p_lo;
-  // 2-bit code (byte >> 1) & 3: 0 = A, 1 = C, 2 = T/U, 3 = G; index into P.s / P.sk (A, C, G, T) = code ^ (code >> 1)
+  // 2-bit code (byte >> 1) & 3: 0 = A, 1 = C, 2 = T/U, 3 = G; index into S / srol^k S (A, C, G, T) = code ^ (code >> 1)
   auto sidx = [](uint32_t c) { const uint32_t x = (c >> 1) & 3u; return x ^ (x >> 1); };
   State st = { 0u, 0u, 0u, 0u };
-  uint32_t run = 0;
+  uint32_t run = 0; // hashable bases in a row, ending at the newest base
   const uint32_t nq = k >> 2;
   for (uint32_t q = 0; q < nq; ++q) { // bases 4q-1 .. 4q+2
     const uint32_t c0 = sq[(int)(4 * q) - 1], c1 = sq[4 * q], c2 = sq[4 * q + 1], c3 = sq[4 * q + 2];
     const uint32_t idx = ((c0 & 6u) << 5) | ((c1 & 6u) << 3) | ((c2 & 6u) << 1) | ((c3 & 6u) >> 1);
-    roll4_in(st, __ldg(P.t4 + idx));
+    roll4_in(st, t4[idx]);
+    // validity of bases 4q .. 4q+3 (base -1 does not count): SWAR test on the four bytes at once
+    if (4 * q + 3 < k - 1) {
+      const uint32_t bw = swar_bad(c1 | (c2 << 8) | (c3 << 16) | ((uint32_t)sq[4 * q + 3] << 24));
+      if (bw == 0) run += 4;
+      else
+        for (uint32_t j = 0; j < 4; ++j) run = ((bw >> (8 * j)) & 0xFFu) ? 0 : run + 1;
+    }
   }
+  for (uint32_t j = (k - 1) / 4 * 4; j + 1 < k; ++j) run = is_acgtu(sq[j]) ? run + 1 : 0; // the bases the whole words above left out
   for (uint32_t j = 4 * nq; j < k; ++j) { // bases j-1
     const uint32_t c = sq[j - 1];
-    const uint64_t fi = P.s[sidx(c)], ri = P.sk[sidx(c ^ 4u)]; // c ^ 4 flips code bit 1: the complement
+    const uint64_t fi = seeds[sidx(c)], ri = seeds[4 + sidx(c ^ 4u)]; // c ^ 4 flips code bit 1: the complement
     roll_step(st, make_uint4((uint32_t)fi, (uint32_t)(fi >> 32), (uint32_t)ri, (uint32_t)(ri >> 32)), P.two);
   }
-  // hashable bases in a row, ending at base k-2
-  for (uint32_t j = 0; j + 1 < k; ++j) run = is_acgtu(sq[j]) ? run + 1 : 0;
   for (uint32_t p = 0; p < n; ++p) {
     const uint32_t cin = sq[p + k - 1], cout = sq[(int)p - 1];
     run = is_acgtu(cin) ? run + 1 : 0;
-    const uint64_t fe = P.s[sidx(cin)] ^ P.sk[sidx(cout)], re = P.sk[sidx(cin ^ 4u)] ^ P.s[sidx(cout ^ 4u)];
+    const uint64_t fe = seeds[sidx(cin)] ^ seeds[4 + sidx(cout)], re = seeds[4 + sidx(cin ^ 4u)] ^ seeds[sidx(cout ^ 4u)];
     roll_step(st, make_uint4((uint32_t)fe, (uint32_t)(fe >> 32), (uint32_t)re, (uint32_t)(re >> 32)), P.two);
     const uint64_t w = w0 + p, h0 = canonical2(st);
     uint64_t* o = P.out + w * h;
@@ -1437,18 +1491,19 @@ constexpr int pack_ws()
 }
 
 // 16-byte chunks of ASCII one warp (32 consecutive items) stages at most
-uint64_t pack_max_chunks(const KmerGeom& g, uint32_t k)
+uint64_t pack_max_chunks(const KmerGeom& g, uint32_t k, bool packed)
 {
   const uint64_t span = g.flat ? 32ull * g.seg + (32ull * g.seg / g.nk + 2) * (k - 1) : 31ull * g.read_len + g.seg + k - 1;
-  return (span + 1 + 15 + 15) / 16 + 1; // base -1, the aligned start, the rounded-up end
+  const uint64_t cb = packed ? 64 : 16;  // bases per chunk
+  return (span + 1 + 2 * (cb - 1)) / cb + 1; // base -1, the aligned start, the rounded-up end
 }
 
-template<int H>
+template<int H, bool PACKED>
 cudaError_t launch_pack_t(const KmerParams& P, uint32_t nt_env, cudaStream_t st)
 {
   constexpr int WS = pack_ws<H>();
   constexpr uint32_t TILE = (uint32_t)(WS * H / 8) * 2048u;
-  const uint32_t strip_bytes = (uint32_t)pack_max_chunks(P.g, P.k) * 8u + 48u;
+  const uint32_t strip_bytes = (uint32_t)pack_max_chunks(P.g, P.k, PACKED) * (PACKED ? 32u : 8u) + 64u;
   auto smem_for = [&](uint32_t nt) { return (nt / 32) * (TILE + strip_bytes + 64u) + (uint32_t)PK_TAB_BYTES; };
   // the CTA size that leaves the most warps resident (shared memory: 227 KB per SM, 1 KB reserved per CTA; registers: <= 32
   // warps at the kernel's ~64 registers per thread); larger CTAs share the tables among more warps and win ties
@@ -1468,7 +1523,7 @@ cudaError_t launch_pack_t(const KmerParams& P, uint32_t nt_env, cudaStream_t st)
   memset(&map, 0, sizeof map);
   cudaError_t e = make_out_map(P, (uint32_t)(WS * H / 8), &map);
   if (e != cudaSuccess) return e;
-  auto fn = kmer_pack_kernel<H, WS>;
+  auto fn = kmer_pack_kernel<H, WS, PACKED>;
   const uint32_t smem_bytes = smem_for(nt);
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return e;
@@ -1489,19 +1544,33 @@ cudaError_t launch_flat_fix(const KmerParams& P, cudaStream_t st)
 {
   const uint64_t n_reads = P.g.total / P.g.nk;
   const uint32_t warp_bytes = (P.g.seg + P.k + 16 + 15) & ~15u; // bytes -1 .. n+k-2 of one item, n <= seg
-  const uint32_t wpb = std::max(1u, std::min(4u, (200u * 1024u) / warp_bytes));
+  const uint32_t fixed = (uint32_t)T4_BYTES + 64u;              // tetramer table + seeds
   if (warp_bytes > 200u * 1024u) return cudaErrorInvalidConfiguration;
-  if (wpb * warp_bytes > 48u * 1024u) {
-    const cudaError_t e = cudaFuncSetAttribute(kmer_flat_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wpb * warp_bytes));
+  const uint32_t wpb = std::max(1u, std::min(4u, (200u * 1024u) / warp_bytes));
+  const uint32_t smem = fixed + wpb * warp_bytes;
+  if (smem > 48u * 1024u) {
+    const cudaError_t e = cudaFuncSetAttribute(kmer_flat_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  kmer_flat_fix_kernel<<<(unsigned)((n_reads + wpb - 1) / wpb), wpb * FIX_LANES, wpb * warp_bytes, st>>>(P, n_reads, warp_bytes);
+  kmer_flat_fix_kernel<<<(unsigned)((n_reads + wpb - 1) / wpb), wpb * FIX_LANES, smem, st>>>(P, n_reads, warp_bytes);
   return cudaGetLastError();
 }
 
 } // namespace
 
 cudaError_t get_t4_table(uint32_t k, const uint4** out) { return get_t4_table_impl(k, out); }
+
+bool kmer_packed_direct_ok(uint64_t n_reads, uint32_t read_len, uint32_t k, uint32_t h)
+{
+  if (n_reads == 0 || read_len < k || h < 1 || h > 4 || getenv("NTHASH_B200_NO_PACKED_DIRECT") || getenv("NTHASH_B200_FAST_NO_BOX")) return false;
+  if (read_len > env_u32("NTHASH_B200_FAST_WHOLE_READ", 400)) return false; // longer reads are cut / flat: ASCII kernels
+  KmerGeom g;
+  g.read_len = read_len;
+  g.nk = read_len - k + 1;
+  g.seg = g.nk;
+  g.segs = 1;
+  return ((uint64_t)g.nk * h) % 8 == 0 && pack_max_chunks(g, k, true) <= PK_MAX_CHUNKS;
+}
 
 bool kmer_fast_ok(const KmerParams& P)
 {
@@ -1603,11 +1672,18 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
   // BOX batches (whole-read items with 64-byte-multiple rows, or flat items), opt-in (NTHASH_B200_PACK=1; measured slower, see
   // kmer_pack_kernel): the warp-private nibble-strip kernel, when a warp's bytes fit its strip (reads up to ~250 bases, any
   // flat item); kmer_fast_kernel keeps everything else
-  if (c.box && !P.reduce_out && !P.out_fwd && !P.bloom_mode && P.h <= 4 && pack_max_chunks(P.g, P.k) <= PK_MAX_CHUNKS &&
+  if (P.packed) { // 2-bit packed input: only kmer_pack_kernel reads it (whole-read items; the flat fix-up kernel wants ASCII)
+    if (!c.box || P.g.flat || P.reduce_out || P.out_fwd || P.bloom_mode || P.h > 4 || pack_max_chunks(P.g, P.k, true) > PK_MAX_CHUNKS)
+      return cudaErrorNotSupported;
+    const uint32_t nt_env = env_u32("NTHASH_B200_PACK_NT", 0);
+    return P.h == 1 ? launch_pack_t<1, true>(P, nt_env, st) : P.h == 2 ? launch_pack_t<2, true>(P, nt_env, st)
+         : P.h == 3 ? launch_pack_t<3, true>(P, nt_env, st) : launch_pack_t<4, true>(P, nt_env, st);
+  }
+  if (c.box && !P.reduce_out && !P.out_fwd && !P.bloom_mode && P.h <= 4 && pack_max_chunks(P.g, P.k, false) <= PK_MAX_CHUNKS &&
       env_u32("NTHASH_B200_PACK", 0) != 0) {
     const uint32_t nt_env = env_u32("NTHASH_B200_PACK_NT", 0);
-    e = P.h == 1 ? launch_pack_t<1>(P, nt_env, st) : P.h == 2 ? launch_pack_t<2>(P, nt_env, st) : P.h == 3 ? launch_pack_t<3>(P, nt_env, st)
-                                                                                                          : launch_pack_t<4>(P, nt_env, st);
+    e = P.h == 1 ? launch_pack_t<1, false>(P, nt_env, st) : P.h == 2 ? launch_pack_t<2, false>(P, nt_env, st)
+      : P.h == 3 ? launch_pack_t<3, false>(P, nt_env, st) : launch_pack_t<4, false>(P, nt_env, st);
     if (e != cudaErrorInvalidConfiguration) {
       if (e == cudaSuccess && P.g.flat) e = launch_flat_fix(P, st);
       return e;
