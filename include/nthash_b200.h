@@ -167,6 +167,16 @@ int nthash_kmer_batch_packed2bit(const uint8_t* packed, const uint32_t* invalid_
 int nthash_kmer_reduce_packed2bit(const uint8_t* packed, const uint32_t* invalid_bits, const uint64_t* read_off,
                                   uint64_t n_reads, uint32_t uniform_read_len, uint32_t k, uint32_t num_hashes,
                                   uint64_t* result, int device);
+/* Device-resident packed input hashed DIRECTLY (no ASCII copy in HBM): n_reads reads of read_len bases back to back, the
+ * first one starting at base `first_base` (< 2^32) of the packed stream / bitmap.  d_packed must be 16-byte aligned and
+ * readable up to the next multiple of 16 bytes past the last base, d_invalid_bits (nullable) up to the next multiple of
+ * 8 bytes.  Served by the nibble-strip kernel for the shapes it takes (num_hashes <= 4, reads of at most ~250 bases whose
+ * (read_len - k + 1) * num_hashes is a multiple of 8 — Illumina-like batches); returns NTHASH_ERR_UNSUPPORTED otherwise:
+ * then expand with nthash_unpack2bit_dev and use nthash_kmer_batch_uniform_dev.  The host entries above make this choice
+ * themselves per pipeline chunk.                                                                                      */
+int nthash_kmer_batch_packed2bit_uniform_dev(const uint8_t* d_packed, const uint32_t* d_invalid_bits, uint64_t first_base,
+                                             uint64_t n_reads, uint32_t read_len, uint32_t k, uint32_t num_hashes,
+                                             uint64_t* d_out, uint32_t* d_valid_bits, void* stream);
 int nthash_unpack2bit_dev(const uint8_t* d_packed, const uint32_t* d_invalid_bits, uint64_t first_base, uint64_t n_bases,
                           uint8_t* d_bases_out, void* stream);
 

@@ -37,6 +37,7 @@ _SIGS = {
     "nthash_kmer_batch_multi": (C.c_int, [u8p, u64p, C.c_uint64, C.c_uint32, C.c_uint32, u64p, u32p, u64p, u64p, C.c_void_p, C.c_int]),
     "nthash_kmer_batch_uniform": (C.c_int, [u8p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u64p, u32p, u64p, u64p, C.c_int]),
     "nthash_unpack2bit_dev": (C.c_int, [u8p, u32p, C.c_uint64, C.c_uint64, u8p, C.c_void_p]),
+    "nthash_kmer_batch_packed2bit_uniform_dev": (C.c_int, [u8p, u32p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u64p, u32p, C.c_void_p]),
     "nthash_seed_reduce": (C.c_int, [u8p, u64p, C.c_uint64, C.POINTER(C.c_char_p), C.c_uint32, C.c_uint32, C.c_uint32, u64p, C.c_int]),
     "nthash_seed_reduce_uniform_dev": (C.c_int, [C.c_void_p, u8p, C.c_uint64, C.c_uint64, C.c_uint32, u64p, C.c_void_p]),
     "nthash_blind_seed_roll_batch_dev": (C.c_int, [C.c_void_p, u8p, C.c_uint64, u8p, C.c_uint64, u64p, u64p, u64p, C.c_void_p]),

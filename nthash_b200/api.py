@@ -66,6 +66,23 @@ def kmer_hashes_uniform(bases, n_reads, read_len, k, num_hashes=1, want_valid=Tr
     return HashBatch(out, valid_bits, None, rows, fwd, rev)
 
 
+def kmer_hashes_packed2bit_uniform(packed, invalid_bits, first_base, n_reads, read_len, k, num_hashes=1, want_valid=True, out=None,
+                                   valid_bits=None, stream=None) -> HashBatch:
+    """NtHash straight from device-resident 2-bit packed bases (nthash_kmer_batch_packed2bit_uniform_dev; raises NtHashError
+    with NTHASH_ERR_UNSUPPORTED for shapes that need the ASCII expansion).  `packed`: uint8 CUDA tensor, readable to the next
+    16-byte multiple; `invalid_bits`: int32 CUDA tensor or None."""
+    rows = n_reads * max(read_len - k + 1, 0)
+    dev = packed.device
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((rows, num_hashes), dtype=torch.int64, device=dev)
+        if want_valid and valid_bits is None:
+            valid_bits = torch.empty(int(LIB.nthash_valid_words(rows)), dtype=torch.int32, device=dev)
+        check(LIB.nthash_kmer_batch_packed2bit_uniform_dev(_ptr(packed), _ptr(invalid_bits), first_base, n_reads, read_len, k, num_hashes,
+                                                           _ptr(out), _ptr(valid_bits) if want_valid else None, _stream_ptr(stream)))
+    return HashBatch(out, valid_bits if want_valid else None, None, rows, None, None)
+
+
 def kmer_hashes(bases, read_off, k, num_hashes=1, want_valid=True, want_strands=False, stream=None, out=None) -> HashBatch:
     """NtHash over ragged reads: read r is bases[read_off[r]:read_off[r+1]] (nthash_kmer_plan_dev + nthash_kmer_batch_dev).
     `out`: optional preallocated int64 CUDA tensor with at least rows * num_hashes elements (reused across calls)."""

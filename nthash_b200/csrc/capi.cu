@@ -988,6 +988,31 @@ int nthash_kmer_reduce_packed2bit(const uint8_t* packed, const uint32_t* invalid
   return host_pipeline(hb, [&](const DevBatch& B, cudaStream_t st) { return kmer_dev_run(B, k, num_hashes, st); });
 }
 
+int nthash_kmer_batch_packed2bit_uniform_dev(const uint8_t* d_packed, const uint32_t* d_invalid_bits, uint64_t first_base,
+                                             uint64_t n_reads, uint32_t read_len, uint32_t k, uint32_t num_hashes,
+                                             uint64_t* d_out, uint32_t* d_valid_bits, void* stream)
+{
+  if (int rc = check_kh(k, num_hashes)) return rc;
+  if (n_reads == 0 || read_len < k) return NTHASH_OK;
+  if (int rc = check_outputs(d_out, nullptr, nullptr)) return rc;
+  if (!d_packed || ((uintptr_t)d_packed & 15)) return fail(NTHASH_ERR_INVALID_ARG, "d_packed must be 16-byte aligned");
+  if ((uintptr_t)d_invalid_bits & 7) return fail(NTHASH_ERR_INVALID_ARG, "d_invalid_bits must be 8-byte aligned");
+  if (first_base > 0xffffffffull) return fail(NTHASH_ERR_INVALID_ARG, "first_base must be below 2^32");
+  if (!kmer_packed_direct_ok(n_reads, read_len, k, num_hashes))
+    return fail(NTHASH_ERR_UNSUPPORTED, "this shape is not hashed from packed bytes directly: expand with nthash_unpack2bit_dev");
+  if (int rc = check_device_ready()) return rc;
+  DevBatch B;
+  B.d_packed = d_packed;
+  B.d_inv = d_invalid_bits;
+  B.packed_first = (uint32_t)first_base;
+  B.n_reads = n_reads;
+  B.uniform_len = read_len;
+  B.d_out = d_out;
+  B.d_valid = d_valid_bits;
+  B.memset_rows = n_reads * (uint64_t)(read_len - k + 1);
+  return kmer_dev_run(B, k, num_hashes, (cudaStream_t)stream);
+}
+
 int nthash_unpack2bit_dev(const uint8_t* d_packed, const uint32_t* d_invalid_bits, uint64_t first_base, uint64_t n_bases,
                           uint8_t* d_bases_out, void* stream)
 {

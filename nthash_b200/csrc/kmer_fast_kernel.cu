@@ -1562,7 +1562,9 @@ cudaError_t get_t4_table(uint32_t k, const uint4** out) { return get_t4_table_im
 
 bool kmer_packed_direct_ok(uint64_t n_reads, uint32_t read_len, uint32_t k, uint32_t h)
 {
-  if (n_reads == 0 || read_len < k || h < 1 || h > 4 || getenv("NTHASH_B200_NO_PACKED_DIRECT") || getenv("NTHASH_B200_FAST_NO_BOX")) return false;
+  if (n_reads == 0 || read_len < k || h < 1 || h > 4 || getenv("NTHASH_B200_NO_PACKED_DIRECT") || getenv("NTHASH_B200_FAST_NO_BOX") ||
+      getenv("NTHASH_B200_DISABLE_TMA_STORE"))
+    return false;
   if (read_len > env_u32("NTHASH_B200_FAST_WHOLE_READ", 400)) return false; // longer reads are cut / flat: ASCII kernels
   KmerGeom g;
   g.read_len = read_len;

@@ -235,6 +235,8 @@ cudaError_t launch_kmer(KmerParams P, cudaStream_t st)
     P.sk[x] = srol_n(base[x], P.k);
   }
   for (unsigned q = 0; q < 4; ++q) P.mult[q] = ext_mult(q, P.k);
+  if (P.packed) // 2-bit packed input: only the nibble-strip kernel reads it (the caller checked kmer_packed_direct_ok)
+    return P.use_tma && kmer_fast_ok(P) ? launch_kmer_fast(P, st) : cudaErrorNotSupported;
   if (P.use_tma && kmer_fast_ok(P)) {
     const cudaError_t e = launch_kmer_fast(P, st);
     if (e != cudaErrorInvalidConfiguration) return e; // does not fit shared memory (huge k): the general kernel below

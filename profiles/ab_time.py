@@ -43,6 +43,22 @@ for name in (sys.argv[3].split(",") if len(sys.argv) > 3 else ["c2", "c3", "c4",
     else:
         b2, m2 = timed(lambda: nthash_b200.kmer_reduce_uniform(w.bases, w.n, w.L, w.k, w.h))
         line += f" | reduce best {b2:.4f} median {m2:.4f} ms"
+    if not w.seeds and w.L <= 250 and (w.nk * w.h) % 8 == 0 and w.h <= 4:
+        # the same reads as 2-bit packed bytes, hashed directly (nthash_kmer_batch_packed2bit_uniform_dev)
+        lut2 = torch.zeros(256, dtype=torch.uint8, device="cuda")
+        lut2[torch.tensor(list(b"ACGT"), device="cuda").long()] = torch.arange(4, dtype=torch.uint8, device="cuda")
+        codes = lut2[w.bases.long()]
+        if codes.numel() % 4:
+            codes = torch.cat([codes, torch.zeros(4 - codes.numel() % 4, dtype=torch.uint8, device="cuda")])
+        c4 = codes.view(-1, 4)
+        packed = torch.zeros(c4.shape[0] + 64, dtype=torch.uint8, device="cuda")
+        packed[: c4.shape[0]] = c4[:, 0] | (c4[:, 1] << 2) | (c4[:, 2] << 4) | (c4[:, 3] << 6)
+        del codes, c4, lut2
+        ref_sum = int(w.out.sum())
+        b3, m3 = timed(lambda: nthash_b200.kmer_hashes_packed2bit_uniform(packed, None, 0, w.n, w.L, w.k, w.h, want_valid=False, out=w.out))
+        abp = w.n * w.L // 4 + w.rows * w.H * 8
+        line += f" | packed2bit direct best {b3:.4f} median {m3:.4f} ms ({abp / b3 / 1e6:.0f} GB/s of its own {abp / 1e9:.2f} GB; same sum: {int(w.out.sum()) == ref_sum})"
+        del packed
     print(line, flush=True)
     del w
     torch.cuda.empty_cache()

@@ -347,6 +347,34 @@ def _pack2bit(ascii_bases):
     return np.ascontiguousarray(packed), np.ascontiguousarray(bits)
 
 
+@pytest.mark.parametrize("n,read_len,k,h,p_n,first", [(3000, 150, 31, 1, 0.002, 0), (2000, 150, 31, 4, 0.0, 7), (1500, 150, 31, 3, 0.001, 31),
+                                                       (1000, 100, 21, 2, 0.01, 64), (33, 150, 31, 1, 0.05, 3), (1, 150, 31, 1, 0.0, 1),
+                                                       (700, 250, 63, 2, 0.001, 129)])
+def test_packed_2bit_hashed_directly_on_the_device(n, read_len, k, h, p_n, first, monkeypatch):
+    """Device-resident 2-bit packed reads (+ invalid-base bitmap) hashed by the nibble-strip kernel without an ASCII copy:
+    same rows as the oracle on the equivalent ASCII batch, for every alignment of the first base in the packed stream."""
+    rng = np.random.default_rng(n + read_len + h + first)
+    bases = rng.choice(np.frombuffer(b"ACGT", np.uint8), n * read_len)
+    if p_n:
+        bases[rng.random(len(bases)) < p_n] = ord("N")
+        bases[0] = ord("N"); bases[-1] = ord("N")
+    lead = rng.choice(np.frombuffer(b"ACGTN", np.uint8), first)              # whatever precedes the batch in the stream
+    packed, inv = _pack2bit(np.concatenate([lead, bases]))
+    d_p = torch.zeros(len(packed) + 64, dtype=torch.uint8, device="cuda"); d_p[: len(packed)] = torch.from_numpy(packed)
+    d_i = torch.zeros(len(inv) + 8, dtype=torch.int32, device="cuda"); d_i[: len(inv)] = torch.from_numpy(inv.view(np.int32))
+    ora = ORACLE.kmer_batch(bases, np.arange(n + 1, dtype=np.uint64) * read_len, k, h, threads=4)
+    res = nthash_b200.kmer_hashes_packed2bit_uniform(d_p, d_i if p_n else None, first, n, read_len, k, h)
+    torch.cuda.synchronize()
+    assert_batch_equal(res, ora, h)
+
+
+def test_packed_2bit_direct_refuses_other_shapes():
+    d_p = torch.zeros(1 << 16, dtype=torch.uint8, device="cuda")
+    for n, L, k, h in ((10, 151, 31, 1), (4, 5000, 31, 1), (10, 150, 31, 5)):   # odd rows, long reads, five hashes
+        with pytest.raises(nthash_b200.NtHashError):
+            nthash_b200.kmer_hashes_packed2bit_uniform(d_p, None, 0, n, L, k, h)
+
+
 @pytest.mark.parametrize("tiny_chunks", [False, True])
 def test_packed_2bit_input(tiny_chunks, monkeypatch):
     # 2-bit packed bases + invalid-base bitmap through the host entries: same rows as the ASCII path / the oracle
