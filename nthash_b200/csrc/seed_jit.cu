@@ -110,6 +110,7 @@ DI void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: 
 DI void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 DI void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 DI uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+DI uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 DI uint2 lds_v2(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 DI uint4 lds_v4(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
 DI uint2 lds_u2x(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
@@ -190,6 +191,15 @@ DI uint64_t ext_hash(uint64_t h0, uint64_t mult)
   const uint32_t nlo = lop3<0x1E>(lo, __umulhi(lo, 32u), hi * 32u); // lo ^ ((lo >> 27) | (hi << 5))
   const uint32_t nhi = hi ^ __umulhi(hi, 32u);
   return ((uint64_t)nhi << 32) | nlo;
+}
+// per byte of x: non-zero iff the byte is not one of ACGTUacgtu (the bytes whose 2-bit code (c >> 1) & 3 is their seed's base)
+DI uint32_t swar_bad(uint32_t x)
+{
+  const uint32_t t1 = lop3<(0xF0 & ~0xCC) & 0xFF>(x, x << 1, 0u);
+  const uint32_t e1 = lop3<(0xF0 ^ 0xCC) & 0xAA>(t1, x >> 2, 0x04040404u);
+  const uint32_t e2 = lop3<(~(0xF0 | 0xCC)) & 0xAA & 0xFF>(x, x >> 4, 0x01010101u);
+  const uint32_t e3 = lop3<(0xF0 ^ 0xCC) & 0xAA>(x, 0x40404040u, 0xC8C8C8C8u);
+  return lop3<0xF0 | 0xCC | 0xAA>(e1, e2, e3);
 }
 DI uint64_t srol_n(uint64_t x, unsigned d)
 {
@@ -283,13 +293,75 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
     mbar_init(bar, 1);
     fence_mbar_init();
   }
+#if !STRIPS
   if (tid < 16) sts_u8(tile + tid, 'A');
+#endif
   __syncthreads();
 #if RAGGED
   const uint64_t lo_byte = s_range[0], g1 = s_range[1] > lo_byte ? s_range[1] : lo_byte;
   const uint64_t g0 = (lo_byte > 16 ? lo_byte - 16 : 0) & ~15ull; // up to 16 bases before the first item are staged too
   if (g1 - g0 > P.tile_cap) __trap();
   if (!n) my_byte = g0 + 16; // nothing to hash: the warm-up below still runs, on bytes that exist
+#elif STRIPS
+  // Warp-private strips of nibble-packed bases (the staging of kmer_pack_kernel, kmer_fast_kernel.cu): every warp loads the
+  // bytes of its own 32 items with coalesced 16-byte loads, keeps one nibble per base (code (c >> 1) & 3) and one flag
+  // per 16-byte chunk (does it hold a byte for the exact path?).  Half the shared memory per base, no CTA-wide tile wait.
+  if (tid == 0) {
+    mbar_expect_tx(bar, TABLE_BYTES);
+    bulk_g2s(sbase, P.tables, TABLE_BYTES, bar);
+  }
+  const uint64_t iw0 = i0 + warp * 32;
+  if (iw0 >= i1) return; // a warp without items (warp 0 always has some)
+  const uint64_t iw1 = iw0 + 32 < i1 ? iw0 + 32 : i1;
+  const uint64_t wlo = item_byte(iw0), wend = item_byte(iw1 - 1) + n + K - 1;
+  const uint64_t a0 = (wlo > 16 ? wlo - 16 : 0) & ~15ull; // up to 16 bases before the first item are staged too
+  const uint32_t n_chunks = (uint32_t)((wend - a0 + 15) >> 4);
+  const uint32_t strip = tile + warp * P.tile_cap, badw = strip + P.tile_cap - 128u; // [nibbles][32 flag words]
+  if (n_chunks * 8u + 48u + 128u > P.tile_cap || n_chunks > 1024u) __trap();
+  if (lane < 2) asm volatile("st.shared.u32 [%0], %1;" ::"r"(strip + lane * 4), "r"(0u) : "memory"); // 16 nibbles of lead-in: code 0
+  {
+    auto load_chunk = [&](uint32_t c) {
+      uint4 x = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+      const uint64_t gb = a0 + 16ull * c;
+      if (c < n_chunks) {
+        if (gb + 16 <= P.n_bases) {
+          x = __ldg((const uint4*)(P.bases + gb));
+        } else {
+          uint32_t w[4] = { 0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u };
+          for (uint32_t j = 0; j < 16 && gb + j < P.n_bases; ++j) w[j >> 2] = (w[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | ((uint32_t)P.bases[gb + j] << (8 * (j & 3)));
+          x = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      return x;
+    };
+    auto nib = [](uint32_t v) {
+      const uint32_t y = (v >> 1) & 0x03030303u;
+      return y | (y >> 4);
+    };
+    for (uint32_t c0 = 0; c0 < n_chunks; c0 += 128) {
+      uint4 x[4];
+#pragma unroll
+      for (uint32_t u = 0; u < 4; ++u) x[u] = load_chunk(c0 + 32 * u + lane);
+#pragma unroll
+      for (uint32_t u = 0; u < 4; ++u) {
+        if (c0 + 32 * u >= n_chunks) break;
+        const uint32_t c = c0 + 32 * u + lane;
+        const uint32_t anybad = swar_bad(x[u].x) | swar_bad(x[u].y) | swar_bad(x[u].z) | swar_bad(x[u].w);
+        const uint32_t m = __ballot_sync(0xffffffffu, anybad != 0);
+        if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(badw + ((c0 + 32 * u) >> 5) * 4), "r"(m) : "memory");
+        const uint32_t lo = __byte_perm(nib(x[u].x), nib(x[u].y), 0x6420u), hi = __byte_perm(nib(x[u].z), nib(x[u].w), 0x6420u);
+        if (c < n_chunks) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(strip + 8u + 8u * c), "r"(lo), "r"(hi) : "memory");
+      }
+    }
+  }
+  __syncwarp();
+  const uint64_t my_byte = active ? item_byte(i0 + tid) : wlo;
+  const uint64_t my_out = (i0 + tid) * (uint64_t)n;
+  const uint32_t q0 = 16u + (uint32_t)(my_byte - a0); // nibble index of the item's base 0
+#define CODE_AT(q) ((lds_u32(strip + ((((uint32_t)(q)) >> 3) << 2)) >> ((((uint32_t)(q)) & 7u) << 2)) & 3u)
+  uint32_t bad = 0;
+  for (uint32_t c = (q0 - 16u) >> 4; c <= (q0 - 16u + n + K - 2) >> 4; ++c) bad |= (lds_u32(badw + (c >> 5) * 4) >> (c & 31)) & 1u;
+  mbar_wait(bar, 0); // the tables
 #else
   const uint64_t lo_byte = item_byte(i0), g1 = item_byte(i1 - 1) + n + K - 1;
   const uint64_t g0 = (lo_byte > 16 ? lo_byte - 16 : 0) & ~15ull; // up to 16 bases before the first item are staged too
@@ -297,6 +369,7 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
   const uint64_t my_byte = active ? item_byte(i0 + tid) : g0 + 16;
   const uint64_t my_out = (i0 + tid) * (uint64_t)n;
 #endif
+#if !STRIPS
   const uint64_t nb16 = P.n_bases & ~15ull;
   const uint64_t bulk_end = ((g1 + 15) & ~15ull) < nb16 ? ((g1 + 15) & ~15ull) : nb16;
   const uint32_t bulk_bytes = bulk_end > g0 ? (uint32_t)(bulk_end - g0) : 0u;
@@ -312,6 +385,7 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
   __syncthreads();
 
   const uint32_t ps = tile + 16 + (uint32_t)(my_byte - g0); // shared address of the item's base 0
+#endif
   const uint32_t tb = sbase;                                 // group tables: two conflict-free 128-byte halves each
 #if RAGGED
   // per warp: [32 descriptors x 16 B][32 private rows x ROW_PITCH]; rows go out through coalesced stores (see MAIN_TILES)
@@ -348,6 +422,10 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
       }
     }
   };
+#elif STRIPS
+  const uint32_t ot0 = ((tile + (NT / 32u) * P.tile_cap + 1023u) & ~1023u) + warp * (NBUF * OT_BYTES);
+  const int row0 = (int)(i0 + warp * 32);
+  const uint32_t lterm = lane * 64 + (((lane >> 1) & 3) << 4); // box3: row inside a block + its 64-byte-swizzle term
 #else
   const uint32_t ot0 = ((tile + 16 + P.tile_cap + 16 + 1023u) & ~1023u) + warp * (NBUF * OT_BYTES);
   const int row0 = (int)(i0 + warp * 32);
@@ -363,6 +441,15 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
   uint64_t acc_sum = 0ull, acc_xor = 0ull;
 #endif
   State full = { 0u, 0u, 0u, 0u };
+#if STRIPS
+  for (int j = -(int)OLDER; j < (int)K - 1; ++j) {
+    const uint32_t c2 = CODE_AT(q0 + (uint32_t)j);
+    SHIFT_IN(c2)
+#if ANY_IGNORE
+    if (j >= -1) roll_step(full, lds_v4(sbase + INTAB_OFF + (c2 << 4)), P.two);
+#endif
+  }
+#else
   uint32_t bad = 0;
   for (int j = -(int)OLDER; j < (int)K - 1; ++j) {
     const uint32_t c = lds_u8(ps + (uint32_t)j);
@@ -372,6 +459,7 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
     if (j >= -1) roll_step(full, lds_v4(sbase + INTAB_OFF + ((c & 6u) << 3)), P.two);
 #endif
   }
+#endif
   WARMUP_BLOCKS
 
 #if RAGGED
@@ -423,7 +511,12 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
     // windows holding a zero-seed byte: byte-exact values (seed.cpp:149-166); then flag the read for the replay
     uint32_t run = 0;
     for (uint32_t j = 0; j < n + K - 1; ++j) {
+#if STRIPS
+      const unsigned cj = P.bases[my_byte + j];
+      run = (seed_of_byte(cj) != 0 && cj > 7) ? run + 1 : 0;
+#else
       run = lds_u8(lut + lds_u8(ps + j)) ? 0 : run + 1;
+#endif
       if (j >= K - 1 && run < K) {
         const uint32_t p = j - (K - 1);
         const uint64_t row = my_out + p;
@@ -432,7 +525,11 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
           const uint32_t* care = P.care + (size_t)s * P.care_words;
           for (uint32_t q = 0; q < K; ++q) {
             if (care[q >> 5] >> (q & 31) & 1u) {
+#if STRIPS
+              const unsigned c = P.bases[my_byte + p + q];
+#else
               const unsigned c = lds_u8(ps + p + q);
+#endif
               f ^= srol_n(seed_of_byte(c), K - 1 - q);
               r ^= srol_n(seed_of_byte(c & 7u), q);
             }
@@ -508,6 +605,8 @@ std::string hex64(uint64_t v)
 
 } // namespace
 
+constexpr bool SEED_JIT_STRIPS_DEFAULT = false;
+
 struct SeedJit
 {
   cudaLibrary_t lib = nullptr;
@@ -524,6 +623,7 @@ struct SeedJit
   mutable SeedJit* alt_str2d = nullptr;  // the same over the 2-D tile variant
   mutable SeedJit* alt_reduce = nullptr; // fused consumer (count / sum / xor, nothing stored), compiled on first use
   bool reduce = false;
+  bool strips = false;           // uniform variants: warp-private nibble strips (tile_cap = bytes per warp then)
   bool strands = false;
   mutable std::mutex mu;
   std::string source; // kept for inspection (nthash_seed_plan_jit_source)
@@ -559,6 +659,9 @@ SeedJit* seed_jit_build(const SeedPlanHost& plan, std::string& why, bool load)
 static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& why, bool load, int mode, bool strands)
 {
   const bool box3 = mode == 1, ragged = mode == 2, reduce = mode == 3;
+  // uniform variants: warp-private nibble strips instead of the CTA's TMA-staged ASCII tile (NTHASH_B200_SEED_JIT_STRIPS=0/1)
+  const char* strips_env = getenv("NTHASH_B200_SEED_JIT_STRIPS");
+  const bool strips = !ragged && (strips_env ? atoi(strips_env) != 0 : SEED_JIT_STRIPS_DEFAULT);
   const uint32_t k = plan.k, m = plan.n_seeds, hps = plan.h, ht = m * hps;
   if (k > 256) { why = "k > 256"; return nullptr; }
   if (strands && (ragged || m > 8)) { why = "strand outputs: uniform batches of at most 8 seeds"; return nullptr; }
@@ -645,8 +748,9 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
     for (uint32_t ph = 0; ph < d; ++ph) {
       decl_blocks << " State b" << bk.id << "_" << ph << " = { 0u, 0u, 0u, 0u };";
       // G(ph - d) by m in-only steps over bases ph - d + q0 + t*d (t = 0..m-1)
-      warm_blocks << "  for (uint32_t t = 0; t < " << mm << "u; ++t) { const uint32_t ix = (lds_u8(ps + (uint32_t)(" << (int)ph - (int)d + (int)q0
-                  << ") + t * " << d << "u) & 6u) << 2; blk_step<" << d << ">(b" << bk.id << "_" << ph << ", lds_v2(tb + " << blk_in_off[bk.id]
+      warm_blocks << "  for (uint32_t t = 0; t < " << mm << "u; ++t) { const uint32_t ix = "
+                  << (strips ? "CODE_AT(q0 + (uint32_t)(" : "(lds_u8(ps + (uint32_t)(") << (int)ph - (int)d + (int)q0 << ") + t * " << d
+                  << (strips ? "u) << 3; blk_step<" : "u) & 6u) << 2; blk_step<") << d << ">(b" << bk.id << "_" << ph << ", lds_v2(tb + " << blk_in_off[bk.id]
                   << "u + ix), lds_v2(tb + " << blk_in_off[bk.id] + 128 << "u + ix)); } \\\n";
     }
   }
@@ -775,7 +879,7 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
     const uint32_t chunk = ht % 2 ? 8 : 16, pitch = (row_bytes + 15) / 16 * 16 + ((((row_bytes + 15) / 16) % 2) ? 0 : 16);
     src << "#define RAGGED " << (ragged ? 1 : 0) << "\n#define CHUNK " << chunk << "u\n#define LANES_PER_ROW " << 256 / chunk << "u\n#define ROW_PITCH " << pitch << "u\n";
   }
-  src << "#define STRANDS " << (strands ? 1 : 0) << "\n#define REDUCE " << (reduce ? 1 : 0) << "\n";
+  src << "#define STRANDS " << (strands ? 1 : 0) << "\n#define REDUCE " << (reduce ? 1 : 0) << "\n#define STRIPS " << (strips ? 1 : 0) << "\n";
   if (strands) {
     // STR_FLUSH(w0): the strand hashes of windows w0 .. w0+3 (4*M u64 per array, contiguous in both arrays) as M whole
     // 32-byte sectors when the group starts on one, else value by value; STR_TAIL: the last n % 4 windows of the row
@@ -809,10 +913,11 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
   // full-window roll for ignore-mode seeds: the outgoing base is the previous window's base 0 (position off, before the shift)
   src << "#define FULL_ROLL";
   if (plan.any_ignore)
-    src << " { const uint32_t po = ((c << 4) & 0x60u) | (rotr(W" << off / 16 << ", " << ((2 * (off % 16) + 32 - 3) % 32)
+    src << " { const uint32_t po = " << (strips ? "(c2 << 5)" : "((c << 4) & 0x60u)") << " | (rotr(W" << off / 16 << ", " << ((2 * (off % 16) + 32 - 3) % 32)
         << "u) & 0x18u); const uint2 ef = lds_v2(sbase + PAIRF_OFF + po), er = lds_v2(sbase + PAIRR_OFF + po);"
            " roll_step(full, make_uint4(ef.x, ef.y, er.x, er.y), P.two); }";
-  src << "\n#define WIN_PRE(P) const uint32_t c = lds_u8(ps + (K - 1) + (P)); bad |= lds_u8(lut + c); FULL_ROLL SHIFT_IN(c >> 1)\n";
+  if (strips) src << "\n#define WIN_PRE(P) const uint32_t c2 = CODE_AT(q0 + (K - 1) + (P)); FULL_ROLL SHIFT_IN(c2)\n";
+  else src << "\n#define WIN_PRE(P) const uint32_t c = lds_u8(ps + (K - 1) + (P)); bad |= lds_u8(lut + c); FULL_ROLL SHIFT_IN(c >> 1)\n";
   // STORE_WINDOW_i(base): window i of the tile row -> shared memory
   for (uint32_t i = 0; i < tw; ++i) {
     src << "#define STORE_WINDOW_" << i << "(base) {";
@@ -901,6 +1006,7 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
   j->ragged = ragged;
   j->strands = strands;
   j->reduce = reduce;
+  j->strips = strips;
   j->row_pitch = (row_bytes + 15) / 16 * 16 + ((((row_bytes + 15) / 16) % 2) ? 0 : 16);
   j->plan = &plan;
   nvrtcProgram prog = nullptr;
@@ -947,6 +1053,10 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
 
 uint32_t seed_jit_smem_bytes(const SeedJit* j, uint32_t tile_cap)
 {
+  if (j->strips) { // tile_cap = bytes of one warp's strip (nibbles + flag words)
+    const uint32_t out_bytes = j->reduce ? 0u : (j->nt / 32) * j->nbuf * j->ot_bytes;
+    return j->table_bytes + 256 + 16 + (j->nt / 32) * tile_cap + 1024 + out_bytes;
+  }
   const uint32_t out_bytes = j->reduce ? 0u : j->ragged ? (j->nt / 32) * 32u * (j->row_pitch + 16u) + 256u : (j->nt / 32) * j->nbuf * j->ot_bytes;
   return j->table_bytes + 256 + 16 + 16 + tile_cap + 16 + 1024 + out_bytes;
 }
@@ -956,6 +1066,12 @@ static uint32_t seed_jit_tile_cap(const SeedJit* j, const SeedParams& P)
 {
   const KmerGeom& g = P.g;
   uint64_t b;
+  if (j->strips) { // per warp: 32 consecutive items, up to 16 bases before the first one, 16-byte chunks, 8 bytes of nibbles per chunk
+    const uint64_t span = g.segs == 1 ? 31ull * g.read_len + g.seg + P.k - 1 : 32ull * g.seg + (32ull / g.segs + 2) * (P.k - 1);
+    const uint64_t chunks = (span + 16 + 15 + 15) / 16 + 1;
+    b = chunks * 8 + 48 + 128;
+    return chunks > 1024 ? 0xffffffffu : (uint32_t)((b + 15) & ~15ull);
+  }
   if (g.item_byte) b = ((uint64_t)P.tile_cap * j->nt + KMER_NT - 1) / KMER_NT + 2 * (uint64_t)P.k + 96; // the caller sized it for KMER_NT items
   else if (g.segs == 1) b = (uint64_t)j->nt * g.read_len + 96;
   else b = (uint64_t)j->nt * g.seg + ((uint64_t)j->nt / g.segs + 2) * (P.k - 1) + 96;
