@@ -571,11 +571,15 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   wp_in += 4;
   wp_out += 4;
 
-  // Four windows (FULL) or the first cnt < 4 of them: consumes one realigned word of each stream.  The next
-  // words are requested before the current ones are used, so their latency hides behind the four rolls.
+  // Four windows (FULL) or the first cnt < 4 of them.  The loop is a two-stage pipeline: while a group is rolled, the words of
+  // the group after the next are requested and the eight pair-table entries of the NEXT group are fetched (each entry right
+  // after the roll that consumed its predecessor), so every shared-memory load has a whole group of rolls to land in.  (With
+  // the loads next to their uses the DIRECT loop, which ptxas keeps at 32-40 registers, had a third of its stall samples on
+  // them: profiles/r02_ncu_ragged_head.txt.)
   uint64_t fw4[4], rv4[4]; // STR: strand hashes of the group's four windows
-  auto roll4 = [&](uint64_t (&hv)[4], auto full, uint32_t cnt) {
-    constexpr bool FULL = decltype(full)::value;
+  uint2 efv[4], erv[4];    // the current group's table entries
+  uint32_t bw_cur = 0;     // ... and its per-byte validity flags
+  auto fetch_codes = [&]() -> uint32_t { // consumes one realigned word of each stream: table offsets of the next group
     const uint32_t x_in = __byte_perm(w_in, w_in_n, sel_in), x_out = __byte_perm(w_out, w_out_n, sel_out);
     w_in = w_in_n;
     w_out = w_out_n;
@@ -583,16 +587,45 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     wp_out += 4;
     w_in_n = lds_u32(wp_in);
     w_out_n = lds_u32(wp_out);
+    bw_cur = swar_bad(x_in); // bytes past the row's end may flag a false alarm: that only costs the exact scrub
     // per byte: code_in at bits 5-6, code_out at bits 3-4  =>  byte = 8 * (4*code_in + code_out) = table offset
-    const uint32_t c4 = lop3<LUT_SEL_C>(x_out << 2, x_in << 4, 0x60606060u) & 0x78787878u;
-    const uint32_t bw = swar_bad(x_in); // bytes past cnt may flag a false alarm: that only costs the exact scrub
+    return lop3<LUT_SEL_C>(x_out << 2, x_in << 4, 0x60606060u) & 0x78787878u;
+  };
+  // (the runtime-h variant, H == 0, sits at ptxas' 128-register ceiling already: the 16 extra live registers spilled and cost
+  // 2-6 % there, so it fetches a group's entries at the start of the group instead)
+  constexpr bool PIPE = H != 0 && (BOX || DIRECT || REDUCE); // (the shared-memory-row variants are near the ceiling too)
+  if (PIPE && n) { // prime: the first group's entries
+    const uint32_t c4 = fetch_codes();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t ea = __byte_perm(c4, pair, 0x7650u | i); // (pair & ~0xFF) | byte i of c4
+      efv[i] = lds_v2(ea);
+      erv[i] = lds_v2(ea + (F_PAIR_R_OFF - F_PAIR_OFF));
+    }
+  }
+  auto roll4 = [&](uint64_t (&hv)[4], auto full, uint32_t cnt) {
+    constexpr bool FULL = decltype(full)::value;
+    uint32_t bw = bw_cur;
+    const uint32_t c4n = fetch_codes(); // PIPE: the group after this one (reads at most two words past the row: staged or padding)
+    if (!PIPE) {
+      bw = bw_cur;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t ea = __byte_perm(c4n, pair, 0x7650u | i);
+        efv[i] = lds_v2(ea);
+        erv[i] = lds_v2(ea + (F_PAIR_R_OFF - F_PAIR_OFF));
+      }
+    }
     if (!REDUCE) bad |= bw;
     if (REDUCE && FULL && bw == 0 && run + 1 >= k) { // consumer, steady state: all four windows are visited ones
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const uint32_t ea = __byte_perm(c4, pair, 0x7650u | i);
-        const uint2 ef = lds_v2(ea), er = lds_v2(ea + (F_PAIR_R_OFF - F_PAIR_OFF));
-        roll_step(s, make_uint4(ef.x, ef.y, er.x, er.y), P.two);
+        roll_step(s, make_uint4(efv[i].x, efv[i].y, erv[i].x, erv[i].y), P.two);
+        if (PIPE) {
+          const uint32_t ea = __byte_perm(c4n, pair, 0x7650u | i);
+          efv[i] = lds_v2(ea);
+          erv[i] = lds_v2(ea + (F_PAIR_R_OFF - F_PAIR_OFF));
+        }
         consume(canonical2(s));
       }
       run += 4;
@@ -601,15 +634,18 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      if (!FULL && i && (uint32_t)i >= cnt) break;
+      if (!FULL && i && (uint32_t)i >= cnt) break; // (a partial group is the item's last: nothing is fetched after it)
       if (REDUCE) {
         const uint32_t v = __byte_perm(bw, 0u, 0x4440u | i);
         bad |= v;
         run = v ? 0 : run + 1;
       }
-      const uint32_t ea = __byte_perm(c4, pair, 0x7650u | i); // (pair & ~0xFF) | byte i of c4
-      const uint2 ef = lds_v2(ea), er = lds_v2(ea + (F_PAIR_R_OFF - F_PAIR_OFF));
-      roll_step(s, make_uint4(ef.x, ef.y, er.x, er.y), P.two);
+      roll_step(s, make_uint4(efv[i].x, efv[i].y, erv[i].x, erv[i].y), P.two);
+      if (PIPE && FULL) {
+        const uint32_t ea = __byte_perm(c4n, pair, 0x7650u | i);
+        efv[i] = lds_v2(ea);
+        erv[i] = lds_v2(ea + (F_PAIR_R_OFF - F_PAIR_OFF));
+      }
       hv[i] = canonical2(s);
       if (STR) {
         fw4[i] = ((uint64_t)s.fhi << 32) | s.flo;
