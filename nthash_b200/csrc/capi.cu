@@ -155,7 +155,30 @@ struct RaggedItems
   uint32_t tile_cap = 0;
   uint64_t* d_items = nullptr;         // [item_byte | item_out | item_read]
   const uint64_t* item_read = nullptr; // NULL when items are reads
+  uint8_t* d_perm = nullptr;           // KmerGeom::item_perm (the items of every block of 256 in length-class order)
+  void release_async(cudaStream_t st)
+  {
+    if (d_items) cudaFreeAsync(d_items, st);
+    if (d_perm) cudaFreeAsync(d_perm, st);
+    d_items = nullptr;
+    d_perm = nullptr;
+  }
 };
+
+// the block-wise length-class order the fast kernel deals its items out by (without it every CTA sorts its own)
+static int plan_item_perm(RaggedItems& R, cudaStream_t st)
+{
+  if (R.g.n_items == 0 || getenv("NTHASH_B200_NO_ITEM_PERM")) return NTHASH_OK;
+  NTH_CUDA(cudaMallocAsync(&R.d_perm, (R.g.n_items + 255) / 256 * 256, st));
+  const cudaError_t e = launch_item_perm(R.g.item_out, R.g.n_items, R.d_perm, st);
+  if (e != cudaSuccess) {
+    cudaFreeAsync(R.d_perm, st);
+    R.d_perm = nullptr;
+    NTH_CUDA(e);
+  }
+  R.g.item_perm = R.d_perm;
+  return NTHASH_OK;
+}
 
 // Nothing is read back: the item tables are sized by a host-side bound of the item count (every read contributes at
 // most ceil(windows / SEG_LONG) <= bases / SEG_LONG + 1 items) and the surplus is padded with empty items.
@@ -167,7 +190,7 @@ static int plan_ragged(const uint64_t* d_read_off, const uint64_t* d_koff, uint6
     R.g.item_out = d_koff;
     R.g.n_items = n_reads;
     R.tile_cap = (uint32_t)(KMER_NT * max_read_len + 64);
-    return NTHASH_OK;
+    return plan_item_perm(R, st);
   }
   R.tile_cap = span_bound(SEG_LONG, 1, k);
   const uint64_t cap = n_reads + n_bases / SEG_LONG + 1;
@@ -183,6 +206,11 @@ static int plan_ragged(const uint64_t* d_read_off, const uint64_t* d_koff, uint6
   R.g.item_byte = R.d_items;
   R.g.item_out = R.d_items + cap + 1;
   R.item_read = R.d_items + 2 * (cap + 1);
+  if (int rc = plan_item_perm(R, st)) {
+    cudaFreeAsync(R.d_items, st);
+    R.d_items = nullptr;
+    return rc;
+  }
   return NTHASH_OK;
 }
 
@@ -312,7 +340,7 @@ static int kmer_dev_run(const DevBatch& B, uint32_t k, uint32_t h, cudaStream_t 
     P.general_fits = kmer_smem_bytes(P.tile_cap) <= SMEM_MAX;
   }
   int rc = run_kmer(P, B.memset_rows, B.d_rows, B.rows_bound, st);
-  if (R.d_items) cudaFreeAsync(R.d_items, st);
+  R.release_async(st);
   return rc;
 }
 
@@ -346,7 +374,7 @@ static int seed_dev_run(const nthash_seed_plan* plan, const DevBatch& B, cudaStr
     P.item_read = I.item_read;
   }
   int rc = run_seed(plan, P, B.n_reads, B.memset_rows, B.d_rows, B.rows_bound, st);
-  if (R.d_items) cudaFreeAsync(R.d_items, st);
+  R.release_async(st);
   return rc;
 }
 
@@ -728,6 +756,7 @@ void nthash_ragged_plan_destroy(nthash_ragged_plan* plan)
 {
   if (!plan) return;
   if (plan->items.d_items) cudaFree(plan->items.d_items);
+  if (plan->items.d_perm) cudaFree(plan->items.d_perm);
   cudaFree(plan->d_koff);
   delete plan;
 }

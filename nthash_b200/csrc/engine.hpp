@@ -19,6 +19,10 @@ struct KmerGeom
 {
   const uint64_t* item_byte = nullptr;
   const uint64_t* item_out = nullptr;
+  // ragged batches, optional: item_perm[256 * b + t] = which of block b's 256 items thread t of the fast kernel's CTA b takes
+  // (the block's items ordered by length class, longest first: a warp runs as long as its longest item).  Computed once per
+  // layout by launch_item_perm; without it the kernel sorts its items itself (six CTA barriers per launch and CTA).
+  const uint8_t* item_perm = nullptr;
   uint64_t n_items = 0;
   uint32_t read_len = 0, nk = 0, seg = 0, segs = 1;
   // flat (fast kernel, uniform long reads): item i = dense windows [i*seg, (i+1)*seg) of the whole batch, whichever
@@ -154,6 +158,8 @@ cudaError_t launch_popcount(const uint32_t* d_bits, uint64_t n_bits, uint64_t* d
 cudaError_t launch_item_fill(const uint64_t* read_off, const uint64_t* koff, uint64_t n_reads, uint32_t k,
                              uint32_t seg, uint64_t* item_byte, uint64_t* item_out, uint64_t* item_read,
                              uint64_t cap, cudaStream_t st);
+// perm[256 * b + t] for every block b of 256 consecutive items (see KmerGeom::item_perm); perm holds ceil(n_items / 256) * 256 bytes
+cudaError_t launch_item_perm(const uint64_t* item_out, uint64_t n_items, uint8_t* perm, cudaStream_t st);
 // valid_bits <- ones for *d_rows rows (<= rows_bound, which only sizes the grid); nothing is read back.
 cudaError_t launch_fill_valid(uint32_t* d_valid, const uint64_t* d_rows, uint64_t rows_bound, cudaStream_t st);
 

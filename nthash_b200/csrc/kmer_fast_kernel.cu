@@ -223,7 +223,7 @@ NTH_D void fast_item_geom(const KmerGeom& g, uint64_t i, uint64_t& byte, uint64_
     uint64_t r = i;
     uint32_t s = 0;
     if (g.segs > 1) {
-      r = i / g.segs;
+      r = (i >> 32) ? i / g.segs : (uint64_t)((uint32_t)i / g.segs); // (a 64-bit division is ~100 instructions)
       s = (uint32_t)(i - r * g.segs);
     }
     byte = r * g.read_len + (uint64_t)s * g.seg;
@@ -296,32 +296,33 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   const uint64_t i1 = min(i0 + (uint64_t)NT, P.g.n_items);
   const uint32_t k = P.k;
 
-  uint64_t my_byte = 0, my_out = 0;
-  uint32_t n = 0;
-  uint32_t slot = tid; // position of this thread's item among the CTA's items (the ragged re-deal below permutes them)
-  if (i0 + tid < i1) {
-    fast_item_geom(P.g, i0 + tid, my_byte, my_out, n);
-    if (tid == 0) s_range[0] = my_byte;
-    if (i0 + tid == i1 - 1) s_range[1] = P.g.flat ? flat_byte(P.g, my_out + n - 1) + k : my_byte + (n ? n + k - 1 : 0);
-  }
-  // ---- stage the CTA's byte range (TMA bulk copy) and build the tables -------------------------
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    fence_mbar_init();
-  }
-  if (tid < F_TILE_PAD) tile[tid] = 'A';
-  __syncthreads();
-  const uint64_t lo_byte = s_range[0], g1 = max(s_range[1], lo_byte);
-  const uint64_t g0 = (lo_byte ? lo_byte - 1 : 0) & ~15ull;
-  if (g1 - g0 > P.tile_cap) __trap();
-  const uint64_t bulk_end = min((g1 + 15) & ~15ull, P.n_bases & ~15ull);
-  const uint32_t bulk_bytes = bulk_end > g0 ? (uint32_t)(bulk_end - g0) : 0u;
+  // ---- stage the CTA's byte range (TMA bulk copy): the very first thing thread 0 does --------------
+  // The range = first byte of the CTA's first item .. last byte of its last item, in batch order (uniform batches: plain
+  // arithmetic; ragged: four entries of the item tables).  Nothing else is in front of the copy — no CTA barrier, no
+  // per-thread geometry — so that everything below (own item, tables, the ragged deal) hides behind its latency: the wait for
+  // the tile was 17 % of the stall samples and the serial prologue in front of the copy another 10 % (profiles/r02_ncu_c2_head.txt).
   // row buffers follow the staged bases; the 4 KB tetramer table is parked in them for the warm-up phase
   const uint32_t rb_base = (sbase + F_TILE_OFF + F_TILE_PAD + P.tile_cap + 16 + 1023u) & ~1023u;
   if (tid == 0) {
+    uint64_t lo_byte, eb, eo;
+    uint32_t en;
+    fast_item_geom(P.g, i0, lo_byte, eo, en);
+    fast_item_geom(P.g, i1 - 1, eb, eo, en);
+    uint64_t g1 = P.g.flat ? flat_byte(P.g, eo + en - 1) + k : eb + (en ? en + k - 1 : 0);
+    g1 = max(g1, lo_byte);
+    const uint64_t g0 = (lo_byte ? lo_byte - 1 : 0) & ~15ull;
+    if (g1 - g0 > P.tile_cap) __trap();
+    const uint64_t bulk_end = min((g1 + 15) & ~15ull, P.n_bases & ~15ull);
+    const uint32_t bulk_bytes = bulk_end > g0 ? (uint32_t)(bulk_end - g0) : 0u;
+    mbar_init(bar, 1);
+    fence_mbar_init();
     mbar_expect_tx(bar, bulk_bytes + T4_BYTES);
     if (bulk_bytes) bulk_g2s(tile + F_TILE_PAD, P.bases + g0, bulk_bytes, bar);
     bulk_g2s(smem + (rb_base - sbase), P.t4, T4_BYTES, bar);
+    s_range[0] = g0;
+    s_range[1] = g1;
+    // the (at most 15) bytes of a range that ends in the buffer's unaligned tail
+    for (uint64_t g = max(bulk_end, g0); g < g1; ++g) tile[F_TILE_PAD + (g - g0)] = P.bases[g];
     // pull the bases of the CTA that will take this SM slot next into L2 (same extent, one residency wave ahead),
     // so that its start-up wait is an L2 hit instead of a DRAM read queued behind the output stream
     if (P.prefetch_ctas) {
@@ -330,8 +331,17 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
       if (len && nxt + len <= (P.n_bases & ~15ull)) bulk_prefetch_l2(P.bases + nxt, (uint32_t)len);
     }
   }
+  if (tid < F_TILE_PAD) tile[tid] = 'A'; // (visible after the barrier in front of the tile wait)
+
+  uint64_t my_byte = 0, my_out = 0;
+  uint32_t n = 0;
+  uint32_t slot = tid; // position of this thread's item among the CTA's items (ragged batches: dealt out by length class)
+  // ragged batch with a precomputed deal (KmerGeom::item_perm, CTAs of 256 threads): take the item straight away
+  const bool presorted = P.g.item_perm != nullptr;
+  if (presorted) slot = P.g.item_perm[i0 + tid];
+  if (i0 + slot < i1) fast_item_geom(P.g, i0 + slot, my_byte, my_out, n);
   // (the loads are in flight from here on; the bookkeeping below hides behind them)
-  if (P.g.item_byte) {
+  if (P.g.item_byte && !presorted) {
     // Ragged batch: a warp runs as long as its longest item, so hand the CTA's items out by length class
     // (32 classes, longest first; counting sort through shared memory that the tables overwrite later).
     // 10 M reads of 100-150 bases: 3.10 -> 2.63 ms per call, of 36-150 bases: 3.55 -> 2.25 ms (profiles/r01_ragged_bench.txt);
@@ -381,9 +391,9 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     }
     for (uint32_t c = tid; c < 256; c += NT) smem[F_LUT_OFF + c] = is_acgtu(c) ? 0 : 1;
   }
-  for (uint64_t g = max(bulk_end, g0) + tid; g < g1; g += NT) tile[F_TILE_PAD + (g - g0)] = P.bases[g];
+  __syncthreads(); // tables, pad and tail bytes written; the barrier's initialisation and the range visible to everybody
+  const uint64_t g0 = s_range[0];
   mbar_wait(bar, 0);
-  __syncthreads();
 
   const bool active = n != 0;
   if (BOX && !REDUCE && !active) { // warp-synchronous output path: idle lanes hash a dummy row that the TMA store clips
@@ -413,14 +423,16 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
       const uint32_t x = __byte_perm(w0, w1, sel);
       w0 = w1;
       // base -1 is checked along with the rest: a false alarm only costs the (exact) scrub pass
-      const uint32_t v0 = lds_u8(lut + __byte_perm(x, 0u, 0x4440u)), v1 = lds_u8(lut + __byte_perm(x, 0u, 0x4441u));
-      const uint32_t v2 = lds_u8(lut + __byte_perm(x, 0u, 0x4442u)), v3 = lds_u8(lut + (x >> 24));
-      bad |= v0 | v1 | v2 | v3;
-      if (REDUCE) {
+      if constexpr (REDUCE) { // per-base flags for the run counter: LUT loads (the consumers are issue-bound, not shared-memory-bound)
+        const uint32_t v0 = lds_u8(lut + __byte_perm(x, 0u, 0x4440u)), v1 = lds_u8(lut + __byte_perm(x, 0u, 0x4441u));
+        const uint32_t v2 = lds_u8(lut + __byte_perm(x, 0u, 0x4442u)), v3 = lds_u8(lut + (x >> 24));
+        bad |= v0 | v1 | v2 | v3;
         run = v0 ? 0 : run + 1;
         run = v1 ? 0 : run + 1;
         run = v2 ? 0 : run + 1;
         run = v3 ? 0 : run + 1;
+      } else { // SWAR test, as in the main loop: the four byte-indexed loads were a fifth of the warm-up's shared-memory traffic
+        bad |= swar_bad(x);
       }
       const uint32_t y2 = (x >> 1) & 0x03030303u;          // 2-bit codes, first base in byte 0
       const uint32_t off = ((y2 * 0x40100401u) >> 20) & 0xFF0u; // 16 * (c0<<6 | c1<<4 | c2<<2 | c3)
@@ -1637,7 +1649,10 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
     // (profiles/r02_c5_flatseg_sweep.txt: 120 0.816, 144 0.851, 168 0.864, 216 0.837, 264 0.840, 360 0.812 of the HBM peak on
     // C5; 192 = 48 words between lanes, 16-way LDS conflicts: 0.636): shorter items leave shared memory for more resident
     // warps, longer ones amortise the k-base warm-up
-    uint32_t flat_seg = env_u32("NTHASH_B200_FLAT_SEG", 168);
+    // h <= 2 (second sweep, profiles/r02_c5_flat_sweep2.txt, after the lookups were pipelined): 200-window items = 5 stores of 40
+    // windows (320-byte pieces, 50 words between lanes' rows) in CTAs of 96 threads: C5 0.979 -> 0.956 ms on the same box
+    const bool flat_long_pieces = P.h <= 2 && !getenv("NTHASH_B200_FAST_WS") && !getenv("NTHASH_B200_FLAT_SEG");
+    uint32_t flat_seg = env_u32("NTHASH_B200_FLAT_SEG", flat_long_pieces ? 200 : 168);
     flat_seg = std::max(24u, flat_seg / 8u * 8u);
     const bool flat_ok = !P.reduce_out && !P.out_fwd && !P.bloom_mode && P.h <= 4 && g.nk >= 2 * flat_seg &&
                          (n_reads * (uint64_t)g.nk) / flat_seg > 0 && !getenv("NTHASH_B200_FAST_NO_BOX") && !getenv("NTHASH_B200_NO_FLAT");
@@ -1656,6 +1671,7 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
       g.seg = flat_seg;
       g.segs = 1;
       c.box = true;
+      if (flat_long_pieces) c.ws = 2;
     } else {
       // balanced items, the last one shorter.  seg = 4 (mod 8): an odd number of 32-bit words between the rows of
       // neighbouring lanes keeps their LDS.32 on distinct banks (seg = 256 ran 1.7x slower than 244), and a
@@ -1691,7 +1707,9 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
     c.nt = nt;
     if (smem <= 227u * 1024u && ((227u * 1024u / smem) * (nt / 32) >= 16 || nt <= 96)) break;
   }
+  if (P.g.flat && c.ws == 2 && !getenv("NTHASH_B200_FAST_WS") && tile_cap_for(96) <= 227u * 1024u) c.nt = 96;
   c.nt = env_u32("NTHASH_B200_FAST_NT", c.nt);
+  if (c.nt != 256) P.g.item_perm = nullptr; // the precomputed deal is per block of 256 items
   if (c.nt < 32 || c.nt > 256 || c.nt % 32) return cudaErrorInvalidValue;
   if (tile_cap_for(c.nt) > 227u * 1024u) return cudaErrorInvalidConfiguration;
   P.tile_cap = (uint32_t)tile_cap_for(c.nt);

@@ -382,6 +382,44 @@ cudaError_t launch_koff_scan(const uint64_t* read_off, uint64_t n_reads, uint32_
   return e;
 }
 
+// Length-class order of every block of 256 consecutive items (the CTAs of kmer_fast_kernel on ragged batches): 32 classes
+// relative to the block's longest item, longest first, counting sort.  perm[slot] = the block-local index of the item that
+// thread `slot` takes.  Items past n_items (the padding of the last block) count as empty.
+__global__ void __launch_bounds__(256) item_perm_kernel(const uint64_t* __restrict__ item_out, uint64_t n_items, uint8_t* __restrict__ perm)
+{
+  __shared__ uint32_t cnt[33];
+  const uint32_t tid = threadIdx.x, lane = tid & 31;
+  const uint64_t i = (uint64_t)blockIdx.x * 256 + tid;
+  const uint32_t n = i < n_items ? (uint32_t)(item_out[i + 1] - item_out[i]) : 0u;
+  if (tid < 33) cnt[tid] = 0;
+  __syncthreads();
+  atomicMax(&cnt[32], n);
+  __syncthreads();
+  const uint32_t cls = 31u - (uint32_t)(((uint64_t)n * 32u) / ((uint64_t)cnt[32] + 1u));
+  const uint32_t pos = atomicAdd(&cnt[cls], 1u);
+  __syncthreads();
+  if (tid < 32) { // exclusive scan of the class counters
+    const uint32_t c = cnt[tid];
+    uint32_t x = c;
+    for (uint32_t o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    cnt[tid] = x - c;
+  }
+  __syncthreads();
+  perm[(uint64_t)blockIdx.x * 256 + cnt[cls] + pos] = (uint8_t)tid;
+}
+
+cudaError_t launch_item_perm(const uint64_t* item_out, uint64_t n_items, uint8_t* perm, cudaStream_t st)
+{
+  if (n_items == 0) return cudaSuccess;
+  const uint64_t blocks = (n_items + 255) / 256;
+  if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+  item_perm_kernel<<<(unsigned)blocks, 256, 0, st>>>(item_out, n_items, perm);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_item_fill(const uint64_t* read_off, const uint64_t* koff, uint64_t n_reads, uint32_t k,
                              uint32_t seg, uint64_t* item_byte, uint64_t* item_out, uint64_t* item_read,
                              uint64_t cap, cudaStream_t st)
