@@ -120,6 +120,7 @@ DI void stg_v4q(uint64_t* p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) { a
 #else
 DI void stg_v4q(uint64_t* p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) { asm volatile("st.global.v2.u64 [%0], {%1,%2};\n\tst.global.v2.u64 [%0+16], {%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory"); }
 #endif
+DI void stg_v2q(uint64_t* p, uint64_t a, uint64_t b) { asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(a), "l"(b) : "memory"); }
 DI void stg_v2(void* p, uint2 v) { asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory"); }
 DI void sts_v2(uint32_t a, uint64_t x, uint64_t y) { asm volatile("st.shared.v2.u64 [%0], {%1,%2};" ::"r"(a), "l"(x), "l"(y) : "memory"); }
 DI void sts_u64(uint32_t a, uint64_t x) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(x) : "memory"); }
@@ -384,7 +385,31 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
   mbar_wait(bar, 0);
   __syncthreads();
 
-  const uint32_t ps = tile + 16 + (uint32_t)(my_byte - g0); // shared address of the item's base 0
+  uint32_t ps = tile + 16 + (uint32_t)(my_byte - g0); // shared address of the item's base 0
+#if RAGGED_DIRECT
+  // Direct sector stores: DG consecutive windows fill whole 32-byte sectors when the first one's row is a multiple of DG.
+  // The lane therefore starts `skip` = row mod DG windows early (on the bytes in front of its item: the previous read's
+  // tail, the pad, at worst the barrier word — junk either way), computes those windows like any other and never stores
+  // them; from then on position u of the unrolled loop is row u (mod DG) in every lane.
+  const uint32_t ps_o = ps, n_o = n;
+  const uint64_t my_out_o = my_out;
+  const uint32_t skip = n ? (uint32_t)(my_out & (uint64_t)(DG - 1u)) : 0u;
+  ps -= skip;
+  my_out -= skip;
+  n += skip;
+#define PS_O ps_o
+#define N_O n_o
+#define MYOUT_O my_out_o
+#else
+#define PS_O ps
+#define N_O n
+#define MYOUT_O my_out
+#endif
+#endif
+#if !RAGGED
+#define PS_O ps
+#define N_O n
+#define MYOUT_O my_out
 #endif
   const uint32_t tb = sbase;                                 // group tables: two conflict-free 128-byte halves each
 #if RAGGED
@@ -510,16 +535,16 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
   if (dirty) {
     // windows holding a zero-seed byte: byte-exact values (seed.cpp:149-166); then flag the read for the replay
     uint32_t run = 0;
-    for (uint32_t j = 0; j < n + K - 1; ++j) {
+    for (uint32_t j = 0; j < N_O + K - 1; ++j) {
 #if STRIPS
       const unsigned cj = P.bases[my_byte + j];
       run = (seed_of_byte(cj) != 0 && cj > 7) ? run + 1 : 0;
 #else
-      run = lds_u8(lut + lds_u8(ps + j)) ? 0 : run + 1;
+      run = lds_u8(lut + lds_u8(PS_O + j)) ? 0 : run + 1;
 #endif
       if (j >= K - 1 && run < K) {
         const uint32_t p = j - (K - 1);
-        const uint64_t row = my_out + p;
+        const uint64_t row = MYOUT_O + p;
         for (uint32_t s = 0; s < M; ++s) {
           uint64_t f = 0, r = 0;
           const uint32_t* care = P.care + (size_t)s * P.care_words;
@@ -528,7 +553,7 @@ seed_jit_kernel(const __grid_constant__ JitParams P, const __grid_constant__ Ten
 #if STRIPS
               const unsigned c = P.bases[my_byte + p + q];
 #else
-              const unsigned c = lds_u8(ps + p + q);
+              const unsigned c = lds_u8(PS_O + p + q);
 #endif
               f ^= srol_n(seed_of_byte(c), K - 1 - q);
               r ^= srol_n(seed_of_byte(c & 7u), q);
@@ -615,6 +640,7 @@ struct SeedJit
   uint32_t table_bytes = 0, tw = 0, row_bytes = 0, ot_bytes = 0, ht = 0, nt = 256, nbuf = 1;
   bool box3 = false;            // output through 3-D tensor stores of 64-byte blocks (rows must be 64-byte multiples)
   bool ragged = false;          // ragged-batch variant (item arrays, per-lane rows, coalesced stores)
+  bool ragged_direct = false;   // ... its direct form: whole-sector stores from registers, no rows in shared memory
   uint32_t row_pitch = 0;       // ragged variant: bytes between the lanes' private rows
   const SeedPlanHost* plan = nullptr;
   mutable SeedJit* alt = nullptr;  // the 2-D tile variant for other row lengths, compiled on first use
@@ -815,6 +841,20 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
     while (b2) { const uint32_t t = a % b2; a = b2; b2 = t; }
     unroll = unroll / a * 4;
   }
+  // ragged batches, direct form: DG = 4 / gcd(ht, 4) consecutive windows are whole 32-byte sectors; they are kept in registers
+  // (DG * ht u64, at most 16) and leave as full-sector stores — no private rows, no descriptors, no copy loop.  Only the two
+  // ends of a row share sectors with its neighbours (16-/8-byte stores there).  NTHASH_B200_SEED_JIT_RAGGED_ROWS=1: the older form.
+  uint32_t dg = 0;
+  if (ragged && !getenv("NTHASH_B200_SEED_JIT_RAGGED_ROWS")) {
+    const uint32_t g4 = ht % 4 == 0 ? 4 : ht % 2 == 0 ? 2 : 1;
+    if ((4 / g4) * ht <= 16) dg = 4 / g4;
+  }
+  if (dg) { // loop body: whole groups and whole block periods, four windows or more
+    uint32_t a = dg, b2 = lcm_d;
+    while (b2) { const uint32_t t = a % b2; a = b2; b2 = t; }
+    unroll = dg / a * lcm_d;
+    while (unroll < 4) unroll *= 2;
+  }
   if (unroll > 24) { why = "strided blocks with incompatible strides"; return nullptr; }
   // CTA size / output buffering: defaults found on C4 (profiles/r01_seed_jit_sweeps.txt), overridable for experiments
   // (box3 on C4: 128 threads with three 6 KB tiles per warp 0.89 of the HBM peak, two 0.85, one 0.76; 2-D tiles 0.63)
@@ -879,6 +919,7 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
     const uint32_t chunk = ht % 2 ? 8 : 16, pitch = (row_bytes + 15) / 16 * 16 + ((((row_bytes + 15) / 16) % 2) ? 0 : 16);
     src << "#define RAGGED " << (ragged ? 1 : 0) << "\n#define CHUNK " << chunk << "u\n#define LANES_PER_ROW " << 256 / chunk << "u\n#define ROW_PITCH " << pitch << "u\n";
   }
+  src << "#define RAGGED_DIRECT " << (dg ? 1 : 0) << "\n#define DG " << (dg ? dg : 1) << "u\n";
   src << "#define STRANDS " << (strands ? 1 : 0) << "\n#define REDUCE " << (reduce ? 1 : 0) << "\n#define STRIPS " << (strips ? 1 : 0) << "\n";
   if (strands) {
     // STR_FLUSH(w0): the strand hashes of windows w0 .. w0+3 (4*M u64 per array, contiguous in both arrays) as M whole
@@ -981,8 +1022,50 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
       << "      __syncwarp(); \\\n      copy_out(); \\\n      __syncwarp(); \\\n";
     return o.str();
   };
+  // ragged variant, direct form: DG windows -> registers gv[] -> whole sectors (see RAGGED_DIRECT in the kernel text)
+  auto ragged_direct_text = [&](uint32_t gi) {
+    std::ostringstream o;
+    o << "      uint64_t gv[" << dg * ht << "]; \\\n";
+    for (uint32_t i = 0; i < dg; ++i) {
+      const uint32_t u = gi * dg + i;
+      std::string body = window_body(u); // writes hv[q]: redirect to gv[i * ht + q]
+      for (size_t at = 0; (at = body.find("hv[", at)) != std::string::npos;) {
+        const size_t e = body.find(']', at);
+        const uint32_t q = (uint32_t)std::stoul(body.substr(at + 3, e - at - 3));
+        const std::string rep = "gv[" + std::to_string(i * ht + q) + "]";
+        body.replace(at, e - at + 1, rep);
+        at += rep.size();
+      }
+      o << "      if (p0 + " << u << "u < n) { \\\n        WIN_PRE(p0 + " << u << "u) \\\n" << body << "      } \\\n";
+    }
+    o << "      if (active) { const uint32_t w0 = p0 + " << gi * dg << "u; uint64_t* o_ = P.out + (my_out + w0) * HT; \\\n"
+      << "        if (w0 >= skip && w0 + " << dg << "u <= n) {";
+    for (uint32_t c = 0; c < dg * ht / 4; ++c)
+      o << " stg_v4q(o_ + " << 4 * c << ", gv[" << 4 * c << "], gv[" << 4 * c + 1 << "], gv[" << 4 * c + 2 << "], gv[" << 4 * c + 3 << "]);";
+    o << " } else { \\\n";
+    for (uint32_t i = 0; i < dg; ++i) { // a row's first / last group: the widest aligned pieces of each window that is the lane's
+      o << "          if (w0 + " << i << "u >= skip && w0 + " << i << "u < n) {";
+      for (uint32_t c = i * ht; c < (i + 1) * ht;) {
+        if (c % 4 == 0 && c + 4 <= (i + 1) * ht) {
+          o << " stg_v4q(o_ + " << c << ", gv[" << c << "], gv[" << c + 1 << "], gv[" << c + 2 << "], gv[" << c + 3 << "]);";
+          c += 4;
+        } else if (c % 2 == 0 && c + 2 <= (i + 1) * ht) {
+          o << " stg_v2q(o_ + " << c << ", gv[" << c << "], gv[" << c + 1 << "]);";
+          c += 2;
+        } else {
+          o << " o_[" << c << "] = gv[" << c << "];";
+          c += 1;
+        }
+      }
+      o << " } \\\n";
+    }
+    o << "        } \\\n      } \\\n";
+    return o.str();
+  };
   src << "#define MAIN_TILES \\\n";
-  for (uint32_t t = 0; ragged && t < unroll / tw; ++t)
+  for (uint32_t gi = 0; dg && gi < unroll / dg; ++gi)
+    src << "    if (__any_sync(0xffffffffu, p0 + " << gi * dg << "u < n)) { \\\n" << ragged_direct_text(gi) << "    } \\\n";
+  for (uint32_t t = 0; ragged && !dg && t < unroll / tw; ++t)
     src << "    if (__any_sync(0xffffffffu, p0 + " << t * tw << "u < n)) { \\\n" << ragged_tile_text(t) << "    } \\\n";
   for (uint32_t t = 0; !ragged && t < unroll / tw; ++t) {
     src << "    if (p0 + " << (t + 1) * tw << "u <= n) { \\\n" << tile_text(t, true) << "    } else if (p0 + " << t * tw << "u < n) { \\\n"
@@ -1004,6 +1087,7 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
   j->nbuf = nbuf;
   j->box3 = box3;
   j->ragged = ragged;
+  j->ragged_direct = dg != 0;
   j->strands = strands;
   j->reduce = reduce;
   j->strips = strips;
@@ -1057,7 +1141,7 @@ uint32_t seed_jit_smem_bytes(const SeedJit* j, uint32_t tile_cap)
     const uint32_t out_bytes = j->reduce ? 0u : (j->nt / 32) * j->nbuf * j->ot_bytes;
     return j->table_bytes + 256 + 16 + (j->nt / 32) * tile_cap + 1024 + out_bytes;
   }
-  const uint32_t out_bytes = j->reduce ? 0u : j->ragged ? (j->nt / 32) * 32u * (j->row_pitch + 16u) + 256u : (j->nt / 32) * j->nbuf * j->ot_bytes;
+  const uint32_t out_bytes = j->reduce ? 0u : j->ragged ? (j->ragged_direct ? 256u : (j->nt / 32) * 32u * (j->row_pitch + 16u) + 256u) : (j->nt / 32) * j->nbuf * j->ot_bytes;
   return j->table_bytes + 256 + 16 + 16 + tile_cap + 16 + 1024 + out_bytes;
 }
 
