@@ -65,6 +65,27 @@ def test_ragged_dirty_reads_all_k(k):
         assert_batch_equal(res, ora, h, check_strands=(h == 3))
 
 
+@pytest.mark.parametrize("h", [1, 2, 3, 4])
+def test_ragged_deal_precomputed_and_in_kernel(h, monkeypatch):
+    """Ragged batches: the CTAs deal their items out by length class.  The deal comes with the layout (KmerGeom::item_perm,
+    blocks of 256 items, computed by item_perm_kernel) or, for CTAs of another size or with NTHASH_B200_NO_ITEM_PERM, from
+    the counting sort inside the kernel.  Same rows either way, and the oracle's; one batch of short reads (reads are
+    items) and one with reads long enough to be cut into items."""
+    k = 31
+    rng = np.random.default_rng(900 + h)
+    for lens in (rng.integers(0, 260, 1500), np.concatenate([rng.integers(20, 400, 300), [30000, 5, 12000, 31, 30]])):
+        off = ragged_offsets(lens)
+        bases = synth(rng, int(off[-1]), p_bad=0.003, lower=0.1)
+        ora = ORACLE.kmer_batch(bases, off.astype(np.uint64), k, h, threads=4)
+        res = run_ragged(bases, off, k, h)
+        assert_batch_equal(res, ora, h)
+        for env, val in (("NTHASH_B200_NO_ITEM_PERM", "1"), ("NTHASH_B200_FAST_NT", "128")):
+            monkeypatch.setenv(env, val)
+            alt = run_ragged(bases, off, k, h)
+            monkeypatch.delenv(env)
+            assert torch.equal(alt.out, res.out) and torch.equal(alt.valid_bits, res.valid_bits), env
+
+
 def test_many_hashes_and_clean_reads():
     rng = np.random.default_rng(99)
     off = ragged_offsets(rng.integers(40, 200, 300))
@@ -127,12 +148,13 @@ def test_fast_kernel_output_paths(n, read_len, k, h, no_box, monkeypatch):
 
 @pytest.mark.parametrize("n,read_len,k,h", [(37, 5000, 63, 1), (100, 1200, 31, 2), (50, 3000, 21, 4), (64, 2113, 31, 3), (3, 700, 31, 1),
                                             (1, 100000, 63, 1), (1000, 600, 33, 1), (700, 1057, 5, 1)])
-@pytest.mark.parametrize("flat_seg", [168, 264, 96])
+@pytest.mark.parametrize("flat_seg", [0, 168, 264, 96])
 def test_flat_items_long_uniform_reads(n, read_len, k, h, flat_seg, monkeypatch):
     """Uniform long reads run as FLAT items (fixed runs of dense windows that ignore read boundaries, 3-D tensor stores)
     plus a fix-up launch for the rows behind every read boundary and the partial last item.  Dirty bytes are planted on
     both sides of read boundaries, where the two kernels' responsibilities meet."""
-    monkeypatch.setenv("NTHASH_B200_FLAT_SEG", str(flat_seg))
+    if flat_seg:  # 0: the defaults (h <= 2: 200-window items, 40-window stores, CTAs of 96 threads)
+        monkeypatch.setenv("NTHASH_B200_FLAT_SEG", str(flat_seg))
     rng = np.random.default_rng(n * 17 + read_len + k + h)
     bases = synth(rng, n * read_len, p_bad=0.0003, lower=0.05)
     for r in range(1, n, max(1, n // 7)):

@@ -151,6 +151,28 @@ def test_ragged_specialised_kernel(seeds, h, capfd, monkeypatch):
     capfd.readouterr()
 
 
+@pytest.mark.parametrize("seeds,h", [([SEED_A31, SEED_B31], 3), (["11100111"], 3), (["110011", "101101"], 2), (["11111"], 1),
+                                     (["111111111101111111111", "110111010010010111011"], 4), (["1101100", "0011011", "1000001"], 1)],
+                         ids=lambda v: v[0][:10] if isinstance(v, list) else str(v))
+def test_ragged_direct_and_row_forms_agree(seeds, h, monkeypatch):
+    """The ragged variant of the generated kernel has two output forms: whole-sector stores straight from registers (groups of
+    1, 2 or 4 windows, lanes started on a sector-aligned row) and the older private rows in shared memory
+    (NTHASH_B200_SEED_JIT_RAGGED_ROWS=1, also what hash counts that do not fit the registers take).  Rows of every length and
+    alignment, dirty bytes and NULs: same values, same validity, and the oracle's."""
+    k = len(seeds[0])
+    rng = np.random.default_rng(4242 + k + h)
+    lens = np.concatenate([rng.integers(0, 3 * k + 150, 900), [k, k + 1, k + 2, k + 3, 0, 5000]])
+    off = ragged_offsets(lens)
+    bases = synth(rng, int(off[-1]), p_bad=0.003, lower=0.1)
+    bases[rng.integers(0, len(bases), 5)] = 0
+    ora = ORACLE.seed_batch(bases, off.astype(np.uint64), seeds, h, threads=4)
+    direct = run_ragged(nthash_b200.SeedPlan(seeds, h), bases, off, strands=False)
+    assert_batch_equal(direct, ora, len(seeds) * h)
+    monkeypatch.setenv("NTHASH_B200_SEED_JIT_RAGGED_ROWS", "1")  # read when a plan's ragged variant is generated: a new plan
+    rows = run_ragged(nthash_b200.SeedPlan(seeds, h), bases, off, strands=False)
+    assert torch.equal(rows.out, direct.out) and torch.equal(rows.valid_bits, direct.valid_bits)
+
+
 def _long_seed(k, rng):
     half = "".join(rng.choice(list("0111"), k // 2))
     s = half + ("1" if k % 2 else "") + half[::-1]
