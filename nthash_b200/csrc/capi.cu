@@ -183,14 +183,14 @@ static int plan_item_perm(RaggedItems& R, cudaStream_t st)
 // Nothing is read back: the item tables are sized by a host-side bound of the item count (every read contributes at
 // most ceil(windows / SEG_LONG) <= bases / SEG_LONG + 1 items) and the surplus is padded with empty items.
 static int plan_ragged(const uint64_t* d_read_off, const uint64_t* d_koff, uint64_t n_reads, uint64_t max_read_len,
-                       uint64_t n_bases, uint32_t k, uint32_t tile_budget, cudaStream_t st, RaggedItems& R)
+                       uint64_t n_bases, uint32_t k, uint32_t tile_budget, cudaStream_t st, RaggedItems& R, bool want_perm = true)
 {
   if ((uint64_t)KMER_NT * max_read_len + 64 <= tile_budget) { // every read is one item
     R.g.item_byte = d_read_off;
     R.g.item_out = d_koff;
     R.g.n_items = n_reads;
     R.tile_cap = (uint32_t)(KMER_NT * max_read_len + 64);
-    return plan_item_perm(R, st);
+    return want_perm ? plan_item_perm(R, st) : NTHASH_OK;
   }
   R.tile_cap = span_bound(SEG_LONG, 1, k);
   const uint64_t cap = n_reads + n_bases / SEG_LONG + 1;
@@ -206,7 +206,7 @@ static int plan_ragged(const uint64_t* d_read_off, const uint64_t* d_koff, uint6
   R.g.item_byte = R.d_items;
   R.g.item_out = R.d_items + cap + 1;
   R.item_read = R.d_items + 2 * (cap + 1);
-  if (int rc = plan_item_perm(R, st)) {
+  if (int rc = want_perm ? plan_item_perm(R, st) : NTHASH_OK) {
     cudaFreeAsync(R.d_items, st);
     R.d_items = nullptr;
     return rc;
@@ -367,7 +367,7 @@ static int seed_dev_run(const nthash_seed_plan* plan, const DevBatch& B, cudaStr
     // still fits this (smaller) budget, or when it is already the cut-up form
     const bool reuse = B.items && (B.items->d_items || (uint64_t)KMER_NT * B.max_len + 64 <= budget);
     if (!reuse)
-      if (int rc = plan_ragged(B.d_read_off, B.d_koff, B.n_reads, B.max_len, B.n_bases, P.k, budget, st, R)) return rc;
+      if (int rc = plan_ragged(B.d_read_off, B.d_koff, B.n_reads, B.max_len, B.n_bases, P.k, budget, st, R, false)) return rc; // (the seed kernels deal their items out themselves)
     const RaggedItems& I = reuse ? *B.items : R;
     P.g = I.g;
     P.tile_cap = I.tile_cap;
