@@ -99,8 +99,9 @@ int nthash_kmer_batch_dev(const uint8_t* d_bases, uint64_t n_bases_readable, con
                           uint64_t* d_out_rev, void* stream);
 
 /* Ragged reads, planned once.  nthash_ragged_plan_create() computes the layout of a batch — koff, the row total, the
- * longest read, and the item tables the kernels use when reads are too long to be one work item — and synchronises the
- * host ONCE; the plan then serves any number of calls on batches with the same read_off (the bases may change: same
+ * longest read, the item tables the kernels use when reads are too long to be one work item, and the order in which
+ * every CTA hands its items to its threads (by length class, so that a warp's lanes finish together) — and synchronises
+ * the host ONCE; the plan then serves any number of calls on batches with the same read_off (the bases may change: same
  * layout, new sequence).  The *_planned_dev entries only enqueue kernels: no allocation that blocks, no read-back, no
  * host synchronisation, so they can be captured into a CUDA graph.  d_read_off is borrowed (keep it alive and
  * unchanged while the plan lives); the plan owns koff (nthash_ragged_plan_koff, device pointer, n_reads + 1 entries).

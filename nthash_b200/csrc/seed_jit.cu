@@ -1117,7 +1117,7 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
   rt.cubin(prog, cubin.data());
   rt.destroy(&prog);
   if (const char* dump = getenv("NTHASH_B200_SEED_JIT_DUMP")) { // inspection: <prefix>.cu and <prefix>.cubin
-    const std::string pre = std::string(dump) + "_mode" + std::to_string(mode);
+    const std::string pre = std::string(dump) + "_mode" + std::to_string(mode) + (strands ? "s" : "");
     if (FILE* f = fopen((pre + ".cu").c_str(), "w")) { fputs(j->source.c_str(), f); fclose(f); }
     if (FILE* f = fopen((pre + ".cubin").c_str(), "wb")) { fwrite(cubin.data(), 1, cubin.size(), f); fclose(f); }
   }
