@@ -367,6 +367,92 @@ def sub_record(torch, nthash_b200, LIB, nd, name, args, rank, world, peak, want_
     return rec
 
 
+RAGGED_CASES = {
+    # trimmed-read shaped batches (no BASELINE config of their own: what short-read data looks like after adapter / quality
+    # trimming, and what the ragged entry points of the C ABI are for): lengths uniform in [lo, hi]
+    "kmer_100_150": dict(n_reads=10_000_000, lo=100, hi=150, k=31, h=1, seeds=None, seed=61),
+    "kmer_36_150": dict(n_reads=10_000_000, lo=36, hi=150, k=31, h=1, seeds=None, seed=62),
+    "seed_100_150": dict(n_reads=5_000_000, lo=100, hi=150, k=31, h=3, seeds=[SEED_A, SEED_B], seed=63),
+}
+
+
+def ragged_records(torch, nthash_b200, nd, args, rank, world, peak, want_cpu):
+    """Ragged batches through the planned entry points (nthash_ragged_plan_create once, then nthash_kmer_batch_planned_dev /
+    nthash_seed_batch_planned_dev: kernels only): device-resident time, roofline fraction on the batch's own algorithmic
+    bytes (bases + rows x H x 8), and a checksum of the first reads' rows against the compiled reference (rank 0)."""
+    import numpy as np
+    out_recs = {}
+    steps = max(3, min(args.steps, args.sub_steps))
+    for name, c in RAGGED_CASES.items():
+        time.sleep(args.sub_pause)
+        try:
+            n, k, h, seeds = c["n_reads"], c["k"], c["h"], c["seeds"]
+            H = h * (len(seeds) if seeds else 1)
+            g = torch.Generator(device="cuda")
+            g.manual_seed(c["seed"] * 1000 + rank)
+            lens = torch.randint(c["lo"], c["hi"] + 1, (n,), device="cuda", generator=g, dtype=torch.int64)
+            off = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+            off[1:] = torch.cumsum(lens, 0)
+            nb = int(off[-1])
+            bases = splitmix_bases_torch(torch, (nb + 31) // 32 * 32, c["seed"], first_base=rank * ((nb + 31) // 32 * 32))[:nb]
+            plan = nthash_b200.RaggedPlan(off, k)
+            rows = plan.rows
+            out = torch.empty((rows, H), dtype=torch.int64, device="cuda")
+            splan = nthash_b200.SeedPlan(seeds, h) if seeds else None
+
+            def step():
+                if splan is not None:
+                    nthash_b200.seed_hashes_planned(splan, plan, bases, want_valid=False, out=out)
+                else:
+                    nthash_b200.kmer_hashes_planned(plan, bases, h, want_valid=False, out=out)
+
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            nd.barrier()
+            with ClockSampler(torch.cuda.current_device()) as clk:
+                marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+                marks[0].record()
+                for i in range(steps):
+                    step()
+                    marks[i + 1].record()
+                torch.cuda.synchronize()
+            each = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(steps))
+            ms = nd.max_over_ranks([marks[0].elapsed_time(marks[steps]) / steps])[0]
+            abytes = nb + rows * H * 8
+            rec = {"workload": f"{n} reads of {c['lo']}-{c['hi']} bp (uniform), k={k}, " + (f"{len(seeds)} spaced seeds x {h}" if seeds else f"h={h}")
+                               + ", planned ragged entry points", "reads_per_gpu": n, "rows_per_gpu": rows, "n_gpus": world,
+                   "value": world * rows / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "clocks": clk.summary(),
+                   "roofline": {"bound": "hbm", "achieved": abytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                "frac": abytes / (ms * 1e-3) / 1e9 / peak, "kernel_ms": ms, "kernel_ms_best": each[0],
+                                "kernel_ms_median": statistics.median(each), "algorithmic_bytes_per_launch": abytes,
+                                "kernel": "seed_jit_kernel (ragged, direct form)" if seeds else "kmer_fast_kernel<H=%d> (ragged, direct stores)" % h}}
+            if rank == 0 and want_cpu:
+                from oracle_lib import ORACLE, REF
+                lib = REF if REF is not None else ORACLE
+                m_reads = min(n, 200_000)
+                off_np = off[: m_reads + 1].cpu().numpy().astype(np.uint64)
+                bases_np = bases[: int(off_np[-1])].cpu().numpy()
+                koff = plan.koff()
+                pre_rows = int(koff[m_reads])
+                t0 = time.perf_counter()
+                r = (lib.seed_batch(bases_np, off_np, seeds, h, want=(), threads=os.cpu_count() or 1) if seeds
+                     else lib.kmer_batch(bases_np, off_np, k, h, want=(), threads=os.cpu_count() or 1))
+                dt = time.perf_counter() - t0
+                gsum = int(out[:pre_rows].sum()) & M64
+                rec["cpu_reference"] = {"value": r["n_emit"] / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": lib.kind,
+                                        "sample": f"first {m_reads} reads of the batch, one pass, {dt:.2f} s"}
+                rec["checksum_matches_reference"] = bool(gsum == r["sum"] and pre_rows == r["n_emit"])
+                del koff
+            out_recs[name] = rec
+            del plan, splan, out, bases, off, lens
+        except Exception as e:  # never take the headline line down
+            out_recs[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+    return out_recs
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -378,6 +464,7 @@ def main():
     ap.add_argument("--ref-sample-reads", type=int, default=0, help="reads of the CPU sample (default: the config's cpu_reads)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--sub-steps", type=int, default=5, help="timed launches per sub-record config")
+    ap.add_argument("--sub-pause", type=float, default=1.5, help="idle seconds in front of every sub-record (lets the power cap of the previous one clear)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sub-records", action="store_true", help="only the headline config (skip configs.c3/c4/c5)")
     ap.add_argument("--no-consumers", action="store_true")
@@ -629,14 +716,19 @@ def main():
     torch.cuda.empty_cache()
     if not args.no_sub_records and not args.reads:
         subs = {}
-        for name in ("c3", "c4", "c5"):
+        # c4 last among the BASELINE configs and a short pause in front of every sub-record: C4's launches run the GPU into its
+        # power cap (sw_power_cap, SM clock down to ~1750 MHz for a few hundred ms afterwards), which otherwise lands on
+        # whichever config is measured next (C5 read 0.73 of the peak right after C4 and 0.90 on its own, same kernel)
+        for name in ("c3", "c5", "c4"):
             if name == args.config:
                 continue
+            time.sleep(args.sub_pause)
             try:
                 subs[name] = sub_record(torch, nthash_b200, LIB, nd, name, args, rank, world, peak, not args.no_cpu_baseline)
             except Exception as e:  # a sub-record must never take the headline line down with it
                 subs[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
                 torch.cuda.empty_cache()
+        subs["ragged"] = ragged_records(torch, nthash_b200, nd, args, rank, world, peak, not args.no_cpu_baseline)
         line["configs"] = subs
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["class_api"] = class_api_record()
