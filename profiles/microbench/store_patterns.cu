@@ -28,6 +28,30 @@ __global__ void __launch_bounds__(256) k_store(uint64_t* out, uint64_t n_rows, u
   }
 }
 
+
+// Round 2: is the lane-strided STG.256 cap a per-request cost?  G lanes (2 or 4) share G rows: every instruction writes
+// G * 32 contiguous bytes of ONE row per lane group (what a shuffle transpose between the lanes of a group would give the
+// DIRECT output path), G instructions cover the group's G rows.  Same bytes, same order per row, 1/G as many requests per line.
+template<int G>
+__global__ void __launch_bounds__(256) k_store_group(uint64_t* out, uint64_t n_rows, uint64_t salt)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= n_rows) return;
+  const uint32_t sub = (uint32_t)(t % G);
+  const uint64_t r0 = t - sub; // the group's first row
+  uint64_t v = t * 0x9e3779b97f4a7c15ull + salt;
+#pragma unroll 1
+  for (int i = 0; i < 120; i += 4 * G) {   // G sectors of every row per round
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      uint64_t* p = out + (r0 + g) * 120 + i + 4 * sub;
+      if (i + 4 * (int)sub < 120)
+        asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(v), "l"(v + 1), "l"(v + 2), "l"(v + 3) : "memory");
+      v = v * 6364136223846793005ull + 1442695040888963407ull;
+    }
+  }
+}
+
 // coalesced reference: the warp writes 1024 contiguous bytes per instruction
 __global__ void __launch_bounds__(256) k_store_coalesced(uint64_t* out, uint64_t n_rows, uint64_t salt)
 {
@@ -52,8 +76,8 @@ int main()
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   const unsigned blocks = (unsigned)((n_rows + 255) / 256);
-  const char* names[] = { "STG.256 lane-strided", "2x STG.128 lane-strided", "4x STG.64 lane-strided", "STG.256 .cs", "STG.256 L1::no_allocate", "STG.256 coalesced" };
-  for (int m = 0; m < 6; ++m) {
+  const char* names[] = { "STG.256 lane-strided", "2x STG.128 lane-strided", "4x STG.64 lane-strided", "STG.256 .cs", "STG.256 L1::no_allocate", "STG.256 coalesced", "STG.256, lane pairs: 64 B per row", "STG.256, lane quads: 128 B per row", "STG.256, 8 lanes: 256 B per row" };
+  for (int m = 0; m < 9; ++m) {
     float best = 1e9f;
     for (int rep = 0; rep < 4; ++rep) {
       cudaEventRecord(e0);
@@ -64,6 +88,9 @@ int main()
         case 3: k_store<3><<<blocks, 256>>>(out, n_rows, rep); break;
         case 4: k_store<4><<<blocks, 256>>>(out, n_rows, rep); break;
         case 5: k_store_coalesced<<<blocks, 256>>>(out, n_rows, rep); break;
+        case 6: k_store_group<2><<<blocks, 256>>>(out, n_rows, rep); break;
+        case 7: k_store_group<4><<<blocks, 256>>>(out, n_rows, rep); break;
+        case 8: k_store_group<8><<<blocks, 256>>>(out, n_rows, rep); break;
       }
       cudaEventRecord(e1);
       cudaEventSynchronize(e1);
@@ -71,7 +98,7 @@ int main()
       cudaEventElapsedTime(&ms, e0, e1);
       if (rep && ms < best) best = ms;
     }
-    printf("%-28s %.3f ms  %.1f GB/s\n", names[m], best, n_rows * 960.0 / best / 1e6);
+    printf("%-40s %.3f ms  %.1f GB/s\n", names[m], best, n_rows * 960.0 / best / 1e6);
   }
   printf("err=%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
