@@ -696,6 +696,14 @@ def main():
         windows, gsum = w.checksum_prefix(m["sample_reads"])
         cpu = {"value": m["value"], "unit": UNIT, "cores": m["threads"], "kind": m["kind"], "sample": cpu_sample_label(cfg, m),
                "checksum_matches_gpu": bool(gsum == m["sum"] and windows == m["emitted_per_pass"])}
+        try:  # the one-core number next to the all-core one (one pass over the first 200 k reads)
+            from oracle_lib import ORACLE, REF
+            one_reads = min(n_reads, 200_000)
+            v1, _, _, dt1 = cpu_reference_pass(REF if REF is not None else ORACLE, splitmix_bases_numpy(one_reads * L, cfg["seed"]), one_reads, L, k, h, 1,
+                                               cfg.get("seeds"))
+            cpu["one_core"] = {"value": v1, "unit": UNIT, "sample": f"first {one_reads} reads, one thread, one pass, {dt1:.2f} s"}
+        except Exception as e:
+            cpu["one_core"] = {"error": str(e)[:200]}
 
     abytes = algorithmic_bytes(n_reads, L, k, H)
     achieved = abytes / (kernel_ms * 1e-3) / 1e9
