@@ -303,6 +303,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   // the tile was 17 % of the stall samples and the serial prologue in front of the copy another 10 % (profiles/r02_ncu_c2_head.txt).
   // row buffers follow the staged bases; the 4 KB tetramer table is parked in them for the warm-up phase
   const uint32_t rb_base = (sbase + F_TILE_OFF + F_TILE_PAD + P.tile_cap + 16 + 1023u) & ~1023u;
+  if (P.g.flat) asm volatile("griddepcontrol.launch_dependents;"); // the fix-up launch may queue up behind this grid's last wave
   if (tid == 0) {
     uint64_t lo_byte, eb, eo;
     uint32_t en;
@@ -1378,6 +1379,11 @@ __global__ void __launch_bounds__(128) kmer_flat_fix_kernel(const __grid_constan
     const uint64_t fi = seeds[sidx(c)], ri = seeds[4 + sidx(c ^ 4u)]; // c ^ 4 flips code bit 1: the complement
     roll_step(st, make_uint4((uint32_t)fi, (uint32_t)(fi >> 32), (uint32_t)ri, (uint32_t)(ri >> 32)), P.two);
   }
+  // Launched with programmatic stream serialisation (launch_flat_fix): everything above — tables, the item's bytes, the k-base
+  // warm-up — only reads the input and runs while the main kernel's last CTAs drain; the rows it overwrites must have
+  // landed first, so the first store waits for the main kernel (a no-op when launched the ordinary way).  (Keeping the
+  // lane's windows in registers across the wait as well was slower: 0.944 vs 0.936 ms on C5.)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   for (uint32_t p = 0; p < n; ++p) {
     const uint32_t cin = sq[p + k - 1], cout = sq[(int)p - 1];
     run = is_acgtu(cin) ? run + 1 : 0;
@@ -1600,8 +1606,19 @@ cudaError_t launch_flat_fix(const KmerParams& P, cudaStream_t st)
     const cudaError_t e = cudaFuncSetAttribute(kmer_flat_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  kmer_flat_fix_kernel<<<(unsigned)((n_reads + wpb - 1) / wpb), wpb * FIX_LANES, smem, st>>>(P, n_reads, warp_bytes);
-  return cudaGetLastError();
+  // programmatic dependent launch: the fix-up's CTAs may start once every CTA of the main kernel has started (it signals
+  // griddepcontrol.launch_dependents first thing) and take the slots its last wave frees; they wait before their first store
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((n_reads + wpb - 1) / wpb));
+  cfg.blockDim = dim3(wpb * FIX_LANES);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = getenv("NTHASH_B200_NO_PDL") ? 0 : 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kmer_flat_fix_kernel, P, n_reads, warp_bytes);
 }
 
 } // namespace
