@@ -40,7 +40,7 @@ constexpr int F_PAIR_R_OFF = 128; // 16 x 8 B : [code_in][code_out] -> Skc[in]^S
 constexpr int F_IN_OFF = 256;     //  4 x 16 B : [code_in] -> {S[in], Skc[in]}  (warm-up)
 constexpr int F_LUT_OFF = 320;    // 256 x 1 B : 0 for ACGTUacgtu, 1 otherwise
 constexpr int F_BAR_OFF = 576;    // mbarrier
-constexpr int F_RANGE_OFF = 592;  // 2 x u64: byte range of the CTA's items
+constexpr int F_RANGE_OFF = 592;  // u64: first staged byte of the CTA (g0), written by thread 0
 constexpr int F_TILE_OFF = 608;   // 16-byte pad + staged bases
 constexpr int F_TILE_PAD = 16;
 constexpr int T4_BYTES = 256 * 16; // tetramer warm-up table
@@ -321,7 +321,6 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     if (bulk_bytes) bulk_g2s(tile + F_TILE_PAD, P.bases + g0, bulk_bytes, bar);
     bulk_g2s(smem + (rb_base - sbase), P.t4, T4_BYTES, bar);
     s_range[0] = g0;
-    s_range[1] = g1;
     // the (at most 15) bytes of a range that ends in the buffer's unaligned tail
     for (uint64_t g = max(bulk_end, g0); g < g1; ++g) tile[F_TILE_PAD + (g - g0)] = P.bases[g];
     // pull the bases of the CTA that will take this SM slot next into L2 (same extent, one residency wave ahead),
