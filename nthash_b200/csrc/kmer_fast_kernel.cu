@@ -133,13 +133,16 @@ NTH_D uint32_t mad_hi(uint32_t a, uint32_t b, uint32_t c)
   asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
+// SH: plain shifts (ALU pipe) instead of shift-by-multiply (FMA pipe).  Measured on one box (profiles/r02_ab_kmer_shifts.txt): the
+// consumers gain 2-4 % and C5's flat items 3 % with the shifts, C2 loses 0.5 %: chosen per kernel variant (ROLL_SHIFTS below).
+template<bool SH = false>
 NTH_D void roll_step(State& s, const uint4 e, const uint32_t two)
 {
 #ifndef NTH_ROLL_V2
   {
     const uint32_t lo = s.flo, hi = s.fhi;
     const uint32_t hi1 = __funnelshift_l(lo, hi, 1);
-    const uint32_t nhi = lop3<LUT_SEL_C>(hi1, __umulhi(hi, 4u), 2u);
+    const uint32_t nhi = lop3<LUT_SEL_C>(hi1, SH ? hi >> 30 : __umulhi(hi, 4u), 2u);
     const uint32_t nlo = lop3<LUT_OR_AND>(lo + lo, hi, 1u);
     s.flo = nlo ^ e.x;
     s.fhi = nhi ^ e.y;
@@ -147,7 +150,7 @@ NTH_D void roll_step(State& s, const uint4 e, const uint32_t two)
   {
     const uint32_t lo = s.rlo ^ e.z, hi = s.rhi ^ e.w;
     s.rlo = __funnelshift_r(lo, hi, 1);
-    const uint32_t y = __funnelshift_r(hi, __umulhi(hi, 0x80000000u), 1);
+    const uint32_t y = __funnelshift_r(hi, SH ? hi >> 1 : __umulhi(hi, 0x80000000u), 1);
     s.rhi = lop3<LUT_SEL_C>(y, lo, 1u);
   }
   (void)two;
@@ -289,6 +292,8 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
   // travel through shared memory to the lane that owns the END of the previous row, which stores the shared sector whole
   constexpr bool MERGE = DIRECT && (H == 1 || (H == 2 && !STR));
   constexpr bool REDUCE = CONS != 0 && CONS != 4;  // consumers proper: nothing is stored
+  // roll_step with plain shifts: the consumers and the long-piece tensor-store variants (flat items of long reads, h <= 2)
+  constexpr bool ROLL_SHIFTS = REDUCE || (BOX && H >= 1 && H <= 2 && WS == (H == 1 ? 40 : 20));
   const uint32_t HH = H ? (uint32_t)H : P.h; // H == 0: runtime number of hashes (5..255, general output path only)
   const uint32_t NT = blockDim.x;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -443,7 +448,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
       const uint32_t v = lds_u8(lut + c);
       bad |= v;
       if (REDUCE) run = v ? 0 : run + 1;
-      roll_step(s, lds_v4(sbase + F_IN_OFF + ((c & 6u) << 3)), P.two);
+      roll_step<ROLL_SHIFTS>(s, lds_v4(sbase + F_IN_OFF + ((c & 6u) << 3)), P.two);
     }
   }
   if (!MERGE) __syncthreads(); // the tetramer table is dead from here on: its bytes become row buffers
@@ -456,7 +461,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     if (REDUCE) run = v ? 0 : run + 1;
     const uint32_t ea = pair + (((ci & 6u) << 4) | ((co & 6u) << 2));
     const uint2 ef = lds_v2(ea), er = lds_v2(ea + (F_PAIR_R_OFF - F_PAIR_OFF));
-    roll_step(s, make_uint4(ef.x, ef.y, er.x, er.y), P.two);
+    roll_step<ROLL_SHIFTS>(s, make_uint4(ef.x, ef.y, er.x, er.y), P.two);
     return canonical2(s);
   };
   auto consume = [&](uint64_t h0) { // one window the reference visits
@@ -632,7 +637,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
     if (REDUCE && FULL && bw == 0 && run + 1 >= k) { // consumer, steady state: all four windows are visited ones
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        roll_step(s, make_uint4(efv[i].x, efv[i].y, erv[i].x, erv[i].y), P.two);
+        roll_step<ROLL_SHIFTS>(s, make_uint4(efv[i].x, efv[i].y, erv[i].x, erv[i].y), P.two);
         if (PIPE) {
           const uint32_t ea = __byte_perm(c4n, pair, 0x7650u | i);
           efv[i] = lds_v2(ea);
@@ -652,7 +657,7 @@ kmer_fast_kernel(const __grid_constant__ KmerParams P, const __grid_constant__ C
         bad |= v;
         run = v ? 0 : run + 1;
       }
-      roll_step(s, make_uint4(efv[i].x, efv[i].y, erv[i].x, erv[i].y), P.two);
+      roll_step<ROLL_SHIFTS>(s, make_uint4(efv[i].x, efv[i].y, erv[i].x, erv[i].y), P.two);
       if (PIPE && FULL) {
         const uint32_t ea = __byte_perm(c4n, pair, 0x7650u | i);
         efv[i] = lds_v2(ea);

@@ -139,7 +139,11 @@ DI void roll_step(State& s, const uint4 e, const uint32_t two)
   {
     const uint32_t lo = s.flo, hi = s.fhi;
     const uint32_t hi1 = __funnelshift_l(lo, hi, 1);
+#if EXT_SHIFTS >= 2
+    const uint32_t nhi = lop3<0x50 | 0x88>(hi1, hi >> 30, 2u);
+#else
     const uint32_t nhi = lop3<0x50 | 0x88>(hi1, __umulhi(hi, 4u), 2u);
+#endif
     const uint32_t nlo = lop3<0xF0 | 0x88>(lo + lo, hi, 1u);
     s.flo = nlo ^ e.x;
     s.fhi = nhi ^ e.y;
@@ -147,7 +151,11 @@ DI void roll_step(State& s, const uint4 e, const uint32_t two)
   {
     const uint32_t lo = s.rlo ^ e.z, hi = s.rhi ^ e.w;
     s.rlo = __funnelshift_r(lo, hi, 1);
+#if EXT_SHIFTS >= 2
+    const uint32_t y = __funnelshift_r(hi, hi >> 1, 1);
+#else
     const uint32_t y = __funnelshift_r(hi, __umulhi(hi, 0x80000000u), 1);
+#endif
     s.rhi = lop3<0x50 | 0x88>(y, lo, 1u);
   }
   return;
@@ -189,8 +197,13 @@ DI uint64_t ext_hash(uint64_t h0, uint64_t mult)
 {
   const uint64_t t = h0 * mult;
   const uint32_t lo = (uint32_t)t, hi = (uint32_t)(t >> 32);
+#if EXT_SHIFTS // plain shifts (ALU pipe) instead of multiplies (FMA pipe): see EXT_SHIFTS in the generator
+  const uint32_t nlo = lo ^ __funnelshift_r(lo, hi, 27);
+  const uint32_t nhi = hi ^ (hi >> 27);
+#else
   const uint32_t nlo = lop3<0x1E>(lo, __umulhi(lo, 32u), hi * 32u); // lo ^ ((lo >> 27) | (hi << 5))
   const uint32_t nhi = hi ^ __umulhi(hi, 32u);
+#endif
   return ((uint64_t)nhi << 32) | nlo;
 }
 // per byte of x: non-zero iff the byte is not one of ACGTUacgtu (the bytes whose 2-bit code (c >> 1) & 3 is their seed's base)
@@ -906,6 +919,11 @@ static SeedJit* seed_jit_build_variant(const SeedPlanHost& plan, std::string& wh
 
   std::ostringstream src;
   src << "#define HAVE_ST256 " << (nvrtc().version >= 1209 ? 1 : 0) << "\n#define ROLL_V2 " << (getenv("NTHASH_B200_ROLL_V2") ? 1 : 0) << "\n";
+  // plain shifts (ALU pipe) instead of shift-by-multiply (FMA pipe) in ext_hash (>= 1) and roll_step (>= 2): level 2 by default.  The
+  // multiplies were the better trade while the ALU pipe was the bottleneck; under sustained load the kernel sits on the power cap
+  // and the cheaper instruction wins: C4 10.36 / 11.33 ms (best / median of 16 back-to-back launches) -> 10.17 / 11.03, fused
+  // consumer 8.28 -> 8.26 (profiles/r02_ab_seed_shifts.txt)
+  src << "#define EXT_SHIFTS " << (getenv("NTHASH_B200_SEED_JIT_EXT_SHIFTS") ? atoi(getenv("NTHASH_B200_SEED_JIT_EXT_SHIFTS")) : 2) << "\n";
   src << JIT_PRELUDE;
   src << "#define NT " << nt << "u\n#define NBUF " << nbuf << "u\n#define BULK_WAIT_READ asm volatile(\"cp.async.bulk.wait_group.read "
       << nbuf - 1 << ";\" ::: \"memory\");\n";
