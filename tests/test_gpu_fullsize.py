@@ -156,3 +156,49 @@ def test_full_size_config5_long_read_shard(shard):
     m = 2000
     pre = ORACLE.kmer_batch(bases[: m * L].cpu().numpy(), np.arange(m + 1, dtype=np.uint64) * L, k, 1, want=(), threads=os.cpu_count() or 1)
     assert pre["n_emit"] == m * nk and pre["sum"] == (int(out[:m].sum()) & M64)
+
+
+@pytest.mark.parametrize("lo,hi,seeds", [(100, 150, None), (36, 150, None), (100, 150, "c4")])
+def test_full_size_ragged_batches(lo, hi, seeds):
+    """The ragged batches bench.py reports (`configs.ragged`): 10 M trimmed-read shaped reads through the planned entry points
+    (the layout's precomputed deal, direct sector stores; the generated seed kernel's direct form).  Sampled blocks of reads
+    bit-exact against the oracle — the first, the last (a partial block of 256 items) and a few in between — plus a 64-bit
+    checksum of a long prefix against the threaded oracle, and validity = "every window" for clean reads."""
+    import nthash_b200
+    n, k = (10_000_000, 31) if seeds is None else (5_000_000, 31)
+    h = 1 if seeds is None else 3
+    seed_list = bench.CONFIGS["c4"]["seeds"] if seeds else None
+    H = h * (len(seed_list) if seed_list else 1)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(lo * 1000 + hi)
+    lens = torch.randint(lo, hi + 1, (n - 3,), device="cuda", generator=g, dtype=torch.int64)
+    lens = torch.cat([lens, torch.tensor([k - 1, k, 0], device="cuda")])  # the last, partial block ends in reads without / with one window
+    off = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    off[1:] = torch.cumsum(lens, 0)
+    nb = int(off[-1])
+    bases = bench.splitmix_bases_torch(torch, (nb + 31) // 32 * 32, 77)[:nb]
+    plan = nthash_b200.RaggedPlan(off, k)
+    if seed_list:
+        res = nthash_b200.seed_hashes_planned(nthash_b200.SeedPlan(seed_list, h), plan, bases)
+    else:
+        res = nthash_b200.kmer_hashes_planned(plan, bases, h)
+    torch.cuda.synchronize()
+    koff = plan.koff()
+    assert plan.rows == int(koff[-1]) == int(torch.clamp(lens - k + 1, min=0).sum())
+    assert bool(res.valid_mask().all())  # ACGT only: the reference visits every window
+    out = res.out
+    off_h, koff_h = off.cpu().numpy(), koff.cpu().numpy()
+
+    def oracle_rows(r0, r1):
+        b = bases[off_h[r0]: off_h[r1]].cpu().numpy()
+        o = (off_h[r0: r1 + 1] - off_h[r0]).astype(np.uint64)
+        return (ORACLE.seed_batch(b, o, seed_list, h, threads=8) if seed_list else ORACLE.kmer_batch(b, o, k, h, threads=8))
+
+    for r0 in (0, 255, 256 * 1234 + 17, n // 2, n - 700, n - 256):
+        r1 = min(n, r0 + 600)
+        ora = oracle_rows(r0, r1)
+        got = u64(out[koff_h[r0]: koff_h[r1]]).reshape(-1, H)
+        assert got.shape == ora["out"].shape and (got == ora["out"]).all(), f"reads {r0}..{r1}"
+    m = 150_000  # whole-prefix checksum
+    ora = oracle_rows(0, m)
+    assert int(out[: koff_h[m]].sum()) & M64 == ora["sum"] and int(koff_h[m]) == ora["n_emit"]
