@@ -153,6 +153,7 @@ struct RaggedItems
 {
   KmerGeom g;
   uint32_t tile_cap = 0;
+  uint32_t tile_cap_256 = 0;           // KmerParams::tile_cap_256 (plan handles only: it takes a read-back)
   uint64_t* d_items = nullptr;         // [item_byte | item_out | item_read]
   const uint64_t* item_read = nullptr; // NULL when items are reads
   uint8_t* d_perm = nullptr;           // KmerGeom::item_perm (the items of every block of 256 in length-class order)
@@ -337,6 +338,7 @@ static int kmer_dev_run(const DevBatch& B, uint32_t k, uint32_t h, cudaStream_t 
     const RaggedItems& I = B.items ? *B.items : R;
     P.g = I.g;
     P.tile_cap = I.tile_cap;
+    P.tile_cap_256 = I.tile_cap_256;
     P.general_fits = kmer_smem_bytes(P.tile_cap) <= SMEM_MAX;
   }
   int rc = run_kmer(P, B.memset_rows, B.d_rows, B.rows_bound, st);
@@ -722,10 +724,12 @@ int nthash_ragged_plan_create(const uint64_t* d_read_off, uint64_t n_reads, uint
   pl->n_reads = n_reads;
   pl->d_read_off = d_read_off;
   uint64_t* d_stats = nullptr;
-  uint64_t h_stats[2] = { 0, 0 }, ends[2] = { 0, 0 };
+  uint64_t h_stats[3] = { 0, 0, 0 }, ends[2] = { 0, 0 };
   cudaError_t e = cudaMalloc(&pl->d_koff, (n_reads + 1) * sizeof(uint64_t));
-  if (e == cudaSuccess) e = cudaMallocAsync(&d_stats, 2 * sizeof(uint64_t), st);
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_stats, 3 * sizeof(uint64_t), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_stats, 0, 3 * sizeof(uint64_t), st);
   if (e == cudaSuccess) e = launch_koff_scan(d_read_off, n_reads, k, 0, pl->d_koff, d_stats, st);
+  if (e == cudaSuccess) e = launch_block_span_max(d_read_off, n_reads, d_stats + 2, st); // longest 256-read block, in bytes
   if (e == cudaSuccess) e = cudaMemcpyAsync(h_stats, d_stats, sizeof h_stats, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(&ends[0], d_read_off, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(&ends[1], d_read_off + n_reads, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
@@ -738,6 +742,9 @@ int nthash_ragged_plan_create(const uint64_t* d_read_off, uint64_t n_reads, uint
     pl->n_bases = ends[1];
     if (pl->rows) {
       rc = plan_ragged(d_read_off, pl->d_koff, n_reads, pl->max_len, ends[1] - ends[0], k, TILE_BUDGET, st, pl->items);
+      // reads are the items: the fast kernel's CTAs of 256 threads stage exactly these blocks, so the measured span bounds them
+      if (rc == NTHASH_OK && !pl->items.d_items && h_stats[2] + 64 < pl->items.tile_cap && !getenv("NTHASH_B200_NO_EXACT_TILE"))
+        pl->items.tile_cap_256 = (uint32_t)h_stats[2] + 64;
       const uint4* t4 = nullptr; // the 4 KB warm-up table of this k is created on first use: do it now, not inside a graph capture
       if (rc == NTHASH_OK) e = get_t4_table(k, &t4);
       if (rc == NTHASH_OK && e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -48,6 +48,9 @@ struct KmerParams
   uint64_t bloom_bits = 0;         // filter size in bits; bit index = hash % bloom_bits
   uint32_t bloom_mode = 0;         // 0: none, 1: insert (atomicOr), 2: query, 3: cardinality sketch (bloom_words = counters, bloom_bits = s << 8 | r)
   uint32_t tile_cap = 0; // bytes of base tile a CTA may stage
+  // ragged batches planned once (reads are items): the longest byte span of any block of 256 consecutive reads, measured on
+  // the device at plan time (+ slack), instead of the 256 x longest-read bound — smaller tiles, more resident CTAs (0: unknown)
+  uint32_t tile_cap_256 = 0;
   bool use_tma = true;   // allow the fast kernel (kmer_fast_kernel.cu) when the request permits
   bool general_fits = true; // false: the general kernel's CTA tile would not fit shared memory (huge k) - fast kernel or nothing
   uint64_t s[4], sk[4], mult[4]; // filled by launch_kmer
@@ -160,6 +163,8 @@ cudaError_t launch_item_fill(const uint64_t* read_off, const uint64_t* koff, uin
                              uint64_t cap, cudaStream_t st);
 // perm[256 * b + t] for every block b of 256 consecutive items (see KmerGeom::item_perm); perm holds ceil(n_items / 256) * 256 bytes
 cudaError_t launch_item_perm(const uint64_t* item_out, uint64_t n_items, uint8_t* perm, cudaStream_t st);
+// *d_max = max(*d_max, longest byte span of a block of 256 consecutive reads) (d_max zeroed by the caller)
+cudaError_t launch_block_span_max(const uint64_t* read_off, uint64_t n_reads, uint64_t* d_max, cudaStream_t st);
 // valid_bits <- ones for *d_rows rows (<= rows_bound, which only sizes the grid); nothing is read back.
 cudaError_t launch_fill_valid(uint32_t* d_valid, const uint64_t* d_rows, uint64_t rows_bound, cudaStream_t st);
 

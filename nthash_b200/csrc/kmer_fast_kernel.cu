@@ -1709,6 +1709,10 @@ cudaError_t launch_kmer_fast(const KmerParams& Pin, cudaStream_t st)
   // uniform reads cut into long items keep the shared-memory rows (0.76 vs 0.67).
   c.direct = env_u32("NTHASH_B200_FAST_DIRECT", (!uniform || P.g.segs == 1) ? 1u : 0u) != 0 && !c.box && P.h <= 4 && !P.reduce_out && !P.bloom_mode;
   auto tile_cap_for = [&](uint32_t nt) -> uint64_t {
+    // measured at plan time (KmerParams::tile_cap_256): 10 M reads of 100-150 bp go from four to five resident CTAs, 0.77 -> 0.81 of
+    // the HBM peak; with two hashes per window the extra CTA is a loss (0.82 -> 0.78: more stores in flight, see the C2 probe), so
+    // h = 1 only (profiles/r02_ab_exact_tile.txt)
+    if (!uniform && nt == 256 && Pin.tile_cap_256 && P.h == 1 && !P.out_fwd) return (uint64_t)Pin.tile_cap_256 + 2 * (uint64_t)P.k + 64;
     if (!uniform) return ((uint64_t)Pin.tile_cap * nt + KMER_NT - 1) / KMER_NT + 2 * (uint64_t)P.k + 64; // sized for KMER_NT items
     if (P.g.flat) return (uint64_t)nt * P.g.seg + ((uint64_t)nt * P.g.seg / P.g.nk + 2) * (P.k - 1) + 64;
     if (P.g.segs == 1) return (uint64_t)nt * P.g.read_len + 64;

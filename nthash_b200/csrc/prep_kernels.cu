@@ -411,6 +411,22 @@ __global__ void __launch_bounds__(256) item_perm_kernel(const uint64_t* __restri
   perm[(uint64_t)blockIdx.x * 256 + cnt[cls] + pos] = (uint8_t)tid;
 }
 
+__global__ void block_span_max_kernel(const uint64_t* __restrict__ read_off, uint64_t n_reads, unsigned long long* d_max)
+{
+  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, r0 = b * 256;
+  if (r0 >= n_reads) return;
+  const uint64_t r1 = r0 + 256 < n_reads ? r0 + 256 : n_reads;
+  atomicMax(d_max, (unsigned long long)(read_off[r1] - read_off[r0]));
+}
+
+cudaError_t launch_block_span_max(const uint64_t* read_off, uint64_t n_reads, uint64_t* d_max, cudaStream_t st)
+{
+  const uint64_t blocks = (n_reads + 255) / 256;
+  if (blocks == 0) return cudaSuccess;
+  block_span_max_kernel<<<(unsigned)((blocks + 255) / 256), 256, 0, st>>>(read_off, n_reads, reinterpret_cast<unsigned long long*>(d_max));
+  return cudaGetLastError();
+}
+
 cudaError_t launch_item_perm(const uint64_t* item_out, uint64_t n_items, uint8_t* perm, cudaStream_t st)
 {
   if (n_items == 0) return cudaSuccess;
